@@ -1,0 +1,109 @@
+"""ctypes binding of ``libhfagp_sm100.so`` (the C ABI declared in ``include/hfagp.h``).
+
+No fallbacks: if the shared library is missing or a call fails this raises.  Nothing here
+imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libhfagp_sm100.so')
+MAX_TAPS = 16
+ACT_LINEAR, ACT_LRELU = 0, 1
+
+# every symbol include/hfagp.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    'hfagp_abi_version', 'hfagp_last_error', 'hfagp_conv2d_fwd', 'hfagp_upfir_act_fwd',
+    'hfagp_torgb_small_fwd', 'hfagp_styles_fwd', 'hfagp_modulate_fwd', 'hfagp_render_fwd',
+    'hfagp_blur_fwd', 'hfagp_linear_fwd', 'hfagp_latent_fwd', 'hfagp_nchw_to_nhwc',
+    'hfagp_nhwc_to_nchw',
+]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ('batch', C.c_int32), ('in_h', C.c_int32), ('in_w', C.c_int32), ('cin', C.c_int32), ('cout', C.c_int32),
+        ('oh', C.c_int32), ('ow', C.c_int32), ('in_stride', C.c_int32),
+        ('out_h', C.c_int32), ('out_w', C.c_int32),
+        ('out_stride', C.c_int32), ('out_off_y', C.c_int32), ('out_off_x', C.c_int32),
+        ('ntaps', C.c_int32),
+        ('dy', C.c_int32 * MAX_TAPS), ('dx', C.c_int32 * MAX_TAPS), ('wtap', C.c_int32 * MAX_TAPS),
+        ('w_batch_stride', C.c_int64),
+        ('act', C.c_int32), ('act_gain', C.c_float), ('clamp', C.c_float),
+        ('noise_gain', C.c_float), ('residual_scale', C.c_float),
+        ('up_h', C.c_int32), ('up_w', C.c_int32),
+    ]
+
+
+class RenderDesc(C.Structure):
+    _fields_ = [
+        ('batch', C.c_int32), ('res', C.c_int32), ('plane_h', C.c_int32), ('plane_w', C.c_int32),
+        ('s_coarse', C.c_int32), ('s_fine', C.c_int32),
+        ('delta', C.c_float), ('box_scale', C.c_float),
+    ]
+
+
+class HfagpError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load the library once.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise HfagpError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                         f'(or `make -C hfa_gp_b200/csrc`). There is no CPU/PyTorch fallback for the hot path.')
+    l = C.CDLL(LIB_PATH)
+    l.hfagp_last_error.restype = C.c_char_p
+    l.hfagp_abi_version.restype = C.c_int
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    l.hfagp_conv2d_fwd.argtypes = [C.POINTER(ConvDesc)] + [vp] * 9
+    l.hfagp_upfir_act_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, f32, f32, vp, vp]
+    l.hfagp_torgb_small_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, vp, vp]
+    l.hfagp_styles_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    l.hfagp_modulate_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    l.hfagp_render_fwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
+    l.hfagp_blur_fwd.argtypes = [i32] * 7 + [vp, vp, vp]
+    l.hfagp_linear_fwd.argtypes = [i32, i32, i32, vp, vp, vp, f32, f32, vp, vp]
+    l.hfagp_latent_fwd.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
+    l.hfagp_nchw_to_nhwc.argtypes = [i32, i32, i32, i32, vp, vp, vp]
+    l.hfagp_nhwc_to_nchw.argtypes = [i32, i32, i32, i32, vp, vp, vp]
+    for s in SYMBOLS:
+        fn = getattr(l, s)
+        if s not in ('hfagp_last_error',):
+            fn.restype = C.c_int
+    if l.hfagp_abi_version() != 1:
+        raise HfagpError(f'ABI version mismatch: library {l.hfagp_abi_version()}, binding 1')
+    _lib = l
+    return l
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().hfagp_last_error()
+        raise HfagpError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}')
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a contiguous fp32/int32 CUDA tensor (None passes NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise HfagpError('hot-path tensors must live on a CUDA device (no CPU fallback)')
+    if not t.is_contiguous():
+        raise HfagpError('hot-path tensors must be contiguous')
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,47 @@
+// Shared helpers for libhfagp_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdint>
+#include "../../include/hfagp.h"
+
+namespace hfagp {
+
+// thread-local last-error string (hfagp_last_error)
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+
+#define HFAGP_CHECK_ARG(cond, ...)                               \
+  do {                                                           \
+    if (!(cond)) return ::hfagp::fail(HFAGP_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define HFAGP_CHECK_LAUNCH(name)                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess)                                                              \
+      return ::hfagp::fail(HFAGP_E_CUDA, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define HFAGP_CUDA(call)                                                                 \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return ::hfagp::fail(HFAGP_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));   \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
+// softplus with torch semantics (beta=1, threshold=20)
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace hfagp

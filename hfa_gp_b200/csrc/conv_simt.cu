@@ -1,0 +1,439 @@
+// fp32 SIMT implicit-GEMM convolution (channels-last) with the fused StyleGAN2 / encoder epilogue,
+// plus the small bandwidth-bound companions (FIR after the transposed conv, small-N ToRGB, blur).
+// This is the exact-fp32 path; see conv_tc.cu for the tcgen05 tensor-core path.
+#include "common.cuh"
+
+namespace hfagp {
+
+struct ConvParams {
+  HfagpConvDesc d;
+  const float* x;
+  const float* w;
+  const float* dcoef;
+  const float* noise;
+  const float* bias;
+  const float* residual;
+  const float* up_img;
+  float* y;
+};
+
+constexpr int BK = 16;
+constexpr int LDK = BK + 4;  // row stride (floats): 8 consecutive rows hit 8 distinct 16B bank groups
+
+// upsample2d(img)[oy][ox][co] for a channels-last low-res image [uh][uw][cout]:
+// zero-insert x2, pad [2,1,2,1], [1,3,3,1]^2/64 * 4  ==  separable {0.25,0.75} polyphase.
+__device__ __forceinline__ float upsample_tap(const float* __restrict__ img, int uh, int uw, int cstride,
+                                              int oy, int ox, int co) {
+  int my = oy >> 1, mx = ox >> 1;
+  int y0, y1, x0, x1;
+  float wy0, wy1, wx0, wx1;
+  if (oy & 1) { y0 = my; y1 = my + 1; wy0 = 0.75f; wy1 = 0.25f; } else { y0 = my - 1; y1 = my; wy0 = 0.25f; wy1 = 0.75f; }
+  if (ox & 1) { x0 = mx; x1 = mx + 1; wx0 = 0.75f; wx1 = 0.25f; } else { x0 = mx - 1; x1 = mx; wx0 = 0.25f; wx1 = 0.75f; }
+  float v = 0.f;
+  bool vy0 = y0 >= 0 && y0 < uh, vy1 = y1 >= 0 && y1 < uh;
+  bool vx0 = x0 >= 0 && x0 < uw, vx1 = x1 >= 0 && x1 < uw;
+  if (vy0 && vx0) v += wy0 * wx0 * __ldg(img + ((size_t)y0 * uw + x0) * cstride + co);
+  if (vy0 && vx1) v += wy0 * wx1 * __ldg(img + ((size_t)y0 * uw + x1) * cstride + co);
+  if (vy1 && vx0) v += wy1 * wx0 * __ldg(img + ((size_t)y1 * uw + x0) * cstride + co);
+  if (vy1 && vx1) v += wy1 * wx1 * __ldg(img + ((size_t)y1 * uw + x1) * cstride + co);
+  return v;
+}
+
+template <int TM, int TN>
+__global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvParams p) {
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  constexpr int A_LD = BM / 64;  // float4 loads per thread per k-chunk
+  constexpr int B_LD = BN / 64;
+  __shared__ __align__(16) float As[2][BM * LDK];
+  __shared__ __align__(16) float Bs[2][BN * LDK];
+
+  const HfagpConvDesc& d = p.d;
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int M = d.oh * d.ow;
+  const int cin = d.cin, cout = d.cout;
+  const bool vec_ok = (cin & 3) == 0;
+
+  const float* xn = p.x + (size_t)n * d.in_h * d.in_w * cin;
+  const float* wn = p.w + (size_t)n * d.w_batch_stride;
+
+  // fixed per-thread load coordinates
+  int a_iy0[A_LD], a_ix0[A_LD];
+  bool a_valid[A_LD];
+#pragma unroll
+  for (int i = 0; i < A_LD; ++i) {
+    int idx = tid + i * 256;
+    int row = idx >> 2;
+    int m = m0 + row;
+    a_valid[i] = m < M;
+    int my = a_valid[i] ? m / d.ow : 0;
+    int mx = a_valid[i] ? m - my * d.ow : 0;
+    a_iy0[i] = my * d.in_stride;
+    a_ix0[i] = mx * d.in_stride;
+  }
+  const int kq = tid & 3;
+  const int chunks = (cin + BK - 1) / BK;
+  const int iters = d.ntaps * chunks;
+
+  float4 a_reg[A_LD], b_reg[B_LD];
+
+  auto load_tiles = [&](int it) {
+    int t = it / chunks;
+    int c = (it - t * chunks) * BK + kq * 4;
+    int dy = d.dy[t], dx = d.dx[t];
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int iy = a_iy0[i] + dy, ix = a_ix0[i] + dx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_valid[i] && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w && c < cin) {
+        const float* ptr = xn + ((size_t)iy * d.in_w + ix) * cin + c;
+        if (vec_ok) {
+          v = __ldg(reinterpret_cast<const float4*>(ptr));
+        } else {
+          v.x = __ldg(ptr);
+          if (c + 1 < cin) v.y = __ldg(ptr + 1);
+          if (c + 2 < cin) v.z = __ldg(ptr + 2);
+          if (c + 3 < cin) v.w = __ldg(ptr + 3);
+        }
+      }
+      a_reg[i] = v;
+    }
+    const float* wt = wn + (size_t)d.wtap[t] * cout * cin;
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      int row = (tid + i * 256) >> 2;
+      int co = n0 + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < cout && c < cin) {
+        const float* ptr = wt + (size_t)co * cin + c;
+        if (vec_ok) {
+          v = __ldg(reinterpret_cast<const float4*>(ptr));
+        } else {
+          v.x = __ldg(ptr);
+          if (c + 1 < cin) v.y = __ldg(ptr + 1);
+          if (c + 2 < cin) v.z = __ldg(ptr + 2);
+          if (c + 3 < cin) v.w = __ldg(ptr + 3);
+        }
+      }
+      b_reg[i] = v;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int row = (tid + i * 256) >> 2;
+      *reinterpret_cast<float4*>(&As[buf][row * LDK + kq * 4]) = a_reg[i];
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      int row = (tid + i * 256) >> 2;
+      *reinterpret_cast<float4*>(&Bs[buf][row * LDK + kq * 4]) = b_reg[i];
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int tx = tid & 15, ty = tid >> 4;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+
+  for (int it = 0; it < iters; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < iters) load_tiles(it + 1);
+    const float* as = As[buf];
+    const float* bs = Bs[buf];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 a4[TM], b4[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a4[i] = *reinterpret_cast<const float4*>(&as[(ty + 16 * i) * LDK + q * 4]);
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b4[j] = *reinterpret_cast<const float4*>(&bs[(tx + 16 * j) * LDK + q * 4]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          acc[i][j] = fmaf(a4[i].x, b4[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].y, b4[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].z, b4[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].w, b4[j].w, acc[i][j]);
+        }
+    }
+    if (it + 1 < iters) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue
+  const float* dco = p.dcoef ? p.dcoef + (size_t)n * cout : nullptr;
+  const size_t out_img = (size_t)d.out_h * d.out_w * cout;
+  float* yn = p.y + (size_t)n * out_img;
+  const float* resn = p.residual ? p.residual + (size_t)n * out_img : nullptr;
+  const float* upn = p.up_img ? p.up_img + (size_t)n * d.up_h * d.up_w * cout : nullptr;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+    int my = m / d.ow, mx = m - my * d.ow;
+    int oy = my * d.out_stride + d.out_off_y;
+    int ox = mx * d.out_stride + d.out_off_x;
+    float nz = p.noise ? __ldg(p.noise + (size_t)oy * d.out_w + ox) * d.noise_gain : 0.f;
+    size_t pix = ((size_t)oy * d.out_w + ox) * cout;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int co = n0 + tx + 16 * j;
+      if (co >= cout) continue;
+      float v = acc[i][j];
+      if (dco) v *= __ldg(dco + co);
+      v += nz;
+      if (p.bias) v += __ldg(p.bias + co);
+      if (d.act == HFAGP_ACT_LRELU) v = lrelu02(v);
+      v *= d.act_gain;
+      if (d.clamp > 0.f) v = fminf(fmaxf(v, -d.clamp), d.clamp);
+      if (resn) v = (v + __ldg(resn + pix + co)) * d.residual_scale;
+      if (upn) v += upsample_tap(upn, d.up_h, d.up_w, cout, oy, ox, co);
+      yn[pix + co] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- FIR after transposed conv
+__global__ void upfir_act_kernel(int batch, int h2, int w2, int c, const float* __restrict__ t,
+                                 const float* __restrict__ dcoef, const float* __restrict__ noise, float noise_gain,
+                                 const float* __restrict__ bias, int act, float act_gain, float clamp,
+                                 float* __restrict__ y) {
+  const int c4 = c >> 2;
+  size_t total = (size_t)batch * h2 * w2 * c4;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int cq = idx % c4;
+  size_t pix = idx / c4;
+  int ox = pix % w2;
+  size_t r = pix / w2;
+  int oy = r % h2;
+  int n = r / h2;
+  const int th = h2 + 1, tw = w2 + 1;
+  const float g[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  const float4* tn = reinterpret_cast<const float4*>(t + (size_t)n * th * tw * c);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    int iy = oy + ky - 1;
+    if (iy < 0 || iy >= th) continue;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      int ix = ox + kx - 1;
+      if (ix < 0 || ix >= tw) continue;
+      float wgt = g[ky] * g[kx];
+      float4 v = __ldg(tn + ((size_t)iy * tw + ix) * c4 + cq);
+      s.x = fmaf(wgt, v.x, s.x);
+      s.y = fmaf(wgt, v.y, s.y);
+      s.z = fmaf(wgt, v.z, s.z);
+      s.w = fmaf(wgt, v.w, s.w);
+    }
+  }
+  float nz = noise ? __ldg(noise + (size_t)oy * w2 + ox) * noise_gain : 0.f;
+  float vals[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int co = cq * 4 + k;
+    float v = vals[k];
+    if (dcoef) v *= __ldg(dcoef + (size_t)n * c + co);
+    v += nz;
+    if (bias) v += __ldg(bias + co);
+    if (act == HFAGP_ACT_LRELU) v = lrelu02(v);
+    v *= act_gain;
+    if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
+    vals[k] = v;
+  }
+  reinterpret_cast<float4*>(y)[idx] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+}
+
+// ---------------------------------------------------------------- small-N ToRGB (cout <= 4)
+__global__ void torgb_small_kernel(int batch, int h, int w_, int cin, int cout, const float* __restrict__ x,
+                                   const float* __restrict__ w, const float* __restrict__ bias, float clamp,
+                                   const float* __restrict__ up_img, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t npix = (size_t)batch * h * w_;
+  if (warp >= npix) return;
+  const int n = warp / ((size_t)h * w_);
+  const size_t rem = warp - (size_t)n * h * w_;
+  const int oy = rem / w_, ox = rem - (size_t)oy * w_;
+  const float4* xp = reinterpret_cast<const float4*>(x + warp * cin);
+  const float4* wp = reinterpret_cast<const float4*>(w + (size_t)n * cout * cin);
+  const int c4 = cin >> 2;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int q = lane; q < c4; q += 32) {
+    float4 xv = __ldg(xp + q);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      if (o < cout) {
+        float4 wv = __ldg(wp + (size_t)o * c4 + q);
+        acc[o] = fmaf(xv.x, wv.x, acc[o]);
+        acc[o] = fmaf(xv.y, wv.y, acc[o]);
+        acc[o] = fmaf(xv.z, wv.z, acc[o]);
+        acc[o] = fmaf(xv.w, wv.w, acc[o]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
+  if (lane < cout) {
+    float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+    if (bias) v += __ldg(bias + lane);
+    if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
+    if (up_img) v += upsample_tap(up_img + (size_t)n * (h / 2) * (w_ / 2) * cout, h / 2, w_ / 2, cout, oy, ox, lane);
+    y[warp * cout + lane] = v;
+  }
+}
+
+// ---------------------------------------------------------------- encoder blur
+__global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow,
+                            const float* __restrict__ x, float* __restrict__ y) {
+  const int c4 = c >> 2;
+  size_t total = (size_t)batch * oh * ow * c4;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int cq = idx % c4;
+  size_t pix = idx / c4;
+  int ox = pix % ow;
+  size_t r = pix / ow;
+  int oy = r % oh;
+  int n = r / oh;
+  const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  const float4* xn = reinterpret_cast<const float4*>(x + (size_t)n * h * w_ * c);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    int iy = oy * stride + ky - pad0;
+    if (iy < 0 || iy >= h) continue;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      int ix = ox * stride + kx - pad0;
+      if (ix < 0 || ix >= w_) continue;
+      float wgt = g[ky] * g[kx];
+      float4 v = __ldg(xn + ((size_t)iy * w_ + ix) * c4 + cq);
+      s.x = fmaf(wgt, v.x, s.x);
+      s.y = fmaf(wgt, v.y, s.y);
+      s.z = fmaf(wgt, v.z, s.z);
+      s.w = fmaf(wgt, v.w, s.w);
+    }
+  }
+  reinterpret_cast<float4*>(y)[idx] = s;
+}
+
+__global__ void nchw_to_nhwc_kernel(int batch, int c, int hw, const float* __restrict__ x, float* __restrict__ y) {
+  size_t total = (size_t)batch * c * hw;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ch = idx % c;
+  size_t r = idx / c;
+  int p = r % hw;
+  int n = r / hw;
+  y[idx] = __ldg(x + ((size_t)n * c + ch) * hw + p);
+}
+
+__global__ void nhwc_to_nchw_kernel(int batch, int c, int hw, const float* __restrict__ x, float* __restrict__ y) {
+  size_t total = (size_t)batch * c * hw;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int p = idx % hw;
+  size_t r = idx / hw;
+  int ch = r % c;
+  int n = r / c;
+  y[idx] = __ldg(x + ((size_t)n * hw + p) * c + ch);
+}
+
+}  // namespace hfagp
+
+using namespace hfagp;
+
+extern "C" int hfagp_conv2d_fwd(const HfagpConvDesc* desc, const float* x, const float* w, const float* dcoef,
+                                const float* noise, const float* bias, const float* residual, const float* up_img,
+                                float* y, void* stream) {
+  HFAGP_CHECK_ARG(desc && x && w && y, "conv2d_fwd: null pointer");
+  const HfagpConvDesc& d = *desc;
+  HFAGP_CHECK_ARG(d.batch > 0 && d.cin > 0 && d.cout > 0 && d.oh > 0 && d.ow > 0, "conv2d_fwd: bad dims");
+  HFAGP_CHECK_ARG(d.ntaps > 0 && d.ntaps <= HFAGP_MAX_TAPS, "conv2d_fwd: ntaps %d out of range", d.ntaps);
+  HFAGP_CHECK_ARG(d.in_stride == 1 || d.in_stride == 2, "conv2d_fwd: in_stride must be 1 or 2");
+  HFAGP_CHECK_ARG(d.out_stride >= 1 && (d.oh - 1) * d.out_stride + d.out_off_y < d.out_h &&
+                      (d.ow - 1) * d.out_stride + d.out_off_x < d.out_w,
+                  "conv2d_fwd: output window exceeds out_h/out_w");
+  HFAGP_CHECK_ARG(!up_img || (d.up_h * 2 == d.out_h && d.up_w * 2 == d.out_w), "conv2d_fwd: up_img must be out/2");
+  HFAGP_CHECK_ARG(d.batch <= 65535, "conv2d_fwd: batch too large");
+  ConvParams p{d, x, w, dcoef, noise, bias, residual, up_img, y};
+  const long long M = (long long)d.oh * d.ow;
+  cudaStream_t st = (cudaStream_t)stream;
+  // large tiles when they still fill the machine, small tiles otherwise
+  long long big_ctas = (long long)cdiv(M, 128) * cdiv(d.cout, 128) * d.batch;
+  if (big_ctas >= 148 && d.cout >= 96) {
+    dim3 grid(cdiv(M, 128), cdiv(d.cout, 128), d.batch);
+    conv_igemm_kernel<8, 8><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid(cdiv(M, 64), cdiv(d.cout, 64), d.batch);
+    conv_igemm_kernel<4, 4><<<grid, 256, 0, st>>>(p);
+  }
+  HFAGP_CHECK_LAUNCH("conv_igemm_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float* t, const float* dcoef,
+                                   const float* noise, float noise_gain, const float* bias, int act, float act_gain,
+                                   float clamp, float* y, void* stream) {
+  HFAGP_CHECK_ARG(t && y, "upfir_act_fwd: null pointer");
+  HFAGP_CHECK_ARG(batch > 0 && h2 > 0 && w2 > 0 && c > 0 && (c & 3) == 0, "upfir_act_fwd: c must be a multiple of 4");
+  size_t total = (size_t)batch * h2 * w2 * (c >> 2);
+  upfir_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain,
+                                                                      bias, act, act_gain, clamp, y);
+  HFAGP_CHECK_LAUNCH("upfir_act_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const float* w,
+                                     const float* bias, float clamp, const float* up_img, float* y, void* stream) {
+  HFAGP_CHECK_ARG(x && w && y, "torgb_small_fwd: null pointer");
+  HFAGP_CHECK_ARG(cout >= 1 && cout <= 4 && (cin & 3) == 0, "torgb_small_fwd: cout<=4 and cin%%4==0 required");
+  HFAGP_CHECK_ARG(!up_img || ((h & 1) == 0 && (w_ & 1) == 0), "torgb_small_fwd: odd size with up_img");
+  size_t warps = (size_t)batch * h * w_;
+  torgb_small_kernel<<<cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(batch, h, w_, cin, cout, x, w, bias,
+                                                                             clamp, up_img, y);
+  HFAGP_CHECK_LAUNCH("torgb_small_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad1, int stride, const float* x,
+                              float* y, void* stream) {
+  HFAGP_CHECK_ARG(x && y, "blur_fwd: null pointer");
+  HFAGP_CHECK_ARG((c & 3) == 0 && (stride == 1 || stride == 2), "blur_fwd: c%%4==0, stride 1|2 required");
+  int oh = (h + pad0 + pad1 - 4) / stride + 1;
+  int ow = (w_ + pad0 + pad1 - 4) / stride + 1;
+  HFAGP_CHECK_ARG(oh > 0 && ow > 0, "blur_fwd: empty output");
+  size_t total = (size_t)batch * oh * ow * (c >> 2);
+  blur_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h, w_, c, pad0, stride, oh, ow, x, y);
+  HFAGP_CHECK_LAUNCH("blur_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_nchw_to_nhwc(int batch, int c, int h, int w_, const float* x, float* y, void* stream) {
+  HFAGP_CHECK_ARG(x && y && batch > 0 && c > 0, "nchw_to_nhwc: bad args");
+  size_t total = (size_t)batch * c * h * w_;
+  nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, c, h * w_, x, y);
+  HFAGP_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_nhwc_to_nchw(int batch, int c, int h, int w_, const float* x, float* y, void* stream) {
+  HFAGP_CHECK_ARG(x && y && batch > 0 && c > 0, "nhwc_to_nchw: bad args");
+  size_t total = (size_t)batch * c * h * w_;
+  nhwc_to_nchw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, c, h * w_, x, y);
+  HFAGP_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+  return HFAGP_OK;
+}

@@ -1,0 +1,379 @@
+"""B200-native EG3D tri-plane generator behind the call surface HFA-GP uses.
+
+HFA-GP never looks inside the generator: it un-pickles NVlabs/eg3d's ``TriPlaneGenerator``
+(``/root/reference/code/networks/headnerf.py:31-38``) and calls
+``generator.synthesis(latent, c=label, noise_mode='const')['image']`` (``headnerf.py:112``),
+iterates ``generator.parameters()`` to freeze/unfreeze it (``trainer_rgb.py:59-60,70-71``) and
+saves / loads its tensors under ``generator.*`` (``trainer_rgb.py:146``, ``run_recon_video_rgb.py:211``).
+This module provides an ``nn.Module`` with exactly that protocol and the EG3D ``state_dict`` names
+(SURVEY.md App. A.9); the arithmetic is the sm_100a library behind ``include/hfagp.h``.
+
+Activations are fp32 channels-last on the device; parameters are kept in their canonical
+PyTorch shapes and re-packed into kernel layouts lazily whenever they change.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._cabi import ACT_LINEAR, ACT_LRELU, HfagpError
+
+SQRT2 = math.sqrt(2.0)
+
+
+@dataclass
+class GeneratorConfig:
+    """What the EG3D pickle carries as constructor kwargs / rendering_kwargs (ffhqrebalanced512-128)."""
+    w_dim: int = 512
+    c_dim: int = 25
+    plane_res: int = 256
+    plane_channels: int = 32
+    channel_base: int = 32768
+    channel_max: int = 512
+    nrr: int = 128                    # neural_rendering_resolution
+    img_resolution: int = 512
+    sr_channels: tuple = (256, 128)
+    sr_clamp: float = 256.0
+    decoder_hidden: int = 64
+    depth_res: int = 48
+    depth_res_importance: int = 48
+    ray_start: float = 2.25
+    ray_end: float = 3.3
+    box_warp: float = 1.0
+
+    @property
+    def block_resolutions(self) -> List[int]:
+        return [2 ** i for i in range(2, int(math.log2(self.plane_res)) + 1)]
+
+    def channels(self, res: int) -> int:
+        return min(self.channel_base // res, self.channel_max)
+
+    @property
+    def num_ws(self) -> int:
+        return 2 * len(self.block_resolutions)
+
+
+def _resample_filter():
+    f = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    f = torch.outer(f, f)
+    return f / f.sum()
+
+
+# ------------------------------------------------------------------ parameter holders (state_dict layout)
+
+class _FC(nn.Module):
+    def __init__(self, cin, cout, bias_init=0.0, lr_mul=1.0):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(cout, cin) / lr_mul)
+        self.bias = nn.Parameter(torch.full([cout], float(bias_init)))
+        self.weight_gain = lr_mul / math.sqrt(cin)
+        self.bias_gain = lr_mul
+
+
+class _SynthesisLayer(nn.Module):
+    def __init__(self, cin, cout, w_dim, res, up, use_noise, clamp):
+        super().__init__()
+        self.cin, self.cout, self.res, self.up, self.use_noise, self.clamp = cin, cout, res, up, use_noise, clamp
+        self.affine = _FC(w_dim, cin, bias_init=1.0)
+        self.weight = nn.Parameter(torch.randn(cout, cin, 3, 3))
+        self.register_buffer('resample_filter', _resample_filter())
+        self.register_buffer('noise_const', torch.randn(res, res))
+        self.noise_strength = nn.Parameter(torch.zeros([]))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class _ToRGB(nn.Module):
+    def __init__(self, cin, cout, w_dim, clamp):
+        super().__init__()
+        self.cin, self.cout, self.clamp = cin, cout, clamp
+        self.affine = _FC(w_dim, cin, bias_init=1.0)
+        self.weight = nn.Parameter(torch.randn(cout, cin, 1, 1))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class _Block(nn.Module):
+    def __init__(self, cin, cout, w_dim, res, img_channels, clamp=None, use_noise=True):
+        super().__init__()
+        self.cin, self.cout, self.res = cin, cout, res
+        self.register_buffer('resample_filter', _resample_filter())
+        if cin == 0:
+            self.const = nn.Parameter(torch.randn(cout, res, res))
+        else:
+            self.conv0 = _SynthesisLayer(cin, cout, w_dim, res, 2, use_noise, clamp)
+        self.conv1 = _SynthesisLayer(cout, cout, w_dim, res, 1, use_noise, clamp)
+        self.torgb = _ToRGB(cout, img_channels, w_dim, clamp)
+        self.num_conv = 1 if cin == 0 else 2
+
+
+class _Synthesis(nn.Module):
+    def __init__(self, cfg: GeneratorConfig):
+        super().__init__()
+        for res in cfg.block_resolutions:
+            cin = cfg.channels(res // 2) if res > 4 else 0
+            setattr(self, f'b{res}', _Block(cin, cfg.channels(res), cfg.w_dim, res, 3 * cfg.plane_channels))
+
+
+class _Mapping(nn.Module):
+    """Present only so checkpoints round-trip; HFA-GP feeds ws from get_latent and never runs it."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.embed = _FC(cfg.c_dim, cfg.w_dim)
+        self.fc0 = _FC(2 * cfg.w_dim, cfg.w_dim, lr_mul=0.01)
+        self.fc1 = _FC(cfg.w_dim, cfg.w_dim, lr_mul=0.01)
+        self.register_buffer('w_avg', torch.zeros(cfg.w_dim))
+
+
+class _Backbone(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.synthesis = _Synthesis(cfg)
+        self.mapping = _Mapping(cfg)
+
+
+class _Superresolution(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        c0, c1 = cfg.sr_channels
+        self.block0 = _Block(cfg.plane_channels, c0, cfg.w_dim, 2 * cfg.nrr, 3, clamp=cfg.sr_clamp)
+        self.block1 = _Block(c0, c1, cfg.w_dim, 4 * cfg.nrr, 3, clamp=cfg.sr_clamp)
+
+
+class _Decoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.net = nn.Sequential(_FC(cfg.plane_channels, cfg.decoder_hidden), nn.Softplus(),
+                                 _FC(cfg.decoder_hidden, 1 + cfg.plane_channels))
+
+
+# ------------------------------------------------------------------ packed (kernel-layout) view
+
+class _PackedLayer:
+    __slots__ = ('w', 'bias', 'noise', 'noise_gain', 'cin', 'cout', 'up', 'clamp', 'use_noise')
+
+
+def _pack_conv(weight: torch.Tensor) -> torch.Tensor:
+    """[O,I,kh,kw] -> [kh*kw][O][I] (cin contiguous: the K-major GEMM operand)."""
+    o, i, kh, kw = weight.shape
+    return weight.detach().permute(2, 3, 0, 1).reshape(kh * kw, o, i).contiguous().float()
+
+
+class TriPlaneGenerator(nn.Module):
+    """Drop-in for the object ``legacy.load_network_pkl(f)['G_ema']`` returns (headnerf.py:34)."""
+
+    def __init__(self, cfg: Optional[GeneratorConfig] = None):
+        super().__init__()
+        self.cfg = cfg or GeneratorConfig()
+        if self.cfg.plane_channels != 32 or self.cfg.decoder_hidden != 64:
+            raise HfagpError('the render kernel is specialised for 32 plane channels and a 64-wide decoder')
+        self.backbone = _Backbone(self.cfg)
+        self.superresolution = _Superresolution(self.cfg)
+        self.decoder = _Decoder(self.cfg)
+        self.neural_rendering_resolution = self.cfg.nrr
+        self.z_dim = self.w_dim = self.cfg.w_dim
+        self.c_dim = self.cfg.c_dim
+        self.img_resolution = self.cfg.img_resolution
+        self.img_channels = 3
+        self.rendering_kwargs = dict(depth_resolution=self.cfg.depth_res,
+                                     depth_resolution_importance=self.cfg.depth_res_importance,
+                                     ray_start=self.cfg.ray_start, ray_end=self.cfg.ray_end,
+                                     box_warp=self.cfg.box_warp, clamp_mode='softplus', white_back=False,
+                                     superresolution_noise_mode='none', avg_camera_radius=2.7,
+                                     avg_camera_pivot=[0, 0, 0.2])
+        self._packed = None
+        self._packed_key = None
+
+    @property
+    def num_ws(self) -> int:
+        return self.cfg.num_ws
+
+    # ---------------------------------------------------------------- packing
+    def _fingerprint(self):
+        dev = None
+        ver = 0
+        for p in self.parameters():
+            ver += p._version
+            dev = p.device
+        for b in self.buffers():
+            ver += b._version
+        return (str(dev), ver)
+
+    def _layers_in_order(self):
+        cfg = self.cfg
+        out = []       # (kind, module, ws index)
+        w_idx = 0
+        for res in cfg.block_resolutions:
+            blk = getattr(self.backbone.synthesis, f'b{res}')
+            i = w_idx
+            if blk.cin != 0:
+                out.append(('conv', blk.conv0, i)); i += 1
+            out.append(('conv', blk.conv1, i)); i += 1
+            out.append(('torgb', blk.torgb, i))
+            w_idx += blk.num_conv
+        last = cfg.num_ws - 1
+        for blk in (self.superresolution.block0, self.superresolution.block1):
+            out.append(('conv', blk.conv0, last))
+            out.append(('conv', blk.conv1, last))
+            out.append(('torgb', blk.torgb, last))
+        return out
+
+    def _ensure_packed(self):
+        key = self._fingerprint()
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        layers = self._layers_in_order()
+        table, packed = [], {}
+        for kind, m, widx in layers:
+            gain = 1.0 if kind == 'conv' else 1.0 / math.sqrt(m.cin)
+            table.append((m.affine.weight.detach().contiguous(), m.affine.bias.detach().contiguous(), m.cin, widx, gain))
+            pl = _PackedLayer()
+            pl.w = _pack_conv(m.weight)
+            pl.bias = m.bias.detach().contiguous().float()
+            pl.cin, pl.cout = m.cin, m.cout
+            pl.clamp = float(m.clamp) if m.clamp is not None else 0.0
+            if kind == 'conv':
+                pl.up = m.up
+                pl.use_noise = m.use_noise
+                pl.noise = m.noise_const.detach().contiguous().float()
+                pl.noise_gain = float(m.noise_strength.detach())
+            packed[id(m)] = pl
+        d0, d2 = self.decoder.net[0], self.decoder.net[2]
+        mlp = torch.cat([(d0.weight.detach() * d0.weight_gain).reshape(-1), d0.bias.detach() * d0.bias_gain,
+                         (d2.weight.detach() * d2.weight_gain).reshape(-1), d2.bias.detach() * d2.bias_gain]).float().contiguous()
+        dev = mlp.device
+        lin = torch.linspace(self.cfg.ray_start, self.cfg.ray_end, self.cfg.depth_res).to(dev)
+        const = self.backbone.synthesis.b4.const.detach().permute(1, 2, 0).contiguous().float()
+        self._packed = dict(order=layers, styles=ops.StyleTable(table), layers=packed, mlp=mlp, lin=lin, const=const)
+        self._packed_key = key
+        return self._packed
+
+    # ---------------------------------------------------------------- layer drivers (channels-last)
+    def _conv_layer(self, x, m, styles, noise_mode, pk):
+        pl: _PackedLayer = pk['layers'][id(m)]
+        b = x.shape[0]
+        wmod, dcoef = ops.modulate(pl.w, styles, True)
+        noise = None
+        if pl.use_noise and noise_mode == 'const' and pl.noise_gain != 0.0:
+            noise = pl.noise
+        elif pl.use_noise and noise_mode == 'random':
+            raise HfagpError("noise_mode='random' is not part of the HFA-GP path (headnerf.py:112 passes 'const')")
+        wbs = wmod.stride(0)
+        if pl.up == 1:
+            h, w = x.shape[1], x.shape[2]
+            return ops.conv2d(x, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batch_stride=wbs, dcoef=dcoef,
+                              noise=noise, noise_gain=pl.noise_gain, bias=pl.bias, act=ACT_LRELU, act_gain=SQRT2,
+                              clamp=pl.clamp)
+        t = ops.conv_transpose_s2(x, wmod, pl.cout, wbs)
+        return ops.upfir_act(t, dcoef=dcoef, noise=noise, noise_gain=pl.noise_gain, bias=pl.bias, act=ACT_LRELU,
+                             act_gain=SQRT2, clamp=pl.clamp)
+
+    def _torgb_layer(self, x, m, styles, img, pk):
+        pl: _PackedLayer = pk['layers'][id(m)]
+        wmod, _ = ops.modulate(pl.w, styles, False)
+        h, w = x.shape[1], x.shape[2]
+        if pl.cout <= 4:
+            return ops.torgb_small(x, wmod, pl.bias, pl.clamp, img, pl.cout)
+        return ops.conv2d(x, wmod, ops.TAPS_1X1, pl.cout, oh=h, ow=w, w_batch_stride=wmod.stride(0), bias=pl.bias,
+                          clamp=pl.clamp, up_img=img)
+
+    def _run_block(self, blk, x, img, styles_iter, noise_mode, pk, tap, name):
+        if blk.cin == 0:
+            x = pk['const'][None].expand(self._batch, -1, -1, -1).contiguous()
+        else:
+            x = self._conv_layer(x, blk.conv0, next(styles_iter), noise_mode, pk)
+            if tap is not None:
+                tap[name + '.conv0'] = x
+        x = self._conv_layer(x, blk.conv1, next(styles_iter), noise_mode, pk)
+        if tap is not None:
+            tap[name + '.conv1'] = x
+        img = self._torgb_layer(x, blk.torgb, next(styles_iter), img, pk)
+        if tap is not None:
+            tap[name + '.img'] = img
+        return x, img
+
+    # ---------------------------------------------------------------- public protocol
+    def synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
+                  use_cached_backbone=False, noise_mode='const', jitter_coarse=None, u_fine=None,
+                  tap: Optional[Dict] = None, **synthesis_kwargs):
+        """``ws [B,num_ws,w_dim]``, ``c [B,25]`` -> ``{'image','image_raw','image_depth'}`` (NCHW fp32).
+
+        ``jitter_coarse [B,rays,S,1]`` / ``u_fine [B*rays,S_imp]`` are upstream's two random draws; when
+        omitted they are drawn here with the same calls, shapes and order on the device.
+        ``tap`` (tests only) collects channels-last intermediates.
+        """
+        cfg = self.cfg
+        if torch.is_grad_enabled() and (ws.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise HfagpError('generator backward is not implemented in this build; call under torch.no_grad()')
+        if not ws.is_cuda:
+            raise HfagpError('TriPlaneGenerator.synthesis needs CUDA tensors (there is no CPU fallback)')
+        if ws.dim() != 3 or ws.shape[1] != cfg.num_ws or ws.shape[2] != cfg.w_dim:
+            raise HfagpError(f'ws must be [B,{cfg.num_ws},{cfg.w_dim}], got {tuple(ws.shape)}')
+        if c.dim() != 2 or c.shape[1] != cfg.c_dim or c.shape[0] != ws.shape[0]:
+            raise HfagpError(f'c must be [B,{cfg.c_dim}], got {tuple(c.shape)}')
+        res = neural_rendering_resolution or self.neural_rendering_resolution
+        ws = ws.detach().float().contiguous()
+        c = c.detach().float().contiguous()
+        b = ws.shape[0]
+        self._batch = b
+        pk = self._ensure_packed()
+        styles = iter(pk['styles'].run(ws))
+
+        x = img = None
+        for r in cfg.block_resolutions:
+            blk = getattr(self.backbone.synthesis, f'b{r}')
+            x, img = self._run_block(blk, x, img, styles, noise_mode, pk, tap, f'b{r}')
+        planes = img                                             # [B,256,256,96] channels-last
+        if tap is not None:
+            tap['planes'] = planes
+
+        rays = res * res
+        s, sf = cfg.depth_res, cfg.depth_res_importance
+        if jitter_coarse is None:
+            jitter_coarse = torch.rand((b, rays, s, 1), device=ws.device)
+        if u_fine is None and sf > 0:
+            u_fine = torch.rand((b * rays, sf), device=ws.device)
+        jitter = jitter_coarse.reshape(b, rays, s).float().contiguous()
+        delta = (cfg.ray_end - cfg.ray_start) / (s - 1)
+        lin = pk['lin']
+        # global clamp range of the composite depth: min/max over every sample depth (coarse ends bound the fine ones)
+        dmin = (lin[0] + jitter[:, :, 0].min() * delta)
+        dmax = (lin[-1] + jitter[:, :, -1].max() * delta)
+        depth_range = torch.stack([dmin, dmax]).float().contiguous()
+        feat, depth, wsum, book = ops.render(planes, c, pk['mlp'], lin, jitter,
+                                             u_fine.float().contiguous() if sf > 0 else None, depth_range, res=res,
+                                             s_coarse=s, s_fine=sf, delta=delta, box_scale=2.0 / cfg.box_warp,
+                                             bookkeeping=tap is not None)
+        if tap is not None:
+            tap.update(book)
+            tap.update(feature_image=feat, weight_sum=wsum)
+
+        rgb_lo = feat[..., :3].contiguous()                       # [B,res,res,3]
+        x, img = feat, rgb_lo
+        for i, blk in enumerate((self.superresolution.block0, self.superresolution.block1)):
+            x, img = self._run_block(blk, x, img, styles, 'none', pk, tap, f'sr{i}')
+        return {'image': ops.nhwc_to_nchw(img),
+                'image_raw': ops.nhwc_to_nchw(rgb_lo),
+                'image_depth': depth.view(b, 1, res, res)}
+
+    def forward(self, *a, **k):
+        raise HfagpError('HFA-GP drives the generator through .synthesis(ws, c=..., noise_mode=...) only '
+                         '(headnerf.py:112); the mapping network is not part of this path')
+
+
+def make_generator(cfg: Optional[GeneratorConfig] = None, seed: int = 0, noise_strength: float = 0.0,
+                   device='cuda') -> TriPlaneGenerator:
+    """Seeded random-init generator for synthetic runs (no EG3D pickle is available offline)."""
+    with torch.random.fork_rng():
+        torch.manual_seed(seed)
+        g = TriPlaneGenerator(cfg)
+    if noise_strength:
+        with torch.no_grad():
+            for name, p in g.named_parameters():
+                if name.endswith('noise_strength') and name.startswith('backbone'):
+                    p.fill_(noise_strength)
+    return g.eval().requires_grad_(False).to(device)

@@ -1,0 +1,206 @@
+"""Drop-in for ``code/networks/encoder3d.py`` of the reference: same class names, constructor
+arguments and ``state_dict`` keys (``net_app.convs.N...``, ``fc.N.weight`` ...), so checkpoints written
+by the reference's trainers load unchanged.  The modules below only *hold* parameters; the arithmetic
+of ``Encoder.forward`` is the sm_100a library (``include/hfagp.h``): channels-last implicit-GEMM
+convolutions with the bias + leaky-ReLU*sqrt2 epilogue and the ResBlock ``(out+skip)/sqrt2`` merge
+fused, a separate [1,3,3,1]^2 blur, and the purely linear EqualLinear head.
+
+Reference behaviour mirrored (file:line in /root/reference/code/networks/encoder3d.py):
+  EqualConv2d scale 1/sqrt(Cin k^2) folded into the weight ........ :86-103
+  FusedLeakyReLU  lrelu(x+b, 0.2)*sqrt(2) .......................... :7-20
+  ConvLayer downsample = Blur(pad) + stride-2 conv, padding 0 ...... :142-179
+  ResBlock (conv1 -> conv2(down)) + skip(down, 1x1, no bias/act) ... :182-198
+  EncoderApp channel table, final 4x4 conv ......................... :201-239
+  Encoder fc: 5 EqualLinear with activation=None; optional pose .... :242-298
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .. import ops
+from .._cabi import ACT_LINEAR, ACT_LRELU, HfagpError
+
+SQRT2 = math.sqrt(2.0)
+INV_SQRT2 = 1.0 / SQRT2
+
+
+def make_kernel(k):
+    k = torch.tensor(k, dtype=torch.float32)
+    if k.ndim == 1:
+        k = torch.outer(k, k)
+    return k / k.sum()
+
+
+class Blur(nn.Module):
+    def __init__(self, kernel, pad, upsample_factor=1):
+        super().__init__()
+        if list(kernel) != [1, 3, 3, 1] or upsample_factor != 1:
+            raise HfagpError('only the [1,3,3,1] blur the encoder uses is implemented')
+        self.register_buffer('kernel', make_kernel(kernel))
+        self.pad = pad
+
+
+class FusedLeakyReLU(nn.Module):
+    def __init__(self, channel, negative_slope=0.2, scale=SQRT2):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(1, channel, 1, 1))
+        self.negative_slope, self.scale = negative_slope, scale
+
+
+class EqualConv2d(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_channel, in_channel, kernel_size, kernel_size))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.stride, self.padding = stride, padding
+        self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
+
+        self._pk, self._pk_key = None, None
+
+    def packed(self):
+        """[k*k][O][I] with the equalised-lr scale folded in (what F.conv2d sees at :103); cached
+        until the parameter is written again."""
+        key = (self.weight._version, self.weight.device, self.weight.data_ptr())
+        if self._pk is None or self._pk_key != key:
+            o, i, kh, kw = self.weight.shape
+            self._pk = (self.weight.detach() * self.scale).permute(2, 3, 0, 1).reshape(kh * kw, o, i).contiguous().float()
+            self._pk_key = key
+        return self._pk
+
+
+class EqualLinear(nn.Module):
+    def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1, activation=None):
+        super().__init__()
+        if activation:
+            raise HfagpError('EqualLinear(activation=...) is never used on the HFA-GP path')
+        self.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul))
+        self.bias = nn.Parameter(torch.zeros(out_dim).fill_(bias_init)) if bias else None
+        self.activation = activation
+        self.scale = (1 / math.sqrt(in_dim)) * lr_mul
+        self.lr_mul = lr_mul
+
+    def forward(self, input):
+        x = input.detach().float().contiguous()
+        return ops.linear(x, self.weight.detach().contiguous(), None if self.bias is None else self.bias.detach(),
+                          self.scale, self.lr_mul)
+
+
+class ConvLayer(nn.Sequential):
+    def __init__(self, in_channel, out_channel, kernel_size, downsample=False, blur_kernel=[1, 3, 3, 1], bias=True,
+                 activate=True):
+        layers = []
+        self.downsample, self.kernel_size, self.activate = downsample, kernel_size, activate
+        if downsample:
+            p = (len(blur_kernel) - 2) + (kernel_size - 1)
+            layers.append(Blur(blur_kernel, pad=((p + 1) // 2, p // 2)))
+            stride, self.padding = 2, 0
+        else:
+            stride, self.padding = 1, kernel_size // 2
+        layers.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=self.padding, stride=stride,
+                                  bias=bias and not activate))
+        if activate:
+            if not bias:
+                raise HfagpError('ScaledLeakyReLU (activate without bias) is never used on the HFA-GP path')
+            layers.append(FusedLeakyReLU(out_channel))
+        super().__init__(*layers)
+
+    def run(self, x, residual=None):
+        """x channels-last [N,H,W,C] -> channels-last output, epilogue fused."""
+        mods = list(self.children())
+        conv = next(m for m in mods if isinstance(m, EqualConv2d))
+        act = mods[-1] if isinstance(mods[-1], FusedLeakyReLU) else None
+        k = self.kernel_size
+        n, h, w, _ = x.shape
+        if self.downsample:
+            pad0, pad1 = mods[0].pad
+            if k == 1:
+                x = ops.blur(x, pad0, pad1, stride=2)          # only the pixels the stride-2 1x1 conv reads
+                taps, stride, oh, ow = ops.TAPS_1X1, 1, x.shape[1], x.shape[2]
+            else:
+                x = ops.blur(x, pad0, pad1, stride=1)
+                taps = tuple((ky, kx, ky * k + kx) for ky in range(k) for kx in range(k))
+                stride, oh, ow = 2, (x.shape[1] - k) // 2 + 1, (x.shape[2] - k) // 2 + 1
+        else:
+            p = self.padding
+            taps = tuple((ky - p, kx - p, ky * k + kx) for ky in range(k) for kx in range(k))
+            stride, oh, ow = 1, h + 2 * p - k + 1, w + 2 * p - k + 1
+        bias = act.bias.detach().reshape(-1).contiguous() if act is not None else (
+            conv.bias.detach() if conv.bias is not None else None)
+        return ops.conv2d(x, conv.packed(), taps, conv.weight.shape[0], oh=oh, ow=ow, in_stride=stride, bias=bias,
+                          act=ACT_LRELU if act is not None else ACT_LINEAR,
+                          act_gain=SQRT2 if act is not None else 1.0, residual=residual,
+                          residual_scale=INV_SQRT2 if residual is not None else 1.0)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, in_channel, out_channel, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channel, in_channel, 3)
+        self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True)
+        self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
+
+    def run(self, x):
+        skip = self.skip.run(x)
+        out = self.conv1.run(x)
+        return self.conv2.run(out, residual=skip)       # (conv2(out) + skip) / sqrt(2) in the epilogue
+
+
+class EncoderApp(nn.Module):
+    def __init__(self, size, w_dim=512):
+        super().__init__()
+        channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256, 128: 128, 256: 64, 512: 32, 1024: 16}
+        self.w_dim = w_dim
+        log_size = int(math.log(size, 2))
+        self.convs = nn.ModuleList()
+        self.convs.append(ConvLayer(3, channels[size], 1))
+        in_channel = channels[size]
+        for i in range(log_size, 2, -1):
+            out_channel = channels[2 ** (i - 1)]
+            self.convs.append(ResBlock(in_channel, out_channel))
+            in_channel = out_channel
+        self.convs.append(EqualConv2d(in_channel, self.w_dim, 4, padding=0, bias=False))
+
+    def forward(self, x):
+        """x NCHW [B,3,S,S] (as the reference passes it) -> [B, w_dim]."""
+        if not x.is_cuda:
+            raise HfagpError('Encoder needs CUDA tensors (there is no CPU fallback)')
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise HfagpError('encoder backward is not implemented in this build; call under torch.no_grad()')
+        h = ops.nchw_to_nhwc(x.detach().float().contiguous())
+        for m in self.convs[:-1]:
+            h = m.run(h)
+        last = self.convs[-1]
+        k = last.weight.shape[-1]
+        taps = tuple((ky, kx, ky * k + kx) for ky in range(k) for kx in range(k))
+        h = ops.conv2d(h, last.packed(), taps, last.weight.shape[0], oh=h.shape[1] - k + 1, ow=h.shape[2] - k + 1)
+        return h.reshape(h.shape[0], -1)                 # 1x1 spatial: channels-last == [B, w_dim]
+
+
+class Encoder(nn.Module):
+    def __init__(self, size, dim=512, dim_motion=20, use_softmax=False, out_pose=False):
+        super().__init__()
+        self.net_app = EncoderApp(size, dim)
+        self.fc = nn.Sequential(*([EqualLinear(dim, dim) for _ in range(4)] + [EqualLinear(dim, dim_motion)]))
+        self.out_pose = out_pose
+        if out_pose:
+            self.pose = nn.Sequential(*([EqualLinear(dim, dim) for _ in range(4)] + [EqualLinear(dim, 25)]))
+        self.use_softmax = use_softmax
+        self.softmax = nn.Softmax(dim=1)
+
+    def enc_app(self, x):
+        return self.net_app(x)
+
+    def get_weights(self, x):
+        h = self.net_app(x)
+        h_weights = self.fc(h)
+        if self.use_softmax:
+            h_weights = self.softmax(h_weights)
+        if self.out_pose:
+            return h_weights, self.pose(h)
+        return h_weights
+
+    def forward(self, input_source, h_start=None):
+        return self.get_weights(input_source)

@@ -1,0 +1,209 @@
+"""Tensor-level wrappers over the C ABI.  Activations are fp32 channels-last ``[N,H,W,C]``.
+
+Every function enqueues on ``torch.cuda.current_stream()`` and returns torch-owned outputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import ACT_LINEAR, ACT_LRELU, ConvDesc, RenderDesc, check, ptr, stream
+
+_desc_cache = {}
+
+
+def _conv_desc(key, build):
+    d = _desc_cache.get(key)
+    if d is None:
+        d = build()
+        _desc_cache[key] = d
+    return d
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, int]], cout: int, *,
+           oh: int, ow: int, in_stride: int = 1, out: Optional[torch.Tensor] = None,
+           out_hw: Optional[Tuple[int, int]] = None, out_stride: int = 1, out_off=(0, 0),
+           w_batch_stride: int = 0, dcoef=None, noise=None, noise_gain: float = 0.0, bias=None,
+           act: int = ACT_LINEAR, act_gain: float = 1.0, clamp: float = 0.0, residual=None,
+           residual_scale: float = 1.0, up_img=None) -> torch.Tensor:
+    """Generic implicit-GEMM convolution, see ``hfagp_conv2d_fwd`` in include/hfagp.h.
+    taps: (dy, dx, weight-tap index) triples."""
+    n, h, wd, cin = x.shape
+    out_h, out_w = out_hw if out_hw is not None else (oh, ow)
+    if out is None:
+        out = torch.empty((n, out_h, out_w, cout), device=x.device, dtype=torch.float32)
+    taps = tuple(taps)
+    key = (n, h, wd, cin, cout, oh, ow, in_stride, out_h, out_w, out_stride, out_off, taps, w_batch_stride, act,
+           act_gain, clamp, noise_gain, residual_scale, up_img is not None)
+
+    def build():
+        d = ConvDesc()
+        d.batch, d.in_h, d.in_w, d.cin, d.cout = n, h, wd, cin, cout
+        d.oh, d.ow, d.in_stride = oh, ow, in_stride
+        d.out_h, d.out_w, d.out_stride = out_h, out_w, out_stride
+        d.out_off_y, d.out_off_x = out_off
+        d.ntaps = len(taps)
+        for i, (dy, dx, wt) in enumerate(taps):
+            d.dy[i], d.dx[i], d.wtap[i] = dy, dx, wt
+        d.w_batch_stride = w_batch_stride
+        d.act, d.act_gain, d.clamp = act, act_gain, clamp
+        d.noise_gain, d.residual_scale = noise_gain, residual_scale
+        d.up_h, d.up_w = (out_h // 2, out_w // 2) if up_img is not None else (0, 0)
+        return d
+
+    d = _conv_desc(key, build)
+    check(_cabi.lib().hfagp_conv2d_fwd(C.byref(d), ptr(x), ptr(w), ptr(dcoef), ptr(noise), ptr(bias), ptr(residual),
+                                       ptr(up_img), ptr(out), stream()), 'hfagp_conv2d_fwd')
+    return out
+
+
+TAPS_3X3 = tuple((ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3))
+TAPS_1X1 = ((0, 0, 0),)
+
+
+def _parity_taps(a: int, b: int):
+    """Tap list of output parity class (a, b) of the stride-2 transposed 3x3 convolution:
+    out[2m+a] += x[m - ky//2] * w[ky] for ky with ky % 2 == a."""
+    kys = (0, 2) if a == 0 else (1,)
+    kxs = (0, 2) if b == 0 else (1,)
+    return tuple((-(ky // 2), -(kx // 2), ky * 3 + kx) for ky in kys for kx in kxs)
+
+
+def conv_transpose_s2(x: torch.Tensor, w: torch.Tensor, cout: int, w_batch_stride: int,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv_transpose2d(stride=2, padding=0) of a 3x3 kernel, channels-last: [N,H,W,Ci] -> [N,2H+1,2W+1,Co]."""
+    n, h, wd, _ = x.shape
+    if out is None:
+        out = torch.empty((n, 2 * h + 1, 2 * wd + 1, cout), device=x.device, dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            conv2d(x, w, _parity_taps(a, b), cout, oh=h + 1 - a, ow=wd + 1 - b, out=out,
+                   out_hw=(2 * h + 1, 2 * wd + 1), out_stride=2, out_off=(a, b), w_batch_stride=w_batch_stride)
+    return out
+
+
+def upfir_act(t: torch.Tensor, *, dcoef=None, noise=None, noise_gain=0.0, bias=None, act=ACT_LRELU,
+              act_gain=math.sqrt(2.0), clamp=0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, th, tw, c = t.shape
+    h2, w2 = th - 1, tw - 1
+    if out is None:
+        out = torch.empty((n, h2, w2, c), device=t.device, dtype=torch.float32)
+    check(_cabi.lib().hfagp_upfir_act_fwd(n, h2, w2, c, ptr(t), ptr(dcoef), ptr(noise), noise_gain, ptr(bias), act,
+                                          act_gain, clamp, ptr(out), stream()), 'hfagp_upfir_act_fwd')
+    return out
+
+
+def torgb_small(x, wmod, bias, clamp, up_img, cout):
+    n, h, wd, cin = x.shape
+    out = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.float32)
+    check(_cabi.lib().hfagp_torgb_small_fwd(n, h, wd, cin, cout, ptr(x), ptr(wmod), ptr(bias), clamp, ptr(up_img),
+                                            ptr(out), stream()), 'hfagp_torgb_small_fwd')
+    return out
+
+
+class StyleTable:
+    """Host-side layer table for ``hfagp_styles_fwd`` (built once per packed generator)."""
+
+    def __init__(self, layers):
+        # layers: list of (affine_weight, affine_bias, cin, ws_index, post_gain)
+        n = len(layers)
+        self.n = n
+        self.keep = [(l[0], l[1]) for l in layers]
+        self.aw = (C.c_void_p * n)(*[l[0].data_ptr() for l in layers])
+        self.ab = (C.c_void_p * n)(*[l[1].data_ptr() for l in layers])
+        self.cin = (C.c_int32 * n)(*[l[2] for l in layers])
+        self.widx = (C.c_int32 * n)(*[l[3] for l in layers])
+        self.gain = (C.c_float * n)(*[l[4] for l in layers])
+        self.cins = [l[2] for l in layers]
+
+    def run(self, ws: torch.Tensor):
+        b, num_ws, w_dim = ws.shape
+        offs, total = [], 0
+        for c in self.cins:
+            offs.append(total)
+            total += b * c
+        off_arr = (C.c_int64 * self.n)(*offs)
+        styles = torch.empty(total, device=ws.device, dtype=torch.float32)
+        check(_cabi.lib().hfagp_styles_fwd(self.n, b, num_ws, w_dim, ptr(ws), self.aw, self.ab, self.cin, self.widx,
+                                           self.gain, off_arr, ptr(styles), stream()), 'hfagp_styles_fwd')
+        return [styles[o:o + b * c].view(b, c) for o, c in zip(offs, self.cins)]
+
+
+def modulate(w: torch.Tensor, styles: torch.Tensor, demodulate: bool):
+    """w [taps][O][I] (shared), styles [B][I] -> wmod [B][taps][O][I], dcoef [B][O] or None."""
+    taps, cout, cin = w.shape
+    b = styles.shape[0]
+    wmod = torch.empty((b, taps, cout, cin), device=w.device, dtype=torch.float32)
+    dcoef = torch.empty((b, cout), device=w.device, dtype=torch.float32) if demodulate else None
+    check(_cabi.lib().hfagp_modulate_fwd(b, taps, cout, cin, ptr(w), ptr(styles), ptr(wmod), ptr(dcoef), stream()),
+          'hfagp_modulate_fwd')
+    return wmod, dcoef
+
+
+def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s_fine, delta, box_scale,
+           bookkeeping: bool = False):
+    """planes [N,PH,PW,96] channels-last -> feat [N,res,res,32], depth [N,res*res], wsum [N,res*res]."""
+    n, ph, pw, _ = planes.shape
+    dev = planes.device
+    rays = res * res
+    feat = torch.empty((n, res, res, 32), device=dev, dtype=torch.float32)
+    depth = torch.empty((n, rays), device=dev, dtype=torch.float32)
+    wsum = torch.empty((n, rays), device=dev, dtype=torch.float32)
+    book = {}
+    if bookkeeping:
+        t = s_coarse + s_fine
+        if s_fine > 0:
+            for k in ('inds', 'below', 'above'):
+                book[k] = torch.empty((n * rays, s_fine), device=dev, dtype=torch.int32)
+        book['sort_idx'] = torch.empty((n, rays, t), device=dev, dtype=torch.int32)
+        book['depths_sorted'] = torch.empty((n, rays, t), device=dev, dtype=torch.float32)
+    d = RenderDesc(n, res, ph, pw, s_coarse, s_fine, delta, box_scale)
+    check(_cabi.lib().hfagp_render_fwd(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
+                                       ptr(depth_range), ptr(feat), ptr(depth), ptr(wsum), ptr(book.get('inds')), ptr(book.get('below')),
+                                       ptr(book.get('above')), ptr(book.get('sort_idx')),
+                                       ptr(book.get('depths_sorted')), stream()), 'hfagp_render_fwd')
+    return feat, depth, wsum, book
+
+
+def blur(x, pad0, pad1, stride=1):
+    n, h, wd, c = x.shape
+    oh = (h + pad0 + pad1 - 4) // stride + 1
+    ow = (wd + pad0 + pad1 - 4) // stride + 1
+    out = torch.empty((n, oh, ow, c), device=x.device, dtype=torch.float32)
+    check(_cabi.lib().hfagp_blur_fwd(n, h, wd, c, pad0, pad1, stride, ptr(x), ptr(out), stream()), 'hfagp_blur_fwd')
+    return out
+
+
+def linear(x, w, b, w_gain, b_gain):
+    n, cin = x.shape
+    cout = w.shape[0]
+    out = torch.empty((n, cout), device=x.device, dtype=torch.float32)
+    check(_cabi.lib().hfagp_linear_fwd(n, cin, cout, ptr(x), ptr(w), ptr(b), w_gain, b_gain, ptr(out), stream()),
+          'hfagp_linear_fwd')
+    return out
+
+
+def latent(weights, q, delta, dim_total):
+    n, k = weights.shape
+    out = torch.empty((n, dim_total), device=weights.device, dtype=torch.float32)
+    check(_cabi.lib().hfagp_latent_fwd(n, k, dim_total, ptr(weights), ptr(q), ptr(delta), ptr(out), stream()),
+          'hfagp_latent_fwd')
+    return out
+
+
+def nchw_to_nhwc(x):
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), device=x.device, dtype=torch.float32)
+    check(_cabi.lib().hfagp_nchw_to_nhwc(n, c, h, w, ptr(x), ptr(out), stream()), 'hfagp_nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    check(_cabi.lib().hfagp_nhwc_to_nchw(n, c, h, w, ptr(x), ptr(out), stream()), 'hfagp_nhwc_to_nchw')
+    return out

@@ -1,0 +1,180 @@
+/*
+ * hfagp.h — C ABI of libhfagp_sm100.so: the B200 (sm_100a) hot path of HFA-GP's per-frame render.
+ *
+ * The reference (bbaaii/HFA-GP) has no FFI of its own: its seam is the Python object protocol
+ *   HeadNeRF_*.get_weights / get_latent / get_image                (code/networks/headnerf.py:76-134)
+ *   generator.synthesis(ws, c=label, noise_mode='const')['image']  (code/networks/headnerf.py:112)
+ * and every arithmetic op below that seam is a torch / NVlabs-eg3d call.  Each entry point here
+ * replaces one of those calls; the comment on it cites the call it replaces.  The Python host
+ * side (hfa_gp_b200/_cabi.py, ctypes) passes raw device pointers, sizes and a cudaStream_t —
+ * no torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative HFAGP_E_* otherwise; never throws;
+ *     hfagp_last_error() returns a thread-local description of the last failure.
+ *   - all pointers are DEVICE pointers owned by the caller unless the name ends in _host.
+ *   - never allocates device memory, never synchronises the stream; work is enqueued on `stream`.
+ *   - activations are fp32, channels-last:  x[n][y][x][c]  ("NHWC").
+ *   - conv weights are fp32 packed  w[tap][cout][cin]  (tap = ky*kw + kx), see hfagp_pack notes.
+ *   - re-entrant: forward and backward may be driven from different host threads.
+ */
+#ifndef HFAGP_H_
+#define HFAGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFAGP_ABI_VERSION 1
+
+enum {
+  HFAGP_OK = 0,
+  HFAGP_E_INVALID = -1,   /* bad argument / unsupported shape */
+  HFAGP_E_CUDA = -2,      /* a CUDA runtime call or launch failed */
+  HFAGP_E_WORKSPACE = -3  /* caller workspace too small */
+};
+
+enum { HFAGP_ACT_LINEAR = 0, HFAGP_ACT_LRELU = 1 };
+
+#define HFAGP_MAX_TAPS 16
+
+int hfagp_abi_version(void);
+const char* hfagp_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution, channels-last.
+ *
+ *   acc[n][my][mx][co] = sum_t sum_ci x[n][my*in_stride + dy[t]][mx*in_stride + dx[t]][ci]
+ *                                      * w[n*w_batch_stride + (wtap[t]*cout + co)*cin + ci]
+ *   (input coordinates outside [0,H)x[0,W) read as zero), for my<oh, mx<ow, then the epilogue
+ *
+ *   v = acc * dcoef[n][co]           (if dcoef)        demodulation      eg3d modulated_conv2d
+ *   v += noise[oy][ox] * noise_gain  (if noise)        per-pixel noise   SynthesisLayer 'const'
+ *   v += bias[co]                    (if bias)
+ *   v = lrelu_0.2(v)                 (if act==LRELU)
+ *   v *= act_gain ; clamp to +-clamp (if clamp > 0)                      bias_act
+ *   v = (v + residual[n][oy][ox][co]) * residual_scale   (if residual)   ResBlock (out+skip)/sqrt2
+ *   v += upsample2d(up_img)[n][oy][ox][co]               (if up_img)     'skip' image path
+ *   y[n][oy][ox][co] = v     with  oy = my*out_stride + out_off_y, ox likewise, in a tensor of
+ *                            out_h x out_w pixels.
+ *
+ * Replaces: F.conv2d in EqualConv2d.forward (code/networks/encoder3d.py:101-103) fused with
+ * FusedLeakyReLU (:7-20) and the ResBlock merge (:191-198); and, inside generator.synthesis
+ * (code/networks/headnerf.py:112 -> NVlabs/eg3d networks_stylegan2.py modulated_conv2d /
+ * conv2d_resample / bias_act / ToRGBLayer / upfirdn2d.upsample2d).  The stride-2 transposed
+ * convolution of the up-sampling layers is expressed as four (dy,dx,wtap) tap lists, one per
+ * output parity class, with out_stride = 2.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HfagpConvDesc {
+  int32_t batch, in_h, in_w, cin, cout;
+  int32_t oh, ow;                 /* extent of the (my,mx) loop */
+  int32_t in_stride;              /* 1 or 2 */
+  int32_t out_h, out_w;           /* extent of the output tensor */
+  int32_t out_stride, out_off_y, out_off_x;
+  int32_t ntaps;
+  int32_t dy[HFAGP_MAX_TAPS], dx[HFAGP_MAX_TAPS], wtap[HFAGP_MAX_TAPS];
+  int64_t w_batch_stride;         /* 0 = weights shared by the batch */
+  int32_t act;                    /* HFAGP_ACT_* */
+  float act_gain, clamp;          /* clamp <= 0 : none */
+  float noise_gain;               /* multiplies noise[] (noise_strength) */
+  float residual_scale;
+  int32_t up_h, up_w;             /* extent of up_img (= out/2) when given */
+} HfagpConvDesc;
+
+int hfagp_conv2d_fwd(const HfagpConvDesc* desc, const float* x, const float* w, const float* dcoef,
+                     const float* noise, const float* bias, const float* residual, const float* up_img,
+                     float* y, void* stream);
+
+/* 4x4 [1,3,3,1]x[1,3,3,1]/64 FIR (gain 4, pad 1) over the (2H+1)x(2W+1) output of the stride-2
+ * transposed convolution, fused with demodulation, noise, bias, leaky-ReLU, gain and clamp.
+ * t[n][2H+1][2W+1][c] -> y[n][2H][2W][c].
+ * Replaces: upfirdn2d(..., padding=[1,1,1,1], gain=4) + fma(dcoef, noise) + bias_act in
+ * eg3d conv2d_resample / SynthesisLayer.forward (reached via code/networks/headnerf.py:112). */
+int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float* t, const float* dcoef,
+                        const float* noise, float noise_gain, const float* bias, int act, float act_gain,
+                        float clamp, float* y, void* stream);
+
+/* 1x1 modulated conv to <=4 output channels (the super-resolution ToRGB layers) fused with bias,
+ * clamp and "+ upsample2d(previous image)".  w is the per-sample modulated weight [n][cout][cin].
+ * Replaces: eg3d ToRGBLayer.forward + SynthesisBlock skip add (via headnerf.py:112). */
+int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const float* w,
+                          const float* bias, float clamp, const float* up_img, float* y, void* stream);
+
+/* Per-layer styles for a whole network in one launch:
+ *   styles[l][n][i] = (ws[n][widx[l]][:] . A_l[i][:] * inv_sqrt_wdim + b_l[i]) * post_gain[l]
+ * Layer table (host arrays of length nlayers): affine weight / bias device pointers, cin, ws index,
+ * post gain (1 for conv layers, 1/sqrt(cin) for ToRGB), and the offset of layer l inside `styles`.
+ * Replaces: FullyConnectedLayer affine(w) of every SynthesisLayer/ToRGBLayer (eg3d). */
+int hfagp_styles_fwd(int nlayers, int batch, int num_ws, int w_dim, const float* ws,
+                     const float* const* aff_w_host, const float* const* aff_b_host,
+                     const int32_t* cin_host, const int32_t* widx_host, const float* post_gain_host,
+                     const int64_t* out_off_host, float* styles, void* stream);
+
+/* Style modulation of one layer's weights, per sample:
+ *   wmod[n][t][o][i] = w[t][o][i] * styles[n][i]
+ *   dcoef[n][o]      = rsqrt(sum_{t,i} wmod^2 + 1e-8)        (only if dcoef != NULL)
+ * Replaces: the `w = weight * styles; dcoefs = ...rsqrt()` head of eg3d modulated_conv2d. */
+int hfagp_modulate_fwd(int batch, int ntaps, int cout, int cin, const float* w, const float* styles,
+                       float* wmod, float* dcoef, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tri-plane volume renderer: ray generation, stratified + importance sampling, tri-plane bilinear
+ * gather, OSG decoder MLP (32 -> 64 softplus -> 1+32), mid-point ray marching; one call per batch.
+ *
+ * planes  [n][ph][pw][3*32]  channels-last, plane p in channels [32p, 32p+32)
+ * c       [n][25]            cam2world 4x4 row-major + intrinsics 3x3 (after the GL flip)
+ * mlp     packed decoder weights with runtime gains folded in:
+ *           w0[64][32], b0[64], w1[33][64], b1[33]   (contiguous, 2048+64+2112+33 floats)
+ * lin     [s_coarse]   torch.linspace(ray_start, ray_end, s_coarse)
+ * jitter  [n][rays][s_coarse]   upstream's torch.rand_like(depths_coarse)
+ * u_fine  [n*rays][s_fine]      upstream's torch.rand(N_rays, N_importance)
+ * feat    [n][res][res][32]  composited feature image, channels-last (rgb*2-1 applied)
+ * depth   [n][rays], wsum [n][rays]
+ * depth_range [2]  global min / max of all sample depths (upstream clamps the composite depth to it)
+ * Optional integer bookkeeping (may be NULL), exactly upstream's tensors as int32:
+ *   inds/below/above [n*rays][s_fine] (searchsorted right=True, clamps), sort_idx [n][rays][s_c+s_f],
+ *   depths_sorted [n][rays][s_c+s_f] (fp32).
+ * Replaces: RaySampler + ImportanceRenderer.forward + OSGDecoder + MipRayMarcher2 of eg3d
+ * (reached via code/networks/headnerf.py:112).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HfagpRenderDesc {
+  int32_t batch, res, plane_h, plane_w;
+  int32_t s_coarse, s_fine;       /* <= 64 each; s_fine may be 0 */
+  float delta;                    /* (ray_end - ray_start) / (s_coarse - 1) */
+  float box_scale;                /* 2 / box_warp */
+} HfagpRenderDesc;
+
+int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                     const float* lin, const float* jitter, const float* u_fine, const float* depth_range,
+                     float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above, int32_t* sort_idx,
+                     float* depths_sorted, void* stream);
+
+/* Encoder blur: zero-pad (pad0,pad1) + 4x4 [1,3,3,1]^2/64 true convolution, optional output
+ * stride (only the positions a following stride-2 1x1 conv reads).  x[n][h][w][c] ->
+ * y[n][oh][ow][c], oh = (h + pad0 + pad1 - 3 + stride - 1) / stride.
+ * Replaces: Blur.forward / upfirdn2d_native (code/networks/encoder3d.py:23-41,59-75). */
+int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad1, int stride, const float* x,
+                   float* y, void* stream);
+
+/* y[n][o] = (x[n][:] . w[o][:]) * w_gain + b[o] * b_gain   — EqualLinear with activation=None
+ * (code/networks/encoder3d.py:128-136) and Weights_3DMM (code/networks/headnerf.py:152-158). */
+int hfagp_linear_fwd(int batch, int cin, int cout, const float* x, const float* w, const float* b,
+                     float w_gain, float b_gain, float* y, void* stream);
+
+/* ws[n][j] = sum_k weights[n][k] * q[j][k] + delta[j]   (q = thin-QR basis [7168][k], row-major)
+ * Replaces: diag_embed/matmul/sum + delta in get_latent (code/networks/headnerf.py:96-100). */
+int hfagp_latent_fwd(int batch, int k, int dim, const float* weights, const float* q, const float* delta,
+                     float* ws, void* stream);
+
+/* Layout helpers (elementwise, bandwidth-bound): NCHW <-> NHWC for the frame entering the encoder
+ * and the image leaving the super-resolution head. */
+int hfagp_nchw_to_nhwc(int batch, int c, int h, int w_, const float* x, float* y, void* stream);
+int hfagp_nhwc_to_nchw(int batch, int c, int h, int w_, const float* x, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFAGP_H_ */

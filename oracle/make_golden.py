@@ -1,0 +1,85 @@
+"""Mint the golden fixtures under tests/golden/ (run in the authoring container: python -m oracle.make_golden).
+
+reference_encoder.npz     outputs of the REFERENCE's own Encoder / get_latent / cam utils
+                          (/root/reference/code/networks, imported through oracle/ref_bridge.py) on
+                          seeded inputs.  Weights are not stored: oracle.hfagp_ref.make_encoder_state(seed)
+                          regenerates them bit-identically (CPU torch.Generator).
+oracle_generator_tiny.npz outputs of the ORACLE generator (parity unpinned upstream — there is no
+                          reference implementation of it on this machine) incl. the integer bookkeeping.
+TEST INFRASTRUCTURE ONLY.
+"""
+import math
+import os
+import types
+import warnings
+
+import numpy as np
+import torch
+
+from oracle import eg3d_ref as E
+from oracle import hfagp_ref as H
+from oracle import ref_bridge
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def reference_encoder(seed=5):
+    mods = ref_bridge.load()
+    assert mods is not None, 'needs /root/reference'
+    enc, head, cam = mods
+    warnings.simplefilter('ignore')
+    z = dict(seed=np.int64(seed))
+    g = torch.Generator().manual_seed(seed + 1)
+    for size, pose in ((64, True), (128, False)):
+        sd = H.make_encoder_state(size, 512, 50, out_pose=pose, seed=seed)
+        e = enc.Encoder(size, 512, 50, False, pose).eval()
+        e.load_state_dict(sd, strict=True)
+        x = torch.rand(2, 3, size, size, generator=g) * 2 - 1
+        with torch.no_grad():
+            out = e(x)
+        z[f'x{size}'] = x.numpy()
+        if pose:
+            z[f'w{size}'], z[f'pose{size}'] = out[0].numpy(), out[1].numpy()
+        else:
+            z[f'w{size}'] = out.numpy()
+    gb = torch.Generator().manual_seed(seed)
+    bases = torch.randn(50, 14 * 512, generator=gb)
+    fake = types.SimpleNamespace(bases=bases, delta=bases.mean(0), dim=512, args=None)
+    w = torch.randn(2, 50, generator=g)
+    z['latent_w'] = w.numpy()
+    z['latent_out'] = head.HeadNeRF_3DMM.get_latent(fake, w).numpy()
+    theta = torch.tensor([0.5 * math.pi, 1.2, 1.9])
+    phi = torch.tensor([0.5 * math.pi, 1.4, 1.7])
+    labels = []
+    for t, p in zip(theta, phi):
+        pts, _, _ = cam.sample_camera_positions('cpu', n=1, r=2.7, horizontal_mean=float(t), vertical_mean=float(p),
+                                                mode=None)
+        c = cam.create_cam2world_matrix(-pts, pts, device='cpu').reshape(1, -1)
+        labels.append(torch.cat([c, torch.tensor(H.INTRINSICS)[None]], -1))
+    z['cam_theta'], z['cam_phi'], z['cam_label'] = theta.numpy(), phi.numpy(), torch.cat(labels).numpy()
+    np.savez_compressed(os.path.join(OUT, 'reference_encoder.npz'), **z)
+
+
+def oracle_generator_tiny(seed=0):
+    cfg = E.tiny_config()
+    gen = E.make_generator(cfg, seed=seed, noise_strength=0.1)
+    g = torch.Generator().manual_seed(seed + 3)
+    ws = torch.randn(1, cfg.num_ws, cfg.w_dim, generator=g)
+    c = H.flip_label_(H.synthetic_labels(1, seed=seed))
+    jit = torch.rand(1, cfg.nrr ** 2, cfg.depth_res, 1, generator=g)
+    u = torch.rand(cfg.nrr ** 2, cfg.depth_res_importance, generator=g)
+    tap = {}
+    out = gen.synthesis(ws, c, jitter_coarse=jit, u_fine=u, tap=tap)
+    np.savez_compressed(os.path.join(OUT, 'oracle_generator_tiny.npz'), seed=np.int64(seed), ws=ws.numpy(),
+                        c=c.numpy(), jitter=jit.numpy(), u=u.numpy(), image=out['image'].numpy(),
+                        image_raw=out['image_raw'].numpy(), inds=tap['inds'].numpy().astype(np.int32),
+                        below=tap['below'].numpy().astype(np.int32), above=tap['above'].numpy().astype(np.int32),
+                        sort_idx=tap['sort_idx'].squeeze(-1).numpy().astype(np.int32),
+                        depths_sorted=tap['depths_sorted'].squeeze(-1).numpy())
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    reference_encoder()
+    oracle_generator_tiny()
+    print(sorted(os.listdir(OUT)), [os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))])

@@ -1,0 +1,56 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hfagp.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'hfagp.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(hfagp_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hfa_gp_b200 import _cabi
+    if not os.path.isfile(_cabi.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 13
+    for s in declared:
+        assert hasattr(lib, s), f'{s} declared in include/hfagp.h but not exported'
+    assert sorted(_cabi.SYMBOLS) == declared, 'python binding list out of sync with the header'
+    lib.hfagp_abi_version.restype = ctypes.c_int
+    assert lib.hfagp_abi_version() == 1
+
+
+def test_invalid_arguments_fail_without_touching_the_gpu():
+    from hfa_gp_b200 import _cabi
+    lib = _cabi.lib()
+    d = _cabi.ConvDesc()
+    rc = lib.hfagp_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None, None, None)
+    assert rc == -1
+    assert b'null pointer' in lib.hfagp_last_error()
+    with pytest.raises(_cabi.HfagpError):
+        _cabi.check(rc, 'hfagp_conv2d_fwd')
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'hfa_gp_b200')
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dp, f)).read()
+                assert 'import oracle' not in txt and 'from oracle' not in txt, os.path.join(dp, f)
+
+
+def test_hot_path_refuses_cpu_tensors():
+    import torch
+    from hfa_gp_b200 import _cabi
+    with pytest.raises(_cabi.HfagpError):
+        _cabi.ptr(torch.zeros(4))

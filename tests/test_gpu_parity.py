@@ -1,0 +1,349 @@
+"""GPU parity tests (``-m gpu``): every CUDA entry point, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  fp32 tolerance: REL_TOL = 1e-3 relative per element (north star);
+integer bookkeeping bit-exact given identical float inputs (ties within 1e-6 of a cdf knot are masked,
+SURVEY.md §7 hard part 6)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import eg3d_ref, hfagp_ref
+import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from hfa_gp_b200 import ops
+    return ops
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def pack(w):
+    o, i, kh, kw = w.shape
+    return w.permute(2, 3, 0, 1).reshape(kh * kw, o, i).contiguous().cuda()
+
+
+# ------------------------------------------------------------------ unit ops
+
+@pytest.mark.parametrize('n,cin,cout,h,w,k,stride,pad', [
+    (2, 64, 64, 16, 16, 3, 1, 1),
+    (1, 3, 64, 32, 32, 1, 1, 0),        # first encoder layer: cin = 3 (scalar loads)
+    (2, 32, 96, 8, 8, 1, 1, 0),         # ToRGB-like, cout not a tile multiple
+    (1, 128, 256, 19, 19, 3, 2, 0),     # stride-2 after blur, odd extent
+    (1, 512, 512, 4, 4, 4, 1, 0),       # final 4x4 conv -> 1x1
+    (1, 128, 128, 64, 64, 3, 1, 1),     # big-tile path (>=148 CTAs at 128x128)
+    (1, 40, 20, 7, 5, 3, 1, 1),         # ragged everything
+])
+def test_conv2d_matches_torch(n, cin, cout, h, w, k, stride, pad):
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, stride=stride, padding=pad), 0.2) * math.sqrt(2)
+    taps = tuple((ky - pad, kx - pad, ky * k + kx) for ky in range(k) for kx in range(k))
+    oh, ow = ref.shape[2], ref.shape[3]
+    y = ops.conv2d(nhwc(x), pack(wt), taps, cout, oh=oh, ow=ow, in_stride=stride, bias=b.cuda(),
+                   act=1, act_gain=math.sqrt(2))
+    assert pu.rel_err(pu.to_nchw(y), ref) < 1e-4
+
+
+def test_conv2d_epilogue_residual_noise_clamp_upimg():
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    n, cin, cout, h = 2, 32, 48, 16
+    x = torch.randn(n, cin, h, h, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / 10
+    d = torch.rand(n, cout, generator=g) + 0.5
+    noise = torch.randn(h, h, generator=g)
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(n, cout, h, h, generator=g)
+    up = torch.randn(n, cout, h // 2, h // 2, generator=g)
+    v = F.conv2d(x, wt, padding=1) * d[:, :, None, None] + noise * 0.3 + b[None, :, None, None]
+    v = (F.leaky_relu(v, 0.2) * 1.3).clamp(-1.0, 1.0)
+    v = (v + res) * 0.7
+    v = v + eg3d_ref.upsample2d_ref(up, eg3d_ref.setup_filter())
+    y = ops.conv2d(nhwc(x), pack(wt), ops.TAPS_3X3, cout, oh=h, ow=h, dcoef=d.cuda(), noise=noise.cuda(),
+                   noise_gain=0.3, bias=b.cuda(), act=1, act_gain=1.3, clamp=1.0, residual=nhwc(res),
+                   residual_scale=0.7, up_img=nhwc(up))
+    assert pu.rel_err(pu.to_nchw(y), v) < 1e-4
+
+
+@pytest.mark.parametrize('n,cin,cout,h', [(2, 32, 64, 8), (1, 64, 32, 17)])
+def test_upconv_matches_oracle(n, cin, cout, h):
+    """modulated up-sampling layer = transposed conv (4 parity classes) + FIR/act kernel."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, cin, h, h, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g)
+    s = torch.randn(n, cin, generator=g) + 1
+    noise = torch.randn(2 * h, 2 * h, generator=g)
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = eg3d_ref.modulated_conv2d_ref(x, wt, s, noise=noise * 0.2, up=2, f=eg3d_ref.setup_filter())
+    ref = eg3d_ref.bias_act_ref(ref, b, act='lrelu', clamp=2.0)
+    wmod, dcoef = ops.modulate(pack(wt), s.cuda(), True)
+    t = ops.conv_transpose_s2(nhwc(x), wmod, cout, wmod.stride(0))
+    y = ops.upfir_act(t, dcoef=dcoef, noise=noise.cuda(), noise_gain=0.2, bias=b.cuda(), clamp=2.0)
+    assert pu.rel_err(pu.to_nchw(y), ref) < 1e-4
+
+
+def test_modulate_and_styles():
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    b, nws, wd = 3, 6, 512
+    ws = torch.randn(b, nws, wd, generator=g)
+    layers = []
+    refs = []
+    for cin, widx, gain in ((64, 0, 1.0), (32, 5, 1 / math.sqrt(32)), (40, 3, 1.0)):
+        a = torch.randn(cin, wd, generator=g)
+        bb = torch.randn(cin, generator=g)
+        layers.append((a.cuda(), bb.cuda(), cin, widx, gain))
+        refs.append((torch.addmm(bb[None], ws[:, widx], (a / math.sqrt(wd)).t())) * gain)
+    outs = ops.StyleTable(layers).run(ws.cuda())
+    for o, r in zip(outs, refs):
+        assert pu.rel_err(o, r) < 1e-5
+    wt = torch.randn(24, 64, 3, 3, generator=g)
+    wmod, dcoef = ops.modulate(pack(wt), refs[0].cuda(), True)
+    wm_ref = wt[None] * refs[0][:, None, :, None, None]
+    d_ref = (wm_ref.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()
+    assert pu.rel_err(dcoef, d_ref) < 1e-5
+    assert pu.rel_err(wmod.view(b, 3, 3, 24, 64).permute(0, 3, 4, 1, 2), wm_ref) < 1e-6
+
+
+def test_small_ops():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 76, generator=g)
+    w = torch.randn(50, 76, generator=g)
+    b = torch.randn(50, generator=g)
+    ref = hfagp_ref.equal_linear_ref(x, w, b)
+    assert pu.rel_err(ops.linear(x.cuda(), w.cuda(), b.cuda(), 1 / math.sqrt(76), 1.0), ref) < 1e-5
+    # blur, both pads / strides
+    xi = torch.randn(2, 8, 13, 13, generator=g)
+    k = hfagp_ref.blur_kernel()
+    assert pu.rel_err(pu.to_nchw(ops.blur(nhwc(xi), 2, 2)), hfagp_ref.blur_ref(xi, k, 2, 2)) < 1e-5
+    assert pu.rel_err(pu.to_nchw(ops.blur(nhwc(xi[..., :12, :12]), 1, 1, stride=2)),
+                      hfagp_ref.blur_ref(xi[..., :12, :12], k, 1, 1)[:, :, ::2, ::2]) < 1e-5
+    # small-N ToRGB + skip upsample
+    xr = torch.randn(2, 64, 8, 8, generator=g)
+    wr = torch.randn(2, 3, 64, generator=g)
+    br = torch.randn(3, generator=g)
+    up = torch.randn(2, 3, 4, 4, generator=g)
+    ref = torch.einsum('nchw,noc->nohw', xr, wr) + br[None, :, None, None]
+    ref = ref.clamp(-3, 3) + eg3d_ref.upsample2d_ref(up, eg3d_ref.setup_filter())
+    y = ops.torgb_small(nhwc(xr), wr.cuda().contiguous(), br.cuda(), 3.0, nhwc(up), 3)
+    assert pu.rel_err(pu.to_nchw(y), ref) < 1e-5
+    # layout helpers
+    assert torch.equal(ops.nhwc_to_nchw(ops.nchw_to_nhwc(xi.cuda())).cpu(), xi)
+    # latent map
+    bases = torch.randn(50, 14 * 512, generator=g)
+    delta = bases.mean(0)
+    wts = torch.randn(2, 50, generator=g)
+    q, _ = torch.linalg.qr((bases + 1e-8).T)
+    ref = hfagp_ref.get_latent_ref(bases, delta, wts).reshape(2, -1)
+    assert pu.rel_err(ops.latent(wts.cuda(), q.contiguous().cuda(), delta.cuda(), 14 * 512), ref) < 1e-5
+
+
+# ------------------------------------------------------------------ renderer
+
+def _render_case(res, s, sf, batch=1, seed=0, plane_res=64):
+    cfg = eg3d_ref.GeneratorConfig(nrr=res, depth_res=s, depth_res_importance=sf, plane_res=plane_res)
+    g = torch.Generator().manual_seed(seed)
+    planes = torch.randn(batch, 3, 32, plane_res, plane_res, generator=g)
+    with torch.random.fork_rng():
+        torch.manual_seed(seed)
+        dec = eg3d_ref.OSGDecoderRef(cfg)
+        with torch.no_grad():
+            dec.net[0].bias.normal_(0, 0.5)
+            dec.net[2].bias.normal_(0, 0.5)
+    c = hfagp_ref.flip_label_(hfagp_ref.synthetic_labels(batch, seed=seed))
+    rays = res * res
+    jitter = torch.rand(batch, rays, s, 1, generator=g)
+    u = torch.rand(batch * rays, max(sf, 1), generator=g)
+    return cfg, planes, dec, c, jitter, u
+
+
+def _run_render_gpu(cfg, planes, dec, c, jitter, u, book=True):
+    ops = _ops()
+    d0, d2 = dec.net[0], dec.net[2]
+    mlp = torch.cat([(d0.weight * d0.weight_gain).reshape(-1), d0.bias * d0.bias_gain,
+                     (d2.weight * d2.weight_gain).reshape(-1), d2.bias * d2.bias_gain]).detach().cuda()
+    b = planes.shape[0]
+    pl = planes.reshape(b, 96, planes.shape[-2], planes.shape[-1]).permute(0, 2, 3, 1).contiguous().cuda()
+    s, sf = cfg.depth_res, cfg.depth_res_importance
+    lin = torch.linspace(cfg.ray_start, cfg.ray_end, s)
+    delta = (cfg.ray_end - cfg.ray_start) / (s - 1)
+    jit = jitter.reshape(b, -1, s)
+    rng = torch.stack([lin[0] + jit[:, :, 0].min() * delta, lin[-1] + jit[:, :, -1].max() * delta])
+    return ops.render(pl, c.cuda(), mlp, lin.cuda(), jit.contiguous().cuda(), u.cuda() if sf > 0 else None,
+                      rng.cuda(), res=cfg.nrr, s_coarse=s, s_fine=sf, delta=delta, box_scale=2.0 / cfg.box_warp,
+                      bookkeeping=book)
+
+
+@pytest.mark.parametrize('res,s,sf,batch', [(16, 48, 0, 1), (16, 48, 48, 2), (8, 12, 12, 1), (8, 33, 20, 1),
+                                            (8, 64, 64, 1)])
+def test_render_matches_oracle(res, s, sf, batch):
+    cfg, planes, dec, c, jitter, u = _render_case(res, s, sf, batch)
+    tap = {}
+    cam = c[:, :16].view(-1, 4, 4)
+    intr = c[:, 16:25].view(-1, 3, 3)
+    ro, rd = eg3d_ref.ray_sampler_ref(cam, intr, res)
+    with torch.no_grad():
+        feat_ref, depth_ref, wsum_ref = eg3d_ref.render_ref(planes, dec, ro, rd, cfg, jitter, u if sf > 0 else None, tap)
+    feat, depth, wsum, book = _run_render_gpu(cfg, planes, dec, c, jitter, u)
+    assert pu.rel_err(feat.reshape(batch, -1, 32), feat_ref) < pu.REL_TOL
+    assert pu.rel_err(depth, depth_ref.reshape(batch, -1)) < pu.REL_TOL
+    assert pu.rel_err(wsum, wsum_ref.reshape(batch, -1)) < pu.REL_TOL
+    if sf > 0:
+        # integer bookkeeping: bit-exact except where u sits within 1e-6 of a cdf knot
+        cdf = tap['cdf']
+        uu = u[:, :sf]
+        near = (uu[:, :, None] - cdf[:, None, :]).abs().min(dim=-1).values < 1e-6
+        for k in ('inds', 'below', 'above'):
+            got = book[k].cpu().long()
+            bad = (got != tap[k]) & ~near
+            assert int(bad.sum()) == 0, f'{k}: {int(bad.sum())} mismatches outside ties'
+        assert float(near.float().mean()) < 1e-3
+        ds = book['depths_sorted'].cpu()
+        assert pu.rel_err(ds, tap['depths_sorted'].reshape(ds.shape)) < 1e-5
+        assert bool((ds[..., 1:] >= ds[..., :-1]).all()), 'merged depths must be sorted'
+        # the permutation must reproduce the oracle's wherever depths are well separated
+        order_ref = tap['sort_idx'].reshape(ds.shape)
+        gap = (tap['depths_sorted'].reshape(ds.shape)[..., 1:] - tap['depths_sorted'].reshape(ds.shape)[..., :-1]) > 1e-5
+        ok = torch.ones_like(order_ref, dtype=torch.bool)
+        ok[..., 1:] &= gap
+        ok[..., :-1] &= gap
+        assert bool((book['sort_idx'].cpu().long()[ok] == order_ref[ok]).all())
+
+
+def test_render_cfg1_micro():
+    """BASELINE.json configs[0]: 128x128 frame, 32 rays x 48 samples, random-init tri-plane MLP."""
+    res = 128
+    cfg, planes, dec, c, jitter, u = _render_case(res, 48, 48, 1, seed=0, plane_res=256)
+    idx = torch.arange(32) * 512 + 64
+    cam = c[:, :16].view(-1, 4, 4)
+    intr = c[:, 16:25].view(-1, 3, 3)
+    ro, rd = eg3d_ref.ray_sampler_ref(cam, intr, res)
+    with torch.no_grad():
+        feat_ref, depth_ref, wsum_ref = eg3d_ref.render_ref(planes, dec, ro[:, idx], rd[:, idx], cfg,
+                                                           jitter[:, idx], u[idx])
+    feat, depth, wsum, _ = _run_render_gpu(cfg, planes, dec, c, jitter, u, book=False)
+    assert pu.rel_err(feat.reshape(1, -1, 32)[:, idx.cuda()], feat_ref) < pu.REL_TOL
+    assert pu.rel_err(wsum[:, idx.cuda()], wsum_ref.reshape(1, -1)) < pu.REL_TOL
+    # depth: the oracle clamps to the min/max of the rays it saw; compare where no clamp is active
+    assert pu.rel_err(depth[:, idx.cuda()], depth_ref.reshape(1, -1)) < pu.REL_TOL
+
+
+# ------------------------------------------------------------------ whole generator
+
+def _generator_case(cfg, batch, seed=0):
+    ref, prod = pu.make_pair(cfg, seed=seed)
+    ws, c, jitter, u = pu.make_inputs(cfg, batch, seed=seed)
+    tap_r, tap_g = {}, {}
+    with torch.no_grad():
+        out_r = ref.synthesis(ws, c.clone(), noise_mode='const', jitter_coarse=jitter, u_fine=u, tap=tap_r)
+        out_g = prod.synthesis(ws.cuda(), c.clone().cuda(), noise_mode='const', jitter_coarse=jitter.cuda(),
+                               u_fine=u.cuda(), tap=tap_g)
+    return out_r, out_g, tap_r, tap_g
+
+
+def test_generator_tiny_stagewise():
+    cfg = eg3d_ref.tiny_config()
+    out_r, out_g, tap_r, tap_g = _generator_case(cfg, batch=2)
+    errs = pu.compare_taps(tap_r, tap_g)
+    report = ', '.join(f'{k}={e:.2e}' for k, e in errs)
+    for k, e in errs:
+        assert e < pu.REL_TOL, f'stage {k}: rel err {e:.3e}  [{report}]'
+    for k in ('image', 'image_raw', 'image_depth'):
+        assert out_g[k].shape == out_r[k].shape
+        assert pu.rel_err(out_g[k], out_r[k]) < pu.REL_TOL, k
+
+
+def test_generator_full_512_frame():
+    """BASELINE.json configs[1]: 512x512, 96 samples/ray, random-init EG3D generator."""
+    cfg = eg3d_ref.GeneratorConfig()
+    out_r, out_g, tap_r, tap_g = _generator_case(cfg, batch=1)
+    assert out_g['image'].shape == (1, 3, 512, 512)
+    errs = dict(pu.compare_taps(tap_r, tap_g))
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    assert worst[1] < pu.REL_TOL, f'worst stage {worst}'
+    assert pu.rel_err(out_g['image'], out_r['image']) < pu.REL_TOL
+    # size-independent properties at full size
+    assert bool(torch.isfinite(out_g['image']).all())
+    ws_sum = tap_g['weight_sum']
+    assert float(ws_sum.max()) <= 1.0 + 1e-5 and float(ws_sum.min()) >= 0.0
+    ds = tap_g['depths_sorted']
+    assert bool((ds[..., 1:] >= ds[..., :-1]).all())
+    assert int(tap_g['inds'].min()) >= 1 and int(tap_g['inds'].max()) <= cfg.depth_res - 2
+
+
+# ------------------------------------------------------------------ encoder + avatar drop-in
+
+@pytest.mark.parametrize('size,out_pose', [(64, True), (256, False)])
+def test_encoder_matches_reference_restatement(size, out_pose):
+    from hfa_gp_b200.networks.encoder3d import Encoder
+    sd = hfagp_ref.make_encoder_state(size, 512, 50, out_pose=out_pose, seed=3)
+    g = torch.Generator().manual_seed(11)
+    for k in sd:
+        if k.endswith('bias'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.2
+    enc = Encoder(size, 512, 50, False, out_pose)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.eval().requires_grad_(False).cuda()
+    x = torch.rand(2, 3, size, size, generator=g) * 2 - 1
+    ref = hfagp_ref.encoder_ref(sd, x, out_pose=out_pose)
+    with torch.no_grad():
+        got = enc(x.cuda())
+    if out_pose:
+        assert pu.rel_err(got[0], ref[0]) < pu.REL_TOL and pu.rel_err(got[1], ref[1]) < pu.REL_TOL
+    else:
+        assert pu.rel_err(got, ref) < pu.REL_TOL
+
+
+def test_headnerf_dropin_frame_loop():
+    """run_recon_video_rgb.py:216-236 per-frame call sequence on the drop-in classes vs the oracle chain."""
+    import argparse
+    from hfa_gp_b200.networks.headnerf import HeadNeRF_final
+    cfg = eg3d_ref.small14_config()
+    args = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='',
+                              synthetic_generator=True, generator_seed=0, generator_config=pu.product_config(cfg))
+    torch.manual_seed(0)
+    model = HeadNeRF_final(args, 64, 'cuda', 512, 50, 'x', './').cuda().eval()
+    # oracle side gets the very same tensors
+    ref_gen = eg3d_ref.TriPlaneGeneratorRef(cfg)
+    ref_gen.load_state_dict({k: v.cpu() for k, v in model.generator.state_dict().items()})
+    sd_enc = {k: v.detach().cpu() for k, v in model.encoder.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+    label = hfagp_ref.synthetic_labels(1, seed=9)
+    rays = cfg.nrr ** 2
+    jitter = torch.rand(1, rays, cfg.depth_res, 1, generator=g)
+    u = torch.rand(rays, cfg.depth_res_importance, generator=g)
+    with torch.no_grad():
+        w_ref = hfagp_ref.encoder_ref(sd_enc, img)
+        lat_ref = hfagp_ref.get_latent_ref(model.bases.detach().cpu(), model.delta.detach().cpu(), w_ref)
+        lab_ref = hfagp_ref.flip_label_(label.clone())
+        img_ref = ref_gen.synthesis(lat_ref, lab_ref, jitter_coarse=jitter, u_fine=u)['image']
+        lab_gpu = label.clone().cuda()
+        w = model.get_weights(img.cuda())
+        lat = model.get_latent(w)
+        latc = lat.clone()
+        lab_before = lab_gpu.clone()
+        out = model.generator.synthesis(latc, c=hfagp_ref.flip_label_(lab_gpu), noise_mode='const',
+                                        jitter_coarse=jitter.cuda(), u_fine=u.cuda())['image']
+    assert pu.rel_err(w, w_ref) < pu.REL_TOL
+    assert lat.shape == (1, 14, 512)
+    # QR is torch.linalg.qr on both sides (cuSOLVER vs LAPACK): same Householder convention expected
+    assert pu.rel_err(lat, lat_ref) < pu.REL_TOL
+    assert pu.rel_err(out, img_ref) < pu.REL_TOL
+    # in-place label flip semantics of get_image (headnerf.py:132)
+    lab2 = lab_before.clone()
+    with torch.no_grad():
+        model.get_image(lat, lab2)
+    assert torch.equal(lab2[:, [1, 2, 5, 6, 9, 10]], -lab_before[:, [1, 2, 5, 6, 9, 10]])
+    assert torch.equal(lab2[:, [0, 3, 4, 7, 8, 11]], lab_before[:, [0, 3, 4, 7, 8, 11]])
