@@ -321,6 +321,16 @@ class TriPlaneGenerator(nn.Module):
         b = ws.shape[0]
         self._batch = b
         pk = self._ensure_packed()
+        pe = getattr(self, 'profile_events', None)      # bench.py: per-stage CUDA events on the launching stream
+
+        def mark():
+            if pe is None:
+                return None
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+
+        t0 = mark()
         styles = iter(pk['styles'].run(ws))
 
         x = img = None
@@ -328,6 +338,7 @@ class TriPlaneGenerator(nn.Module):
             blk = getattr(self.backbone.synthesis, f'b{r}')
             x, img = self._run_block(blk, x, img, styles, noise_mode, pk, tap, f'b{r}')
         planes = img                                             # [B,256,256,96] channels-last
+        t1 = mark()
         if tap is not None:
             tap['planes'] = planes
 
@@ -344,10 +355,12 @@ class TriPlaneGenerator(nn.Module):
         dmin = (lin[0] + jitter[:, :, 0].min() * delta)
         dmax = (lin[-1] + jitter[:, :, -1].max() * delta)
         depth_range = torch.stack([dmin, dmax]).float().contiguous()
+        t2 = mark()
         feat, depth, wsum, book = ops.render(planes, c, pk['mlp'], lin, jitter,
                                              u_fine.float().contiguous() if sf > 0 else None, depth_range, res=res,
                                              s_coarse=s, s_fine=sf, delta=delta, box_scale=2.0 / cfg.box_warp,
                                              bookkeeping=tap is not None)
+        t3 = mark()
         if tap is not None:
             tap.update(book)
             tap.update(feature_image=feat, weight_sum=wsum)
@@ -356,9 +369,13 @@ class TriPlaneGenerator(nn.Module):
         x, img = feat, rgb_lo
         for i, blk in enumerate((self.superresolution.block0, self.superresolution.block1)):
             x, img = self._run_block(blk, x, img, styles, 'none', pk, tap, f'sr{i}')
-        return {'image': ops.nhwc_to_nchw(img),
-                'image_raw': ops.nhwc_to_nchw(rgb_lo),
-                'image_depth': depth.view(b, 1, res, res)}
+        out = {'image': ops.nhwc_to_nchw(img),
+               'image_raw': ops.nhwc_to_nchw(rgb_lo),
+               'image_depth': depth.view(b, 1, res, res)}
+        if pe is not None:
+            t4 = mark()
+            pe.extend([('backbone', t0, t1), ('render', t2, t3), ('superres', t3, t4), ('synthesis', t0, t4)])
+        return out
 
     def forward(self, *a, **k):
         raise HfagpError('HFA-GP drives the generator through .synthesis(ws, c=..., noise_mode=...) only '

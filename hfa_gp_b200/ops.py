@@ -14,6 +14,17 @@ from . import _cabi
 from ._cabi import ACT_LINEAR, ACT_LRELU, ConvDesc, RenderDesc, check, ptr, stream
 
 _desc_cache = {}
+_launches = [0]
+
+
+def launch_count() -> int:
+    """Kernels launched through the C ABI so far (every entry point enqueues exactly one kernel)."""
+    return _launches[0]
+
+
+def _ok(rc, what):
+    check(rc, what)
+    _launches[0] += 1
 
 
 def _conv_desc(key, build):
@@ -56,7 +67,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, int]
         return d
 
     d = _conv_desc(key, build)
-    check(_cabi.lib().hfagp_conv2d_fwd(C.byref(d), ptr(x), ptr(w), ptr(dcoef), ptr(noise), ptr(bias), ptr(residual),
+    _ok(_cabi.lib().hfagp_conv2d_fwd(C.byref(d), ptr(x), ptr(w), ptr(dcoef), ptr(noise), ptr(bias), ptr(residual),
                                        ptr(up_img), ptr(out), stream()), 'hfagp_conv2d_fwd')
     return out
 
@@ -92,7 +103,7 @@ def upfir_act(t: torch.Tensor, *, dcoef=None, noise=None, noise_gain=0.0, bias=N
     h2, w2 = th - 1, tw - 1
     if out is None:
         out = torch.empty((n, h2, w2, c), device=t.device, dtype=torch.float32)
-    check(_cabi.lib().hfagp_upfir_act_fwd(n, h2, w2, c, ptr(t), ptr(dcoef), ptr(noise), noise_gain, ptr(bias), act,
+    _ok(_cabi.lib().hfagp_upfir_act_fwd(n, h2, w2, c, ptr(t), ptr(dcoef), ptr(noise), noise_gain, ptr(bias), act,
                                           act_gain, clamp, ptr(out), stream()), 'hfagp_upfir_act_fwd')
     return out
 
@@ -100,7 +111,7 @@ def upfir_act(t: torch.Tensor, *, dcoef=None, noise=None, noise_gain=0.0, bias=N
 def torgb_small(x, wmod, bias, clamp, up_img, cout):
     n, h, wd, cin = x.shape
     out = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.float32)
-    check(_cabi.lib().hfagp_torgb_small_fwd(n, h, wd, cin, cout, ptr(x), ptr(wmod), ptr(bias), clamp, ptr(up_img),
+    _ok(_cabi.lib().hfagp_torgb_small_fwd(n, h, wd, cin, cout, ptr(x), ptr(wmod), ptr(bias), clamp, ptr(up_img),
                                             ptr(out), stream()), 'hfagp_torgb_small_fwd')
     return out
 
@@ -128,7 +139,7 @@ class StyleTable:
             total += b * c
         off_arr = (C.c_int64 * self.n)(*offs)
         styles = torch.empty(total, device=ws.device, dtype=torch.float32)
-        check(_cabi.lib().hfagp_styles_fwd(self.n, b, num_ws, w_dim, ptr(ws), self.aw, self.ab, self.cin, self.widx,
+        _ok(_cabi.lib().hfagp_styles_fwd(self.n, b, num_ws, w_dim, ptr(ws), self.aw, self.ab, self.cin, self.widx,
                                            self.gain, off_arr, ptr(styles), stream()), 'hfagp_styles_fwd')
         return [styles[o:o + b * c].view(b, c) for o, c in zip(offs, self.cins)]
 
@@ -139,7 +150,7 @@ def modulate(w: torch.Tensor, styles: torch.Tensor, demodulate: bool):
     b = styles.shape[0]
     wmod = torch.empty((b, taps, cout, cin), device=w.device, dtype=torch.float32)
     dcoef = torch.empty((b, cout), device=w.device, dtype=torch.float32) if demodulate else None
-    check(_cabi.lib().hfagp_modulate_fwd(b, taps, cout, cin, ptr(w), ptr(styles), ptr(wmod), ptr(dcoef), stream()),
+    _ok(_cabi.lib().hfagp_modulate_fwd(b, taps, cout, cin, ptr(w), ptr(styles), ptr(wmod), ptr(dcoef), stream()),
           'hfagp_modulate_fwd')
     return wmod, dcoef
 
@@ -162,7 +173,7 @@ def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s
         book['sort_idx'] = torch.empty((n, rays, t), device=dev, dtype=torch.int32)
         book['depths_sorted'] = torch.empty((n, rays, t), device=dev, dtype=torch.float32)
     d = RenderDesc(n, res, ph, pw, s_coarse, s_fine, delta, box_scale)
-    check(_cabi.lib().hfagp_render_fwd(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
+    _ok(_cabi.lib().hfagp_render_fwd(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
                                        ptr(depth_range), ptr(feat), ptr(depth), ptr(wsum), ptr(book.get('inds')), ptr(book.get('below')),
                                        ptr(book.get('above')), ptr(book.get('sort_idx')),
                                        ptr(book.get('depths_sorted')), stream()), 'hfagp_render_fwd')
@@ -174,7 +185,7 @@ def blur(x, pad0, pad1, stride=1):
     oh = (h + pad0 + pad1 - 4) // stride + 1
     ow = (wd + pad0 + pad1 - 4) // stride + 1
     out = torch.empty((n, oh, ow, c), device=x.device, dtype=torch.float32)
-    check(_cabi.lib().hfagp_blur_fwd(n, h, wd, c, pad0, pad1, stride, ptr(x), ptr(out), stream()), 'hfagp_blur_fwd')
+    _ok(_cabi.lib().hfagp_blur_fwd(n, h, wd, c, pad0, pad1, stride, ptr(x), ptr(out), stream()), 'hfagp_blur_fwd')
     return out
 
 
@@ -182,7 +193,7 @@ def linear(x, w, b, w_gain, b_gain):
     n, cin = x.shape
     cout = w.shape[0]
     out = torch.empty((n, cout), device=x.device, dtype=torch.float32)
-    check(_cabi.lib().hfagp_linear_fwd(n, cin, cout, ptr(x), ptr(w), ptr(b), w_gain, b_gain, ptr(out), stream()),
+    _ok(_cabi.lib().hfagp_linear_fwd(n, cin, cout, ptr(x), ptr(w), ptr(b), w_gain, b_gain, ptr(out), stream()),
           'hfagp_linear_fwd')
     return out
 
@@ -190,7 +201,7 @@ def linear(x, w, b, w_gain, b_gain):
 def latent(weights, q, delta, dim_total):
     n, k = weights.shape
     out = torch.empty((n, dim_total), device=weights.device, dtype=torch.float32)
-    check(_cabi.lib().hfagp_latent_fwd(n, k, dim_total, ptr(weights), ptr(q), ptr(delta), ptr(out), stream()),
+    _ok(_cabi.lib().hfagp_latent_fwd(n, k, dim_total, ptr(weights), ptr(q), ptr(delta), ptr(out), stream()),
           'hfagp_latent_fwd')
     return out
 
@@ -198,12 +209,12 @@ def latent(weights, q, delta, dim_total):
 def nchw_to_nhwc(x):
     n, c, h, w = x.shape
     out = torch.empty((n, h, w, c), device=x.device, dtype=torch.float32)
-    check(_cabi.lib().hfagp_nchw_to_nhwc(n, c, h, w, ptr(x), ptr(out), stream()), 'hfagp_nchw_to_nhwc')
+    _ok(_cabi.lib().hfagp_nchw_to_nhwc(n, c, h, w, ptr(x), ptr(out), stream()), 'hfagp_nchw_to_nhwc')
     return out
 
 
 def nhwc_to_nchw(x):
     n, h, w, c = x.shape
     out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
-    check(_cabi.lib().hfagp_nhwc_to_nchw(n, c, h, w, ptr(x), ptr(out), stream()), 'hfagp_nhwc_to_nchw')
+    _ok(_cabi.lib().hfagp_nhwc_to_nchw(n, c, h, w, ptr(x), ptr(out), stream()), 'hfagp_nhwc_to_nchw')
     return out
