@@ -21,7 +21,7 @@ SYMBOLS = [
     'hfagp_abi_version', 'hfagp_last_error', 'hfagp_conv2d_fwd', 'hfagp_upfir_act_fwd',
     'hfagp_torgb_small_fwd', 'hfagp_styles_fwd', 'hfagp_modulate_fwd', 'hfagp_render_fwd',
     'hfagp_blur_fwd', 'hfagp_linear_fwd', 'hfagp_latent_fwd', 'hfagp_nchw_to_nhwc',
-    'hfagp_nhwc_to_nchw',
+    'hfagp_nhwc_to_nchw', 'hfagp_conv2d_tc_fwd', 'hfagp_split_bf16', 'hfagp_modulate_split_fwd',
 ]
 
 
@@ -68,8 +68,8 @@ def lib() -> C.CDLL:
     l.hfagp_abi_version.restype = C.c_int
     vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
     l.hfagp_conv2d_fwd.argtypes = [C.POINTER(ConvDesc)] + [vp] * 9
-    l.hfagp_upfir_act_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, f32, f32, vp, vp]
-    l.hfagp_torgb_small_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, f32, vp, vp, vp]
+    l.hfagp_upfir_act_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, f32, f32, vp, vp, vp, vp]
+    l.hfagp_torgb_small_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp]
     l.hfagp_styles_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     l.hfagp_modulate_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_render_fwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
@@ -78,6 +78,9 @@ def lib() -> C.CDLL:
     l.hfagp_latent_fwd.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_nchw_to_nhwc.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     l.hfagp_nhwc_to_nchw.argtypes = [i32, i32, i32, i32, vp, vp, vp]
+    l.hfagp_conv2d_tc_fwd.argtypes = [C.POINTER(ConvDesc), vp, vp, vp, vp, i32] + [vp] * 9
+    l.hfagp_split_bf16.argtypes = [C.c_longlong, vp, vp, vp, vp]
+    l.hfagp_modulate_split_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(l, s)
         if s not in ('hfagp_last_error',):

@@ -1,43 +1,14 @@
 // fp32 SIMT implicit-GEMM convolution (channels-last) with the fused StyleGAN2 / encoder epilogue,
 // plus the small bandwidth-bound companions (FIR after the transposed conv, small-N ToRGB, blur).
 // This is the exact-fp32 path; see conv_tc.cu for the tcgen05 tensor-core path.
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace hfagp {
 
-struct ConvParams {
-  HfagpConvDesc d;
-  const float* x;
-  const float* w;
-  const float* dcoef;
-  const float* noise;
-  const float* bias;
-  const float* residual;
-  const float* up_img;
-  float* y;
-};
-
 constexpr int BK = 16;
 constexpr int LDK = BK + 4;  // row stride (floats): 8 consecutive rows hit 8 distinct 16B bank groups
-
-// upsample2d(img)[oy][ox][co] for a channels-last low-res image [uh][uw][cout]:
-// zero-insert x2, pad [2,1,2,1], [1,3,3,1]^2/64 * 4  ==  separable {0.25,0.75} polyphase.
-__device__ __forceinline__ float upsample_tap(const float* __restrict__ img, int uh, int uw, int cstride,
-                                              int oy, int ox, int co) {
-  int my = oy >> 1, mx = ox >> 1;
-  int y0, y1, x0, x1;
-  float wy0, wy1, wx0, wx1;
-  if (oy & 1) { y0 = my; y1 = my + 1; wy0 = 0.75f; wy1 = 0.25f; } else { y0 = my - 1; y1 = my; wy0 = 0.25f; wy1 = 0.75f; }
-  if (ox & 1) { x0 = mx; x1 = mx + 1; wx0 = 0.75f; wx1 = 0.25f; } else { x0 = mx - 1; x1 = mx; wx0 = 0.25f; wx1 = 0.75f; }
-  float v = 0.f;
-  bool vy0 = y0 >= 0 && y0 < uh, vy1 = y1 >= 0 && y1 < uh;
-  bool vx0 = x0 >= 0 && x0 < uw, vx1 = x1 >= 0 && x1 < uw;
-  if (vy0 && vx0) v += wy0 * wx0 * __ldg(img + ((size_t)y0 * uw + x0) * cstride + co);
-  if (vy0 && vx1) v += wy0 * wx1 * __ldg(img + ((size_t)y0 * uw + x1) * cstride + co);
-  if (vy1 && vx0) v += wy1 * wx0 * __ldg(img + ((size_t)y1 * uw + x0) * cstride + co);
-  if (vy1 && vx1) v += wy1 * wx1 * __ldg(img + ((size_t)y1 * uw + x1) * cstride + co);
-  return v;
-}
 
 template <int TM, int TN>
 __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvParams p) {
@@ -172,34 +143,18 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvParams p) {
   }
 
   // ---- epilogue
-  const float* dco = p.dcoef ? p.dcoef + (size_t)n * cout : nullptr;
-  const size_t out_img = (size_t)d.out_h * d.out_w * cout;
-  float* yn = p.y + (size_t)n * out_img;
-  const float* resn = p.residual ? p.residual + (size_t)n * out_img : nullptr;
-  const float* upn = p.up_img ? p.up_img + (size_t)n * d.up_h * d.up_w * cout : nullptr;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int m = m0 + ty + 16 * i;
     if (m >= M) continue;
     int my = m / d.ow, mx = m - my * d.ow;
-    int oy = my * d.out_stride + d.out_off_y;
-    int ox = mx * d.out_stride + d.out_off_x;
-    float nz = p.noise ? __ldg(p.noise + (size_t)oy * d.out_w + ox) * d.noise_gain : 0.f;
-    size_t pix = ((size_t)oy * d.out_w + ox) * cout;
+    EpiCtx ec;
+    epi_setup(ec, p, n, my, mx);
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int co = n0 + tx + 16 * j;
       if (co >= cout) continue;
-      float v = acc[i][j];
-      if (dco) v *= __ldg(dco + co);
-      v += nz;
-      if (p.bias) v += __ldg(p.bias + co);
-      if (d.act == HFAGP_ACT_LRELU) v = lrelu02(v);
-      v *= d.act_gain;
-      if (d.clamp > 0.f) v = fminf(fmaxf(v, -d.clamp), d.clamp);
-      if (resn) v = (v + __ldg(resn + pix + co)) * d.residual_scale;
-      if (upn) v += upsample_tap(upn, d.up_h, d.up_w, cout, oy, ox, co);
-      yn[pix + co] = v;
+      p.y[ec.out_base + co] = epi_apply(ec, p, acc[i][j], co);
     }
   }
 }
@@ -208,7 +163,8 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvParams p) {
 __global__ void upfir_act_kernel(int batch, int h2, int w2, int c, const float* __restrict__ t,
                                  const float* __restrict__ dcoef, const float* __restrict__ noise, float noise_gain,
                                  const float* __restrict__ bias, int act, float act_gain, float clamp,
-                                 float* __restrict__ y) {
+                                 float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
+                                 __nv_bfloat16* __restrict__ y_lo) {
   const int c4 = c >> 2;
   size_t total = (size_t)batch * h2 * w2 * c4;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,11 +209,36 @@ __global__ void upfir_act_kernel(int batch, int h2, int w2, int c, const float* 
     if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
     vals[k] = v;
   }
-  reinterpret_cast<float4*>(y)[idx] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+  if (y_hi) {  // split-bf16 output for a following tensor-core layer
+    uint32_t hw[2], lw[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      __nv_bfloat16 h0 = __float2bfloat16_rn(vals[2 * e]), h1 = __float2bfloat16_rn(vals[2 * e + 1]);
+      __nv_bfloat16 l0 = __float2bfloat16_rn(vals[2 * e] - __bfloat162float(h0));
+      __nv_bfloat16 l1 = __float2bfloat16_rn(vals[2 * e + 1] - __bfloat162float(h1));
+      hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    reinterpret_cast<uint2*>(y_hi)[idx] = make_uint2(hw[0], hw[1]);
+    reinterpret_cast<uint2*>(y_lo)[idx] = make_uint2(lw[0], lw[1]);
+  } else {
+    reinterpret_cast<float4*>(y)[idx] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+  }
 }
 
 // ---------------------------------------------------------------- small-N ToRGB (cout <= 4)
+__device__ __forceinline__ float4 bf16x4_sum(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t q) {
+  const uint2 a = __ldg(reinterpret_cast<const uint2*>(hi) + q), b = __ldg(reinterpret_cast<const uint2*>(lo) + q);
+  float4 r;
+  r.x = __uint_as_float(a.x << 16) + __uint_as_float(b.x << 16);
+  r.y = __uint_as_float(a.x & 0xffff0000u) + __uint_as_float(b.x & 0xffff0000u);
+  r.z = __uint_as_float(a.y << 16) + __uint_as_float(b.y << 16);
+  r.w = __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u);
+  return r;
+}
+
 __global__ void torgb_small_kernel(int batch, int h, int w_, int cin, int cout, const float* __restrict__ x,
+                                   const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
                                    const float* __restrict__ w, const float* __restrict__ bias, float clamp,
                                    const float* __restrict__ up_img, float* __restrict__ y) {
   const int lane = threadIdx.x & 31;
@@ -267,12 +248,13 @@ __global__ void torgb_small_kernel(int batch, int h, int w_, int cin, int cout, 
   const int n = warp / ((size_t)h * w_);
   const size_t rem = warp - (size_t)n * h * w_;
   const int oy = rem / w_, ox = rem - (size_t)oy * w_;
-  const float4* xp = reinterpret_cast<const float4*>(x + warp * cin);
+  const float4* xp = x ? reinterpret_cast<const float4*>(x + warp * cin) : nullptr;
+  const size_t xq = warp * (size_t)(cin >> 2);
   const float4* wp = reinterpret_cast<const float4*>(w + (size_t)n * cout * cin);
   const int c4 = cin >> 2;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int q = lane; q < c4; q += 32) {
-    float4 xv = __ldg(xp + q);
+    float4 xv = xp ? __ldg(xp + q) : bf16x4_sum(x_hi, x_lo, xq + q);
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       if (o < cout) {
@@ -387,24 +369,30 @@ extern "C" int hfagp_conv2d_fwd(const HfagpConvDesc* desc, const float* x, const
 
 extern "C" int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float* t, const float* dcoef,
                                    const float* noise, float noise_gain, const float* bias, int act, float act_gain,
-                                   float clamp, float* y, void* stream) {
-  HFAGP_CHECK_ARG(t && y, "upfir_act_fwd: null pointer");
+                                   float clamp, float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream) {
+  HFAGP_CHECK_ARG(t && ((y != nullptr) != (y_hi != nullptr && y_lo != nullptr)),
+                  "upfir_act_fwd: give t and either y or (y_hi, y_lo)");
   HFAGP_CHECK_ARG(batch > 0 && h2 > 0 && w2 > 0 && c > 0 && (c & 3) == 0, "upfir_act_fwd: c must be a multiple of 4");
   size_t total = (size_t)batch * h2 * w2 * (c >> 2);
   upfir_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain,
-                                                                      bias, act, act_gain, clamp, y);
+                                                                      bias, act, act_gain, clamp, y,
+                                                                      reinterpret_cast<__nv_bfloat16*>(y_hi),
+                                                                      reinterpret_cast<__nv_bfloat16*>(y_lo));
   HFAGP_CHECK_LAUNCH("upfir_act_kernel");
   return HFAGP_OK;
 }
 
-extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const float* w,
-                                     const float* bias, float clamp, const float* up_img, float* y, void* stream) {
-  HFAGP_CHECK_ARG(x && w && y, "torgb_small_fwd: null pointer");
+extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const uint16_t* x_hi,
+                                     const uint16_t* x_lo, const float* w, const float* bias, float clamp,
+                                     const float* up_img, float* y, void* stream) {
+  HFAGP_CHECK_ARG(w && y && ((x != nullptr) != (x_hi != nullptr && x_lo != nullptr)),
+                  "torgb_small_fwd: give w, y and either x or (x_hi, x_lo)");
   HFAGP_CHECK_ARG(cout >= 1 && cout <= 4 && (cin & 3) == 0, "torgb_small_fwd: cout<=4 and cin%%4==0 required");
   HFAGP_CHECK_ARG(!up_img || ((h & 1) == 0 && (w_ & 1) == 0), "torgb_small_fwd: odd size with up_img");
   size_t warps = (size_t)batch * h * w_;
-  torgb_small_kernel<<<cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(batch, h, w_, cin, cout, x, w, bias,
-                                                                             clamp, up_img, y);
+  torgb_small_kernel<<<cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      batch, h, w_, cin, cout, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
+      reinterpret_cast<const __nv_bfloat16*>(x_lo), w, bias, clamp, up_img, y);
   HFAGP_CHECK_LAUNCH("torgb_small_kernel");
   return HFAGP_OK;
 }

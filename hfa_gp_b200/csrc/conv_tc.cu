@@ -1,0 +1,389 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: TMA (cp.async.bulk.tensor, SWIZZLE_128B) feeds a
+// 3-stage shared-memory ring, one elected thread issues tcgen05.mma with the fp32 accumulator in TMEM, and
+// four epilogue warps read it back with tcgen05.ld and apply the fused StyleGAN2 / encoder epilogue.
+//
+// Precision: fp32-class results on the bf16 tensor pipe.  Every fp32 operand is stored as a pair of bf16
+// tensors (hi = bf16(x), lo = bf16(x - hi), ~16 mantissa bits together) and each K step issues three MMAs
+// into the same accumulator:  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is ~2^-18 relative).
+//
+// GEMM view (channels-last):  M = a BHxBW patch of 128 output pixels, N = BN output channels,
+// K = taps x cin in chunks of 64 channels.  The A tile of tap (dy,dx) is the TMA box {64ch, BW, BH, 1} at
+// (c0, x0+dx, y0+dy, n): out-of-range coordinates are zero-filled by the TMA unit, which *is* the conv padding.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+#include <unordered_map>
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace hfagp {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                       // bf16 elements per K chunk = one 128 B swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB per (hi|lo) A tile
+constexpr int TC_THREADS = 192;                 // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr uint32_t SPIN_LIMIT = 1u << 22;       // a broken pipeline traps instead of hanging the GPU
+
+struct TcParams {
+  ConvParams cp;          // epilogue operands + geometry (x / w pointers unused here)
+  int tile_w, tile_h;     // BW x BH = 128
+  int bn;                 // N tile (multiple of 16, <= 128)
+  int tiles_x, tiles_y;   // M tiles per frame
+  int taps_per_frame;     // weight taps stored per batch sample (B map z-coordinate stride)
+  int w_batched;          // 1: weights are per sample
+  __nv_bfloat16* y_hi;    // split output (or null -> cp.y fp32)
+  __nv_bfloat16* y_lo;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > SPIN_LIMIT) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* smem, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* smem, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row x 128 B atoms, 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stage][A_hi | A_lo | B_hi | B_lo] (each 1024-aligned), then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.bn * TC_BK * 2;
+  const int b_pad = (b_bytes + 1023) & ~1023;
+  const int stage_bytes = 2 * TC_A_BYTES + 2 * b_pad;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * stage_bytes);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* acc_full = empty + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const HfagpConvDesc& d = p.cp.d;
+  const int n = blockIdx.z;
+  const int tile = blockIdx.x;
+  const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+  const int y0 = ty * p.tile_h, x0 = tx * p.tile_w;
+  const int n0 = blockIdx.y * p.bn;
+  const int kchunks = d.cin / TC_BK;
+  const int iters = d.ntaps * kchunks;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.bn) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one thread)
+    if (lane == 0) {
+      const int wz0 = p.w_batched ? n * p.taps_per_frame : 0;
+      const uint32_t tx_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int t = it / kchunks;
+        const int c0 = (it - t * kchunks) * TC_BK;
+        uint8_t* st = smem + s * stage_bytes;
+        mbar_expect_tx(&full[s], tx_bytes);
+        const int ax = x0 * d.in_stride + d.dx[t], ay = y0 * d.in_stride + d.dy[t];
+        tma_load_4d(&map_a_hi, st, &full[s], c0, ax, ay, n);
+        tma_load_4d(&map_a_lo, st + TC_A_BYTES, &full[s], c0, ax, ay, n);
+        tma_load_3d(&map_b_hi, st + 2 * TC_A_BYTES, &full[s], c0, n0, wz0 + d.wtap[t]);
+        tma_load_3d(&map_b_lo, st + 2 * TC_A_BYTES + b_pad, &full[s], c0, n0, wz0 + d.wtap[t]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread)
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((TC_BM >> 4) << 24);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + s * stage_bytes);
+        const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + b_pad;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
+          umma_bf16(tmem_base, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, (it | k) ? 1u : 0u);
+          umma_bf16(tmem_base, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, 1u);
+          umma_bf16(tmem_base, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1u);
+        }
+        umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(acc_full);     // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                     // accumulator row = pixel inside the tile
+    const int ly = r / p.tile_w, lx = r - ly * p.tile_w;
+    const int my = y0 + ly, mx = x0 + lx;
+    const bool valid = my < d.oh && mx < d.ow;
+    mbar_wait(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    EpiCtx ec;
+    epi_setup(ec, p.cp, n, valid ? my : 0, valid ? mx : 0);
+    for (int cb = 0; cb < p.bn; cb += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb, v);   // warp-collective: no early exit before this
+      if (!valid) continue;
+      const int co0 = n0 + cb;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (co0 + j < d.cout) v[j] = epi_apply(ec, p.cp, v[j], co0 + j);
+      if (p.y_hi) {
+        __nv_bfloat16* oh = p.y_hi + ec.out_base + co0;
+        __nv_bfloat16* ol = p.y_lo + ec.out_base + co0;
+        if (co0 + 32 <= d.cout && (d.cout & 7) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat16 h0 = __float2bfloat16_rn(v[j + 2 * e]), h1 = __float2bfloat16_rn(v[j + 2 * e + 1]);
+              __nv_bfloat16 l0 = __float2bfloat16_rn(v[j + 2 * e] - __bfloat162float(h0));
+              __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 2 * e + 1] - __bfloat162float(h1));
+              hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        } else {
+          for (int j = 0; j < 32 && co0 + j < d.cout; ++j) {
+            __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+            oh[j] = h;
+            ol[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+          }
+        }
+      } else {
+        float* o = p.cp.y + ec.out_base + co0;
+        if (co0 + 32 <= d.cout && (d.cout & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32 && co0 + j < d.cout; ++j) o[j] = v[j];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, d2, d3;
+  uint32_t b0, b1, b2, b3, es;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b0 == o.b0 && b1 == o.b1 &&
+           b2 == o.b2 && b3 == o.b3 && es == o.es;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.d0); mix(k.d1); mix(k.d2); mix(k.d3); mix(k.b0); mix(k.b1); mix(k.b2); mix(k.b3); mix(k.es);
+    return h;
+  }
+};
+
+// rank-4 bf16 map (rank-3 tensors pass d3 = b3 = 1).  Cached: PyTorch's allocator hands the same
+// pointers back every frame, so steady state does no driver calls.
+static int get_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t b0,
+                   uint32_t b1, uint32_t b2, uint32_t b3, uint32_t estride, int rank) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, d0, d1, d2, d3, b0, b1, b2, b3, estride * 8u + (uint32_t)rank};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return HFAGP_OK;
+    }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(HFAGP_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, d0 * d1 * d2 * 2};
+  cuuint32_t box[4] = {b0, b1, b2, b3};
+  cuuint32_t es[4] = {1, estride, estride, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HFAGP_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return HFAGP_OK;
+}
+
+}  // namespace hfagp
+
+using namespace hfagp;
+
+extern "C" int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_hi, const uint16_t* x_lo,
+                                   const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
+                                   const float* noise, const float* bias, const float* residual, const float* up_img,
+                                   float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream) {
+  HFAGP_CHECK_ARG(desc && x_hi && x_lo && w_hi && w_lo, "conv2d_tc_fwd: null pointer");
+  HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "conv2d_tc_fwd: give y or (y_hi, y_lo)");
+  const HfagpConvDesc& d = *desc;
+  HFAGP_CHECK_ARG(d.batch > 0 && d.batch <= 65535 && d.oh > 0 && d.ow > 0 && d.cout > 0, "conv2d_tc_fwd: bad dims");
+  HFAGP_CHECK_ARG(d.cin % TC_BK == 0, "conv2d_tc_fwd: cin must be a multiple of 64 (got %d)", d.cin);
+  HFAGP_CHECK_ARG(d.ntaps > 0 && d.ntaps <= HFAGP_MAX_TAPS, "conv2d_tc_fwd: ntaps out of range");
+  HFAGP_CHECK_ARG(d.in_stride == 1 || d.in_stride == 2, "conv2d_tc_fwd: in_stride must be 1 or 2");
+  HFAGP_CHECK_ARG((d.oh - 1) * d.out_stride + d.out_off_y < d.out_h && (d.ow - 1) * d.out_stride + d.out_off_x < d.out_w,
+                  "conv2d_tc_fwd: output window exceeds out_h/out_w");
+  HFAGP_CHECK_ARG(!up_img || (d.up_h * 2 == d.out_h && d.up_w * 2 == d.out_w), "conv2d_tc_fwd: up_img must be out/2");
+  HFAGP_CHECK_ARG(w_taps_total > 0, "conv2d_tc_fwd: w_taps_total");
+
+  TcParams p;
+  p.cp = ConvParams{d, nullptr, nullptr, dcoef, noise, bias, residual, up_img, y};
+  p.y_hi = reinterpret_cast<__nv_bfloat16*>(y_hi);
+  p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
+  // M tile shape: the BW x BH (=128) rectangle that wastes the fewest pixels
+  long long best = -1;
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    int bh = 128 / bw;
+    long long padded = (long long)cdiv(d.ow, bw) * bw * cdiv(d.oh, bh) * bh;
+    if (best < 0 || padded < best) {
+      best = padded;
+      p.tile_w = bw;
+      p.tile_h = bh;
+    }
+  }
+  p.tiles_x = cdiv(d.ow, p.tile_w);
+  p.tiles_y = cdiv(d.oh, p.tile_h);
+  p.bn = d.cout >= 128 ? 128 : ((d.cout + 15) / 16) * 16;
+  p.w_batched = d.w_batch_stride != 0;
+  p.taps_per_frame = w_taps_total;
+
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  const uint32_t es = (uint32_t)d.in_stride;
+  // box extents are given in un-strided coordinates: a stride-2 traversal of BW outputs spans 2*BW-1 inputs
+  const uint32_t box_w = (uint32_t)(p.tile_w * d.in_stride - (d.in_stride - 1));
+  const uint32_t box_h = (uint32_t)(p.tile_h * d.in_stride - (d.in_stride - 1));
+  int rc;
+  if ((rc = get_map(&ma_hi, x_hi, d.cin, d.in_w, d.in_h, d.batch, TC_BK, box_w, box_h, 1, es, 4))) return rc;
+  if ((rc = get_map(&ma_lo, x_lo, d.cin, d.in_w, d.in_h, d.batch, TC_BK, box_w, box_h, 1, es, 4))) return rc;
+  const uint64_t wz = (uint64_t)w_taps_total * (p.w_batched ? d.batch : 1);
+  if ((rc = get_map(&mb_hi, w_hi, d.cin, d.cout, wz, 1, TC_BK, p.bn, 1, 1, 1, 3))) return rc;
+  if ((rc = get_map(&mb_lo, w_lo, d.cin, d.cout, wz, 1, TC_BK, p.bn, 1, 1, 1, 3))) return rc;
+
+  const int b_pad = (p.bn * TC_BK * 2 + 1023) & ~1023;
+  const size_t smem = (size_t)TC_STAGES * (2 * TC_A_BYTES + 2 * b_pad) + 1024 + 128;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  dim3 grid(p.tiles_x * p.tiles_y, cdiv(d.cout, p.bn), d.batch);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  HFAGP_CHECK_LAUNCH("conv_tc_kernel");
+  return HFAGP_OK;
+}

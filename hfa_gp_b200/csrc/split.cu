@@ -1,0 +1,70 @@
+// Split-bf16 operand producers for the tensor-core path: x (fp32) -> hi = bf16(x), lo = bf16(x - hi).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace hfagp {
+
+__device__ __forceinline__ void split2(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(v);
+  l = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__global__ void split_kernel(size_t count, const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  split2(__ldg(x + i), hi[i], lo[i]);
+}
+
+// block per (o, n): wmod = w * s written as split bf16, dcoef from the fp32 products
+__global__ void modulate_split_kernel(int ntaps, int cout, int cin, const float* __restrict__ w,
+                                      const float* __restrict__ styles, __nv_bfloat16* __restrict__ whi,
+                                      __nv_bfloat16* __restrict__ wlo, float* __restrict__ dcoef) {
+  const int o = blockIdx.x, n = blockIdx.y;
+  const float* sn = styles + (size_t)n * cin;
+  float ss = 0.f;
+  for (int t = 0; t < ntaps; ++t) {
+    const float* wr = w + ((size_t)t * cout + o) * cin;
+    const size_t ob = (((size_t)n * ntaps + t) * cout + o) * cin;
+    for (int i = threadIdx.x; i < cin; i += blockDim.x) {
+      float v = __ldg(wr + i) * __ldg(sn + i);
+      split2(v, whi[ob + i], wlo[ob + i]);
+      ss = fmaf(v, v, ss);
+    }
+  }
+  if (dcoef) {
+    __shared__ float red[32];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) dcoef[(size_t)n * cout + o] = rsqrtf(v + 1e-8f);
+    }
+  }
+}
+
+}  // namespace hfagp
+
+using namespace hfagp;
+
+extern "C" int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, uint16_t* lo, void* stream) {
+  HFAGP_CHECK_ARG(x && hi && lo && count > 0, "split_bf16: bad args");
+  split_kernel<<<cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>((size_t)count, x, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                   reinterpret_cast<__nv_bfloat16*>(lo));
+  HFAGP_CHECK_LAUNCH("split_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_modulate_split_fwd(int batch, int ntaps, int cout, int cin, const float* w, const float* styles,
+                                        uint16_t* wmod_hi, uint16_t* wmod_lo, float* dcoef, void* stream) {
+  HFAGP_CHECK_ARG(w && styles && wmod_hi && wmod_lo, "modulate_split_fwd: null pointer");
+  HFAGP_CHECK_ARG(batch > 0 && batch <= 65535 && ntaps > 0 && cout > 0 && cin > 0, "modulate_split_fwd: bad dims");
+  int threads = cin >= 256 ? 256 : (cin >= 128 ? 128 : 64);
+  modulate_split_kernel<<<dim3(cout, batch), threads, 0, (cudaStream_t)stream>>>(
+      ntaps, cout, cin, w, styles, reinterpret_cast<__nv_bfloat16*>(wmod_hi), reinterpret_cast<__nv_bfloat16*>(wmod_lo),
+      dcoef);
+  HFAGP_CHECK_LAUNCH("modulate_split_kernel");
+  return HFAGP_OK;
+}

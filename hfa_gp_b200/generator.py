@@ -187,6 +187,7 @@ class TriPlaneGenerator(nn.Module):
                                      avg_camera_pivot=[0, 0, 0.2])
         self._packed = None
         self._packed_key = None
+        self.precision = 'tc'      # 'tc': tcgen05 split-bf16 convolutions (fp32-class); 'fp32': SIMT kernels only
 
     @property
     def num_ws(self) -> int:
@@ -248,49 +249,85 @@ class TriPlaneGenerator(nn.Module):
         dev = mlp.device
         lin = torch.linspace(self.cfg.ray_start, self.cfg.ray_end, self.cfg.depth_res).to(dev)
         const = self.backbone.synthesis.b4.const.detach().permute(1, 2, 0).contiguous().float()
-        self._packed = dict(order=layers, styles=ops.StyleTable(table), layers=packed, mlp=mlp, lin=lin, const=const)
+        self._packed = dict(order=layers, styles=ops.StyleTable(table), layers=packed, mlp=mlp, lin=lin, const=const,
+                            const_split=ops.split(const) if const.is_cuda else None)
         self._packed_key = key
         return self._packed
 
     # ---------------------------------------------------------------- layer drivers (channels-last)
-    def _conv_layer(self, x, m, styles, noise_mode, pk):
+    # Kernel selection per layer: the tcgen05 path (split-bf16 operands, fp32 accumulate in TMEM) whenever the
+    # layer's cin is a multiple of its 64-channel K chunk, else the exact-fp32 SIMT kernel (cin = 32 first SR
+    # layer, thin test configs).  ``self.precision = 'fp32'`` forces the SIMT kernels everywhere.
+    def _use_tc(self, cin):
+        return self.precision == 'tc' and cin % 64 == 0
+
+    @staticmethod
+    def _as_f32(x):
+        return x.float() if isinstance(x, ops.Split) else x
+
+    def _conv_layer(self, x, m, styles, noise_mode, pk, split_out):
         pl: _PackedLayer = pk['layers'][id(m)]
-        b = x.shape[0]
-        wmod, dcoef = ops.modulate(pl.w, styles, True)
         noise = None
         if pl.use_noise and noise_mode == 'const' and pl.noise_gain != 0.0:
             noise = pl.noise
         elif pl.use_noise and noise_mode == 'random':
             raise HfagpError("noise_mode='random' is not part of the HFA-GP path (headnerf.py:112 passes 'const')")
+        epi = dict(dcoef=None, noise=noise, noise_gain=pl.noise_gain, bias=pl.bias, act=ACT_LRELU, act_gain=SQRT2,
+                   clamp=pl.clamp)
+        h, w = x.shape[1], x.shape[2]
+        if self._use_tc(pl.cin):
+            xs = x if isinstance(x, ops.Split) else ops.split(x)
+            wmod, epi['dcoef'] = ops.modulate_split(pl.w, styles, True)
+            if pl.up == 1:
+                return ops.conv2d_tc(xs, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batched=True,
+                                     split_out=split_out, **epi)
+            t = torch.empty((x.shape[0], 2 * h + 1, 2 * w + 1, pl.cout), device=xs.device, dtype=torch.float32)
+            for a in (0, 1):
+                for b in (0, 1):
+                    ops.conv2d_tc(xs, wmod, ops._parity_taps(a, b), pl.cout, oh=h + 1 - a, ow=w + 1 - b, out=t,
+                                  out_hw=(2 * h + 1, 2 * w + 1), out_stride=2, out_off=(a, b), w_batched=True)
+            return ops.upfir_act(t, split_out=split_out, **epi)
+        xf = self._as_f32(x)
+        wmod, epi['dcoef'] = ops.modulate(pl.w, styles, True)
         wbs = wmod.stride(0)
         if pl.up == 1:
-            h, w = x.shape[1], x.shape[2]
-            return ops.conv2d(x, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batch_stride=wbs, dcoef=dcoef,
-                              noise=noise, noise_gain=pl.noise_gain, bias=pl.bias, act=ACT_LRELU, act_gain=SQRT2,
-                              clamp=pl.clamp)
-        t = ops.conv_transpose_s2(x, wmod, pl.cout, wbs)
-        return ops.upfir_act(t, dcoef=dcoef, noise=noise, noise_gain=pl.noise_gain, bias=pl.bias, act=ACT_LRELU,
-                             act_gain=SQRT2, clamp=pl.clamp)
+            y = ops.conv2d(xf, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batch_stride=wbs, **epi)
+            return ops.split(y) if split_out else y
+        t = ops.conv_transpose_s2(xf, wmod, pl.cout, wbs)
+        return ops.upfir_act(t, split_out=split_out, **epi)
 
     def _torgb_layer(self, x, m, styles, img, pk):
         pl: _PackedLayer = pk['layers'][id(m)]
-        wmod, _ = ops.modulate(pl.w, styles, False)
         h, w = x.shape[1], x.shape[2]
         if pl.cout <= 4:
+            wmod, _ = ops.modulate(pl.w, styles, False)
             return ops.torgb_small(x, wmod, pl.bias, pl.clamp, img, pl.cout)
-        return ops.conv2d(x, wmod, ops.TAPS_1X1, pl.cout, oh=h, ow=w, w_batch_stride=wmod.stride(0), bias=pl.bias,
-                          clamp=pl.clamp, up_img=img)
+        if self._use_tc(pl.cin):
+            xs = x if isinstance(x, ops.Split) else ops.split(x)
+            wmod, _ = ops.modulate_split(pl.w, styles, False)
+            return ops.conv2d_tc(xs, wmod, ops.TAPS_1X1, pl.cout, oh=h, ow=w, w_batched=True, bias=pl.bias,
+                                 clamp=pl.clamp, up_img=img)
+        wmod, _ = ops.modulate(pl.w, styles, False)
+        return ops.conv2d(self._as_f32(x), wmod, ops.TAPS_1X1, pl.cout, oh=h, ow=w, w_batch_stride=wmod.stride(0),
+                          bias=pl.bias, clamp=pl.clamp, up_img=img)
 
     def _run_block(self, blk, x, img, styles_iter, noise_mode, pk, tap, name):
+        # activations between layers of a block stay in the operand format of their consumer
+        tc_next = self._use_tc(blk.cout)
         if blk.cin == 0:
-            x = pk['const'][None].expand(self._batch, -1, -1, -1).contiguous()
+            c = pk['const_split'] if tc_next else pk['const']
+            if tc_next:
+                x = ops.Split(c.hi[None].expand(self._batch, -1, -1, -1).contiguous(),
+                              c.lo[None].expand(self._batch, -1, -1, -1).contiguous())
+            else:
+                x = c[None].expand(self._batch, -1, -1, -1).contiguous()
         else:
-            x = self._conv_layer(x, blk.conv0, next(styles_iter), noise_mode, pk)
+            x = self._conv_layer(x, blk.conv0, next(styles_iter), noise_mode, pk, split_out=tc_next)
             if tap is not None:
-                tap[name + '.conv0'] = x
-        x = self._conv_layer(x, blk.conv1, next(styles_iter), noise_mode, pk)
+                tap[name + '.conv0'] = self._as_f32(x)
+        x = self._conv_layer(x, blk.conv1, next(styles_iter), noise_mode, pk, split_out=tc_next)
         if tap is not None:
-            tap[name + '.conv1'] = x
+            tap[name + '.conv1'] = self._as_f32(x)
         img = self._torgb_layer(x, blk.torgb, next(styles_iter), img, pk)
         if tap is not None:
             tap[name + '.img'] = img

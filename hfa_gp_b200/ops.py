@@ -98,21 +98,30 @@ def conv_transpose_s2(x: torch.Tensor, w: torch.Tensor, cout: int, w_batch_strid
 
 
 def upfir_act(t: torch.Tensor, *, dcoef=None, noise=None, noise_gain=0.0, bias=None, act=ACT_LRELU,
-              act_gain=math.sqrt(2.0), clamp=0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              act_gain=math.sqrt(2.0), clamp=0.0, split_out: bool = False):
     n, th, tw, c = t.shape
     h2, w2 = th - 1, tw - 1
-    if out is None:
+    if split_out:
+        out = Split(torch.empty((n, h2, w2, c), device=t.device, dtype=torch.bfloat16),
+                    torch.empty((n, h2, w2, c), device=t.device, dtype=torch.bfloat16))
+        y, yh, yl = None, ptr(out.hi), ptr(out.lo)
+    else:
         out = torch.empty((n, h2, w2, c), device=t.device, dtype=torch.float32)
+        y, yh, yl = ptr(out), None, None
     _ok(_cabi.lib().hfagp_upfir_act_fwd(n, h2, w2, c, ptr(t), ptr(dcoef), ptr(noise), noise_gain, ptr(bias), act,
-                                          act_gain, clamp, ptr(out), stream()), 'hfagp_upfir_act_fwd')
+                                        act_gain, clamp, y, yh, yl, stream()), 'hfagp_upfir_act_fwd')
     return out
 
 
 def torgb_small(x, wmod, bias, clamp, up_img, cout):
     n, h, wd, cin = x.shape
     out = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.float32)
-    _ok(_cabi.lib().hfagp_torgb_small_fwd(n, h, wd, cin, cout, ptr(x), ptr(wmod), ptr(bias), clamp, ptr(up_img),
-                                            ptr(out), stream()), 'hfagp_torgb_small_fwd')
+    if isinstance(x, Split):
+        xs = (None, ptr(x.hi), ptr(x.lo))
+    else:
+        xs = (ptr(x), None, None)
+    _ok(_cabi.lib().hfagp_torgb_small_fwd(n, h, wd, cin, cout, *xs, ptr(wmod), ptr(bias), clamp, ptr(up_img),
+                                          ptr(out), stream()), 'hfagp_torgb_small_fwd')
     return out
 
 
@@ -217,4 +226,87 @@ def nhwc_to_nchw(x):
     n, h, w, c = x.shape
     out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
     _ok(_cabi.lib().hfagp_nhwc_to_nchw(n, c, h, w, ptr(x), ptr(out), stream()), 'hfagp_nhwc_to_nchw')
+    return out
+
+
+# ------------------------------------------------------------------ tensor-core (split-bf16) path
+
+class Split:
+    """An fp32 tensor carried as two bf16 tensors (hi + lo) — the operand format of the tcgen05 path."""
+    __slots__ = ('hi', 'lo')
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def float(self):
+        return self.hi.float() + self.lo.float()
+
+
+def split(x: torch.Tensor) -> Split:
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _ok(_cabi.lib().hfagp_split_bf16(x.numel(), ptr(x), ptr(hi), ptr(lo), stream()), 'hfagp_split_bf16')
+    return Split(hi, lo)
+
+
+def modulate_split(w: torch.Tensor, styles: torch.Tensor, demodulate: bool):
+    """w [taps][O][I] fp32 (shared), styles [B][I] -> Split wmod [B][taps][O][I], dcoef [B][O] or None."""
+    taps, cout, cin = w.shape
+    b = styles.shape[0]
+    hi = torch.empty((b, taps, cout, cin), device=w.device, dtype=torch.bfloat16)
+    lo = torch.empty((b, taps, cout, cin), device=w.device, dtype=torch.bfloat16)
+    dcoef = torch.empty((b, cout), device=w.device, dtype=torch.float32) if demodulate else None
+    _ok(_cabi.lib().hfagp_modulate_split_fwd(b, taps, cout, cin, ptr(w), ptr(styles), ptr(hi), ptr(lo), ptr(dcoef),
+                                             stream()), 'hfagp_modulate_split_fwd')
+    return Split(hi, lo), dcoef
+
+
+def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_stride: int = 1, out=None,
+              out_hw=None, out_stride: int = 1, out_off=(0, 0), w_batched: bool = False, split_out: bool = False,
+              dcoef=None, noise=None, noise_gain: float = 0.0, bias=None, act: int = ACT_LINEAR,
+              act_gain: float = 1.0, clamp: float = 0.0, residual=None, residual_scale: float = 1.0, up_img=None):
+    """tcgen05 implicit-GEMM convolution on split-bf16 operands; same semantics as conv2d()."""
+    n, h, wd, cin = x.shape
+    out_h, out_w = out_hw if out_hw is not None else (oh, ow)
+    w_taps_total = w.shape[-3]
+    taps = tuple(taps)
+    if out is None:
+        if split_out:
+            out = Split(torch.empty((n, out_h, out_w, cout), device=x.device, dtype=torch.bfloat16),
+                        torch.empty((n, out_h, out_w, cout), device=x.device, dtype=torch.bfloat16))
+        else:
+            out = torch.empty((n, out_h, out_w, cout), device=x.device, dtype=torch.float32)
+    wbs = w_taps_total * cout * cin if w_batched else 0
+    key = ('tc', n, h, wd, cin, cout, oh, ow, in_stride, out_h, out_w, out_stride, out_off, taps, wbs, act, act_gain,
+           clamp, noise_gain, residual_scale, up_img is not None)
+
+    def build():
+        d = ConvDesc()
+        d.batch, d.in_h, d.in_w, d.cin, d.cout = n, h, wd, cin, cout
+        d.oh, d.ow, d.in_stride = oh, ow, in_stride
+        d.out_h, d.out_w, d.out_stride = out_h, out_w, out_stride
+        d.out_off_y, d.out_off_x = out_off
+        d.ntaps = len(taps)
+        for i, (dy, dx, wt) in enumerate(taps):
+            d.dy[i], d.dx[i], d.wtap[i] = dy, dx, wt
+        d.w_batch_stride = wbs
+        d.act, d.act_gain, d.clamp = act, act_gain, clamp
+        d.noise_gain, d.residual_scale = noise_gain, residual_scale
+        d.up_h, d.up_w = (out_h // 2, out_w // 2) if up_img is not None else (0, 0)
+        return d
+
+    d = _conv_desc(key, build)
+    is_split = isinstance(out, Split)
+    _ok(_cabi.lib().hfagp_conv2d_tc_fwd(C.byref(d), ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total,
+                                        ptr(dcoef), ptr(noise), ptr(bias), ptr(residual), ptr(up_img),
+                                        None if is_split else ptr(out), ptr(out.hi) if is_split else None,
+                                        ptr(out.lo) if is_split else None, stream()), 'hfagp_conv2d_tc_fwd')
     return out

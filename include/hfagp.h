@@ -88,20 +88,44 @@ int hfagp_conv2d_fwd(const HfagpConvDesc* desc, const float* x, const float* w, 
                      const float* noise, const float* bias, const float* residual, const float* up_img,
                      float* y, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core path (tcgen05 + TMEM, TMA-fed) of the same convolution, fp32-class accuracy.
+ *
+ * Operands are "split bf16": every fp32 value v is carried as two bf16 tensors of the same shape,
+ * hi = bf16(v), lo = bf16(v - hi); the kernel accumulates hi*hi + lo*hi + hi*lo in fp32 (TMEM).
+ *   x_hi/x_lo  [n][in_h][in_w][cin]      cin % 64 == 0
+ *   w_hi/w_lo  [n or 1][w_taps_total][cout][cin]   (per-sample when desc->w_batch_stride != 0)
+ * Output: either y (fp32) or the split pair (y_hi, y_lo) for a following tensor-core layer.
+ * Semantics, tap lists and the epilogue are exactly those of hfagp_conv2d_fwd.
+ * ------------------------------------------------------------------------------------------- */
+int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_hi, const uint16_t* x_lo,
+                        const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
+                        const float* noise, const float* bias, const float* residual, const float* up_img,
+                        float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
+
+/* fp32 -> split bf16 (elementwise). */
+int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, uint16_t* lo, void* stream);
+
+/* hfagp_modulate_fwd writing the modulated weights as split bf16 (dcoef from the fp32 products). */
+int hfagp_modulate_split_fwd(int batch, int ntaps, int cout, int cin, const float* w, const float* styles,
+                             uint16_t* wmod_hi, uint16_t* wmod_lo, float* dcoef, void* stream);
+
 /* 4x4 [1,3,3,1]x[1,3,3,1]/64 FIR (gain 4, pad 1) over the (2H+1)x(2W+1) output of the stride-2
  * transposed convolution, fused with demodulation, noise, bias, leaky-ReLU, gain and clamp.
- * t[n][2H+1][2W+1][c] -> y[n][2H][2W][c].
+ * t[n][2H+1][2W+1][c] -> y[n][2H][2W][c] (fp32), or the split-bf16 pair (y_hi, y_lo) when y is NULL.
  * Replaces: upfirdn2d(..., padding=[1,1,1,1], gain=4) + fma(dcoef, noise) + bias_act in
  * eg3d conv2d_resample / SynthesisLayer.forward (reached via code/networks/headnerf.py:112). */
 int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float* t, const float* dcoef,
                         const float* noise, float noise_gain, const float* bias, int act, float act_gain,
-                        float clamp, float* y, void* stream);
+                        float clamp, float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
 
 /* 1x1 modulated conv to <=4 output channels (the super-resolution ToRGB layers) fused with bias,
- * clamp and "+ upsample2d(previous image)".  w is the per-sample modulated weight [n][cout][cin].
+ * clamp and "+ upsample2d(previous image)".  w is the per-sample modulated weight [n][cout][cin];
+ * the input is x (fp32) or, when x is NULL, the split-bf16 pair (x_hi, x_lo).
  * Replaces: eg3d ToRGBLayer.forward + SynthesisBlock skip add (via headnerf.py:112). */
-int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const float* w,
-                          const float* bias, float clamp, const float* up_img, float* y, void* stream);
+int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const uint16_t* x_hi,
+                          const uint16_t* x_lo, const float* w, const float* bias, float clamp,
+                          const float* up_img, float* y, void* stream);
 
 /* Per-layer styles for a whole network in one launch:
  *   styles[l][n][i] = (ws[n][widx[l]][:] . A_l[i][:] * inv_sqrt_wdim + b_l[i]) * post_gain[l]

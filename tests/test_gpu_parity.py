@@ -241,8 +241,9 @@ def test_render_cfg1_micro():
 
 # ------------------------------------------------------------------ whole generator
 
-def _generator_case(cfg, batch, seed=0):
+def _generator_case(cfg, batch, seed=0, precision='tc'):
     ref, prod = pu.make_pair(cfg, seed=seed)
+    prod.precision = precision
     ws, c, jitter, u = pu.make_inputs(cfg, batch, seed=seed)
     tap_r, tap_g = {}, {}
     with torch.no_grad():
@@ -252,9 +253,10 @@ def _generator_case(cfg, batch, seed=0):
     return out_r, out_g, tap_r, tap_g
 
 
-def test_generator_tiny_stagewise():
+@pytest.mark.parametrize('precision', ['tc', 'fp32'])
+def test_generator_tiny_stagewise(precision):
     cfg = eg3d_ref.tiny_config()
-    out_r, out_g, tap_r, tap_g = _generator_case(cfg, batch=2)
+    out_r, out_g, tap_r, tap_g = _generator_case(cfg, batch=2, precision=precision)
     errs = pu.compare_taps(tap_r, tap_g)
     report = ', '.join(f'{k}={e:.2e}' for k, e in errs)
     for k, e in errs:
@@ -264,10 +266,13 @@ def test_generator_tiny_stagewise():
         assert pu.rel_err(out_g[k], out_r[k]) < pu.REL_TOL, k
 
 
-def test_generator_full_512_frame():
-    """BASELINE.json configs[1]: 512x512, 96 samples/ray, random-init EG3D generator."""
+@pytest.mark.parametrize('precision', ['tc', 'fp32'])
+def test_generator_full_512_frame(precision):
+    """BASELINE.json configs[1]: 512x512, 96 samples/ray, random-init EG3D generator.
+    'tc' = tcgen05 split-bf16 convolutions (the shipped path), 'fp32' = SIMT kernels only."""
     cfg = eg3d_ref.GeneratorConfig()
-    out_r, out_g, tap_r, tap_g = _generator_case(cfg, batch=1)
+    out_r, out_g, tap_r, tap_g = _generator_case(cfg, batch=1, precision=precision)
+    print('stage errors', precision, sorted(pu.compare_taps(tap_r, tap_g), key=lambda kv: -kv[1])[:6])
     assert out_g['image'].shape == (1, 3, 512, 512)
     errs = dict(pu.compare_taps(tap_r, tap_g))
     worst = max(errs.items(), key=lambda kv: kv[1])
@@ -347,3 +352,50 @@ def test_headnerf_dropin_frame_loop():
         model.get_image(lat, lab2)
     assert torch.equal(lab2[:, [1, 2, 5, 6, 9, 10]], -lab_before[:, [1, 2, 5, 6, 9, 10]])
     assert torch.equal(lab2[:, [0, 3, 4, 7, 8, 11]], lab_before[:, [0, 3, 4, 7, 8, 11]])
+
+
+# ------------------------------------------------------------------ tensor-core (tcgen05) convolution
+
+@pytest.mark.parametrize('n,cin,cout,h,w,k,batched', [
+    (1, 64, 128, 16, 8, 1, False),       # plain GEMM: one M tile, one K chunk
+    (1, 128, 128, 16, 16, 1, False),     # two K chunks, two M tiles
+    (2, 64, 64, 16, 16, 3, True),        # 3x3 taps (TMA zero padding), per-sample weights, bn = 64
+    (1, 256, 96, 32, 32, 1, True),       # ToRGB-like: bn = 96
+    (1, 128, 256, 24, 40, 3, False),     # ragged spatial extent, two N tiles
+    (1, 512, 512, 8, 8, 3, True),        # low-res block: half-empty M tile, 72 K iterations
+])
+def test_conv2d_tc_matches_fp64(n, cin, cout, h, w, k, batched):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(n if batched else 1, cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g)
+    pad = k // 2
+    ref = torch.cat([F.conv2d(x[i:i + 1].double(), wt[i if batched else 0].double(), b.double(), padding=pad)
+                     for i in range(n)])
+    ref = (F.leaky_relu(ref, 0.2) * math.sqrt(2)).float()
+    taps = tuple((ky - pad, kx - pad, ky * k + kx) for ky in range(k) for kx in range(k))
+    wp = wt.permute(0, 3, 4, 1, 2).reshape(wt.shape[0], k * k, cout, cin).contiguous().cuda()
+    xs, ws = ops.split(nhwc(x)), ops.split(wp)
+    y = ops.conv2d_tc(xs, ws, taps, cout, oh=h, ow=w, w_batched=batched, bias=b.cuda(), act=1, act_gain=math.sqrt(2))
+    err = pu.rel_err(pu.to_nchw(y), ref)
+    assert err < 1e-4, err          # split-bf16: ~2^-16 per product, K up to 4608
+    ys = ops.conv2d_tc(xs, ws, taps, cout, oh=h, ow=w, w_batched=batched, bias=b.cuda(), act=1,
+                       act_gain=math.sqrt(2), split_out=True)
+    assert pu.rel_err(pu.to_nchw(ys.float()), ref) < 1e-4
+
+
+def test_conv_transpose_tc_parity_classes():
+    ops = _ops()
+    g = torch.Generator().manual_seed(10)
+    n, cin, cout, h = 1, 64, 128, 16
+    x = torch.randn(n, cin, h, h, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    ref = F.conv_transpose2d(x.double(), wt.double().transpose(0, 1), stride=2).float()
+    xs, ws = ops.split(nhwc(x)), ops.split(pack(wt)[None].contiguous())
+    out = torch.zeros(n, 2 * h + 1, 2 * h + 1, cout, device='cuda')
+    for a in (0, 1):
+        for b in (0, 1):
+            ops.conv2d_tc(xs, ws, ops._parity_taps(a, b), cout, oh=h + 1 - a, ow=h + 1 - b, out=out,
+                          out_hw=(2 * h + 1, 2 * h + 1), out_stride=2, out_off=(a, b))
+    assert pu.rel_err(pu.to_nchw(out), ref) < 1e-4
