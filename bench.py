@@ -157,6 +157,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--frames-per-step', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='drive the frame loop eagerly instead of replaying the CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', 0))
@@ -171,6 +172,7 @@ def main():
     from hfa_gp_b200 import _cabi, ops
     from hfa_gp_b200.networks.headnerf import HeadNeRF_final
     from hfa_gp_b200 import cam_utils
+    from hfa_gp_b200.frame_loop import FrameLoop
 
     _cabi.lib()                      # no extension -> fail loudly, never fall back
     torch.cuda.set_device(local_rank)
@@ -205,11 +207,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value) with per-stage CUDA events on the launching stream
+    # ---- (a) eager pass with per-stage CUDA events on the launching stream: stage breakdown + the render
+    #      kernel's live duration for the roofline (same K frames as the timed region below)
     for i in range(args.warmup):
         frame_step(dev_frames[i], dev_labels[i].clone())
     stage_events = []
     model.generator.profile_events = stage_events
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for i in range(args.steps):
+        frame_step(dev_frames[args.warmup + i], dev_labels[args.warmup + i].clone())
+    x1.record()
+    barrier()
+    ms_eager = x0.elapsed_time(x1)
+    model.generator.profile_events = None
+    stage_ms = {}
+    for name, a, b in stage_events:
+        stage_ms.setdefault(name, []).append(a.elapsed_time(b))
+    stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+
+    # ---- (b) the product path: the frame-loop body captured once as a CUDA graph (hfa_gp_b200.frame_loop)
+    loop = FrameLoop(model, batch=fps_, size=ENC_SIZE, device=dev, use_graph=not args.no_graph)
+    launches_per_step = loop.launches_per_replay
+    for i in range(args.warmup):
+        loop(dev_frames[i], dev_labels[i])
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -217,29 +239,21 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        frame_step(dev_frames[args.warmup + i], dev_labels[args.warmup + i].clone())
+        loop(dev_frames[args.warmup + i], dev_labels[args.warmup + i])
     e1.record()
     barrier()
-    launches = ops.launch_count() - launches0
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
-    model.generator.profile_events = None
-    stage_ms = {}
-    for name, a, b in stage_events:
-        stage_ms.setdefault(name, []).append(a.elapsed_time(b))
-    stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+    launches = launches_per_step * args.steps if launches_per_step is not None else ops.launch_count() - launches0
 
-    # ---- end-to-end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    # ---- (c) end-to-end through the same public call with HOST buffers (H2D + D2H inside the timed region)
     for i in range(3):
-        out = frame_step(host_frames[i].to(dev, non_blocking=True), host_labels[i].to(dev, non_blocking=True))
-        host_out.copy_(out, non_blocking=True)
+        host_out.copy_(loop(host_frames[i], host_labels[i]), non_blocking=True)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        out = frame_step(host_frames[args.warmup + i].to(dev, non_blocking=True),
-                         host_labels[args.warmup + i].to(dev, non_blocking=True))
-        host_out.copy_(out, non_blocking=True)
+        host_out.copy_(loop(host_frames[args.warmup + i], host_labels[args.warmup + i]), non_blocking=True)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -266,13 +280,15 @@ def main():
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'frames_per_step': fps_, 'sharding': 'frame i -> rank i mod N, no collective',
-                       'l2': 'per-frame working set ~1.25 GB (weights 113 MB + activations) exceeds the 126 MB L2; no flush'},
+                       'l2': 'per-frame working set ~1.25 GB (weights 113 MB + activations) exceeds the 126 MB L2; no flush',
+                       'launch': 'eager' if args.no_graph else 'one CUDA graph replay per frame (hfa_gp_b200.frame_loop.FrameLoop)'},
             'clocks': clocks,
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': fps_ * (3 * ENC_SIZE * ENC_SIZE + 25) * 4,
                     'd2h_bytes_per_step': fps_ * 3 * 512 * 512 * 4},
             'gpu_launches': launches,
             'roofline': roof,
             'stage_ms': stage_avg,
+            'eager_ms_per_step': ms_eager / args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_sample()

@@ -73,7 +73,7 @@ def lib() -> C.CDLL:
     l.hfagp_styles_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     l.hfagp_modulate_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_render_fwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
-    l.hfagp_blur_fwd.argtypes = [i32] * 7 + [vp, vp, vp]
+    l.hfagp_blur_fwd.argtypes = [i32] * 7 + [vp] * 7
     l.hfagp_linear_fwd.argtypes = [i32, i32, i32, vp, vp, vp, f32, f32, vp, vp]
     l.hfagp_latent_fwd.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_nchw_to_nhwc.argtypes = [i32, i32, i32, i32, vp, vp, vp]

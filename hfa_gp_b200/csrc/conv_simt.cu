@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "splitio.cuh"
 
 namespace hfagp {
 
@@ -209,34 +210,10 @@ __global__ void upfir_act_kernel(int batch, int h2, int w2, int c, const float* 
     if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
     vals[k] = v;
   }
-  if (y_hi) {  // split-bf16 output for a following tensor-core layer
-    uint32_t hw[2], lw[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      __nv_bfloat16 h0 = __float2bfloat16_rn(vals[2 * e]), h1 = __float2bfloat16_rn(vals[2 * e + 1]);
-      __nv_bfloat16 l0 = __float2bfloat16_rn(vals[2 * e] - __bfloat162float(h0));
-      __nv_bfloat16 l1 = __float2bfloat16_rn(vals[2 * e + 1] - __bfloat162float(h1));
-      hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-    reinterpret_cast<uint2*>(y_hi)[idx] = make_uint2(hw[0], hw[1]);
-    reinterpret_cast<uint2*>(y_lo)[idx] = make_uint2(lw[0], lw[1]);
-  } else {
-    reinterpret_cast<float4*>(y)[idx] = make_float4(vals[0], vals[1], vals[2], vals[3]);
-  }
+  st4_any(y, y_hi, y_lo, idx, vals);
 }
 
 // ---------------------------------------------------------------- small-N ToRGB (cout <= 4)
-__device__ __forceinline__ float4 bf16x4_sum(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t q) {
-  const uint2 a = __ldg(reinterpret_cast<const uint2*>(hi) + q), b = __ldg(reinterpret_cast<const uint2*>(lo) + q);
-  float4 r;
-  r.x = __uint_as_float(a.x << 16) + __uint_as_float(b.x << 16);
-  r.y = __uint_as_float(a.x & 0xffff0000u) + __uint_as_float(b.x & 0xffff0000u);
-  r.z = __uint_as_float(a.y << 16) + __uint_as_float(b.y << 16);
-  r.w = __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u);
-  return r;
-}
-
 __global__ void torgb_small_kernel(int batch, int h, int w_, int cin, int cout, const float* __restrict__ x,
                                    const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
                                    const float* __restrict__ w, const float* __restrict__ bias, float clamp,
@@ -279,7 +256,9 @@ __global__ void torgb_small_kernel(int batch, int h, int w_, int cin, int cout, 
 
 // ---------------------------------------------------------------- encoder blur
 __global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow,
-                            const float* __restrict__ x, float* __restrict__ y) {
+                            const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi,
+                            const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
+                            __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
   const int c4 = c >> 2;
   size_t total = (size_t)batch * oh * ow * c4;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,8 +270,8 @@ __global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int strid
   int oy = r % oh;
   int n = r / oh;
   const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-  const float4* xn = reinterpret_cast<const float4*>(x + (size_t)n * h * w_ * c);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t nb = (size_t)n * h * w_ * c4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int ky = 0; ky < 4; ++ky) {
     int iy = oy * stride + ky - pad0;
@@ -302,14 +281,14 @@ __global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int strid
       int ix = ox * stride + kx - pad0;
       if (ix < 0 || ix >= w_) continue;
       float wgt = g[ky] * g[kx];
-      float4 v = __ldg(xn + ((size_t)iy * w_ + ix) * c4 + cq);
-      s.x = fmaf(wgt, v.x, s.x);
-      s.y = fmaf(wgt, v.y, s.y);
-      s.z = fmaf(wgt, v.z, s.z);
-      s.w = fmaf(wgt, v.w, s.w);
+      float4 v = ld4_any(x, x_hi, x_lo, nb + ((size_t)iy * w_ + ix) * c4 + cq);
+      s[0] = fmaf(wgt, v.x, s[0]);
+      s[1] = fmaf(wgt, v.y, s[1]);
+      s[2] = fmaf(wgt, v.z, s[2]);
+      s[3] = fmaf(wgt, v.w, s[3]);
     }
   }
-  reinterpret_cast<float4*>(y)[idx] = s;
+  st4_any(y, y_hi, y_lo, idx, s);
 }
 
 __global__ void nchw_to_nhwc_kernel(int batch, int c, int hw, const float* __restrict__ x, float* __restrict__ y) {
@@ -398,14 +377,19 @@ extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout
 }
 
 extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad1, int stride, const float* x,
-                              float* y, void* stream) {
-  HFAGP_CHECK_ARG(x && y, "blur_fwd: null pointer");
+                              const uint16_t* x_hi, const uint16_t* x_lo, float* y, uint16_t* y_hi, uint16_t* y_lo,
+                              void* stream) {
+  HFAGP_CHECK_ARG((x != nullptr) != (x_hi != nullptr && x_lo != nullptr), "blur_fwd: give x or (x_hi, x_lo)");
+  HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "blur_fwd: give y or (y_hi, y_lo)");
   HFAGP_CHECK_ARG((c & 3) == 0 && (stride == 1 || stride == 2), "blur_fwd: c%%4==0, stride 1|2 required");
   int oh = (h + pad0 + pad1 - 4) / stride + 1;
   int ow = (w_ + pad0 + pad1 - 4) / stride + 1;
   HFAGP_CHECK_ARG(oh > 0 && ow > 0, "blur_fwd: empty output");
   size_t total = (size_t)batch * oh * ow * (c >> 2);
-  blur_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h, w_, c, pad0, stride, oh, ow, x, y);
+  blur_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      batch, h, w_, c, pad0, stride, oh, ow, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
+      reinterpret_cast<const __nv_bfloat16*>(x_lo), y, reinterpret_cast<__nv_bfloat16*>(y_hi),
+      reinterpret_cast<__nv_bfloat16*>(y_lo));
   HFAGP_CHECK_LAUNCH("blur_kernel");
   return HFAGP_OK;
 }

@@ -126,7 +126,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
   const int y0 = ty * p.tile_h, x0 = tx * p.tile_w;
   const int n0 = blockIdx.y * p.bn;
-  const int kchunks = d.cin / TC_BK;
+  const int kchunks = (d.cin + TC_BK - 1) / TC_BK;   // a partial last chunk is zero-filled by TMA (both operands)
   const int iters = d.ntaps * kchunks;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < p.bn) tmem_cols <<= 1;
@@ -335,7 +335,7 @@ extern "C" int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_
   HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "conv2d_tc_fwd: give y or (y_hi, y_lo)");
   const HfagpConvDesc& d = *desc;
   HFAGP_CHECK_ARG(d.batch > 0 && d.batch <= 65535 && d.oh > 0 && d.ow > 0 && d.cout > 0, "conv2d_tc_fwd: bad dims");
-  HFAGP_CHECK_ARG(d.cin % TC_BK == 0, "conv2d_tc_fwd: cin must be a multiple of 64 (got %d)", d.cin);
+  HFAGP_CHECK_ARG(d.cin % 8 == 0, "conv2d_tc_fwd: cin must be a multiple of 8 (got %d)", d.cin);
   HFAGP_CHECK_ARG(d.ntaps > 0 && d.ntaps <= HFAGP_MAX_TAPS, "conv2d_tc_fwd: ntaps out of range");
   HFAGP_CHECK_ARG(d.in_stride == 1 || d.in_stride == 2, "conv2d_tc_fwd: in_stride must be 1 or 2");
   HFAGP_CHECK_ARG((d.oh - 1) * d.out_stride + d.out_off_y < d.out_h && (d.ow - 1) * d.out_stride + d.out_off_x < d.out_w,

@@ -3,6 +3,7 @@
 // from shared memory) -> mid-point march -> importance resampling -> second gather/MLP -> stable rank-sort
 // merge -> final compositing (lane = channel).  All per-ray state lives in shared memory / registers; HBM
 // traffic is the plane reads (L2-resident) and one 128 B feature row + 2 scalars per ray.
+#include <mutex>
 #include "common.cuh"
 
 namespace hfagp {
@@ -354,7 +355,9 @@ extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes
   RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, depth_range, feat, depth, wsum, inds, below, above, sort_idx, depths_sorted};
   const int T = d.s_coarse + d.s_fine;
   size_t smem = (MLP_PAD + R_WARPS * render_warp_floats(T, d.s_coarse)) * sizeof(float);
-  HFAGP_CUDA(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::once_flag attr_once;   // opt in to the full 227 KB once; not repeated on the (graph-captured) hot path
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  HFAGP_CHECK_ARG(smem <= 227 * 1024, "render_fwd: shared memory need exceeds 227 KB");
   long long total_rays = (long long)d.batch * d.res * d.res;
   int blocks = (int)((total_rays + R_WARPS - 1) / R_WARPS);
   render_fwd_kernel<<<blocks, R_WARPS * 32, smem, (cudaStream_t)stream>>>(p);

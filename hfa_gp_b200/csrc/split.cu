@@ -1,13 +1,9 @@
 // Split-bf16 operand producers for the tensor-core path: x (fp32) -> hi = bf16(x), lo = bf16(x - hi).
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "splitio.cuh"
 
 namespace hfagp {
-
-__device__ __forceinline__ void split2(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
-  h = __float2bfloat16_rn(v);
-  l = __float2bfloat16_rn(v - __bfloat162float(h));
-}
 
 __global__ void split_kernel(size_t count, const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                              __nv_bfloat16* __restrict__ lo) {

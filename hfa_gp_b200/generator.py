@@ -187,6 +187,7 @@ class TriPlaneGenerator(nn.Module):
                                      avg_camera_pivot=[0, 0, 0.2])
         self._packed = None
         self._packed_key = None
+        self.fixed_draws = None    # (jitter_coarse, u_fine) used instead of torch.rand when synthesis() gets none
         self.precision = 'tc'      # 'tc': tcgen05 split-bf16 convolutions (fp32-class); 'fp32': SIMT kernels only
 
     @property
@@ -256,10 +257,10 @@ class TriPlaneGenerator(nn.Module):
 
     # ---------------------------------------------------------------- layer drivers (channels-last)
     # Kernel selection per layer: the tcgen05 path (split-bf16 operands, fp32 accumulate in TMEM) whenever the
-    # layer's cin is a multiple of its 64-channel K chunk, else the exact-fp32 SIMT kernel (cin = 32 first SR
-    # layer, thin test configs).  ``self.precision = 'fp32'`` forces the SIMT kernels everywhere.
+    # layer's cin is a multiple of 8 (TMA's 16-byte stride rule; K is walked in 64-channel chunks and a partial
+    # chunk is zero-filled), else the exact-fp32 SIMT kernel.  ``self.precision = 'fp32'`` forces SIMT everywhere.
     def _use_tc(self, cin):
-        return self.precision == 'tc' and cin % 64 == 0
+        return self.precision == 'tc' and cin % 8 == 0
 
     @staticmethod
     def _as_f32(x):
@@ -381,6 +382,8 @@ class TriPlaneGenerator(nn.Module):
 
         rays = res * res
         s, sf = cfg.depth_res, cfg.depth_res_importance
+        if jitter_coarse is None and u_fine is None and self.fixed_draws is not None:
+            jitter_coarse, u_fine = self.fixed_draws          # tests: pin upstream's two random tensors
         if jitter_coarse is None:
             jitter_coarse = torch.rand((b, rays, s, 1), device=ws.device)
         if u_fine is None and sf > 0:

@@ -70,6 +70,22 @@ class EqualConv2d(nn.Module):
             self._pk_key = key
         return self._pk
 
+    def packed_split(self):
+        """packed() as the split-bf16 pair the tcgen05 kernel reads (cached alongside)."""
+        pk = self.packed()
+        if getattr(self, '_pks_src', None) is not pk:
+            self._pks, self._pks_src = ops.split(pk), pk
+        return self._pks
+
+    def packed_linear(self):
+        """[O][(ky,kx,ci)]: the kernel as one row per output channel, matching a channels-last flatten of the
+        k x k input window (the final 4x4 conv sees exactly one window, so it is a plain linear map)."""
+        pk = self.packed()
+        if getattr(self, '_pkl_src', None) is not pk:
+            t, o, i = pk.shape
+            self._pkl, self._pkl_src = pk.permute(1, 0, 2).reshape(o, t * i).contiguous(), pk
+        return self._pkl
+
 
 class EqualLinear(nn.Module):
     def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1, activation=None):
@@ -107,20 +123,22 @@ class ConvLayer(nn.Sequential):
             layers.append(FusedLeakyReLU(out_channel))
         super().__init__(*layers)
 
-    def run(self, x, residual=None):
-        """x channels-last [N,H,W,C] -> channels-last output, epilogue fused."""
+    def run(self, x, residual=None, tc=False, split_out=False):
+        """x channels-last [N,H,W,C] (fp32 tensor or ops.Split) -> channels-last output, epilogue fused.
+        ``tc``: tcgen05 split-bf16 kernel (fp32-class accuracy) instead of the exact-fp32 SIMT kernel."""
         mods = list(self.children())
         conv = next(m for m in mods if isinstance(m, EqualConv2d))
         act = mods[-1] if isinstance(mods[-1], FusedLeakyReLU) else None
         k = self.kernel_size
-        n, h, w, _ = x.shape
+        n, h, w, cin = x.shape
+        tc = tc and cin % 8 == 0
         if self.downsample:
             pad0, pad1 = mods[0].pad
             if k == 1:
-                x = ops.blur(x, pad0, pad1, stride=2)          # only the pixels the stride-2 1x1 conv reads
+                x = ops.blur(x, pad0, pad1, stride=2, split_out=tc)   # only the pixels the stride-2 1x1 conv reads
                 taps, stride, oh, ow = ops.TAPS_1X1, 1, x.shape[1], x.shape[2]
             else:
-                x = ops.blur(x, pad0, pad1, stride=1)
+                x = ops.blur(x, pad0, pad1, stride=1, split_out=tc)
                 taps = tuple((ky, kx, ky * k + kx) for ky in range(k) for kx in range(k))
                 stride, oh, ow = 2, (x.shape[1] - k) // 2 + 1, (x.shape[2] - k) // 2 + 1
         else:
@@ -129,10 +147,17 @@ class ConvLayer(nn.Sequential):
             stride, oh, ow = 1, h + 2 * p - k + 1, w + 2 * p - k + 1
         bias = act.bias.detach().reshape(-1).contiguous() if act is not None else (
             conv.bias.detach() if conv.bias is not None else None)
-        return ops.conv2d(x, conv.packed(), taps, conv.weight.shape[0], oh=oh, ow=ow, in_stride=stride, bias=bias,
-                          act=ACT_LRELU if act is not None else ACT_LINEAR,
-                          act_gain=SQRT2 if act is not None else 1.0, residual=residual,
-                          residual_scale=INV_SQRT2 if residual is not None else 1.0)
+        epi = dict(bias=bias, act=ACT_LRELU if act is not None else ACT_LINEAR,
+                   act_gain=SQRT2 if act is not None else 1.0, residual=residual,
+                   residual_scale=INV_SQRT2 if residual is not None else 1.0)
+        cout = conv.weight.shape[0]
+        if tc:
+            xs = x if isinstance(x, ops.Split) else ops.split(x)
+            return ops.conv2d_tc(xs, conv.packed_split(), taps, cout, oh=oh, ow=ow, in_stride=stride,
+                                 split_out=split_out, **epi)
+        xf = x.float() if isinstance(x, ops.Split) else x
+        y = ops.conv2d(xf, conv.packed(), taps, cout, oh=oh, ow=ow, in_stride=stride, **epi)
+        return ops.split(y) if split_out else y
 
 
 class ResBlock(nn.Module):
@@ -142,10 +167,10 @@ class ResBlock(nn.Module):
         self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True)
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
 
-    def run(self, x):
-        skip = self.skip.run(x)
-        out = self.conv1.run(x)
-        return self.conv2.run(out, residual=skip)       # (conv2(out) + skip) / sqrt(2) in the epilogue
+    def run(self, x, tc=False):
+        skip = self.skip.run(x, tc=tc)                                # fp32: it is the residual operand
+        out = self.conv1.run(x, tc=tc, split_out=tc)
+        return self.conv2.run(out, residual=skip, tc=tc, split_out=tc)   # (conv2(out) + skip) / sqrt(2) in the epilogue
 
 
 class EncoderApp(nn.Module):
@@ -153,6 +178,7 @@ class EncoderApp(nn.Module):
         super().__init__()
         channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256, 128: 128, 256: 64, 512: 32, 1024: 16}
         self.w_dim = w_dim
+        self.precision = 'tc'      # 'tc': tcgen05 split-bf16 convolutions (fp32-class); 'fp32': SIMT kernels only
         log_size = int(math.log(size, 2))
         self.convs = nn.ModuleList()
         self.convs.append(ConvLayer(3, channels[size], 1))
@@ -169,14 +195,20 @@ class EncoderApp(nn.Module):
             raise HfagpError('Encoder needs CUDA tensors (there is no CPU fallback)')
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise HfagpError('encoder backward is not implemented in this build; call under torch.no_grad()')
+        tc = self.precision == 'tc'
         h = ops.nchw_to_nhwc(x.detach().float().contiguous())
-        for m in self.convs[:-1]:
-            h = m.run(h)
+        h = self.convs[0].run(h, split_out=tc)           # cin = 3: exact-fp32 SIMT kernel
+        for m in self.convs[1:-1]:
+            h = m.run(h, tc=tc)
         last = self.convs[-1]
         k = last.weight.shape[-1]
+        hf = h.float() if isinstance(h, ops.Split) else h
+        if hf.shape[1] == k and hf.shape[2] == k:
+            # one k x k window -> [B, w_dim]: a linear map over the channels-last flatten (weights-bandwidth bound)
+            return ops.linear(hf.reshape(hf.shape[0], -1), last.packed_linear(), None, 1.0, 1.0)
         taps = tuple((ky, kx, ky * k + kx) for ky in range(k) for kx in range(k))
-        h = ops.conv2d(h, last.packed(), taps, last.weight.shape[0], oh=h.shape[1] - k + 1, ow=h.shape[2] - k + 1)
-        return h.reshape(h.shape[0], -1)                 # 1x1 spatial: channels-last == [B, w_dim]
+        hf = ops.conv2d(hf, last.packed(), taps, last.weight.shape[0], oh=hf.shape[1] - k + 1, ow=hf.shape[2] - k + 1)
+        return hf.reshape(hf.shape[0], -1)                 # 1x1 spatial: channels-last == [B, w_dim]
 
 
 class Encoder(nn.Module):

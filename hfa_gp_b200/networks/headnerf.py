@@ -29,6 +29,20 @@ from ..generator import GeneratorConfig, TriPlaneGenerator, make_generator
 from .encoder3d import Encoder, EqualLinear
 
 FLIP_IDX = [1, 2, 5, 6, 9, 10]
+_flip_sign_cache = {}
+
+
+def flip_label_(label):
+    """``label[:, [1,2,5,6,9,10]] *= -1`` in place (headnerf.py:108,132), as one multiply by a cached per-device
+    sign vector: the fancy-index form builds its index tensor on the host every call, which costs an H2D copy
+    per frame and cannot be captured into a CUDA graph."""
+    key = (label.device, label.dtype)
+    sign = _flip_sign_cache.get(key)
+    if sign is None:
+        sign = torch.ones(25, dtype=label.dtype)
+        sign[FLIP_IDX] = -1
+        sign = _flip_sign_cache[key] = sign.to(label.device)
+    return label.mul_(sign)
 
 
 def toogle_grad(model, flag=True):
@@ -118,11 +132,11 @@ class HeadNeRF_final(nn.Module, _LatentSubspace):
         return self.encoder(image)                      # (weights, pose) when out_pose
 
     def get_image(self, latent, label):
-        label[:, FLIP_IDX] *= -1                        # in place, as the reference does
+        flip_label_(label)                              # in place, as the reference does
         return self.generator.synthesis(latent, c=label, noise_mode='const')['image']
 
     def forward(self, image, label, person_2=False):
-        label[:, FLIP_IDX] *= -1
+        flip_label_(label)
         if self.out_pose:
             weights, pose = self.encoder(image)
             latent = self.get_latent(weights, person_2)
@@ -167,11 +181,11 @@ class _DrivenAvatar(nn.Module, _LatentSubspace):
         return self.weights_3dmm(params)
 
     def get_image(self, latent, label):
-        label[:, FLIP_IDX] *= -1
+        flip_label_(label)
         return self.generator.synthesis(latent, c=label, noise_mode='const')['image']
 
     def forward(self, params, label, person_2=False):
-        label[:, FLIP_IDX] *= -1
+        flip_label_(label)
         latent = self.get_latent(self.weights_3dmm(params), person_2)
         return self.generator.synthesis(latent, c=label, noise_mode='const')['image']
 

@@ -189,12 +189,20 @@ def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s
     return feat, depth, wsum, book
 
 
-def blur(x, pad0, pad1, stride=1):
+def blur(x, pad0, pad1, stride=1, split_out: bool = False):
+    """[1,3,3,1]^2/64 blur of a channels-last activation (fp32 tensor or Split) -> fp32 or Split."""
     n, h, wd, c = x.shape
     oh = (h + pad0 + pad1 - 4) // stride + 1
     ow = (wd + pad0 + pad1 - 4) // stride + 1
-    out = torch.empty((n, oh, ow, c), device=x.device, dtype=torch.float32)
-    _ok(_cabi.lib().hfagp_blur_fwd(n, h, wd, c, pad0, pad1, stride, ptr(x), ptr(out), stream()), 'hfagp_blur_fwd')
+    xin = (None, ptr(x.hi), ptr(x.lo)) if isinstance(x, Split) else (ptr(x), None, None)
+    if split_out:
+        out = Split(torch.empty((n, oh, ow, c), device=x.device, dtype=torch.bfloat16),
+                    torch.empty((n, oh, ow, c), device=x.device, dtype=torch.bfloat16))
+        yout = (None, ptr(out.hi), ptr(out.lo))
+    else:
+        out = torch.empty((n, oh, ow, c), device=x.device, dtype=torch.float32)
+        yout = (ptr(out), None, None)
+    _ok(_cabi.lib().hfagp_blur_fwd(n, h, wd, c, pad0, pad1, stride, *xin, *yout, stream()), 'hfagp_blur_fwd')
     return out
 
 

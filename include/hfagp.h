@@ -93,7 +93,7 @@ int hfagp_conv2d_fwd(const HfagpConvDesc* desc, const float* x, const float* w, 
  *
  * Operands are "split bf16": every fp32 value v is carried as two bf16 tensors of the same shape,
  * hi = bf16(v), lo = bf16(v - hi); the kernel accumulates hi*hi + lo*hi + hi*lo in fp32 (TMEM).
- *   x_hi/x_lo  [n][in_h][in_w][cin]      cin % 64 == 0
+ *   x_hi/x_lo  [n][in_h][in_w][cin]      cin % 8 == 0 (K is walked in 64-channel chunks; TMA zero-fills a partial one)
  *   w_hi/w_lo  [n or 1][w_taps_total][cout][cin]   (per-sample when desc->w_batch_stride != 0)
  * Output: either y (fp32) or the split pair (y_hi, y_lo) for a following tensor-core layer.
  * Semantics, tap lists and the epilogue are exactly those of hfagp_conv2d_fwd.
@@ -178,10 +178,12 @@ int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes, const flo
 
 /* Encoder blur: zero-pad (pad0,pad1) + 4x4 [1,3,3,1]^2/64 true convolution, optional output
  * stride (only the positions a following stride-2 1x1 conv reads).  x[n][h][w][c] ->
- * y[n][oh][ow][c], oh = (h + pad0 + pad1 - 3 + stride - 1) / stride.
+ * y[n][oh][ow][c], oh = (h + pad0 + pad1 - 4) / stride + 1.  Input is x (fp32) or the split-bf16
+ * pair (x_hi, x_lo); output is y (fp32) or the split pair (y_hi, y_lo) for a tensor-core consumer.
  * Replaces: Blur.forward / upfirdn2d_native (code/networks/encoder3d.py:23-41,59-75). */
 int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad1, int stride, const float* x,
-                   float* y, void* stream);
+                   const uint16_t* x_hi, const uint16_t* x_lo, float* y, uint16_t* y_hi, uint16_t* y_lo,
+                   void* stream);
 
 /* y[n][o] = (x[n][:] . w[o][:]) * w_gain + b[o] * b_gain   — EqualLinear with activation=None
  * (code/networks/encoder3d.py:128-136) and Weights_3DMM (code/networks/headnerf.py:152-158). */

@@ -129,6 +129,9 @@ def test_small_ops():
     assert pu.rel_err(pu.to_nchw(ops.blur(nhwc(xi), 2, 2)), hfagp_ref.blur_ref(xi, k, 2, 2)) < 1e-5
     assert pu.rel_err(pu.to_nchw(ops.blur(nhwc(xi[..., :12, :12]), 1, 1, stride=2)),
                       hfagp_ref.blur_ref(xi[..., :12, :12], k, 1, 1)[:, :, ::2, ::2]) < 1e-5
+    # blur with split-bf16 input and output (tensor-core encoder path)
+    ys = ops.blur(ops.split(nhwc(xi)), 2, 2, split_out=True)
+    assert pu.rel_err(pu.to_nchw(ys.float()), hfagp_ref.blur_ref(xi, k, 2, 2)) < 1e-4
     # small-N ToRGB + skip upsample
     xr = torch.randn(2, 64, 8, 8, generator=g)
     wr = torch.randn(2, 3, 64, generator=g)
@@ -289,8 +292,9 @@ def test_generator_full_512_frame(precision):
 
 # ------------------------------------------------------------------ encoder + avatar drop-in
 
+@pytest.mark.parametrize('precision', ['tc', 'fp32'])
 @pytest.mark.parametrize('size,out_pose', [(64, True), (256, False)])
-def test_encoder_matches_reference_restatement(size, out_pose):
+def test_encoder_matches_reference_restatement(size, out_pose, precision):
     from hfa_gp_b200.networks.encoder3d import Encoder
     sd = hfagp_ref.make_encoder_state(size, 512, 50, out_pose=out_pose, seed=3)
     g = torch.Generator().manual_seed(11)
@@ -300,6 +304,7 @@ def test_encoder_matches_reference_restatement(size, out_pose):
     enc = Encoder(size, 512, 50, False, out_pose)
     enc.load_state_dict(sd, strict=True)
     enc = enc.eval().requires_grad_(False).cuda()
+    enc.net_app.precision = precision
     x = torch.rand(2, 3, size, size, generator=g) * 2 - 1
     ref = hfagp_ref.encoder_ref(sd, x, out_pose=out_pose)
     with torch.no_grad():
@@ -363,6 +368,9 @@ def test_headnerf_dropin_frame_loop():
     (1, 256, 96, 32, 32, 1, True),       # ToRGB-like: bn = 96
     (1, 128, 256, 24, 40, 3, False),     # ragged spatial extent, two N tiles
     (1, 512, 512, 8, 8, 3, True),        # low-res block: half-empty M tile, 72 K iterations
+    (1, 32, 256, 16, 16, 3, True),       # first SR layer: cin = 32 = half a K chunk (TMA zero-fills the rest)
+    (2, 96, 64, 16, 16, 1, False),       # 1.5 K chunks (dgrad of the 96-channel ToRGB)
+    (1, 40, 24, 9, 7, 3, True),          # ragged everything, cin % 8 == 0 only
 ])
 def test_conv2d_tc_matches_fp64(n, cin, cout, h, w, k, batched):
     ops = _ops()
@@ -399,3 +407,30 @@ def test_conv_transpose_tc_parity_classes():
             ops.conv2d_tc(xs, ws, ops._parity_taps(a, b), cout, oh=h + 1 - a, ow=h + 1 - b, out=out,
                           out_hw=(2 * h + 1, 2 * h + 1), out_stride=2, out_off=(a, b))
     assert pu.rel_err(pu.to_nchw(out), ref) < 1e-4
+
+
+def test_frame_loop_graph_matches_eager():
+    """hfa_gp_b200.frame_loop.FrameLoop: the captured CUDA graph replays exactly what the eager
+    get_weights -> get_latent -> get_image sequence computes (random draws pinned)."""
+    import argparse
+    from hfa_gp_b200.frame_loop import FrameLoop
+    from hfa_gp_b200.networks.headnerf import HeadNeRF_final
+    cfg = eg3d_ref.small14_config()
+    args = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='',
+                              synthetic_generator=True, generator_seed=0, generator_config=pu.product_config(cfg))
+    torch.manual_seed(0)
+    model = HeadNeRF_final(args, 64, 'cuda', 512, 50, 'x', './').cuda().eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(5)
+    rays = cfg.nrr ** 2
+    model.generator.fixed_draws = (torch.rand(1, rays, cfg.depth_res, 1, generator=g).cuda(),
+                                   torch.rand(rays, cfg.depth_res_importance, generator=g).cuda())
+    loop = FrameLoop(model, batch=1, size=64)
+    for seed in (1, 2):
+        img = (torch.rand(1, 3, 64, 64, generator=g) * 2 - 1).cuda()
+        label = hfagp_ref.synthetic_labels(1, seed=seed).cuda()
+        lab_e, lab_g = label.clone(), label.clone()
+        with torch.no_grad():
+            want = model.get_image(model.get_latent(model.get_weights(img)), lab_e).clone()
+        got = loop(img, lab_g).clone()
+        assert torch.equal(got, want)
+        assert torch.equal(lab_g, lab_e)            # the in-place GL flip is visible to the caller
