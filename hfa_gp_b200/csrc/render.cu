@@ -1,9 +1,26 @@
-// Tri-plane volume renderer, one warp per ray: ray generation -> stratified depths -> tri-plane bilinear
-// gather (lane = channel, one 128 B texel line per tap) -> OSG decoder MLP (lane = sample, weights broadcast
-// from shared memory) -> mid-point march -> importance resampling -> second gather/MLP -> stable rank-sort
-// merge -> final compositing (lane = channel).  All per-ray state lives in shared memory / registers; HBM
-// traffic is the plane reads (L2-resident) and one 128 B feature row + 2 scalars per ray.
+// Tri-plane volume renderer (forward).  One warp owns one ray end to end; a CTA is a vertical strip of 16 rays
+// (one persistent CTA per SM looping over strips).
+//
+//   ray generation -> stratified depths -> [ tri-plane bilinear gather -> OSG decoder MLP ] (coarse)
+//   -> mid-point march -> smoothed pdf / cdf / searchsorted -> fine depths -> [ gather -> MLP ] (fine)
+//   -> stable rank-sort merge -> final mid-point march -> composite (lane = channel)
+//
+// Gather: planes are channels-last, so one bilinear tap of one plane is one 128 B line.  Four samples are
+// gathered per pass with lane = (sample, channel quad): each lane issues 12 independent 16 B loads (8 lanes cover
+// a line) and no cross-lane reduction is needed.  The rays of a strip share their x pixel coordinate, so at equal
+// sample index they hit (nearly) the same texels of planes 1 and 2 (both are functions of world x and z only);
+// along a ray, plane 0 moves < 1 texel per sample.  The planes themselves (25 MB) stay L2-resident.
+//
+// Decoder MLP (32 -> 64 softplus -> 1+32) runs on the tensor pipe per 16-sample tile with warp-level
+// mma.sync.m16n8k16 (bf16 operands, fp32 accumulate): rays have 48 samples = 3 x 16 rows, so the 16-row MMA
+// keeps every warp autonomous (no CTA-wide barrier in the ray loop; tcgen05's 128-row tile would couple 2.7 rays
+// and its share of the kernel is ~5 % of issue slots either way).  fp32-class accuracy comes from the same
+// split-bf16 scheme as the convolutions (hi*hi + lo*hi + hi*lo); the layer-1 accumulator fragments of two
+// n-tiles are, after softplus, exactly the layer-2 A fragment of one k-step, so the hidden layer never leaves
+// registers.
+#include <cuda_bf16.h>
 #include <mutex>
+#include <type_traits>
 #include "common.cuh"
 
 namespace hfagp {
@@ -11,10 +28,14 @@ namespace hfagp {
 constexpr int RC = 32;        // channels per plane == decoder input width
 constexpr int RH = 64;        // decoder hidden width
 constexpr int RO = 33;        // 1 sigma + 32 colour features
-constexpr int COL_LD = 33;    // padded row stride of the per-sample feature/colour rows
-constexpr int R_WARPS = 4;
+constexpr int R_WARPS = 16;   // rays per strip / warps per CTA (8 when 16 rays' scratch does not fit in 227 KB)
+constexpr int TILE = 16;      // samples per MMA tile and per gather batch
 constexpr int MLP_FLOATS = RH * RC + RH + RO * RH + RO;  // 4257
-constexpr int MLP_PAD = 4260;
+
+// shared-memory weight image (per CTA): B fragments of both layers as split bf16 + fp32 biases
+constexpr int W0F_U2 = 8 * 2 * 2 * 32;   // [ntile 8][kstep 2][hi|lo][lane] uint2
+constexpr int W1F_U2 = 5 * 4 * 2 * 32;   // [ntile 5][kstep 4][hi|lo][lane] uint2
+constexpr int WEIGHT_BYTES = (W0F_U2 + W1F_U2) * 8 + (RH + 40) * 4;
 
 struct RenderParams {
   HfagpRenderDesc d;
@@ -36,14 +57,23 @@ struct RenderParams {
 };
 
 struct Tap {
-  int off;   // float offset of the texel's channel 0 inside this sample's frame, or -1 (outside -> zero)
-  float w;
+  uint32_t off;   // byte offset of the texel's channel 0 inside this sample's frame (0 when outside)
+  float w;        // bilinear weight (0 when outside: grid_sample padding_mode='zeros')
 };
 
-__host__ __device__ inline size_t render_warp_floats(int T, int s_coarse) {
-  // taps[32*12*2] + col[T][33] + dep,sig,sdep,ssig,wts [T] + order[T] + cdf[s_coarse+2] + zmid[s_coarse]
-  size_t f = (size_t)T * COL_LD + 6 * (size_t)T + (s_coarse + 2) + s_coarse + 32 * 12 * 2;
-  return (f + 3) & ~(size_t)3;
+__host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
+
+// Per-warp shared memory:
+//   colq  [round16(S) + round16(SF)] rows x 32 u16   decoded colours as 16-bit fixed point (see quantise note)
+//   ftile [16][32] fp32                               features of the tile being decoded (MMA A operand)
+//   dep, sig, sdep, ssig [Tp] fp32 ; order [Tp] u8 ; cdf [S+2], zmid [S] fp32 ; taps [16*12]
+// wts (march weights) aliases sdep during the coarse pass (sdep is first written by the sort) and dep during the
+// final pass (unsorted depths are dead after the sort).
+__host__ __device__ inline size_t render_warp_bytes(int S, int SF) {
+  const size_t Tp = (size_t)(S + SF + 3) & ~(size_t)3;   // per-sample arrays padded so each stays 16 B aligned
+  size_t b = (size_t)(round16(S) + round16(SF)) * RC * 2 + TILE * RC * 4 + 4 * Tp * 4 + Tp + (size_t)(2 * S + 2) * 4;
+  b = (b + 15) & ~(size_t)15;
+  return b + TILE * 12 * sizeof(Tap);
 }
 
 // exclusive product scan over n values held as v(k) for k = lane + 32q; returns weights into wts[k] = alpha*T
@@ -71,49 +101,129 @@ __device__ __forceinline__ float march_weights(int nint, int lane, float* wts, F
   return warp_sum(wsum);
 }
 
-__global__ void __launch_bounds__(R_WARPS * 32) render_fwd_kernel(const RenderParams p) {
-  extern __shared__ __align__(16) float smem[];
+// ---- split-bf16 helpers (packed pairs: element 0 in the low half)
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));   // first source -> upper half
+  return r;
+}
+// (a, b) -> hi pair and residual lo pair
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16x2(a - ah, b - bh);
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+// softplus(x) = max(x,0) + ln2 * log2(1 + 2^(-|x| log2e)); equals torch's (beta 1, threshold 20) to fp32 rounding
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float softplus_fast(float x) {
+  return fmaf(lg2f(1.f + ex2f(-1.4426950408889634f * fabsf(x))), 0.6931471805599453f, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid01(float x) { return rcpf(1.f + ex2f(-1.4426950408889634f * x)); }
+
+// physical column of logical channel c in row r of the feature tile (row stride 32 floats): XOR-ing bits 3..4
+// with the row keeps the gather's float4 stores and the MMA fragment float2 loads conflict-free
+__device__ __forceinline__ int colx(int r, int c) { return c ^ ((r & 3) << 3); }
+// physical 32-bit word (2 channels) of channel pair cw = c/2 in row r of the colour buffer (row stride 16 words)
+__device__ __forceinline__ int colqx(int r, int cw) { return cw ^ (((r >> 1) & 3) << 2); }
+// Quantise note: colour = sigmoid*1.002 - 0.001 is stored between decode and composite as q = round(65535*sigmoid)
+// (step 1.53e-5, |error| <= 7.7e-6 per colour, <= 1.6e-5 on the composited feature): half the bytes per row lets
+// 16 instead of 8 rays live on an SM, which is what hides the gather latency.
+constexpr float QSCALE = 65535.f;
+constexpr float QSTEP = 1.002f / 65535.f;
+
+__global__ void __launch_bounds__(R_WARPS * 32, 1) render_fwd_kernel(const RenderParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const HfagpRenderDesc& d = p.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
   const int S = d.s_coarse, SF = d.s_fine, T = S + SF;
-  const int rays_per_frame = d.res * d.res;
-  const long long total_rays = (long long)d.batch * rays_per_frame;
 
-  // block-shared decoder weights
-  float* mlp = smem;
-  for (int i = threadIdx.x; i < MLP_FLOATS; i += blockDim.x) mlp[i] = __ldg(p.mlp + i);
-  const float* w0 = mlp;
-  const float* b0 = mlp + RH * RC;
-  const float* w1 = b0 + RH;
-  const float* b1 = w1 + RO * RH;
+  // ---- CTA-shared decoder weights as MMA B fragments (split bf16)
+  uint2* w0f = reinterpret_cast<uint2*>(smem_raw);
+  uint2* w1f = w0f + W0F_U2;
+  float* b0s = reinterpret_cast<float*>(w1f + W1F_U2);
+  float* b1s = b0s + RH;     // permuted: [0..31] colour biases, [32] sigma bias, rest 0
+  {
+    const float* W0 = p.mlp;
+    const float* B0 = W0 + RH * RC;
+    const float* W1 = B0 + RH;
+    const float* B1 = W1 + RO * RH;
+    for (int i = threadIdx.x; i < 8 * 2 * 32; i += blockDim.x) {       // (ntile j, kstep s, lane)
+      const int l = i & 31, s = (i >> 5) & 1, j = i >> 6;
+      const int n = 8 * j + (l >> 2), k0 = 16 * s + 2 * (l & 3);
+      const float* r = W0 + n * RC + k0;
+      uint2 hi, lo;
+      split_pair(__ldg(r), __ldg(r + 1), hi.x, lo.x);
+      split_pair(__ldg(r + 8), __ldg(r + 9), hi.y, lo.y);
+      w0f[((j * 2 + s) * 2 + 0) * 32 + l] = hi;
+      w0f[((j * 2 + s) * 2 + 1) * 32 + l] = lo;
+    }
+    for (int i = threadIdx.x; i < 5 * 4 * 32; i += blockDim.x) {
+      const int l = i & 31, s = (i >> 5) & 3, j = i >> 7;
+      const int np = 8 * j + (l >> 2), k0 = 16 * s + 2 * (l & 3);
+      const int o = np < 32 ? np + 1 : (np == 32 ? 0 : -1);              // output row permutation: colours first
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (o >= 0) {
+        const float* r = W1 + o * RH + k0;
+        v[0] = __ldg(r); v[1] = __ldg(r + 1); v[2] = __ldg(r + 8); v[3] = __ldg(r + 9);
+      }
+      uint2 hi, lo;
+      split_pair(v[0], v[1], hi.x, lo.x);
+      split_pair(v[2], v[3], hi.y, lo.y);
+      w1f[((j * 4 + s) * 2 + 0) * 32 + l] = hi;
+      w1f[((j * 4 + s) * 2 + 1) * 32 + l] = lo;
+    }
+    for (int i = threadIdx.x; i < RH; i += blockDim.x) b0s[i] = __ldg(B0 + i);
+    for (int i = threadIdx.x; i < 40; i += blockDim.x) b1s[i] = i < 32 ? __ldg(B1 + i + 1) : (i == 32 ? __ldg(B1) : 0.f);
+  }
   __syncthreads();
 
-  float* ws = smem + MLP_PAD + (size_t)warp * render_warp_floats(T, S);
-  Tap* taps = reinterpret_cast<Tap*>(ws);  // first: keeps the 8-byte records aligned for any T
-  float* col = ws + 32 * 12 * 2;
-  float* dep = col + (size_t)T * COL_LD;
-  float* sig = dep + T;
-  float* sdep = sig + T;
-  float* ssig = sdep + T;
-  float* wts = ssig + T;
-  int* order = reinterpret_cast<int*>(wts + T);
-  float* cdf = reinterpret_cast<float*>(order + T);
+  // ---- per-warp scratch
+  const size_t wbytes = render_warp_bytes(S, SF);
+  uint8_t* wbase = smem_raw + ((WEIGHT_BYTES + 15) & ~15) + (size_t)warp * wbytes;
+  const int S16 = round16(S);
+  const int crows = S16 + round16(SF);
+  const int Tp = (T + 3) & ~3;
+  uint32_t* colq = reinterpret_cast<uint32_t*>(wbase);                  // [crows][16] words of 2 x u16
+  float* ftile = reinterpret_cast<float*>(colq + (size_t)crows * 16);   // [16][32]
+  float* dep = ftile + TILE * RC;
+  float* sig = dep + Tp;
+  float* sdep = sig + Tp;
+  float* ssig = sdep + Tp;
+  uint8_t* order = reinterpret_cast<uint8_t*>(ssig + Tp);
+  float* cdf = reinterpret_cast<float*>(order + Tp);
   float* zmid = cdf + (S + 2);
+  Tap* taps = reinterpret_cast<Tap*>(wbase + wbytes - TILE * 12 * sizeof(Tap));
 
   const int PW = d.plane_w, PH = d.plane_h;
   const int texel_stride = 3 * RC;
+  const int res = d.res;
+  const int nwarps = blockDim.x >> 5;            // rays per strip
+  const int ytiles = (res + nwarps - 1) / nwarps;
+  const long long strips = (long long)d.batch * ytiles * res;
 
-  for (long long ray = (long long)blockIdx.x * R_WARPS + warp; ray < total_rays; ray += (long long)gridDim.x * R_WARPS) {
-    const int n = (int)(ray / rays_per_frame);
-    const int r = (int)(ray - (long long)n * rays_per_frame);
+  for (long long strip = blockIdx.x; strip < strips; strip += gridDim.x) {
+    const int n = (int)(strip / ((long long)ytiles * res));
+    const int rem = (int)(strip - (long long)n * ytiles * res);
+    const int yt = rem / res, px = rem - yt * res;
+    const int py = yt * nwarps + warp;
+    if (py >= res) continue;                       // warp-uniform; no CTA barrier inside the loop
+    const long long ray = ((long long)n * res + py) * res + px;
     const float* cam = p.cam + (size_t)n * 25;
     const float* pl = p.planes + (size_t)n * PH * PW * texel_stride;
 
     // ---- ray generation (uniform across the warp)
     float ox_, oy_, oz_, dx_, dy_, dz_;
     {
-      const int py = r / d.res, px = r - py * d.res;
-      const float inv = 1.0f / d.res, half = 0.5f / d.res;
+      const float inv = 1.0f / res, half = 0.5f / res;
       const float xc = px * inv + half, yc = py * inv + half;
       const float fx = __ldg(cam + 16), sk = __ldg(cam + 17), cx = __ldg(cam + 18);
       const float fy = __ldg(cam + 20), cy = __ldg(cam + 21);
@@ -136,100 +246,166 @@ __global__ void __launch_bounds__(R_WARPS * 32) render_fwd_kernel(const RenderPa
       dep[s] = __ldg(p.lin + s) + __ldg(p.jitter + (size_t)ray * S + s) * d.delta;
     __syncwarp();
 
-    // ---- gather + decode a run of samples [s_begin, s_end) whose depths are in dep[]
-    auto shade = [&](int s_begin, int s_end) {
-      for (int base = s_begin; base < s_end; base += 32) {
-        const int cnt = min(32, s_end - base);
-        // phase A: lane = sample, 12 (offset, weight) taps
-        if (lane < cnt) {
-          const float t = dep[base + lane];
-          const float qx = (ox_ + t * dx_) * d.box_scale;
-          const float qy = (oy_ + t * dy_) * d.box_scale;
-          const float qz = (oz_ + t * dz_) * d.box_scale;
-#pragma unroll
-          for (int pidx = 0; pidx < 3; ++pidx) {
-            const float gx = pidx == 2 ? qz : qx;
-            const float gy = pidx == 0 ? qy : (pidx == 1 ? qz : qx);
-            const float ix = ((gx + 1.f) * PW - 1.f) * 0.5f;
-            const float iy = ((gy + 1.f) * PH - 1.f) * 0.5f;
-            const float fx0 = floorf(ix), fy0 = floorf(iy);
-            const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
-            const float wl = fx1 - ix, wr = ix - fx0, wt = fy1 - iy, wb = iy - fy0;
-            // clamp before the int conversion so far-away samples cannot overflow
-            const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)PW + 1.f);
-            const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)PH + 1.f);
-            const int x1 = x0 + 1, y1 = y0 + 1;
-            const bool vx0 = x0 >= 0 && x0 < PW, vx1 = x1 >= 0 && x1 < PW;
-            const bool vy0 = y0 >= 0 && y0 < PH, vy1 = y1 >= 0 && y1 < PH;
-            Tap* tp = taps + (lane * 12 + pidx * 4);
-            tp[0].off = (vx0 && vy0) ? (y0 * PW + x0) * texel_stride + pidx * RC : -1; tp[0].w = wl * wt;
-            tp[1].off = (vx1 && vy0) ? (y0 * PW + x1) * texel_stride + pidx * RC : -1; tp[1].w = wr * wt;
-            tp[2].off = (vx0 && vy1) ? (y1 * PW + x0) * texel_stride + pidx * RC : -1; tp[2].w = wl * wb;
-            tp[3].off = (vx1 && vy1) ? (y1 * PW + x1) * texel_stride + pidx * RC : -1; tp[3].w = wr * wb;
+    // ---- gather + decode the samples [s_begin, s_end) whose depths are in dep[], 16 at a time
+    auto shade = [&](int s_begin, int s_end, int crow_begin) {
+      for (int base = s_begin; base < s_end; base += TILE) {
+        const int crow0 = crow_begin + (base - s_begin);          // colour-buffer row of the tile's first sample
+        const int cnt = min(TILE, s_end - base);
+        // phase A: lanes 0-15 build the taps of planes 0 and 1, lanes 16-31 those of plane 2
+        {
+          const int sl = lane & 15;
+          if (sl < cnt) {
+            const float t = dep[base + sl];
+            const float qx = (ox_ + t * dx_) * d.box_scale;
+            const float qy = (oy_ + t * dy_) * d.box_scale;
+            const float qz = (oz_ + t * dz_) * d.box_scale;
+            const int p_begin = lane < 16 ? 0 : 2, p_end = lane < 16 ? 2 : 3;
+            for (int pidx = p_begin; pidx < p_end; ++pidx) {
+              const float gx = pidx == 2 ? qz : qx;
+              const float gy = pidx == 0 ? qy : (pidx == 1 ? qz : qx);
+              const float ix = ((gx + 1.f) * PW - 1.f) * 0.5f;
+              const float iy = ((gy + 1.f) * PH - 1.f) * 0.5f;
+              const float fx0 = floorf(ix), fy0 = floorf(iy);
+              const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+              const float wl = fx1 - ix, wr = ix - fx0, wt = fy1 - iy, wb = iy - fy0;
+              // clamp before the int conversion so far-away samples cannot overflow
+              const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)PW + 1.f);
+              const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)PH + 1.f);
+              const int x1 = x0 + 1, y1 = y0 + 1;
+              const bool vx0 = x0 >= 0 && x0 < PW, vx1 = x1 >= 0 && x1 < PW;
+              const bool vy0 = y0 >= 0 && y0 < PH, vy1 = y1 >= 0 && y1 < PH;
+              Tap* tp = taps + (sl * 12 + pidx * 4);
+              const int cbase = pidx * RC;
+              const int b00 = ((y0 * PW + x0) * texel_stride + cbase) * 4, dxb = texel_stride * 4, dyb = PW * texel_stride * 4;
+              tp[0] = (vx0 && vy0) ? Tap{(uint32_t)b00, wl * wt} : Tap{0u, 0.f};
+              tp[1] = (vx1 && vy0) ? Tap{(uint32_t)(b00 + dxb), wr * wt} : Tap{0u, 0.f};
+              tp[2] = (vx0 && vy1) ? Tap{(uint32_t)(b00 + dyb), wl * wb} : Tap{0u, 0.f};
+              tp[3] = (vx1 && vy1) ? Tap{(uint32_t)(b00 + dyb + dxb), wr * wb} : Tap{0u, 0.f};
+            }
           }
         }
         __syncwarp();
-        // phase B: lane = channel
-        for (int s = 0; s < cnt; ++s) {
-          float acc[3] = {0.f, 0.f, 0.f};
-          const Tap* tp = taps + s * 12;
-#pragma unroll
-          for (int k = 0; k < 12; ++k) {
-            const Tap tk = tp[k];
-            if (tk.off >= 0) acc[k >> 2] = fmaf(tk.w, __ldg(pl + tk.off + lane), acc[k >> 2]);
-          }
-          col[(size_t)(base + s) * COL_LD + lane] = (acc[0] + acc[1] + acc[2]) / 3.f;
-        }
-        __syncwarp();
-        // phase C: lane = sample, decoder MLP 32 -> 64 (softplus) -> 33
-        if (lane < cnt) {
-          float* row = col + (size_t)(base + lane) * COL_LD;
-          float f[RC];
-#pragma unroll
-          for (int c = 0; c < RC; ++c) f[c] = row[c];
-          float out[RO];
-#pragma unroll
-          for (int o = 0; o < RO; ++o) out[o] = b1[o];
+        // phase B: four samples per pass, lane = (sample sq, channel quad cg): 12 unconditional 16 B loads per lane
+        // (8 lanes cover one 128 B texel line; outside taps carry weight 0), no cross-lane reduction needed
+        {
+          const int sq = lane >> 3, cg = lane & 7;
+          const char* lb = reinterpret_cast<const char*>(pl) + cg * 16;
 #pragma unroll 1
-          for (int jc = 0; jc < RH; jc += 8) {
-            float h[8];
+          for (int q = 0; q < TILE; q += 4) {
+            if (q >= cnt) break;
+            const int sl = min(q + sq, cnt - 1);       // lanes past the end redo the last sample (not stored)
+            const Tap* tp = taps + sl * 12;
+            Tap rec[12];
+            float4 v[12];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) h[jj] = b0[jc + jj];
+            for (int k = 0; k < 12; ++k) {
+              rec[k] = tp[k];
+              v[k] = __ldg(reinterpret_cast<const float4*>(lb + rec[k].off));
+            }
+            float4 a[3];
 #pragma unroll
-            for (int c = 0; c < RC; c += 4) {
+            for (int pi = 0; pi < 3; ++pi) {
+              a[pi] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float4 w4 = *reinterpret_cast<const float4*>(w0 + (jc + jj) * RC + c);
-                h[jj] = fmaf(w4.x, f[c], h[jj]);
-                h[jj] = fmaf(w4.y, f[c + 1], h[jj]);
-                h[jj] = fmaf(w4.z, f[c + 2], h[jj]);
-                h[jj] = fmaf(w4.w, f[c + 3], h[jj]);
+              for (int k = 4 * pi; k < 4 * pi + 4; ++k) {
+                a[pi].x = fmaf(rec[k].w, v[k].x, a[pi].x);
+                a[pi].y = fmaf(rec[k].w, v[k].y, a[pi].y);
+                a[pi].z = fmaf(rec[k].w, v[k].z, a[pi].z);
+                a[pi].w = fmaf(rec[k].w, v[k].w, a[pi].w);
               }
             }
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) h[jj] = softplus_t(h[jj]);
-#pragma unroll
-            for (int o = 0; o < RO; ++o) {
-              const float4 wa = *reinterpret_cast<const float4*>(w1 + o * RH + jc);
-              const float4 wb = *reinterpret_cast<const float4*>(w1 + o * RH + jc + 4);
-              float v = out[o];
-              v = fmaf(wa.x, h[0], v); v = fmaf(wa.y, h[1], v); v = fmaf(wa.z, h[2], v); v = fmaf(wa.w, h[3], v);
-              v = fmaf(wb.x, h[4], v); v = fmaf(wb.y, h[5], v); v = fmaf(wb.z, h[6], v); v = fmaf(wb.w, h[7], v);
-              out[o] = v;
+            const float third = 1.f / 3.f;
+            if (q + sq < cnt) {
+              const int r = q + sq;
+              *reinterpret_cast<float4*>(ftile + r * RC + colx(r, 4 * cg)) =
+                  make_float4((a[0].x + a[1].x + a[2].x) * third, (a[0].y + a[1].y + a[2].y) * third,
+                              (a[0].z + a[1].z + a[2].z) * third, (a[0].w + a[1].w + a[2].w) * third);
             }
           }
-          sig[base + lane] = out[0];
-#pragma unroll
-          for (int c = 0; c < RC; ++c) row[c] = (1.f / (1.f + expf(-out[1 + c]))) * 1.002f - 0.001f;
         }
         __syncwarp();
+
+        // phase C: decoder MLP on the 16-row tile [base, base+16) with mma.sync (rows beyond cnt are don't-care)
+        const int r0 = g, r1 = g + 8;
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int c0 = 16 * s + 2 * t4;
+          const float2 f00 = *reinterpret_cast<const float2*>(ftile + r0 * RC + colx(r0, c0));
+          const float2 f10 = *reinterpret_cast<const float2*>(ftile + r1 * RC + colx(r1, c0));
+          const float2 f01 = *reinterpret_cast<const float2*>(ftile + r0 * RC + colx(r0, c0 + 8));
+          const float2 f11 = *reinterpret_cast<const float2*>(ftile + r1 * RC + colx(r1, c0 + 8));
+          split_pair(f00.x, f00.y, ah[s][0], al[s][0]);
+          split_pair(f10.x, f10.y, ah[s][1], al[s][1]);
+          split_pair(f01.x, f01.y, ah[s][2], al[s][2]);
+          split_pair(f11.x, f11.y, ah[s][3], al[s][3]);
+        }
+        // layer 1 two n-tiles at a time: after softplus their accumulator fragments are exactly the A fragment of
+        // layer-2 k-step s, so the hidden layer never leaves registers (and only 8 of its 32 values are live)
+        float o2[5][4];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const float2 bb = *reinterpret_cast<const float2*>(b1s + 8 * j + 2 * t4);
+          o2[j][0] = bb.x; o2[j][1] = bb.y; o2[j][2] = bb.x; o2[j][3] = bb.y;
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          float h[2][4];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * s + jj;
+            const float2 bb = *reinterpret_cast<const float2*>(b0s + 8 * j + 2 * t4);
+            h[jj][0] = bb.x; h[jj][1] = bb.y; h[jj][2] = bb.x; h[jj][3] = bb.y;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint2 bh = w0f[((j * 2 + ks) * 2 + 0) * 32 + lane];
+              const uint2 bl = w0f[((j * 2 + ks) * 2 + 1) * 32 + lane];
+              mma_bf16(h[jj], ah[ks], bh);
+              mma_bf16(h[jj], al[ks], bh);
+              mma_bf16(h[jj], ah[ks], bl);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[jj][e] = softplus_fast(h[jj][e]);
+          }
+          uint32_t a2h[4], a2l[4];
+          split_pair(h[0][0], h[0][1], a2h[0], a2l[0]);
+          split_pair(h[0][2], h[0][3], a2h[1], a2l[1]);
+          split_pair(h[1][0], h[1][1], a2h[2], a2l[2]);
+          split_pair(h[1][2], h[1][3], a2h[3], a2l[3]);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const uint2 bh = w1f[((j * 4 + s) * 2 + 0) * 32 + lane];
+            const uint2 bl = w1f[((j * 4 + s) * 2 + 1) * 32 + lane];
+            mma_bf16(o2[j], a2h, bh);
+            mma_bf16(o2[j], a2l, bh);
+            mma_bf16(o2[j], a2h, bl);
+          }
+        }
+        // colours (n-tiles 0..3 = channels 8j+2t, +1) into the 16-bit colour rows; sigma = column 32 (n-tile 4, t == 0)
+        {
+          const int q0 = crow0 + g, q1 = crow0 + g + 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cw = 4 * j + t4;
+            const uint32_t a = __float2uint_rn(sigmoid01(o2[j][0]) * QSCALE), b = __float2uint_rn(sigmoid01(o2[j][1]) * QSCALE);
+            const uint32_t c = __float2uint_rn(sigmoid01(o2[j][2]) * QSCALE), e = __float2uint_rn(sigmoid01(o2[j][3]) * QSCALE);
+            colq[q0 * 16 + colqx(q0, cw)] = a | (b << 16);
+            colq[q1 * 16 + colqx(q1, cw)] = c | (e << 16);
+          }
+        }
+        if (t4 == 0) {
+          if (g < cnt) sig[base + g] = o2[4][0];
+          if (g + 8 < cnt) sig[base + g + 8] = o2[4][2];
+        }
+        __syncwarp();   // the feature tile and tap records are reused by the next tile
       }
     };
 
-    shade(0, S);
+    shade(0, S, 0);
 
     if (SF > 0) {
       // ---- coarse march (weights only) -> smoothed pdf -> inverse-CDF fine depths
+      float* wts = sdep;                           // sdep is not live until the sort
       march_weights(S - 1, lane, wts, [&](int k) {
         float sm = softplus_t(0.5f * (sig[k] + sig[k + 1]) - 1.f);
         return 1.f - expf(-(sm * (dep[k + 1] - dep[k])));
@@ -268,8 +444,12 @@ __global__ void __launch_bounds__(R_WARPS * 32) render_fwd_kernel(const RenderPa
       __syncwarp();
       for (int k = lane; k < SF; k += 32) {
         const float u = __ldg(p.u_fine + (size_t)ray * SF + k);
-        int ind = 0;  // searchsorted(cdf[0..NB], u, right=True) = #{cdf[i] <= u}
-        for (int i = 0; i <= NB; ++i) ind += cdf[i] <= u ? 1 : 0;
+        // searchsorted(cdf[0..NB], u, right=True) = #{cdf[i] <= u}; cdf is non-decreasing (running sum of positives)
+        int ind = 0;
+        for (int len = NB + 1; len > 0;) {
+          const int half = len >> 1;
+          if (cdf[ind + half] <= u) { ind += half + 1; len -= half + 1; } else { len = half; }
+        }
         const int lo = max(ind - 1, 0), hi = min(ind, NB);
         const float c0 = cdf[lo], c1 = cdf[hi];
         float den = c1 - c0;
@@ -283,22 +463,55 @@ __global__ void __launch_bounds__(R_WARPS * 32) render_fwd_kernel(const RenderPa
         }
       }
       __syncwarp();
-      shade(S, T);
-      // ---- stable rank sort of the T depths (coarse first, as torch.cat + sort sees them)
-      for (int i = lane; i < T; i += 32) {
-        const float di = dep[i];
-        int rank = 0;
+      shade(S, T, S16);
+      // ---- stable rank sort of the T depths (coarse first, as torch.cat + sort sees them).  Fast path counts
+      // strictly-smaller depths for the lane's (up to 4) elements against one broadcast read of each depth;
+      // if any two depths are equal the ranks no longer sum to T(T-1)/2 and the exact tie-aware path redoes it.
+      auto rank_sort = [&](auto ne_tag) {
+        constexpr int NE = decltype(ne_tag)::value;       // elements per lane = ceil(T / 32)
+        float de[NE];
+        int rk[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { de[e] = lane + 32 * e < T ? dep[lane + 32 * e] : 0.f; rk[e] = 0; }
         for (int j = 0; j < T; ++j) {
           const float dj = dep[j];
-          rank += (dj < di || (dj == di && j < i)) ? 1 : 0;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) rk[e] += dj < de[e] ? 1 : 0;
         }
-        order[rank] = i;
-        sdep[rank] = di;
-        ssig[rank] = sig[i];
-      }
+        int rsum = 0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) rsum += lane + 32 * e < T ? rk[e] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+        if (rsum != T * (T - 1) / 2) {
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const int i = lane + 32 * e;
+            int rank = 0;
+            for (int j = 0; j < T; ++j) {
+              const float dj = dep[j];
+              rank += (dj < de[e] || (dj == de[e] && j < i)) ? 1 : 0;
+            }
+            rk[e] = rank;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          const int i = lane + 32 * e;
+          if (i < T) {
+            order[rk[e]] = (uint8_t)i;
+            sdep[rk[e]] = de[e];
+            ssig[rk[e]] = sig[i];
+          }
+        }
+      };
+      if (T <= 32) rank_sort(std::integral_constant<int, 1>{});
+      else if (T <= 64) rank_sort(std::integral_constant<int, 2>{});
+      else if (T <= 96) rank_sort(std::integral_constant<int, 3>{});
+      else rank_sort(std::integral_constant<int, 4>{});
     } else {
       for (int i = lane; i < T; i += 32) {
-        order[i] = i;
+        order[i] = (uint8_t)i;
         sdep[i] = dep[i];
         ssig[i] = sig[i];
       }
@@ -306,6 +519,7 @@ __global__ void __launch_bounds__(R_WARPS * 32) render_fwd_kernel(const RenderPa
     __syncwarp();
 
     // ---- final march
+    float* wts = dep;                              // unsorted depths are dead after the sort
     const float wtot = march_weights(T - 1, lane, wts, [&](int k) {
       float sm = softplus_t(0.5f * (ssig[k] + ssig[k + 1]) - 1.f);
       return 1.f - expf(-(sm * (sdep[k + 1] - sdep[k])));
@@ -314,13 +528,42 @@ __global__ void __launch_bounds__(R_WARPS * 32) render_fwd_kernel(const RenderPa
     float dacc = 0.f;
     for (int k = lane; k < T - 1; k += 32) dacc = fmaf(wts[k], 0.5f * (sdep[k] + sdep[k + 1]), dacc);
     dacc = warp_sum(dacc);
-    float acc = 0.f;
-    float prev = col[(size_t)order[0] * COL_LD + lane];
-    for (int k = 0; k < T - 1; ++k) {
-      const float cur = col[(size_t)order[k + 1] * COL_LD + lane];
-      acc = fmaf(wts[k], 0.5f * (prev + cur), acc);
-      prev = cur;
+    // composite: sum_k w_k (c_k + c_{k+1})/2 over the sorted samples == sum_j omega_j c_j over the samples in
+    // storage order with omega(order[k]) = (w_{k-1} + w_k)/2; omega overwrites sig[] (no longer needed).
+    // c_j = q_j * QSTEP - 0.001 and sum_j omega_j = sum_k w_k, so the dequantisation is applied once at the end.
+    float osum = 0.f;
+    for (int k = lane; k < T; k += 32) {
+      const float om = 0.5f * ((k > 0 ? wts[k - 1] : 0.f) + (k < T - 1 ? wts[k] : 0.f));
+      sig[order[k]] = om;
+      osum += om;
     }
+    osum = warp_sum(osum);
+    __syncwarp();
+    float acc = 0.f;
+    {
+      const int cw = lane >> 1, sh = (lane & 1) * 16;
+      auto qcol = [&](int crow) { return (float)((colq[crow * 16 + colqx(crow, cw)] >> sh) & 0xffffu); };
+      int j = 0;
+      for (; j + 4 <= S; j += 4) {
+        const float4 om = *reinterpret_cast<const float4*>(sig + j);
+        acc = fmaf(om.x, qcol(j), acc);
+        acc = fmaf(om.y, qcol(j + 1), acc);
+        acc = fmaf(om.z, qcol(j + 2), acc);
+        acc = fmaf(om.w, qcol(j + 3), acc);
+      }
+      for (; j < S; ++j) acc = fmaf(sig[j], qcol(j), acc);
+      const int shift = S16 - S;                   // fine sample j lives in colour row j + shift
+      for (; j < T && (j & 3); ++j) acc = fmaf(sig[j], qcol(j + shift), acc);
+      for (; j + 4 <= T; j += 4) {
+        const float4 om = *reinterpret_cast<const float4*>(sig + j);
+        acc = fmaf(om.x, qcol(j + shift), acc);
+        acc = fmaf(om.y, qcol(j + shift + 1), acc);
+        acc = fmaf(om.z, qcol(j + shift + 2), acc);
+        acc = fmaf(om.w, qcol(j + shift + 3), acc);
+      }
+      for (; j < T; ++j) acc = fmaf(sig[j], qcol(j + shift), acc);
+    }
+    acc = fmaf(acc, QSTEP, -0.001f * osum);
     p.feat[(size_t)ray * RC + lane] = acc * 2.f - 1.f;
     if (lane == 0) {
       float dv = dacc / wtot;
@@ -352,15 +595,27 @@ extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes
                   "render_fwd: samples per ray must be 4..64 coarse, 0..64 fine");
   HFAGP_CHECK_ARG(d.s_fine == 0 || u_fine, "render_fwd: u_fine required when s_fine > 0");
   HFAGP_CHECK_ARG(!inds || (below && above), "render_fwd: inds/below/above go together");
+  HFAGP_CHECK_ARG((long long)d.plane_h * d.plane_w * 96 < (1ll << 31), "render_fwd: plane too large for 32-bit tap offsets");
   RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, depth_range, feat, depth, wsum, inds, below, above, sort_idx, depths_sorted};
-  const int T = d.s_coarse + d.s_fine;
-  size_t smem = (MLP_PAD + R_WARPS * render_warp_floats(T, d.s_coarse)) * sizeof(float);
+  int nwarps = R_WARPS;
+  size_t smem = ((WEIGHT_BYTES + 15) & ~15) + nwarps * render_warp_bytes(d.s_coarse, d.s_fine);
+  if (smem > 227 * 1024) {
+    nwarps = R_WARPS / 2;
+    smem = ((WEIGHT_BYTES + 15) & ~15) + nwarps * render_warp_bytes(d.s_coarse, d.s_fine);
+  }
   static std::once_flag attr_once;   // opt in to the full 227 KB once; not repeated on the (graph-captured) hot path
   std::call_once(attr_once, [] { cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   HFAGP_CHECK_ARG(smem <= 227 * 1024, "render_fwd: shared memory need exceeds 227 KB");
-  long long total_rays = (long long)d.batch * d.res * d.res;
-  int blocks = (int)((total_rays + R_WARPS - 1) / R_WARPS);
-  render_fwd_kernel<<<blocks, R_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+  static int cached_sms = 0;
+  if (!cached_sms) {
+    int dev = 0, sms = 148;
+    HFAGP_CUDA(cudaGetDevice(&dev));
+    HFAGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cached_sms = sms;
+  }
+  const long long strips = (long long)d.batch * ((d.res + nwarps - 1) / nwarps) * d.res;
+  const int blocks = (int)(strips < cached_sms ? strips : cached_sms);   // persistent: one CTA per SM
+  render_fwd_kernel<<<blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(p);
   HFAGP_CHECK_LAUNCH("render_fwd_kernel");
   return HFAGP_OK;
 }
