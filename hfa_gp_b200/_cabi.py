@@ -22,6 +22,8 @@ SYMBOLS = [
     'hfagp_torgb_small_fwd', 'hfagp_styles_fwd', 'hfagp_modulate_fwd', 'hfagp_render_fwd',
     'hfagp_blur_fwd', 'hfagp_linear_fwd', 'hfagp_latent_fwd', 'hfagp_nchw_to_nhwc',
     'hfagp_nhwc_to_nchw', 'hfagp_conv2d_tc_fwd', 'hfagp_split_bf16', 'hfagp_modulate_split_fwd',
+    'hfagp_blur_up', 'hfagp_act_bwd', 'hfagp_styles_bwd', 'hfagp_demod_bwd', 'hfagp_linear_bwd',
+    'hfagp_conv2d_wgrad',
 ]
 
 
@@ -45,6 +47,14 @@ class RenderDesc(C.Structure):
         ('batch', C.c_int32), ('res', C.c_int32), ('plane_h', C.c_int32), ('plane_w', C.c_int32),
         ('s_coarse', C.c_int32), ('s_fine', C.c_int32),
         ('delta', C.c_float), ('box_scale', C.c_float),
+    ]
+
+
+class ActBwdDesc(C.Structure):
+    _fields_ = [
+        ('batch', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('c', C.c_int32),
+        ('act', C.c_int32), ('act_gain', C.c_float), ('clamp', C.c_float), ('noise_gain', C.c_float),
+        ('residual_scale', C.c_float), ('post_scale', C.c_float), ('rgb_k', C.c_int32),
     ]
 
 
@@ -73,7 +83,13 @@ def lib() -> C.CDLL:
     l.hfagp_styles_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     l.hfagp_modulate_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_render_fwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
-    l.hfagp_blur_fwd.argtypes = [i32] * 7 + [vp] * 7
+    l.hfagp_blur_fwd.argtypes = [i32] * 7 + [f32] + [vp] * 7
+    l.hfagp_blur_up.argtypes = [i32] * 7 + [f32, vp, vp, vp]
+    l.hfagp_act_bwd.argtypes = [C.POINTER(ActBwdDesc)] + [vp] * 23
+    l.hfagp_styles_bwd.argtypes = [i32, i32, i32, i32] + [vp] * 8
+    l.hfagp_demod_bwd.argtypes = [i32, i32, i32] + [vp] * 6
+    l.hfagp_linear_bwd.argtypes = [i32, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp, vp]
+    l.hfagp_conv2d_wgrad.argtypes = [C.POINTER(ConvDesc)] + [vp] * 6 + [f32, vp, vp]
     l.hfagp_linear_fwd.argtypes = [i32, i32, i32, vp, vp, vp, f32, f32, vp, vp]
     l.hfagp_latent_fwd.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_nchw_to_nhwc.argtypes = [i32, i32, i32, i32, vp, vp, vp]

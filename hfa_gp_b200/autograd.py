@@ -1,0 +1,181 @@
+"""Backward of the generator's convolution stacks (StyleGAN2 backbone and super-resolution head) for the
+training step ``Trainer.gen_update`` (``/root/reference/code/trainer_rgb.py:73-98``): forward through
+``generator.synthesis`` (``headnerf.py:112``) then ``loss.backward()``.
+
+With the generator frozen (the reference's state until ``tune_iter``, ``trainer_rgb.py:59-60``) the gradient
+that has to reach the encoder / ``bases`` / ``delta`` flows  image -> super-resolution -> feature image ->
+renderer -> planes -> backbone -> styles -> ws.  Each network stage is one ``torch.autograd.Function`` whose
+forward is the inference code (recording a tape of the activations it produced anyway) and whose backward walks
+the tape with the sm_100a kernels:
+
+  * ``hfagp_act_bwd``     everything between two convolutions (activation/clamp derivative, demodulation, the
+                          per-sample style scales of the consumers, and the d(styles)/d(dcoef) reductions);
+  * data-gradient convs   the forward kernels (tcgen05 split-bf16 or fp32 SIMT) on transposed, *unmodulated*
+                          weights: modulation is a per-(sample, channel) scale, applied by ``hfagp_act_bwd`` of
+                          the layer below, so one shared weight tensor serves the whole batch;
+  * ``hfagp_blur_fwd``    transposes of the [1,3,3,1] FIRs (symmetric filter: same kernel, other pads);
+  * ``hfagp_demod_bwd`` / ``hfagp_styles_bwd``   back to ``ws``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from ._cabi import ACT_LINEAR, ACT_LRELU, HfagpError
+
+SQRT2 = math.sqrt(2.0)
+
+TAPS_3X3_T = tuple((-(ky - 1), -(kx - 1), ky * 3 + kx) for ky in range(3) for kx in range(3))   # dgrad of a same-conv
+TAPS_UP_T = tuple((ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3))                  # dgrad of the stride-2 transposed conv
+
+
+def _dgrad(gen, dz, pl, taps, *, oh, ow, in_stride=1):
+    """Unscaled data gradient  dxu = conv(dz, W^T)  of one layer: [B,*,*,cout] -> fp32 [B,oh,ow,cin]."""
+    bw = pl.bwd()
+    if gen.precision == 'tc' and bw['wT_split'] is not None:
+        dzs = dz if isinstance(dz, ops.Split) else ops.split(dz)
+        return ops.conv2d_tc(dzs, bw['wT_split'], taps, pl.cin, oh=oh, ow=ow, in_stride=in_stride)
+    dzf = dz.float() if isinstance(dz, ops.Split) else dz
+    return ops.conv2d(dzf, bw['wT'], taps, pl.cin, oh=oh, ow=ow, in_stride=in_stride)
+
+
+def blocks_backward(gen, recs, dimg, dviews):
+    """Walk the recorded blocks in reverse.  ``dimg``: gradient of the last block's output image (fp32 NHWC).
+    ``dviews[i]``: [B,cin] accumulator of d(styles) of layer i.  Returns (gx, dimg_in): the unscaled data gradient
+    into the first block's input with its style scale / d(styles) view (or None), and the gradient of the first
+    block's input image (or None)."""
+    gx = None
+    tc = gen.precision == 'tc'
+    for blk in reversed(recs):
+        r0, r1, rt = blk['conv0'], blk['conv1'], blk['torgb']
+        pl1, plt = r1['pl'], rt['pl']
+        y1 = r1['y']
+        b, h, w = y1.shape[0], y1.shape[1], y1.shape[2]
+        dev = dimg.device
+        # ---- ToRGB branch
+        dimg_t = dimg * rt['mask'] if rt['mask'] is not None else dimg
+        kw = {}
+        if rt['small']:
+            kw = dict(dimg=dimg_t.contiguous(), wrgb=plt.w[0], srgb=rt['styles'], dsrgb=dviews[plt.index])
+        else:
+            dxu_rgb = _dgrad(gen, dimg_t, plt, ops.TAPS_1X1, oh=h, ow=w)
+            kw = dict(g1=dxu_rgb, s1=rt['styles'], ds1=dviews[plt.index])
+        if gx is not None:
+            kw.update(g0=gx[0], s0=gx[1], ds0=gx[2])
+        # ---- conv1: activation / demodulation backward, then its data gradient
+        ddc = torch.zeros((b, pl1.cout), device=dev)
+        use_tc1 = tc and pl1.bwd()['wT_split'] is not None
+        dz1 = ops.act_bwd(y1, dcoef=r1['dcoef'], noise=r1['noise'], noise_gain=pl1.noise_gain, bias=pl1.bias,
+                          act=ACT_LRELU, act_gain=SQRT2, clamp=pl1.clamp, out='split' if use_tc1 else 'f32',
+                          ddcoef=ddc, **kw)
+        ops.demod_bwd(pl1.bwd()['w2'], r1['styles'], r1['dcoef'], ddc, dviews[pl1.index])
+        dxu1 = _dgrad(gen, dz1, pl1, TAPS_3X3_T, oh=h, ow=w)
+        # ---- skip image path: img_out = upsample2d(img_prev) + torgb
+        dimg = ops.blur(dimg, 1, 1, stride=2, gain=4.0) if blk['has_img_prev'] else None
+        if r0 is None:
+            # first backbone block: conv1 reads the learned constant; only its d(styles) is needed
+            ops.act_bwd(blk['x_in'], g0=dxu1, ds0=dviews[pl1.index], act=ACT_LINEAR, act_gain=1.0, out='none')
+            gx = None
+            continue
+        # ---- conv0 (x2 up): act/demod backward at 2H, FIR transpose, then the stride-2 data gradient
+        pl0 = r0['pl']
+        ddc0 = torch.zeros((b, pl0.cout), device=dev)
+        dz0 = ops.act_bwd(r0['y'], g0=dxu1, s0=r1['styles'], ds0=dviews[pl1.index], dcoef=r0['dcoef'],
+                          noise=r0['noise'], noise_gain=pl0.noise_gain, bias=pl0.bias, act=ACT_LRELU, act_gain=SQRT2,
+                          clamp=pl0.clamp, out='f32', ddcoef=ddc0)
+        ops.demod_bwd(pl0.bwd()['w2'], r0['styles'], r0['dcoef'], ddc0, dviews[pl0.index])
+        use_tc0 = tc and pl0.bwd()['wT_split'] is not None
+        dt = ops.blur(dz0, 2, 2, stride=1, gain=4.0, split_out=use_tc0)          # [B,2H+1,2W+1,cout]
+        hin, win = h // 2, w // 2
+        dxu0 = _dgrad(gen, dt, pl0, TAPS_UP_T, oh=hin, ow=win, in_stride=2)
+        gx = (dxu0, r0['styles'], dviews[pl0.index])
+    return gx, dimg
+
+
+class StylesFn(torch.autograd.Function):
+    """ws [B,num_ws,w_dim] -> flat styles of all 32 layers (one launch each way)."""
+
+    @staticmethod
+    def forward(ctx, ws, gen):
+        pk = gen._ensure_packed()
+        flat, offs = pk['styles'].run_flat(ws)
+        ctx.gen, ctx.offs, ctx.shape = gen, offs, ws.shape
+        return flat
+
+    @staticmethod
+    def backward(ctx, dflat):
+        pk = ctx.gen._ensure_packed()
+        b, num_ws, w_dim = ctx.shape
+        dws = ops.StyleTableBwd(pk['styles']).run(dflat.contiguous(), ctx.offs, b, num_ws, w_dim)
+        return dws, None
+
+
+def _dviews(pk, dflat, b):
+    table = pk['styles']
+    offs, _ = table.offsets(b)
+    return table.views(dflat, offs, b)
+
+
+class BackboneFn(torch.autograd.Function):
+    """styles -> tri-planes [B,R,R,96] (channels-last)."""
+
+    @staticmethod
+    def forward(ctx, styles_flat, gen, noise_mode, batch, tap):
+        pk = gen._ensure_packed()
+        cfg = gen.cfg
+        offs, _ = pk['styles'].offsets(batch)
+        views = pk['styles'].views(styles_flat, offs, batch)
+        nb = sum(3 if r > 4 else 2 for r in cfg.block_resolutions)
+        styles = iter(views[:nb])
+        recs, x, img = [], None, None
+        gen._batch = batch
+        for r in cfg.block_resolutions:
+            rec = {}
+            x, img = gen._run_block(getattr(gen.backbone.synthesis, f'b{r}'), x, img, styles, noise_mode, pk, tap,
+                                    f'b{r}', rec=rec)
+            recs.append(rec)
+        ctx.gen, ctx.recs, ctx.batch, ctx.total = gen, recs, batch, styles_flat.numel()
+        return img
+
+    @staticmethod
+    def backward(ctx, dplanes):
+        gen = ctx.gen
+        pk = gen._ensure_packed()
+        dflat = torch.zeros(ctx.total, device=dplanes.device)
+        blocks_backward(gen, ctx.recs, dplanes.contiguous(), _dviews(pk, dflat, ctx.batch))
+        ctx.recs = None
+        return dflat, None, None, None, None
+
+
+class SuperresFn(torch.autograd.Function):
+    """(feature image [B,r,r,32], styles) -> image [B,4r,4r,3] (channels-last)."""
+
+    @staticmethod
+    def forward(ctx, feat, styles_flat, gen, batch, tap):
+        pk = gen._ensure_packed()
+        offs, _ = pk['styles'].offsets(batch)
+        views = pk['styles'].views(styles_flat, offs, batch)
+        styles = iter(views[-6:])
+        gen._batch = batch
+        rgb_lo = feat[..., :3].contiguous()
+        recs, x, img = [], feat, rgb_lo
+        for i, blk in enumerate((gen.superresolution.block0, gen.superresolution.block1)):
+            rec = {}
+            x, img = gen._run_block(blk, x, img, styles, 'none', pk, tap, f'sr{i}', rec=rec)
+            recs.append(rec)
+        ctx.gen, ctx.recs, ctx.batch, ctx.total, ctx.feat = gen, recs, batch, styles_flat.numel(), feat
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        gen = ctx.gen
+        pk = gen._ensure_packed()
+        dflat = torch.zeros(ctx.total, device=dimg.device)
+        gx, drgb_lo = blocks_backward(gen, ctx.recs, dimg.contiguous(), _dviews(pk, dflat, ctx.batch))
+        # first SR layer reads the feature image itself: dfeat = dxu * styles, d(styles) += sum dxu * feat
+        dfeat = ops.act_bwd(ctx.feat, g0=gx[0], s0=gx[1], ds0=gx[2], act=ACT_LINEAR, act_gain=1.0, out='f32')
+        dfeat[..., :3] += drgb_lo
+        ctx.recs = ctx.feat = None
+        return dfeat, dflat, None, None, None

@@ -1,0 +1,448 @@
+// Backward companions of the convolution path (training step, trainer_rgb.py:73-98):
+//   act_bwd      fused "everything between two convolutions": sums the incoming gradients (each with its
+//                per-(sample, channel) style scale), applies the activation / gain / clamp / residual-merge
+//                derivative and the demodulation coefficient, writes the gradient of the convolution output
+//                (fp32 or split-bf16 for the tensor-core dgrad), and reduces d(styles), d(bias), d(dcoef).
+//   blur_up      transpose of the strided encoder blur; the stride-1 blurs and the FIR transposes reuse blur_fwd.
+//   styles_bwd / demod_bwd   gradients of all style affines back to ws; demodulation coefficient backward.
+//   linear_bwd   EqualLinear backward (dx, dW, db).
+//   wgrad        fp32 SIMT weight gradient of the encoder convolutions (split-K, atomics).
+// The data-gradient convolutions themselves are hfagp_conv2d_tc_fwd / hfagp_conv2d_fwd calls on transposed
+// weights with mirrored tap lists (see hfa_gp_b200/autograd.py).
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "splitio.cuh"
+
+namespace hfagp {
+
+struct ActBwdParams {
+  HfagpActBwdDesc d;
+  const float* y; const __nv_bfloat16* y_hi; const __nv_bfloat16* y_lo;
+  const float* g0; const float* s0;
+  const float* g1; const float* s1;
+  const float* dimg; const float* wrgb; const float* srgb;
+  const float* dcoef; const float* noise; const float* bias; const float* residual;
+  float* dz; __nv_bfloat16* dz_hi; __nv_bfloat16* dz_lo;
+  float* ds0; float* ds1; float* dsrgb; float* dbias; float* ddcoef;
+  int pix_per_block;
+};
+
+__device__ __forceinline__ void atomic_add4(float* p, const float v[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) atomicAdd(p + k, v[k]);
+}
+
+__global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
+  const HfagpActBwdDesc& d = p.d;
+  const int c4 = d.c >> 2;
+  const int planes = 256 / c4;                 // pixels processed side by side
+  const int cq = threadIdx.x % c4, plane = threadIdx.x / c4;
+  if (plane >= planes) return;
+  const int n = blockIdx.y;
+  const int hw = d.h * d.w;
+  const int p_begin = blockIdx.x * p.pix_per_block;
+  const int p_end = min(hw, p_begin + p.pix_per_block);
+  const int c0 = cq * 4;
+  const size_t nc = (size_t)n * d.c + c0;
+
+  float sc0[4] = {1.f, 1.f, 1.f, 1.f}, sc1[4] = {1.f, 1.f, 1.f, 1.f}, scr[4] = {0.f, 0.f, 0.f, 0.f};
+  float dco[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+  float wr[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (p.s0) sc0[k] = __ldg(p.s0 + nc + k);
+    if (p.g1 && p.s1) sc1[k] = __ldg(p.s1 + nc + k);
+    if (p.dimg) scr[k] = p.srgb ? __ldg(p.srgb + nc + k) : 1.f;
+    if (p.dcoef) dco[k] = __ldg(p.dcoef + nc + k);
+    if (p.bias) bs[k] = __ldg(p.bias + c0 + k);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) wr[o][k] = (p.dimg && o < d.rgb_k) ? __ldg(p.wrgb + (size_t)o * d.c + c0 + k) : 0.f;
+  }
+  const float slope_pos = d.act_gain, slope_neg = d.act == HFAGP_ACT_LRELU ? 0.2f * d.act_gain : d.act_gain;
+  const float inv_rs = d.residual_scale != 0.f ? 1.f / d.residual_scale : 1.f;
+
+  float r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f}, rr[4] = {0.f, 0.f, 0.f, 0.f};
+  float rb[4] = {0.f, 0.f, 0.f, 0.f}, rd[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int pix = p_begin + plane; pix < p_end; pix += planes) {
+    const size_t q = ((size_t)n * hw + pix) * c4 + cq;
+    const float4 y4 = ld4_any(p.y, p.y_hi, p.y_lo, q);
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.g0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.g0) + q);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { gsum[k] = av[k] * sc0[k]; r0[k] = fmaf(av[k], yv[k], r0[k]); }
+    }
+    if (p.g1) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.g1) + q);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { gsum[k] = fmaf(av[k], sc1[k], gsum[k]); r1[k] = fmaf(av[k], yv[k], r1[k]); }
+    }
+    if (p.dimg) {
+      const float* di = p.dimg + ((size_t)n * hw + pix) * d.rgb_k;
+      float gr[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int o = 0; o < d.rgb_k; ++o) {
+        const float dv = __ldg(di + o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gr[k] = fmaf(dv, wr[o][k], gr[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { gsum[k] = fmaf(gr[k], scr[k], gsum[k]); rr[k] = fmaf(gr[k], yv[k], rr[k]); }
+    }
+    // derivative of  y = merge(clamp(act(pre) * gain))  w.r.t. pre
+    float av[4];
+    if (p.residual) {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual) + q);
+      av[0] = yv[0] * inv_rs - r4.x; av[1] = yv[1] * inv_rs - r4.y; av[2] = yv[2] * inv_rs - r4.z; av[3] = yv[3] * inv_rs - r4.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) av[k] = yv[k];
+    }
+    const float nz = p.noise ? __ldg(p.noise + pix) * d.noise_gain : 0.f;
+    float dzv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float slope = av[k] > 0.f ? slope_pos : slope_neg;
+      const bool pass = !(d.clamp > 0.f) || fabsf(av[k]) < d.clamp;
+      const float dpre = pass ? gsum[k] * d.post_scale * slope : 0.f;
+      rb[k] += dpre;
+      if (p.ddcoef) {
+        const float z = (av[k] / slope - nz - bs[k]) / dco[k];   // conv output before demodulation
+        rd[k] = fmaf(dpre, z, rd[k]);
+      }
+      dzv[k] = dpre * dco[k];
+    }
+    if (p.dz || p.dz_hi) st4_any(p.dz, p.dz_hi, p.dz_lo, q, dzv);
+  }
+  if (p.ds0 && p.g0) atomic_add4(p.ds0 + nc, r0);
+  if (p.ds1 && p.g1) atomic_add4(p.ds1 + nc, r1);
+  if (p.dsrgb && p.dimg) atomic_add4(p.dsrgb + nc, rr);
+  if (p.dbias) atomic_add4(p.dbias + c0, rb);
+  if (p.ddcoef) atomic_add4(p.ddcoef + nc, rd);
+}
+
+// dx[n][iy][ix][c] = gain * sum_{ky,kx} g[ky] g[kx] dy[n][(iy + pad0 - ky)/s][(ix + pad0 - kx)/s][c]   (exact divisions only)
+template <int V>
+__global__ void blur_up_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow, float gain,
+                               const float* __restrict__ dy, float* __restrict__ dx) {
+  const int cv = c / V;
+  size_t total = (size_t)batch * h * w_ * cv;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int cq = idx % cv;
+  size_t pix = idx / cv;
+  int ix = pix % w_;
+  size_t r = pix / w_;
+  int iy = r % h;
+  int n = r / h;
+  const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  float s[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) s[k] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    int ty = iy + pad0 - ky;
+    if (ty < 0 || ty % stride) continue;
+    int oy = ty / stride;
+    if (oy >= oh) continue;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      int tx = ix + pad0 - kx;
+      if (tx < 0 || tx % stride) continue;
+      int ox = tx / stride;
+      if (ox >= ow) continue;
+      const float wgt = g[ky] * g[kx] * gain;
+      const size_t o = (((size_t)n * oh + oy) * ow + ox) * cv + cq;
+      if (V == 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(dy) + o);
+        s[0] = fmaf(wgt, v.x, s[0]); s[1 % V] = fmaf(wgt, v.y, s[1 % V]);
+        s[2 % V] = fmaf(wgt, v.z, s[2 % V]); s[3 % V] = fmaf(wgt, v.w, s[3 % V]);
+      } else {
+        s[0] = fmaf(wgt, __ldg(dy + o), s[0]);
+      }
+    }
+  }
+  if (V == 4) reinterpret_cast<float4*>(dx)[idx] = make_float4(s[0], s[1 % V], s[2 % V], s[3 % V]);
+  else dx[idx] = s[0];
+}
+
+// ---------------------------------------------------------------- styles / demodulation backward
+constexpr int MAX_STYLE_LAYERS_B = 48;
+struct StyleBwdTable {
+  const float* aw[MAX_STYLE_LAYERS_B];
+  long long off[MAX_STYLE_LAYERS_B];
+  int cin[MAX_STYLE_LAYERS_B];
+  int widx[MAX_STYLE_LAYERS_B];
+  float gain[MAX_STYLE_LAYERS_B];
+};
+
+// block (layer, n): dws[n][widx][k] += gain/sqrt(wdim) * sum_i dstyles[l][n][i] * A_l[i][k]
+__global__ void styles_bwd_kernel(const StyleBwdTable tb, int num_ws, int w_dim, float inv_sqrt,
+                                  const float* __restrict__ dstyles, float* __restrict__ dws) {
+  const int l = blockIdx.x, n = blockIdx.y;
+  const int cin = tb.cin[l];
+  const float* ds = dstyles + tb.off[l] + (size_t)n * cin;
+  const float* a = tb.aw[l];
+  for (int k = threadIdx.x; k < w_dim; k += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < cin; ++i) acc = fmaf(__ldg(ds + i), __ldg(a + (size_t)i * w_dim + k), acc);
+    atomicAdd(dws + ((size_t)n * num_ws + tb.widx[l]) * w_dim + k, acc * tb.gain[l] * inv_sqrt);
+  }
+}
+
+// ds[n][i] -= s[n][i] * sum_o ddcoef[n][o] * dcoef[n][o]^3 * w2[o][i]      (w2 = sum_taps w^2)
+__global__ void demod_bwd_kernel(int cout, int cin, const float* __restrict__ w2, const float* __restrict__ styles,
+                                 const float* __restrict__ dcoef, const float* __restrict__ ddcoef,
+                                 float* __restrict__ dstyles) {
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cin) return;
+  float acc = 0.f;
+  for (int o = 0; o < cout; ++o) {
+    const float dc = __ldg(dcoef + (size_t)n * cout + o);
+    acc = fmaf(__ldg(ddcoef + (size_t)n * cout + o) * dc * dc * dc, __ldg(w2 + (size_t)o * cin + i), acc);
+  }
+  dstyles[(size_t)n * cin + i] -= __ldg(styles + (size_t)n * cin + i) * acc;
+}
+
+// ---------------------------------------------------------------- EqualLinear backward
+__global__ void linear_bwd_dx_kernel(int batch, int cin, int cout, const float* __restrict__ dy,
+                                     const float* __restrict__ w, float w_gain, float* __restrict__ dx) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * cin) return;
+  int n = idx / cin, i = idx - n * cin;
+  float acc = 0.f;
+  for (int o = 0; o < cout; ++o) acc = fmaf(__ldg(dy + (size_t)n * cout + o), __ldg(w + (size_t)o * cin + i), acc);
+  dx[idx] = acc * w_gain;
+}
+__global__ void linear_bwd_dw_kernel(int batch, int cin, int cout, const float* __restrict__ dy,
+                                     const float* __restrict__ x, float w_gain, float b_gain, float* __restrict__ dw,
+                                     float* __restrict__ db) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cout * cin) return;
+  int o = idx / cin, i = idx - o * cin;
+  float acc = 0.f, bacc = 0.f;
+  for (int n = 0; n < batch; ++n) {
+    const float g = __ldg(dy + (size_t)n * cout + o);
+    acc = fmaf(g, __ldg(x + (size_t)n * cin + i), acc);
+    bacc += g;
+  }
+  dw[idx] += acc * w_gain;
+  if (db && i == 0) db[o] += bacc * b_gain;
+}
+
+// ---------------------------------------------------------------- weight gradient (fp32 SIMT, split-K)
+// dw[t][o][i] += scale * sum_{n,my,mx} dz[n][my][mx][o] * x[n][my*stride + dy_t][mx*stride + dx_t][i]
+struct WgradParams {
+  int batch, in_h, in_w, cin, cout, oh, ow, in_stride, ntaps;
+  int dy[HFAGP_MAX_TAPS], dx[HFAGP_MAX_TAPS], wtap[HFAGP_MAX_TAPS];
+  const float* x; const __nv_bfloat16* x_hi; const __nv_bfloat16* x_lo;
+  const float* dz; const __nv_bfloat16* dz_hi; const __nv_bfloat16* dz_lo;
+  float* dw;
+  float scale;
+  int k_per_split;
+};
+
+constexpr int WG_T = 64, WG_K = 16, WG_LD = WG_T + 4;
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
+  __shared__ __align__(16) float As[2][WG_K * WG_LD];   // dz tile: [pixel][cout]
+  __shared__ __align__(16) float Bs[2][WG_K * WG_LD];   // x tile:  [pixel][cin]
+  const int tid = threadIdx.x;
+  const int tiles_i = (p.cin + WG_T - 1) / WG_T;
+  const int o0 = (blockIdx.x / tiles_i) * WG_T, i0 = (blockIdx.x % tiles_i) * WG_T;
+  const int t = blockIdx.y;
+  const long long K = (long long)p.batch * p.oh * p.ow;
+  const long long k_begin = (long long)blockIdx.z * p.k_per_split;
+  const long long k_end = k_begin + p.k_per_split < K ? k_begin + p.k_per_split : K;
+  const int row = tid >> 4, quad = tid & 15;          // load coordinates: pixel row of the chunk, channel quad
+  const int ty = tid >> 4, tx = tid & 15;             // compute coordinates: 4 couts x 4 cins
+  const int tdy = p.dy[t], tdx = p.dx[t];
+  const int ohw = p.oh * p.ow;
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  float4 ra, rb;
+  auto load = [&](long long kb) {
+    const long long k = kb + row;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = ra;
+    if (k < k_end) {
+      const int n = (int)(k / ohw);
+      const int rem = (int)(k - (long long)n * ohw);
+      const int my = rem / p.ow, mx = rem - my * p.ow;
+      const int co = o0 + quad * 4;
+      if (co < p.cout) ra = ld4_any(p.dz, p.dz_hi, p.dz_lo, ((size_t)k * p.cout + co) >> 2);
+      const int iy = my * p.in_stride + tdy, ix = mx * p.in_stride + tdx, ci = i0 + quad * 4;
+      if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w && ci < p.cin)
+        rb = ld4_any(p.x, p.x_hi, p.x_lo, ((((size_t)n * p.in_h + iy) * p.in_w + ix) * p.cin + ci) >> 2);
+    }
+  };
+  auto store = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][row * WG_LD + quad * 4]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf][row * WG_LD + quad * 4]) = rb;
+  };
+  load(k_begin);
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  for (long long kb = k_begin; kb < k_end; kb += WG_K) {
+    if (kb + WG_K < k_end) load(kb + WG_K);
+#pragma unroll
+    for (int kk = 0; kk < WG_K; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk * WG_LD + ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk * WG_LD + tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) acc[aa][bb] = fmaf(av[aa], bv[bb], acc[aa][bb]);
+    }
+    if (kb + WG_K < k_end) store(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  float* out = p.dw + (size_t)p.wtap[t] * p.cout * p.cin;
+#pragma unroll
+  for (int aa = 0; aa < 4; ++aa) {
+    const int o = o0 + ty * 4 + aa;
+    if (o >= p.cout) continue;
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int i = i0 + tx * 4 + bb;
+      if (i < p.cin) atomicAdd(out + (size_t)o * p.cin + i, acc[aa][bb] * p.scale);
+    }
+  }
+}
+
+}  // namespace hfagp
+
+using namespace hfagp;
+
+extern "C" int hfagp_act_bwd(const HfagpActBwdDesc* desc, const float* y, const uint16_t* y_hi, const uint16_t* y_lo,
+                             const float* g0, const float* s0, const float* g1, const float* s1, const float* dimg,
+                             const float* wrgb, const float* srgb, const float* dcoef, const float* noise,
+                             const float* bias, const float* residual, float* dz, uint16_t* dz_hi, uint16_t* dz_lo,
+                             float* ds0, float* ds1, float* dsrgb, float* dbias, float* ddcoef, void* stream) {
+  HFAGP_CHECK_ARG(desc && (g0 || dimg), "act_bwd: null pointer (need g0 and/or dimg)");
+  const HfagpActBwdDesc& d = *desc;
+  HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "act_bwd: give y or (y_hi, y_lo)");
+  HFAGP_CHECK_ARG(!(dz && dz_hi), "act_bwd: give dz or (dz_hi, dz_lo), not both");
+  HFAGP_CHECK_ARG(d.batch > 0 && d.batch <= 65535 && d.h > 0 && d.w > 0 && d.c >= 4 && (d.c & 3) == 0 && d.c <= 1024,
+                  "act_bwd: c must be a multiple of 4 in [4, 1024]");
+  HFAGP_CHECK_ARG(!dimg || (wrgb && d.rgb_k >= 1 && d.rgb_k <= 4), "act_bwd: small-ToRGB fusion needs wrgb and rgb_k <= 4");
+  HFAGP_CHECK_ARG(!ddcoef || dcoef, "act_bwd: ddcoef needs dcoef");
+  ActBwdParams p{d, y, reinterpret_cast<const __nv_bfloat16*>(y_hi), reinterpret_cast<const __nv_bfloat16*>(y_lo),
+                 g0, s0, g1, s1, dimg, wrgb, srgb, dcoef, noise, bias, residual, dz,
+                 reinterpret_cast<__nv_bfloat16*>(dz_hi), reinterpret_cast<__nv_bfloat16*>(dz_lo),
+                 ds0, ds1, dsrgb, dbias, ddcoef, 0};
+  const int hw = d.h * d.w;
+  const int planes = 256 / (d.c >> 2);
+  // ~4 waves of CTAs, at least 8 pixels per side-by-side lane so the atomics stay a small share
+  int ppb = cdiv((long long)hw * d.batch, 148 * 4);
+  if (ppb < planes * 8) ppb = planes * 8;
+  p.pix_per_block = ppb;
+  dim3 grid(cdiv(hw, ppb), d.batch);
+  act_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  HFAGP_CHECK_LAUNCH("act_bwd_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_blur_up(int batch, int h, int w_, int c, int pad0, int pad1, int stride, float gain,
+                             const float* dy, float* dx, void* stream) {
+  HFAGP_CHECK_ARG(dy && dx && batch > 0 && c > 0 && (stride == 1 || stride == 2), "blur_up: bad args");
+  const int oh = (h + pad0 + pad1 - 4) / stride + 1, ow = (w_ + pad0 + pad1 - 4) / stride + 1;
+  HFAGP_CHECK_ARG(oh > 0 && ow > 0, "blur_up: empty gradient");
+  if ((c & 3) == 0) {
+    size_t total = (size_t)batch * h * w_ * (c >> 2);
+    blur_up_kernel<4><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h, w_, c, pad0, stride, oh, ow, gain, dy, dx);
+  } else {
+    size_t total = (size_t)batch * h * w_ * c;
+    blur_up_kernel<1><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h, w_, c, pad0, stride, oh, ow, gain, dy, dx);
+  }
+  HFAGP_CHECK_LAUNCH("blur_up_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_styles_bwd(int nlayers, int batch, int num_ws, int w_dim, const float* const* aff_w_host,
+                                const int32_t* cin_host, const int32_t* widx_host, const float* post_gain_host,
+                                const int64_t* off_host, const float* dstyles, float* dws, void* stream) {
+  HFAGP_CHECK_ARG(nlayers > 0 && nlayers <= MAX_STYLE_LAYERS_B && batch > 0 && batch <= 65535, "styles_bwd: bad dims");
+  HFAGP_CHECK_ARG(aff_w_host && cin_host && widx_host && post_gain_host && off_host && dstyles && dws, "styles_bwd: null pointer");
+  StyleBwdTable tb;
+  for (int l = 0; l < nlayers; ++l) {
+    HFAGP_CHECK_ARG(widx_host[l] >= 0 && widx_host[l] < num_ws, "styles_bwd: ws index out of range");
+    tb.aw[l] = aff_w_host[l];
+    tb.off[l] = off_host[l];
+    tb.cin[l] = cin_host[l];
+    tb.widx[l] = widx_host[l];
+    tb.gain[l] = post_gain_host[l];
+  }
+  styles_bwd_kernel<<<dim3(nlayers, batch), 256, 0, (cudaStream_t)stream>>>(tb, num_ws, w_dim, 1.0f / sqrtf((float)w_dim),
+                                                                          dstyles, dws);
+  HFAGP_CHECK_LAUNCH("styles_bwd_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_demod_bwd(int batch, int cout, int cin, const float* w2, const float* styles, const float* dcoef,
+                               const float* ddcoef, float* dstyles, void* stream) {
+  HFAGP_CHECK_ARG(w2 && styles && dcoef && ddcoef && dstyles && batch > 0 && batch <= 65535, "demod_bwd: bad args");
+  demod_bwd_kernel<<<dim3(cdiv(cin, 128), batch), 128, 0, (cudaStream_t)stream>>>(cout, cin, w2, styles, dcoef, ddcoef, dstyles);
+  HFAGP_CHECK_LAUNCH("demod_bwd_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_linear_bwd(int batch, int cin, int cout, const float* dy, const float* x, const float* w,
+                                float w_gain, float b_gain, float* dx, float* dw, float* db, void* stream) {
+  HFAGP_CHECK_ARG(dy && w && batch > 0 && cin > 0 && cout > 0, "linear_bwd: bad args");
+  HFAGP_CHECK_ARG(!dw || x, "linear_bwd: dw needs x");
+  if (dx) {
+    linear_bwd_dx_kernel<<<cdiv((long long)batch * cin, 256), 256, 0, (cudaStream_t)stream>>>(batch, cin, cout, dy, w, w_gain, dx);
+    HFAGP_CHECK_LAUNCH("linear_bwd_dx_kernel");
+  }
+  if (dw) {
+    linear_bwd_dw_kernel<<<cdiv((long long)cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(batch, cin, cout, dy, x, w_gain,
+                                                                                          b_gain, dw, db);
+    HFAGP_CHECK_LAUNCH("linear_bwd_dw_kernel");
+  }
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_conv2d_wgrad(const HfagpConvDesc* desc, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
+                                  const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, float scale, float* dw,
+                                  void* stream) {
+  HFAGP_CHECK_ARG(desc && dw, "conv2d_wgrad: null pointer");
+  HFAGP_CHECK_ARG((x != nullptr) != (x_hi != nullptr && x_lo != nullptr), "conv2d_wgrad: give x or (x_hi, x_lo)");
+  HFAGP_CHECK_ARG((dz != nullptr) != (dz_hi != nullptr && dz_lo != nullptr), "conv2d_wgrad: give dz or (dz_hi, dz_lo)");
+  const HfagpConvDesc& d = *desc;
+  HFAGP_CHECK_ARG(d.batch > 0 && d.cin > 0 && d.cout > 0 && (d.cin & 3) == 0 && (d.cout & 3) == 0,
+                  "conv2d_wgrad: cin and cout must be multiples of 4");
+  HFAGP_CHECK_ARG(d.ntaps > 0 && d.ntaps <= HFAGP_MAX_TAPS && (d.in_stride == 1 || d.in_stride == 2), "conv2d_wgrad: bad taps/stride");
+  HFAGP_CHECK_ARG(d.out_stride == 1 && d.out_h == d.oh && d.out_w == d.ow, "conv2d_wgrad: dz must be dense [n][oh][ow][cout]");
+  WgradParams p;
+  p.batch = d.batch; p.in_h = d.in_h; p.in_w = d.in_w; p.cin = d.cin; p.cout = d.cout; p.oh = d.oh; p.ow = d.ow;
+  p.in_stride = d.in_stride; p.ntaps = d.ntaps;
+  for (int t = 0; t < d.ntaps; ++t) { p.dy[t] = d.dy[t]; p.dx[t] = d.dx[t]; p.wtap[t] = d.wtap[t]; }
+  p.x = x; p.x_hi = reinterpret_cast<const __nv_bfloat16*>(x_hi); p.x_lo = reinterpret_cast<const __nv_bfloat16*>(x_lo);
+  p.dz = dz; p.dz_hi = reinterpret_cast<const __nv_bfloat16*>(dz_hi); p.dz_lo = reinterpret_cast<const __nv_bfloat16*>(dz_lo);
+  p.dw = dw; p.scale = scale;
+  const long long K = (long long)d.batch * d.oh * d.ow;
+  const int tiles = cdiv(d.cout, WG_T) * cdiv(d.cin, WG_T);
+  int splits = cdiv(148 * 6, (long long)tiles * d.ntaps);
+  const int max_splits = cdiv(K, 4 * WG_K);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.k_per_split = cdiv(cdiv(K, splits), WG_K) * WG_K;
+  splits = cdiv(K, p.k_per_split);
+  dim3 grid(tiles, d.ntaps, splits);
+  wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  HFAGP_CHECK_LAUNCH("wgrad_kernel");
+  return HFAGP_OK;
+}

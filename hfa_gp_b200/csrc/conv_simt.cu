@@ -255,7 +255,7 @@ __global__ void torgb_small_kernel(int batch, int h, int w_, int cin, int cout, 
 }
 
 // ---------------------------------------------------------------- encoder blur
-__global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow,
+__global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow, float gain,
                             const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi,
                             const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
                             __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
@@ -280,7 +280,7 @@ __global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int strid
     for (int kx = 0; kx < 4; ++kx) {
       int ix = ox * stride + kx - pad0;
       if (ix < 0 || ix >= w_) continue;
-      float wgt = g[ky] * g[kx];
+      float wgt = g[ky] * g[kx] * gain;
       float4 v = ld4_any(x, x_hi, x_lo, nb + ((size_t)iy * w_ + ix) * c4 + cq);
       s[0] = fmaf(wgt, v.x, s[0]);
       s[1] = fmaf(wgt, v.y, s[1]);
@@ -289,6 +289,34 @@ __global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int strid
     }
   }
   st4_any(y, y_hi, y_lo, idx, s);
+}
+
+// any channel count (3-channel images of the super-resolution skip path), fp32 only
+__global__ void blur_scalar_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow, float gain,
+                                   const float* __restrict__ x, float* __restrict__ y) {
+  size_t total = (size_t)batch * oh * ow * c;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ch = idx % c;
+  size_t pix = idx / c;
+  int ox = pix % ow;
+  size_t r = pix / ow;
+  int oy = r % oh;
+  int n = r / oh;
+  const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  float s = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    int iy = oy * stride + ky - pad0;
+    if (iy < 0 || iy >= h) continue;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      int ix = ox * stride + kx - pad0;
+      if (ix < 0 || ix >= w_) continue;
+      s = fmaf(g[ky] * g[kx] * gain, __ldg(x + (((size_t)n * h + iy) * w_ + ix) * c + ch), s);
+    }
+  }
+  y[idx] = s;
 }
 
 __global__ void nchw_to_nhwc_kernel(int batch, int c, int hw, const float* __restrict__ x, float* __restrict__ y) {
@@ -376,20 +404,26 @@ extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout
   return HFAGP_OK;
 }
 
-extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad1, int stride, const float* x,
-                              const uint16_t* x_hi, const uint16_t* x_lo, float* y, uint16_t* y_hi, uint16_t* y_lo,
-                              void* stream) {
+extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad1, int stride, float gain,
+                              const float* x, const uint16_t* x_hi, const uint16_t* x_lo, float* y, uint16_t* y_hi,
+                              uint16_t* y_lo, void* stream) {
   HFAGP_CHECK_ARG((x != nullptr) != (x_hi != nullptr && x_lo != nullptr), "blur_fwd: give x or (x_hi, x_lo)");
   HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "blur_fwd: give y or (y_hi, y_lo)");
-  HFAGP_CHECK_ARG((c & 3) == 0 && (stride == 1 || stride == 2), "blur_fwd: c%%4==0, stride 1|2 required");
+  HFAGP_CHECK_ARG(stride == 1 || stride == 2, "blur_fwd: stride 1|2 required");
   int oh = (h + pad0 + pad1 - 4) / stride + 1;
   int ow = (w_ + pad0 + pad1 - 4) / stride + 1;
   HFAGP_CHECK_ARG(oh > 0 && ow > 0, "blur_fwd: empty output");
-  size_t total = (size_t)batch * oh * ow * (c >> 2);
-  blur_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      batch, h, w_, c, pad0, stride, oh, ow, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
-      reinterpret_cast<const __nv_bfloat16*>(x_lo), y, reinterpret_cast<__nv_bfloat16*>(y_hi),
-      reinterpret_cast<__nv_bfloat16*>(y_lo));
+  if ((c & 3) == 0) {
+    size_t total = (size_t)batch * oh * ow * (c >> 2);
+    blur_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        batch, h, w_, c, pad0, stride, oh, ow, gain, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
+        reinterpret_cast<const __nv_bfloat16*>(x_lo), y, reinterpret_cast<__nv_bfloat16*>(y_hi),
+        reinterpret_cast<__nv_bfloat16*>(y_lo));
+  } else {
+    HFAGP_CHECK_ARG(x && y, "blur_fwd: split-bf16 I/O needs c%%4 == 0");
+    size_t total = (size_t)batch * oh * ow * c;
+    blur_scalar_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h, w_, c, pad0, stride, oh, ow, gain, x, y);
+  }
   HFAGP_CHECK_LAUNCH("blur_kernel");
   return HFAGP_OK;
 }

@@ -154,7 +154,16 @@ class _Decoder(nn.Module):
 # ------------------------------------------------------------------ packed (kernel-layout) view
 
 class _PackedLayer:
-    __slots__ = ('w', 'bias', 'noise', 'noise_gain', 'cin', 'cout', 'up', 'clamp', 'use_noise')
+    __slots__ = ('w', 'bias', 'noise', 'noise_gain', 'cin', 'cout', 'up', 'clamp', 'use_noise', 'index', '_bwd')
+
+    def bwd(self):
+        """Operands of the backward pass, built on first use: transposed weights wT[tap][cin][cout] (fp32 and
+        split bf16) for the data-gradient convolution and w2[cout][cin] = sum_taps w^2 for the demod backward."""
+        if self._bwd is None:
+            wt = self.w.transpose(1, 2).contiguous()
+            self._bwd = dict(wT=wt, wT_split=ops.split(wt) if self.cout % 8 == 0 else None,
+                             w2=self.w.square().sum(0).contiguous())
+        return self._bwd
 
 
 def _pack_conv(weight: torch.Tensor) -> torch.Tensor:
@@ -234,6 +243,8 @@ class TriPlaneGenerator(nn.Module):
             gain = 1.0 if kind == 'conv' else 1.0 / math.sqrt(m.cin)
             table.append((m.affine.weight.detach().contiguous(), m.affine.bias.detach().contiguous(), m.cin, widx, gain))
             pl = _PackedLayer()
+            pl._bwd = None
+            pl.index = len(table) - 1
             pl.w = _pack_conv(m.weight)
             pl.bias = m.bias.detach().contiguous().float()
             pl.cin, pl.cout = m.cin, m.cout
@@ -266,7 +277,7 @@ class TriPlaneGenerator(nn.Module):
     def _as_f32(x):
         return x.float() if isinstance(x, ops.Split) else x
 
-    def _conv_layer(self, x, m, styles, noise_mode, pk, split_out):
+    def _conv_layer(self, x, m, styles, noise_mode, pk, split_out, rec=None):
         pl: _PackedLayer = pk['layers'][id(m)]
         noise = None
         if pl.use_noise and noise_mode == 'const' and pl.noise_gain != 0.0:
@@ -280,29 +291,42 @@ class TriPlaneGenerator(nn.Module):
             xs = x if isinstance(x, ops.Split) else ops.split(x)
             wmod, epi['dcoef'] = ops.modulate_split(pl.w, styles, True)
             if pl.up == 1:
-                return ops.conv2d_tc(xs, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batched=True,
-                                     split_out=split_out, **epi)
-            t = torch.empty((x.shape[0], 2 * h + 1, 2 * w + 1, pl.cout), device=xs.device, dtype=torch.float32)
-            for a in (0, 1):
-                for b in (0, 1):
-                    ops.conv2d_tc(xs, wmod, ops._parity_taps(a, b), pl.cout, oh=h + 1 - a, ow=w + 1 - b, out=t,
-                                  out_hw=(2 * h + 1, 2 * w + 1), out_stride=2, out_off=(a, b), w_batched=True)
-            return ops.upfir_act(t, split_out=split_out, **epi)
-        xf = self._as_f32(x)
-        wmod, epi['dcoef'] = ops.modulate(pl.w, styles, True)
-        wbs = wmod.stride(0)
-        if pl.up == 1:
-            y = ops.conv2d(xf, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batch_stride=wbs, **epi)
-            return ops.split(y) if split_out else y
-        t = ops.conv_transpose_s2(xf, wmod, pl.cout, wbs)
-        return ops.upfir_act(t, split_out=split_out, **epi)
+                y = ops.conv2d_tc(xs, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batched=True,
+                                  split_out=split_out, **epi)
+            else:
+                t = torch.empty((x.shape[0], 2 * h + 1, 2 * w + 1, pl.cout), device=xs.device, dtype=torch.float32)
+                for a in (0, 1):
+                    for b in (0, 1):
+                        ops.conv2d_tc(xs, wmod, ops._parity_taps(a, b), pl.cout, oh=h + 1 - a, ow=w + 1 - b, out=t,
+                                      out_hw=(2 * h + 1, 2 * w + 1), out_stride=2, out_off=(a, b), w_batched=True)
+                y = ops.upfir_act(t, split_out=split_out, **epi)
+        else:
+            xs = self._as_f32(x)
+            wmod, epi['dcoef'] = ops.modulate(pl.w, styles, True)
+            wbs = wmod.stride(0)
+            if pl.up == 1:
+                y = ops.conv2d(xs, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batch_stride=wbs, **epi)
+                y = ops.split(y) if split_out else y
+            else:
+                t = ops.conv_transpose_s2(xs, wmod, pl.cout, wbs)
+                y = ops.upfir_act(t, split_out=split_out, **epi)
+        if rec is not None:
+            rec.update(pl=pl, x=xs, y=y, styles=styles, dcoef=epi['dcoef'], noise=noise)
+        return y
 
-    def _torgb_layer(self, x, m, styles, img, pk):
+    def _torgb_layer(self, x, m, styles, img, pk, rec=None):
         pl: _PackedLayer = pk['layers'][id(m)]
         h, w = x.shape[1], x.shape[2]
+        if rec is not None:
+            rec.update(pl=pl, x=x, styles=styles, small=pl.cout <= 4, mask=None)
         if pl.cout <= 4:
             wmod, _ = ops.modulate(pl.w, styles, False)
+            if rec is not None and pl.clamp > 0:
+                # training: the clamp mask of the ToRGB branch needs its output before the skip-image add
+                rec['mask'] = ops.torgb_small(x, wmod, pl.bias, 0.0, None, pl.cout).abs() < pl.clamp
             return ops.torgb_small(x, wmod, pl.bias, pl.clamp, img, pl.cout)
+        if rec is not None and pl.clamp > 0:
+            raise HfagpError('backward of a clamped wide ToRGB is not implemented (EG3D clamps only the 3-channel SR ToRGB)')
         if self._use_tc(pl.cin):
             xs = x if isinstance(x, ops.Split) else ops.split(x)
             wmod, _ = ops.modulate_split(pl.w, styles, False)
@@ -312,9 +336,13 @@ class TriPlaneGenerator(nn.Module):
         return ops.conv2d(self._as_f32(x), wmod, ops.TAPS_1X1, pl.cout, oh=h, ow=w, w_batch_stride=wmod.stride(0),
                           bias=pl.bias, clamp=pl.clamp, up_img=img)
 
-    def _run_block(self, blk, x, img, styles_iter, noise_mode, pk, tap, name):
+    def _run_block(self, blk, x, img, styles_iter, noise_mode, pk, tap, name, rec=None):
         # activations between layers of a block stay in the operand format of their consumer
         tc_next = self._use_tc(blk.cout)
+        r0 = r1 = rt = None
+        if rec is not None:
+            r0, r1, rt = ({} if blk.cin != 0 else None), {}, {}
+            rec.update(conv0=r0, conv1=r1, torgb=rt, has_img_prev=img is not None, x_in=x)
         if blk.cin == 0:
             c = pk['const_split'] if tc_next else pk['const']
             if tc_next:
@@ -322,14 +350,16 @@ class TriPlaneGenerator(nn.Module):
                               c.lo[None].expand(self._batch, -1, -1, -1).contiguous())
             else:
                 x = c[None].expand(self._batch, -1, -1, -1).contiguous()
+            if rec is not None:
+                rec['x_in'] = x
         else:
-            x = self._conv_layer(x, blk.conv0, next(styles_iter), noise_mode, pk, split_out=tc_next)
+            x = self._conv_layer(x, blk.conv0, next(styles_iter), noise_mode, pk, split_out=tc_next, rec=r0)
             if tap is not None:
                 tap[name + '.conv0'] = self._as_f32(x)
-        x = self._conv_layer(x, blk.conv1, next(styles_iter), noise_mode, pk, split_out=tc_next)
+        x = self._conv_layer(x, blk.conv1, next(styles_iter), noise_mode, pk, split_out=tc_next, rec=r1)
         if tap is not None:
             tap[name + '.conv1'] = self._as_f32(x)
-        img = self._torgb_layer(x, blk.torgb, next(styles_iter), img, pk)
+        img = self._torgb_layer(x, blk.torgb, next(styles_iter), img, pk, rec=rt)
         if tap is not None:
             tap[name + '.img'] = img
         return x, img

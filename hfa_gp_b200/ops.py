@@ -11,7 +11,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import ACT_LINEAR, ACT_LRELU, ConvDesc, RenderDesc, check, ptr, stream
+from ._cabi import ACT_LINEAR, ACT_LRELU, ActBwdDesc, ConvDesc, RenderDesc, check, ptr, stream
 
 _desc_cache = {}
 _launches = [0]
@@ -140,17 +140,29 @@ class StyleTable:
         self.gain = (C.c_float * n)(*[l[4] for l in layers])
         self.cins = [l[2] for l in layers]
 
-    def run(self, ws: torch.Tensor):
-        b, num_ws, w_dim = ws.shape
+    def offsets(self, b):
         offs, total = [], 0
         for c in self.cins:
             offs.append(total)
             total += b * c
+        return offs, total
+
+    def run_flat(self, ws: torch.Tensor):
+        """-> (styles_flat [sum_l B*cin_l], offsets): layer l occupies [off_l, off_l + B*cin_l) as [B][cin_l]."""
+        b, num_ws, w_dim = ws.shape
+        offs, total = self.offsets(b)
         off_arr = (C.c_int64 * self.n)(*offs)
         styles = torch.empty(total, device=ws.device, dtype=torch.float32)
         _ok(_cabi.lib().hfagp_styles_fwd(self.n, b, num_ws, w_dim, ptr(ws), self.aw, self.ab, self.cin, self.widx,
                                            self.gain, off_arr, ptr(styles), stream()), 'hfagp_styles_fwd')
-        return [styles[o:o + b * c].view(b, c) for o, c in zip(offs, self.cins)]
+        return styles, offs
+
+    def views(self, flat, offs, b):
+        return [flat[o:o + b * c].view(b, c) for o, c in zip(offs, self.cins)]
+
+    def run(self, ws: torch.Tensor):
+        flat, offs = self.run_flat(ws)
+        return self.views(flat, offs, ws.shape[0])
 
 
 def modulate(w: torch.Tensor, styles: torch.Tensor, demodulate: bool):
@@ -189,8 +201,8 @@ def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s
     return feat, depth, wsum, book
 
 
-def blur(x, pad0, pad1, stride=1, split_out: bool = False):
-    """[1,3,3,1]^2/64 blur of a channels-last activation (fp32 tensor or Split) -> fp32 or Split."""
+def blur(x, pad0, pad1, stride=1, split_out: bool = False, gain: float = 1.0):
+    """gain * [1,3,3,1]^2/64 FIR of a channels-last activation (fp32 tensor or Split) -> fp32 or Split."""
     n, h, wd, c = x.shape
     oh = (h + pad0 + pad1 - 4) // stride + 1
     ow = (wd + pad0 + pad1 - 4) // stride + 1
@@ -202,8 +214,17 @@ def blur(x, pad0, pad1, stride=1, split_out: bool = False):
     else:
         out = torch.empty((n, oh, ow, c), device=x.device, dtype=torch.float32)
         yout = (ptr(out), None, None)
-    _ok(_cabi.lib().hfagp_blur_fwd(n, h, wd, c, pad0, pad1, stride, *xin, *yout, stream()), 'hfagp_blur_fwd')
+    _ok(_cabi.lib().hfagp_blur_fwd(n, h, wd, c, pad0, pad1, stride, gain, *xin, *yout, stream()), 'hfagp_blur_fwd')
     return out
+
+
+def blur_up(dy, h, wd, pad0, pad1, stride, gain: float = 1.0):
+    """Transpose of blur(x[n,h,wd,c], pad0, pad1, stride): dy [n,oh,ow,c] -> dx [n,h,wd,c]."""
+    n, oh, ow, c = dy.shape
+    assert oh == (h + pad0 + pad1 - 4) // stride + 1 and ow == (wd + pad0 + pad1 - 4) // stride + 1
+    dx = torch.empty((n, h, wd, c), device=dy.device, dtype=torch.float32)
+    _ok(_cabi.lib().hfagp_blur_up(n, h, wd, c, pad0, pad1, stride, gain, ptr(dy), ptr(dx), stream()), 'hfagp_blur_up')
+    return dx
 
 
 def linear(x, w, b, w_gain, b_gain):
@@ -318,3 +339,87 @@ def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_strid
                                         None if is_split else ptr(out), ptr(out.hi) if is_split else None,
                                         ptr(out.lo) if is_split else None, stream()), 'hfagp_conv2d_tc_fwd')
     return out
+
+
+# ------------------------------------------------------------------ backward path
+
+def _act_in(y):
+    return (None, ptr(y.hi), ptr(y.lo)) if isinstance(y, Split) else (ptr(y), None, None)
+
+
+def act_bwd(y, g0=None, s0=None, g1=None, s1=None, dimg=None, wrgb=None, srgb=None, dcoef=None, noise=None,
+            noise_gain: float = 0.0, bias=None, residual=None, residual_scale: float = 1.0, act: int = ACT_LRELU,
+            act_gain: float = math.sqrt(2.0), clamp: float = 0.0, post_scale: float = 1.0, out: str = 'f32',
+            ds0=None, ds1=None, dsrgb=None, dbias=None, ddcoef=None):
+    """See ``hfagp_act_bwd`` in include/hfagp.h.  ``out``: 'f32' | 'split' | 'none' selects the form of dz."""
+    if g0 is None and g1 is not None:        # a single incoming gradient always travels in slot 0
+        g0, s0, ds0, g1, s1, ds1 = g1, s1, ds1, None, None, None
+    n, h, wd, c = y.shape
+    d = ActBwdDesc(n, h, wd, c, act, act_gain, clamp, noise_gain, residual_scale if residual is not None else 0.0,
+                   post_scale, dimg.shape[-1] if dimg is not None else 0)
+    dz, dzp = None, (None, None, None)
+    if out == 'split':
+        dz = Split(torch.empty((n, h, wd, c), device=y.device, dtype=torch.bfloat16),
+                   torch.empty((n, h, wd, c), device=y.device, dtype=torch.bfloat16))
+        dzp = (None, ptr(dz.hi), ptr(dz.lo))
+    elif out == 'f32':
+        dz = torch.empty((n, h, wd, c), device=y.device, dtype=torch.float32)
+        dzp = (ptr(dz), None, None)
+    _ok(_cabi.lib().hfagp_act_bwd(C.byref(d), *_act_in(y), ptr(g0), ptr(s0), ptr(g1), ptr(s1), ptr(dimg), ptr(wrgb),
+                                    ptr(srgb), ptr(dcoef), ptr(noise), ptr(bias), ptr(residual), *dzp, ptr(ds0),
+                                    ptr(ds1), ptr(dsrgb), ptr(dbias), ptr(ddcoef), stream()), 'hfagp_act_bwd')
+    return dz
+
+
+def demod_bwd(w2, styles, dcoef, ddcoef, dstyles):
+    """dstyles[n][i] -= styles[n][i] * sum_o ddcoef[n][o] dcoef[n][o]^3 w2[o][i]   (in place)."""
+    cout, cin = w2.shape
+    _ok(_cabi.lib().hfagp_demod_bwd(styles.shape[0], cout, cin, ptr(w2), ptr(styles), ptr(dcoef), ptr(ddcoef),
+                                      ptr(dstyles), stream()), 'hfagp_demod_bwd')
+
+
+def linear_bwd(dy, x, w, w_gain, b_gain, need_dx=True, dw=None, db=None):
+    n, cout = dy.shape
+    cin = w.shape[1]
+    dx = torch.empty((n, cin), device=dy.device, dtype=torch.float32) if need_dx else None
+    _ok(_cabi.lib().hfagp_linear_bwd(n, cin, cout, ptr(dy), ptr(x), ptr(w), w_gain, b_gain, ptr(dx), ptr(dw), ptr(db),
+                                       stream()), 'hfagp_linear_bwd')
+    return dx
+
+
+def conv2d_wgrad(x, dz, taps, dw, *, oh, ow, in_stride=1, scale=1.0):
+    """dw [taps_total][cout][cin] += scale * sum dz (x) x, see ``hfagp_conv2d_wgrad``."""
+    n, h, wd, cin = x.shape
+    cout = dz.shape[-1]
+    taps = tuple(taps)
+    key = ('wg', n, h, wd, cin, cout, oh, ow, in_stride, taps)
+
+    def build():
+        d = ConvDesc()
+        d.batch, d.in_h, d.in_w, d.cin, d.cout = n, h, wd, cin, cout
+        d.oh, d.ow, d.in_stride = oh, ow, in_stride
+        d.out_h, d.out_w, d.out_stride = oh, ow, 1
+        d.ntaps = len(taps)
+        for i, (dy_, dx_, wt) in enumerate(taps):
+            d.dy[i], d.dx[i], d.wtap[i] = dy_, dx_, wt
+        return d
+
+    d = _conv_desc(key, build)
+    _ok(_cabi.lib().hfagp_conv2d_wgrad(C.byref(d), *_act_in(x), *_act_in(dz), scale, ptr(dw), stream()),
+          'hfagp_conv2d_wgrad')
+    return dw
+
+
+class StyleTableBwd:
+    """dstyles (flat, layout of StyleTable.run) -> dws, all layers in one launch."""
+
+    def __init__(self, table: 'StyleTable'):
+        self.t = table
+
+    def run(self, dstyles_flat, offs, batch, num_ws, w_dim):
+        t = self.t
+        dws = torch.zeros((batch, num_ws, w_dim), device=dstyles_flat.device, dtype=torch.float32)
+        off_arr = (C.c_int64 * t.n)(*offs)
+        _ok(_cabi.lib().hfagp_styles_bwd(t.n, batch, num_ws, w_dim, t.aw, t.cin, t.widx, t.gain, off_arr,
+                                           ptr(dstyles_flat), ptr(dws), stream()), 'hfagp_styles_bwd')
+        return dws

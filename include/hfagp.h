@@ -176,14 +176,23 @@ int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes, const flo
                      float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above, int32_t* sort_idx,
                      float* depths_sorted, void* stream);
 
-/* Encoder blur: zero-pad (pad0,pad1) + 4x4 [1,3,3,1]^2/64 true convolution, optional output
- * stride (only the positions a following stride-2 1x1 conv reads).  x[n][h][w][c] ->
- * y[n][oh][ow][c], oh = (h + pad0 + pad1 - 4) / stride + 1.  Input is x (fp32) or the split-bf16
- * pair (x_hi, x_lo); output is y (fp32) or the split pair (y_hi, y_lo) for a tensor-core consumer.
- * Replaces: Blur.forward / upfirdn2d_native (code/networks/encoder3d.py:23-41,59-75). */
-int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad1, int stride, const float* x,
+/* [1,3,3,1]^2/64 FIR, zero-pad (pad0,pad1), optional output stride and gain:
+ *   y[n][oy][ox][c] = gain * sum_{ky,kx} g[ky] g[kx] x[n][oy*stride + ky - pad0][ox*stride + kx - pad0][c]
+ * with oh = (h + pad0 + pad1 - 4) / stride + 1.  Input is x (fp32) or the split-bf16 pair (x_hi, x_lo);
+ * output is y (fp32) or the split pair (y_hi, y_lo) for a tensor-core consumer (split I/O needs c % 4 == 0).
+ * Forward use: Blur.forward / upfirdn2d_native (code/networks/encoder3d.py:23-41,59-75), stride 2 = only the
+ * positions a following stride-2 1x1 conv reads.  Backward uses (the filter is symmetric): transpose of a
+ * stride-1 blur (pads 3-pad0, ...), transpose of the FIR after the up-sampling transposed conv (pads 2,2,
+ * gain 4) and transpose of upsample2d (pads 1,1, stride 2, gain 4). */
+int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad1, int stride, float gain, const float* x,
                    const uint16_t* x_hi, const uint16_t* x_lo, float* y, uint16_t* y_hi, uint16_t* y_lo,
                    void* stream);
+
+/* Transpose of hfagp_blur_fwd (needed for stride 2): dy[n][oh][ow][c] -> dx[n][h][w][c],
+ *   dx[iy][ix] = gain * sum_{ky,kx} g[ky] g[kx] dy[(iy + pad0 - ky)/stride][(ix + pad0 - kx)/stride]  (exact divisions)
+ * Replaces: autograd of Blur + stride-2 conv sampling in the encoder skip path (encoder3d.py:165-171). */
+int hfagp_blur_up(int batch, int h, int w_, int c, int pad0, int pad1, int stride, float gain, const float* dy,
+                  float* dx, void* stream);
 
 /* y[n][o] = (x[n][:] . w[o][:]) * w_gain + b[o] * b_gain   — EqualLinear with activation=None
  * (code/networks/encoder3d.py:128-136) and Weights_3DMM (code/networks/headnerf.py:152-158). */
@@ -194,6 +203,64 @@ int hfagp_linear_fwd(int batch, int cin, int cout, const float* x, const float* 
  * Replaces: diag_embed/matmul/sum + delta in get_latent (code/networks/headnerf.py:96-100). */
 int hfagp_latent_fwd(int batch, int k, int dim, const float* weights, const float* q, const float* delta,
                      float* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward path (training step: Trainer.gen_update, code/trainer_rgb.py:73-98 -> loss.backward()).
+ * Data gradients of the convolutions are hfagp_conv2d[_tc]_fwd calls on transposed weights with mirrored tap
+ * lists; the entries below are what sits between them.  Reductions ACCUMULATE into their outputs (atomics):
+ * the caller zeroes them once per step.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HfagpActBwdDesc {
+  int32_t batch, h, w, c;         /* geometry of the layer output y[n][h][w][c]; c % 4 == 0 */
+  int32_t act;                    /* forward activation, HFAGP_ACT_* */
+  float act_gain, clamp;          /* forward gain / clamp (clamp <= 0: none) */
+  float noise_gain;               /* forward noise gain (only used to rebuild the pre-demod output for ddcoef) */
+  float residual_scale;           /* forward y = (act_out + residual) * residual_scale when residual is given */
+  float post_scale;               /* extra factor on the summed incoming gradient (residual_scale for a merge) */
+  int32_t rgb_k;                  /* channels of dimg for the fused small-ToRGB gradient (<= 4) */
+} HfagpActBwdDesc;
+
+/* Everything between two data-gradient convolutions, for one layer output y = epilogue(conv(x)):
+ *   g      = post_scale * ( g0*s0[n][c] + g1*s1[n][c] + (sum_o dimg[..][o] * wrgb[o][c]) * srgb[n][c] )
+ *   dpre   = g * d(epilogue)/d(pre)            (leaky-ReLU slope, gain, clamp mask, residual merge)
+ *   dz     = dpre * dcoef[n][c]                -> gradient of the raw convolution output (fp32 or split-bf16)
+ *   ds0[n][c]   += sum_pix g0 * y              d(styles) of the consumer whose unscaled data gradient is g0
+ *   ds1[n][c]   += sum_pix g1 * y              (second consumer: the block's ToRGB)
+ *   dsrgb[n][c] += sum_pix (dimg . wrgb) * y   (small ToRGB of the super-resolution blocks, fused)
+ *   dbias[c]    += sum_{n,pix} dpre
+ *   ddcoef[n][c]+= sum_pix dpre * z            z = conv output before demodulation, rebuilt from y
+ * g1/s1, dimg/wrgb/srgb, dcoef, noise, bias, residual and every reduction output may be NULL.
+ * Replaces: autograd of bias_act / modulated_conv2d's x*styles and *dcoefs / ToRGBLayer (eg3d, via
+ * headnerf.py:112) and of FusedLeakyReLU + ResBlock merge (encoder3d.py:7-20,191-198). */
+int hfagp_act_bwd(const HfagpActBwdDesc* desc, const float* y, const uint16_t* y_hi, const uint16_t* y_lo,
+                  const float* g0, const float* s0, const float* g1, const float* s1, const float* dimg,
+                  const float* wrgb, const float* srgb, const float* dcoef, const float* noise,
+                  const float* bias, const float* residual, float* dz, uint16_t* dz_hi, uint16_t* dz_lo,
+                  float* ds0, float* ds1, float* dsrgb, float* dbias, float* ddcoef, void* stream);
+
+/* dws[n][widx[l]][k] += post_gain[l]/sqrt(w_dim) * sum_i dstyles[l][n][i] * A_l[i][k]  for every layer l
+ * (layer table as in hfagp_styles_fwd; dstyles uses the same flat layout as styles). */
+int hfagp_styles_bwd(int nlayers, int batch, int num_ws, int w_dim, const float* const* aff_w_host,
+                     const int32_t* cin_host, const int32_t* widx_host, const float* post_gain_host,
+                     const int64_t* off_host, const float* dstyles, float* dws, void* stream);
+
+/* Demodulation backward: dstyles[n][i] -= styles[n][i] * sum_o ddcoef[n][o] * dcoef[n][o]^3 * w2[o][i],
+ * w2[o][i] = sum_taps w[t][o][i]^2. */
+int hfagp_demod_bwd(int batch, int cout, int cin, const float* w2, const float* styles, const float* dcoef,
+                    const float* ddcoef, float* dstyles, void* stream);
+
+/* EqualLinear backward (forward: hfagp_linear_fwd): dx = (dy . w) * w_gain (written), dw += dy^T x * w_gain,
+ * db += sum_n dy * b_gain.  dx / dw / db may be NULL. */
+int hfagp_linear_bwd(int batch, int cin, int cout, const float* dy, const float* x, const float* w,
+                     float w_gain, float b_gain, float* dx, float* dw, float* db, void* stream);
+
+/* Weight gradient of hfagp_conv2d_fwd (fp32 SIMT, split-K with atomics), same desc / tap lists:
+ *   dw[wtap[t]][co][ci] += scale * sum_{n,my,mx} dz[n][my][mx][co] * x[n][my*in_stride+dy[t]][mx*in_stride+dx[t]][ci]
+ * x and dz may each be fp32 or a split-bf16 pair; dz is dense [n][oh][ow][cout].
+ * Replaces: autograd of F.conv2d w.r.t. weight in EqualConv2d (encoder3d.py:101-103). */
+int hfagp_conv2d_wgrad(const HfagpConvDesc* desc, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
+                       const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, float scale, float* dw,
+                       void* stream);
 
 /* Layout helpers (elementwise, bandwidth-bound): NCHW <-> NHWC for the frame entering the encoder
  * and the image leaving the super-resolution head. */

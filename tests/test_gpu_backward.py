@@ -1,0 +1,193 @@
+"""GPU gradient-parity tests (``-m gpu``): the backward kernels, called through the C ABI, against PyTorch
+autograd of the CPU oracle on the same seeded inputs.  Tolerance: 1e-3 relative (parity_utils.rel_err)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import eg3d_ref, hfagp_ref
+import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 1e-3          # per element, exact-fp32 kernels (precision='fp32')
+GRAD_TOL_TC_L2 = 5e-3    # relative L2, tensor-core path (see parity_utils.rel_l2)
+
+
+def _check_grad(got, want, precision, what):
+    e_max, e_l2 = pu.rel_err(got, want), pu.rel_l2(got, want)
+    print(f'{what} [{precision}]: max-rel {e_max:.3e}  rel-L2 {e_l2:.3e}')
+    if precision == 'fp32':
+        assert e_max < GRAD_TOL, (what, e_max)
+    else:
+        assert e_l2 < GRAD_TOL_TC_L2, (what, e_l2)
+
+
+def _ops():
+    from hfa_gp_b200 import ops
+    return ops
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+# ------------------------------------------------------------------ unit kernels
+
+def test_act_bwd_matches_autograd():
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    n, c, h = 2, 24, 9
+    z = torch.randn(n, c, h, h, generator=g, requires_grad=True)
+    dco = (torch.rand(n, c, generator=g) + 0.5).requires_grad_(True)
+    noise = torch.randn(h, h, generator=g)
+    bias = torch.randn(c, generator=g, requires_grad=True)
+    s0 = torch.rand(n, c, generator=g) + 0.5
+    s1 = torch.rand(n, c, generator=g) + 0.5
+    g0 = torch.randn(n, c, h, h, generator=g)
+    g1 = torch.randn(n, c, h, h, generator=g)
+    pre = z * dco[:, :, None, None] + noise * 0.3 + bias[None, :, None, None]
+    y = (F.leaky_relu(pre, 0.2) * 1.3).clamp(-1.0, 1.0)
+    gtot = g0 * s0[:, :, None, None] + g1 * s1[:, :, None, None]
+    (y * gtot).sum().backward()
+    yc = y.detach()
+    ds0 = torch.zeros(n, c).cuda(); ds1 = torch.zeros(n, c).cuda(); db = torch.zeros(c).cuda(); ddc = torch.zeros(n, c).cuda()
+    for form in ('f32', 'split'):
+        ds0.zero_(); ds1.zero_(); db.zero_(); ddc.zero_()
+        yin = nhwc(yc) if form == 'f32' else ops.split(nhwc(yc))
+        dz = ops.act_bwd(yin, g0=nhwc(g0), s0=s0.cuda(), g1=nhwc(g1), s1=s1.cuda(), dcoef=dco.detach().cuda(),
+                         noise=noise.cuda(), noise_gain=0.3, bias=bias.detach().cuda(), act=1, act_gain=1.3, clamp=1.0,
+                         out=form, ds0=ds0, ds1=ds1, dbias=db, ddcoef=ddc)
+        dz = dz.float() if form == 'split' else dz
+        assert pu.rel_err(pu.to_nchw(dz), z.grad) < 1e-4
+        assert pu.rel_err(db, bias.grad) < 1e-4
+        assert pu.rel_err(ddc, dco.grad) < 1e-3
+        assert pu.rel_err(ds0, (g0 * yc).sum(dim=[2, 3])) < 1e-4
+        assert pu.rel_err(ds1, (g1 * yc).sum(dim=[2, 3])) < 1e-4
+
+
+def test_act_bwd_residual_merge_and_small_torgb():
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    n, c, h = 1, 16, 8
+    pre = torch.randn(n, c, h, h, generator=g, requires_grad=True)
+    skip = torch.randn(n, c, h, h, generator=g)
+    y = (F.leaky_relu(pre, 0.2) * math.sqrt(2) + skip) / math.sqrt(2)
+    dimg = torch.randn(n, 3, h, h, generator=g)
+    wrgb = torch.randn(3, c, generator=g)
+    srgb = torch.rand(n, c, generator=g) + 0.5
+    gy = torch.einsum('nohw,oc->nchw', dimg, wrgb) * srgb[:, :, None, None]
+    (y * gy).sum().backward()
+    dsr = torch.zeros(n, c).cuda()
+    dz = ops.act_bwd(nhwc(y.detach()), dimg=nhwc(dimg), wrgb=wrgb.cuda(), srgb=srgb.cuda(), residual=nhwc(skip),
+                     residual_scale=1 / math.sqrt(2), post_scale=1 / math.sqrt(2), act=1, act_gain=math.sqrt(2),
+                     out='f32', dsrgb=dsr)
+    assert pu.rel_err(pu.to_nchw(dz), pre.grad) < 1e-4
+    ref = (torch.einsum('nohw,oc->nchw', dimg, wrgb) * y.detach()).sum(dim=[2, 3])
+    assert pu.rel_err(dsr, ref) < 1e-4
+
+
+@pytest.mark.parametrize('c', [8, 3])
+def test_blur_transposes(c):
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    k = hfagp_ref.blur_kernel()
+    # stride-2 skip-path blur: transpose via blur_up
+    x = torch.randn(2, c, 12, 12, generator=g, requires_grad=True)
+    y = hfagp_ref.blur_ref(x, k, 1, 1)[:, :, ::2, ::2]
+    gy = torch.randn(y.shape, generator=g)
+    (y * gy).sum().backward()
+    dx = ops.blur_up(nhwc(gy), 12, 12, 1, 1, 2)
+    assert pu.rel_err(pu.to_nchw(dx), x.grad) < 1e-5
+    # stride-1 blur (pad 2,2): its transpose is the same FIR with pads (1,1)
+    x2 = torch.randn(1, c, 9, 9, generator=g, requires_grad=True)
+    y2 = hfagp_ref.blur_ref(x2, k, 2, 2)
+    gy2 = torch.randn(y2.shape, generator=g)
+    (y2 * gy2).sum().backward()
+    assert pu.rel_err(pu.to_nchw(ops.blur(nhwc(gy2), 1, 1)), x2.grad) < 1e-5
+    # upsample2d transpose = stride-2 FIR with pads (1,1), gain 4
+    lo = torch.randn(1, c, 6, 6, generator=g, requires_grad=True)
+    up = eg3d_ref.upsample2d_ref(lo, eg3d_ref.setup_filter())
+    gu = torch.randn(up.shape, generator=g)
+    (up * gu).sum().backward()
+    assert pu.rel_err(pu.to_nchw(ops.blur(nhwc(gu), 1, 1, stride=2, gain=4.0)), lo.grad) < 1e-5
+
+
+def test_linear_and_wgrad():
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 40, generator=g, requires_grad=True)
+    w = torch.randn(24, 40, generator=g, requires_grad=True)
+    b = torch.randn(24, generator=g, requires_grad=True)
+    y = hfagp_ref.equal_linear_ref(x, w, b)
+    gy = torch.randn(y.shape, generator=g)
+    (y * gy).sum().backward()
+    dw = torch.zeros(24, 40).cuda(); db = torch.zeros(24).cuda()
+    dx = ops.linear_bwd(gy.cuda(), x.detach().cuda(), w.detach().cuda(), 1 / math.sqrt(40), 1.0, dw=dw, db=db)
+    assert pu.rel_err(dx, x.grad) < 1e-5 and pu.rel_err(dw, w.grad) < 1e-5 and pu.rel_err(db, b.grad) < 1e-5
+    # conv weight gradient: 3x3 stride 1 pad 1, and 3x3 stride 2 pad 0 (encoder down-conv)
+    for stride, pad, hh in ((1, 1, 10), (2, 0, 11)):
+        xi = torch.randn(2, 16, hh, hh, generator=g)
+        wt = torch.randn(24, 16, 3, 3, generator=g, requires_grad=True)
+        yo = F.conv2d(xi, wt * 0.5, stride=stride, padding=pad)
+        gz = torch.randn(yo.shape, generator=g)
+        (yo * gz).sum().backward()
+        taps = tuple((ky - pad, kx - pad, ky * 3 + kx) for ky in range(3) for kx in range(3))
+        dwp = torch.zeros(9, 24, 16).cuda()
+        ops.conv2d_wgrad(nhwc(xi), nhwc(gz), taps, dwp, oh=yo.shape[2], ow=yo.shape[3], in_stride=stride, scale=0.5)
+        got = dwp.view(3, 3, 24, 16).permute(2, 3, 0, 1)
+        assert pu.rel_err(got, wt.grad) < 1e-4
+        dwp.zero_()
+        ops.conv2d_wgrad(ops.split(nhwc(xi)), ops.split(nhwc(gz)), taps, dwp, oh=yo.shape[2], ow=yo.shape[3],
+                         in_stride=stride, scale=0.5)
+        assert pu.rel_err(dwp.view(3, 3, 24, 16).permute(2, 3, 0, 1), wt.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ generator stages
+
+def _pair(cfg, precision):
+    ref, prod = pu.make_pair(cfg, seed=0)
+    prod.precision = precision
+    return ref, prod
+
+
+@pytest.mark.parametrize('precision', ['tc', 'fp32'])
+def test_backbone_backward(precision):
+    from hfa_gp_b200 import autograd as ag
+    cfg = eg3d_ref.small14_config()
+    ref, prod = _pair(cfg, precision)
+    g = torch.Generator().manual_seed(4)
+    b = 2
+    ws = torch.randn(b, cfg.num_ws, cfg.w_dim, generator=g)
+    ws_r = ws.clone().requires_grad_(True)
+    planes_r = ref.backbone.synthesis(ws_r, noise_mode='const')
+    gp = torch.randn(planes_r.shape, generator=g)
+    (planes_r * gp).sum().backward()
+    ws_g = ws.clone().cuda().requires_grad_(True)
+    planes = ag.BackboneFn.apply(ag.StylesFn.apply(ws_g, prod), prod, 'const', b, None)
+    assert pu.rel_err(pu.to_nchw(planes), planes_r) < pu.REL_TOL
+    (planes * nhwc(gp)).sum().backward()
+    _check_grad(ws_g.grad, ws_r.grad, precision, 'backbone dws')
+
+
+@pytest.mark.parametrize('precision', ['tc', 'fp32'])
+def test_superres_backward(precision):
+    from hfa_gp_b200 import autograd as ag
+    cfg = eg3d_ref.small14_config()
+    ref, prod = _pair(cfg, precision)
+    g = torch.Generator().manual_seed(5)
+    b = 2
+    ws = torch.randn(b, cfg.num_ws, cfg.w_dim, generator=g)
+    feat = torch.randn(b, 32, cfg.nrr, cfg.nrr, generator=g) * 0.5
+    ws_r, feat_r = ws.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    img_r = ref.superresolution(feat_r[:, :3], feat_r, ws_r)
+    gi = torch.randn(img_r.shape, generator=g)
+    (img_r * gi).sum().backward()
+    ws_g = ws.clone().cuda().requires_grad_(True)
+    feat_g = nhwc(feat).requires_grad_(True)
+    img = ag.SuperresFn.apply(feat_g, ag.StylesFn.apply(ws_g, prod), prod, b, None)
+    assert pu.rel_err(pu.to_nchw(img), img_r) < pu.REL_TOL
+    (img * nhwc(gi)).sum().backward()
+    _check_grad(pu.to_nchw(feat_g.grad), feat_r.grad, precision, 'superres dfeat')
+    _check_grad(ws_g.grad, ws_r.grad, precision, 'superres dws')
