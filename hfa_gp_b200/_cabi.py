@@ -23,7 +23,7 @@ SYMBOLS = [
     'hfagp_blur_fwd', 'hfagp_linear_fwd', 'hfagp_latent_fwd', 'hfagp_nchw_to_nhwc',
     'hfagp_nhwc_to_nchw', 'hfagp_conv2d_tc_fwd', 'hfagp_split_bf16', 'hfagp_modulate_split_fwd',
     'hfagp_blur_up', 'hfagp_act_bwd', 'hfagp_styles_bwd', 'hfagp_demod_bwd', 'hfagp_linear_bwd',
-    'hfagp_conv2d_wgrad',
+    'hfagp_conv2d_wgrad', 'hfagp_render_bwd',
 ]
 
 
@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     l.hfagp_styles_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     l.hfagp_modulate_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_render_fwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
+    l.hfagp_render_bwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 9
     l.hfagp_blur_fwd.argtypes = [i32] * 7 + [f32] + [vp] * 7
     l.hfagp_blur_up.argtypes = [i32] * 7 + [f32, vp, vp, vp]
     l.hfagp_act_bwd.argtypes = [C.POINTER(ActBwdDesc)] + [vp] * 23

@@ -179,3 +179,26 @@ class SuperresFn(torch.autograd.Function):
         dfeat[..., :3] += drgb_lo
         ctx.recs = ctx.feat = None
         return dfeat, dflat, None, None, None
+
+
+class RenderFn(torch.autograd.Function):
+    """tri-planes [B,R,R,96] -> (feature image [B,r,r,32], depth [B,r*r], weight sum [B,r*r]); gradient to the
+    planes only (camera, depths and the frozen decoder carry none)."""
+
+    @staticmethod
+    def forward(ctx, planes, gen, c, jitter, u_fine, depth_range, kw, bookkeeping):
+        pk = gen._ensure_packed()
+        feat, depth, wsum, book = ops.render(planes, c, pk['mlp'], pk['lin'], jitter, u_fine, depth_range,
+                                             bookkeeping=bookkeeping, **kw)
+        ctx.gen, ctx.kw, ctx.book = gen, kw, book
+        ctx.save_for_backward(planes, c, jitter, u_fine if u_fine is not None else torch.empty(0, device=planes.device))
+        ctx.mark_non_differentiable(depth, wsum)
+        return feat, depth, wsum
+
+    @staticmethod
+    def backward(ctx, dfeat, _ddepth, _dwsum):
+        planes, c, jitter, u_fine = ctx.saved_tensors
+        pk = ctx.gen._ensure_packed()
+        dplanes = ops.render_bwd(planes, c, pk['mlp'], pk['lin'], jitter, u_fine if u_fine.numel() else None,
+                                 dfeat.contiguous(), **ctx.kw)
+        return dplanes, None, None, None, None, None, None, None

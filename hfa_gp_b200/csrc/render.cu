@@ -36,6 +36,10 @@ constexpr int MLP_FLOATS = RH * RC + RH + RO * RH + RO;  // 4257
 constexpr int W0F_U2 = 8 * 2 * 2 * 32;   // [ntile 8][kstep 2][hi|lo][lane] uint2
 constexpr int W1F_U2 = 5 * 4 * 2 * 32;   // [ntile 5][kstep 4][hi|lo][lane] uint2
 constexpr int WEIGHT_BYTES = (W0F_U2 + W1F_U2) * 8 + (RH + 40) * 4;
+// backward adds the transposed operands: dh = dout . W1 (K = 48 padded outputs, N = 64) and df = dpre . W0 (K = 64, N = 32)
+constexpr int W1T_U2 = 8 * 3 * 2 * 32;   // [ntile 8][kstep 3][hi|lo][lane] uint2
+constexpr int W0T_U2 = 4 * 4 * 2 * 32;   // [ntile 4][kstep 4][hi|lo][lane] uint2
+constexpr int WEIGHT_BYTES_BWD = ((WEIGHT_BYTES + 15) & ~15) + (W1T_U2 + W0T_U2) * 8;
 
 struct RenderParams {
   HfagpRenderDesc d;
@@ -54,6 +58,8 @@ struct RenderParams {
   int32_t* above;
   int32_t* sort_idx;
   float* depths_sorted;
+  const float* dfeat;     // backward only: gradient of feat [n][res][res][32]
+  float* dplanes;         // backward only: gradient of planes (accumulated with red.global.add)
 };
 
 struct Tap {
@@ -69,9 +75,10 @@ __host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
 //   dep, sig, sdep, ssig [Tp] fp32 ; order [Tp] u8 ; cdf [S+2], zmid [S] fp32 ; taps [16*12]
 // wts (march weights) aliases sdep during the coarse pass (sdep is first written by the sort) and dep during the
 // final pass (unsorted depths are dead after the sort).
-__host__ __device__ inline size_t render_warp_bytes(int S, int SF) {
+__host__ __device__ inline size_t render_warp_bytes(int S, int SF, bool bwd = false) {
   const size_t Tp = (size_t)(S + SF + 3) & ~(size_t)3;   // per-sample arrays padded so each stays 16 B aligned
   size_t b = (size_t)(round16(S) + round16(SF)) * RC * 2 + TILE * RC * 4 + 4 * Tp * 4 + Tp + (size_t)(2 * S + 2) * 4;
+  if (bwd) b += 5 * Tp * 4 + 32 * 4;     // tarr (T_k), aarr (alpha_k), dsg (d sigma), pj (dfeat . colour), final weights + dfeat row
   b = (b + 15) & ~(size_t)15;
   return b + TILE * 12 * sizeof(Tap);
 }
@@ -79,7 +86,8 @@ __host__ __device__ inline size_t render_warp_bytes(int S, int SF) {
 // exclusive product scan over n values held as v(k) for k = lane + 32q; returns weights into wts[k] = alpha*T
 // and the sum of weights.  alpha(k) supplied through a lambda.
 template <typename FA>
-__device__ __forceinline__ float march_weights(int nint, int lane, float* wts, FA alpha_of) {
+__device__ __forceinline__ float march_weights(int nint, int lane, float* wts, FA alpha_of, float* tarr = nullptr,
+                                               float* aarr = nullptr) {
   float carry = 1.f, wsum = 0.f;
   for (int base = 0; base < nint; base += 32) {
     int k = base + lane;
@@ -95,6 +103,7 @@ __device__ __forceinline__ float march_weights(int nint, int lane, float* wts, F
     if (lane == 0) excl = 1.f;
     float w = a * (carry * excl);
     if (k < nint) wts[k] = w;
+    if (tarr && k < nint) { tarr[k] = carry * excl; aarr[k] = a; }
     wsum += k < nint ? w : 0.f;
     carry *= __shfl_sync(0xffffffffu, incl, 31);
   }
@@ -139,7 +148,14 @@ __device__ __forceinline__ int colqx(int r, int cw) { return cw ^ (((r >> 1) & 3
 constexpr float QSCALE = 65535.f;
 constexpr float QSTEP = 1.002f / 65535.f;
 
-__global__ void __launch_bounds__(R_WARPS * 32, 1) render_fwd_kernel(const RenderParams p) {
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// BWD = false: the forward renderer.  BWD = true: recompute the forward per ray (same code), then back-propagate
+// d(feat) through the composite / march / decoder MLP / bilinear gather into d(planes) (8 rays per CTA).
+template <bool BWD>
+__global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(const RenderParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const HfagpRenderDesc& d = p.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -183,12 +199,43 @@ __global__ void __launch_bounds__(R_WARPS * 32, 1) render_fwd_kernel(const Rende
     }
     for (int i = threadIdx.x; i < RH; i += blockDim.x) b0s[i] = __ldg(B0 + i);
     for (int i = threadIdx.x; i < 40; i += blockDim.x) b1s[i] = i < 32 ? __ldg(B1 + i + 1) : (i == 32 ? __ldg(B1) : 0.f);
+    if constexpr (BWD) {
+      uint2* w1t = reinterpret_cast<uint2*>(smem_raw + ((WEIGHT_BYTES + 15) & ~15));
+      uint2* w0t = w1t + W1T_U2;
+      // dh[s][j] = sum_op dout[s][op] W1[perm(op)][j]:  B(k = op, n = j)
+      for (int i = threadIdx.x; i < 8 * 3 * 32; i += blockDim.x) {
+        const int l = i & 31, ks = (i >> 5) % 3, jn = i / 96;
+        const int nn = 8 * jn + (l >> 2), k0 = 16 * ks + 2 * (l & 3);
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int op = k0 + (e & 1) + (e >> 1) * 8;
+          const int o = op < 32 ? op + 1 : (op == 32 ? 0 : -1);
+          v[e] = o >= 0 ? __ldg(W1 + o * RH + nn) : 0.f;
+        }
+        uint2 hi, lo;
+        split_pair(v[0], v[1], hi.x, lo.x);
+        split_pair(v[2], v[3], hi.y, lo.y);
+        w1t[((jn * 3 + ks) * 2 + 0) * 32 + l] = hi;
+        w1t[((jn * 3 + ks) * 2 + 1) * 32 + l] = lo;
+      }
+      // df[s][c] = sum_j dpre[s][j] W0[j][c]:  B(k = j, n = c)
+      for (int i = threadIdx.x; i < 4 * 4 * 32; i += blockDim.x) {
+        const int l = i & 31, ks = (i >> 5) & 3, cn = i >> 7;
+        const int nn = 8 * cn + (l >> 2), k0 = 16 * ks + 2 * (l & 3);
+        uint2 hi, lo;
+        split_pair(__ldg(W0 + k0 * RC + nn), __ldg(W0 + (k0 + 1) * RC + nn), hi.x, lo.x);
+        split_pair(__ldg(W0 + (k0 + 8) * RC + nn), __ldg(W0 + (k0 + 9) * RC + nn), hi.y, lo.y);
+        w0t[((cn * 4 + ks) * 2 + 0) * 32 + l] = hi;
+        w0t[((cn * 4 + ks) * 2 + 1) * 32 + l] = lo;
+      }
+    }
   }
   __syncthreads();
 
   // ---- per-warp scratch
-  const size_t wbytes = render_warp_bytes(S, SF);
-  uint8_t* wbase = smem_raw + ((WEIGHT_BYTES + 15) & ~15) + (size_t)warp * wbytes;
+  const size_t wbytes = render_warp_bytes(S, SF, BWD);
+  uint8_t* wbase = smem_raw + (BWD ? WEIGHT_BYTES_BWD : ((WEIGHT_BYTES + 15) & ~15)) + (size_t)warp * wbytes;
   const int S16 = round16(S);
   const int crows = S16 + round16(SF);
   const int Tp = (T + 3) & ~3;
@@ -201,6 +248,12 @@ __global__ void __launch_bounds__(R_WARPS * 32, 1) render_fwd_kernel(const Rende
   uint8_t* order = reinterpret_cast<uint8_t*>(ssig + Tp);
   float* cdf = reinterpret_cast<float*>(order + Tp);
   float* zmid = cdf + (S + 2);
+  float* tarr = zmid + S;          // backward only (5 * Tp + 32 floats)
+  float* aarr = tarr + Tp;
+  float* dsg = aarr + Tp;
+  float* pj = dsg + Tp;
+  float* wts_b = pj + Tp;
+  float* dfs = wts_b + Tp;
   Tap* taps = reinterpret_cast<Tap*>(wbase + wbytes - TILE * 12 * sizeof(Tap));
 
   const int PW = d.plane_w, PH = d.plane_h;
@@ -246,11 +299,8 @@ __global__ void __launch_bounds__(R_WARPS * 32, 1) render_fwd_kernel(const Rende
       dep[s] = __ldg(p.lin + s) + __ldg(p.jitter + (size_t)ray * S + s) * d.delta;
     __syncwarp();
 
-    // ---- gather + decode the samples [s_begin, s_end) whose depths are in dep[], 16 at a time
-    auto shade = [&](int s_begin, int s_end, int crow_begin) {
-      for (int base = s_begin; base < s_end; base += TILE) {
-        const int crow0 = crow_begin + (base - s_begin);          // colour-buffer row of the tile's first sample
-        const int cnt = min(TILE, s_end - base);
+    // ---- gather the features of samples [base, base+cnt) (depths in dep[]) into ftile rows 0..cnt-1
+    auto gather_tile = [&](int base, int cnt) {
         // phase A: lanes 0-15 build the taps of planes 0 and 1, lanes 16-31 those of plane 2
         {
           const int sl = lane & 15;
@@ -324,22 +374,33 @@ __global__ void __launch_bounds__(R_WARPS * 32, 1) render_fwd_kernel(const Rende
           }
         }
         __syncwarp();
-
-        // phase C: decoder MLP on the 16-row tile [base, base+16) with mma.sync (rows beyond cnt are don't-care)
-        const int r0 = g, r1 = g + 8;
-        uint32_t ah[2][4], al[2][4];
+    };
+    // feature tile -> split-bf16 MMA A fragments of layer 1 (rows g, g+8; k-steps = channels 0-15, 16-31)
+    auto feature_frags = [&](uint32_t (&ah)[2][4], uint32_t (&al)[2][4]) {
+      const int r0 = g, r1 = g + 8;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int c0 = 16 * s + 2 * t4;
-          const float2 f00 = *reinterpret_cast<const float2*>(ftile + r0 * RC + colx(r0, c0));
-          const float2 f10 = *reinterpret_cast<const float2*>(ftile + r1 * RC + colx(r1, c0));
-          const float2 f01 = *reinterpret_cast<const float2*>(ftile + r0 * RC + colx(r0, c0 + 8));
-          const float2 f11 = *reinterpret_cast<const float2*>(ftile + r1 * RC + colx(r1, c0 + 8));
-          split_pair(f00.x, f00.y, ah[s][0], al[s][0]);
-          split_pair(f10.x, f10.y, ah[s][1], al[s][1]);
-          split_pair(f01.x, f01.y, ah[s][2], al[s][2]);
-          split_pair(f11.x, f11.y, ah[s][3], al[s][3]);
-        }
+      for (int s = 0; s < 2; ++s) {
+        const int c0 = 16 * s + 2 * t4;
+        const float2 f00 = *reinterpret_cast<const float2*>(ftile + r0 * RC + colx(r0, c0));
+        const float2 f10 = *reinterpret_cast<const float2*>(ftile + r1 * RC + colx(r1, c0));
+        const float2 f01 = *reinterpret_cast<const float2*>(ftile + r0 * RC + colx(r0, c0 + 8));
+        const float2 f11 = *reinterpret_cast<const float2*>(ftile + r1 * RC + colx(r1, c0 + 8));
+        split_pair(f00.x, f00.y, ah[s][0], al[s][0]);
+        split_pair(f10.x, f10.y, ah[s][1], al[s][1]);
+        split_pair(f01.x, f01.y, ah[s][2], al[s][2]);
+        split_pair(f11.x, f11.y, ah[s][3], al[s][3]);
+      }
+    };
+
+    // ---- gather + decode the samples [s_begin, s_end) whose depths are in dep[], 16 at a time
+    auto shade = [&](int s_begin, int s_end, int crow_begin) {
+      for (int base = s_begin; base < s_end; base += TILE) {
+        const int crow0 = crow_begin + (base - s_begin);          // colour-buffer row of the tile's first sample
+        const int cnt = min(TILE, s_end - base);
+        gather_tile(base, cnt);
+        // decoder MLP on the 16-row tile [base, base+16) with mma.sync (rows beyond cnt are don't-care)
+        uint32_t ah[2][4], al[2][4];
+        feature_frags(ah, al);
         // layer 1 two n-tiles at a time: after softplus their accumulator fragments are exactly the A fragment of
         // layer-2 k-step s, so the hidden layer never leaves registers (and only 8 of its 32 values are live)
         float o2[5][4];
@@ -519,12 +580,203 @@ __global__ void __launch_bounds__(R_WARPS * 32, 1) render_fwd_kernel(const Rende
     __syncwarp();
 
     // ---- final march
-    float* wts = dep;                              // unsorted depths are dead after the sort
+    float* wts = BWD ? wts_b : dep;                // forward: unsorted depths are dead after the sort; backward re-gathers
     const float wtot = march_weights(T - 1, lane, wts, [&](int k) {
       float sm = softplus_t(0.5f * (ssig[k] + ssig[k + 1]) - 1.f);
       return 1.f - expf(-(sm * (sdep[k + 1] - sdep[k])));
-    });
+    }, BWD ? tarr : nullptr, BWD ? aarr : nullptr);
     __syncwarp();
+    if constexpr (BWD) {
+      // ================= backward of this ray =================
+      // feat = 2 rgb - 1, rgb = sum_k w_k (c_k + c_{k+1})/2, w_k = alpha_k T_k, T_k = prod_{m<k} (1 - alpha_m + 1e-10),
+      // alpha_k = 1 - exp(-softplus(sigma_mid_k - 1) delta_k).  Sample positions carry no gradient (upstream
+      // computes the importance samples under no_grad); depth and weight-sum outputs are not differentiated.
+      const int shift = S16 - S;
+      auto crow_of = [&](int j) { return j < S ? j : j + shift; };
+      dfs[lane] = 2.f * __ldg(p.dfeat + (size_t)ray * RC + lane);
+      // omega_j (colour weights, storage order) -> sig[]
+      for (int k = lane; k < T; k += 32)
+        sig[order[k]] = 0.5f * ((k > 0 ? wts[k - 1] : 0.f) + (k < T - 1 ? wts[k] : 0.f));
+      __syncwarp();
+      // P_j = dfeat2 . colour_j  (lane = sample)
+      for (int j = lane; j < T; j += 32) {
+        const int cr = crow_of(j);
+        float acc = 0.f;
+#pragma unroll 4
+        for (int cw = 0; cw < 16; ++cw) {
+          const uint32_t wq = colq[cr * 16 + colqx(cr, cw)];
+          acc = fmaf(dfs[2 * cw], fmaf((float)(wq & 0xffffu), QSTEP, -0.001f), acc);
+          acc = fmaf(dfs[2 * cw + 1], fmaf((float)(wq >> 16), QSTEP, -0.001f), acc);
+        }
+        pj[j] = acc;
+      }
+      __syncwarp();
+      // d sigma_mid per interval (lane = interval), suffix sums R_k = sum_{m>k} G_m w_m by a forward scan
+      float total = 0.f;
+      for (int k = lane; k < T - 1; k += 32) total = fmaf(0.5f * (pj[order[k]] + pj[order[k + 1]]), wts[k], total);
+      total = warp_sum(total);
+      float carry = 0.f;
+      for (int base = 0; base < T - 1; base += 32) {
+        const int k = base + lane;
+        const bool ok = k < T - 1;
+        const float G = ok ? 0.5f * (pj[order[k]] + pj[order[k + 1]]) : 0.f;
+        float v = ok ? G * wts[k] : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float t = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += t;
+        }
+        const float R = total - (carry + v);
+        carry += __shfl_sync(0xffffffffu, v, 31);
+        if (ok) {
+          const float a = aarr[k];
+          const float dalpha = G * tarr[k] - R / (1.f - a + 1e-10f);
+          const float dsp = dalpha * (sdep[k + 1] - sdep[k]) * (1.f - a);
+          const float xm = 0.5f * (ssig[k] + ssig[k + 1]) - 1.f;
+          tarr[k] = dsp / (1.f + expf(-xm));              // d sigma_mid_k (softplus' = sigmoid); overwrites T_k
+        }
+      }
+      __syncwarp();
+      for (int k = lane; k < T; k += 32)
+        dsg[order[k]] = 0.5f * ((k > 0 ? tarr[k - 1] : 0.f) + (k < T - 1 ? tarr[k] : 0.f));
+      __syncwarp();
+
+      const uint2* w1t = reinterpret_cast<const uint2*>(smem_raw + ((WEIGHT_BYTES + 15) & ~15));
+      const uint2* w0t = w1t + W1T_U2;
+      float dfv[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        dfv[ks][0] = dfs[16 * ks + 2 * t4]; dfv[ks][1] = dfs[16 * ks + 2 * t4 + 1];
+        dfv[ks][2] = dfs[16 * ks + 2 * t4 + 8]; dfv[ks][3] = dfs[16 * ks + 2 * t4 + 9];
+      }
+      float* dpl = p.dplanes + (size_t)n * PH * PW * texel_stride;
+
+      auto bwd_tiles = [&](int s_begin, int s_end, int crow_begin) {
+        for (int base = s_begin; base < s_end; base += TILE) {
+          const int crow0 = crow_begin + (base - s_begin);
+          const int cnt = min(TILE, s_end - base);
+          gather_tile(base, cnt);
+          uint32_t ah[2][4], al[2][4];
+          feature_frags(ah, al);
+          // layer 1 forward again: h = softplus(pre), all 8 n-tiles stay in registers
+          float h[8][4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 bb = *reinterpret_cast<const float2*>(b0s + 8 * j + 2 * t4);
+            h[j][0] = bb.x; h[j][1] = bb.y; h[j][2] = bb.x; h[j][3] = bb.y;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint2 bh = w0f[((j * 2 + ks) * 2 + 0) * 32 + lane];
+              const uint2 bl = w0f[((j * 2 + ks) * 2 + 1) * 32 + lane];
+              mma_bf16(h[j], ah[ks], bh);
+              mma_bf16(h[j], al[ks], bh);
+              mma_bf16(h[j], ah[ks], bl);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[j][e] = softplus_fast(h[j][e]);
+          }
+          // d(out) rows of this thread: samples base+g and base+g+8 (zero beyond cnt)
+          const bool v0 = g < cnt, v1 = g + 8 < cnt;
+          const float om0 = v0 ? sig[base + g] : 0.f, om1 = v1 ? sig[base + g + 8] : 0.f;
+          const float ds0 = v0 ? dsg[base + g] : 0.f, ds1 = v1 ? dsg[base + g + 8] : 0.f;
+          const int q0 = crow0 + g, q1 = crow0 + g + 8;
+          float dh[8][4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { dh[j][0] = dh[j][1] = dh[j][2] = dh[j][3] = 0.f; }
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks) {
+            float av[8];
+            if (ks < 2) {
+              // colour columns: d(out) = omega * dfeat2 * 1.002 * s (1 - s), s = q / 65535
+              const uint32_t w00 = colq[q0 * 16 + colqx(q0, 8 * ks + t4)], w10 = colq[q1 * 16 + colqx(q1, 8 * ks + t4)];
+              const uint32_t w01 = colq[q0 * 16 + colqx(q0, 8 * ks + t4 + 4)], w11 = colq[q1 * 16 + colqx(q1, 8 * ks + t4 + 4)];
+              auto dsg_ = [](uint32_t q16) { const float sg = (float)q16 * (1.f / 65535.f); return 1.002f * sg * (1.f - sg); };
+              av[0] = om0 * dfv[ks][0] * dsg_(w00 & 0xffffu); av[1] = om0 * dfv[ks][1] * dsg_(w00 >> 16);
+              av[2] = om1 * dfv[ks][0] * dsg_(w10 & 0xffffu); av[3] = om1 * dfv[ks][1] * dsg_(w10 >> 16);
+              av[4] = om0 * dfv[ks][2] * dsg_(w01 & 0xffffu); av[5] = om0 * dfv[ks][3] * dsg_(w01 >> 16);
+              av[6] = om1 * dfv[ks][2] * dsg_(w11 & 0xffffu); av[7] = om1 * dfv[ks][3] * dsg_(w11 >> 16);
+            } else {
+              // permuted output 32 is sigma; outputs 33..47 are padding
+#pragma unroll
+              for (int e = 0; e < 8; ++e) av[e] = 0.f;
+              if (t4 == 0) { av[0] = ds0; av[2] = ds1; }
+            }
+            uint32_t a2h[4], a2l[4];
+            split_pair(av[0], av[1], a2h[0], a2l[0]);
+            split_pair(av[2], av[3], a2h[1], a2l[1]);
+            split_pair(av[4], av[5], a2h[2], a2l[2]);
+            split_pair(av[6], av[7], a2h[3], a2l[3]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint2 bh = w1t[((j * 3 + ks) * 2 + 0) * 32 + lane];
+              const uint2 bl = w1t[((j * 3 + ks) * 2 + 1) * 32 + lane];
+              mma_bf16(dh[j], a2h, bh);
+              mma_bf16(dh[j], a2l, bh);
+              mma_bf16(dh[j], a2h, bl);
+            }
+          }
+          // d(pre) = dh * softplus'(pre) = dh * (1 - exp(-h)); then df = d(pre) . W0
+          float df[4][4];
+#pragma unroll
+          for (int cn = 0; cn < 4; ++cn) { df[cn][0] = df[cn][1] = df[cn][2] = df[cn][3] = 0.f; }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            float dp[2][4];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                dp[jj][e] = dh[2 * ks + jj][e] * (1.f - ex2f(-1.4426950408889634f * h[2 * ks + jj][e]));
+            uint32_t a1h[4], a1l[4];
+            split_pair(dp[0][0], dp[0][1], a1h[0], a1l[0]);
+            split_pair(dp[0][2], dp[0][3], a1h[1], a1l[1]);
+            split_pair(dp[1][0], dp[1][1], a1h[2], a1l[2]);
+            split_pair(dp[1][2], dp[1][3], a1h[3], a1l[3]);
+#pragma unroll
+            for (int cn = 0; cn < 4; ++cn) {
+              const uint2 bh = w0t[((cn * 4 + ks) * 2 + 0) * 32 + lane];
+              const uint2 bl = w0t[((cn * 4 + ks) * 2 + 1) * 32 + lane];
+              mma_bf16(df[cn], a1h, bh);
+              mma_bf16(df[cn], a1l, bh);
+              mma_bf16(df[cn], a1h, bl);
+            }
+          }
+          __syncwarp();      // every lane holds its feature fragments; the tile can now carry d(feature) / 3
+          {
+            const float third = 1.f / 3.f;
+#pragma unroll
+            for (int cn = 0; cn < 4; ++cn) {
+              const int c0 = 8 * cn + 2 * t4;
+              *reinterpret_cast<float2*>(ftile + g * RC + colx(g, c0)) = make_float2(df[cn][0] * third, df[cn][1] * third);
+              *reinterpret_cast<float2*>(ftile + (g + 8) * RC + colx(g + 8, c0)) = make_float2(df[cn][2] * third, df[cn][3] * third);
+            }
+          }
+          __syncwarp();
+          // scatter: lane = (sample, channel quad); one 16 B reduction per tap
+          {
+            const int sq = lane >> 3, cg = lane & 7;
+            char* lbw = reinterpret_cast<char*>(dpl) + cg * 16;
+            for (int q = 0; q < cnt; q += 4) {
+              const int sl = q + sq;
+              if (sl < cnt) {
+                const float4 d4 = *reinterpret_cast<const float4*>(ftile + sl * RC + colx(sl, 4 * cg));
+                const Tap* tp = taps + sl * 12;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                  const Tap rec = tp[k];
+                  if (rec.w != 0.f)
+                    red_add_v4(reinterpret_cast<float*>(lbw + rec.off), rec.w * d4.x, rec.w * d4.y, rec.w * d4.z, rec.w * d4.w);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      };
+      bwd_tiles(0, S, 0);
+      if (SF > 0) bwd_tiles(S, T, S16);
+      continue;
+    }
     float dacc = 0.f;
     for (int k = lane; k < T - 1; k += 32) dacc = fmaf(wts[k], 0.5f * (sdep[k] + sdep[k + 1]), dacc);
     dacc = warp_sum(dacc);
@@ -596,7 +848,8 @@ extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes
   HFAGP_CHECK_ARG(d.s_fine == 0 || u_fine, "render_fwd: u_fine required when s_fine > 0");
   HFAGP_CHECK_ARG(!inds || (below && above), "render_fwd: inds/below/above go together");
   HFAGP_CHECK_ARG((long long)d.plane_h * d.plane_w * 96 < (1ll << 31), "render_fwd: plane too large for 32-bit tap offsets");
-  RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, depth_range, feat, depth, wsum, inds, below, above, sort_idx, depths_sorted};
+  RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, depth_range, feat, depth, wsum, inds, below, above, sort_idx, depths_sorted,
+                 nullptr, nullptr};
   int nwarps = R_WARPS;
   size_t smem = ((WEIGHT_BYTES + 15) & ~15) + nwarps * render_warp_bytes(d.s_coarse, d.s_fine);
   if (smem > 227 * 1024) {
@@ -604,7 +857,7 @@ extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes
     smem = ((WEIGHT_BYTES + 15) & ~15) + nwarps * render_warp_bytes(d.s_coarse, d.s_fine);
   }
   static std::once_flag attr_once;   // opt in to the full 227 KB once; not repeated on the (graph-captured) hot path
-  std::call_once(attr_once, [] { cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   HFAGP_CHECK_ARG(smem <= 227 * 1024, "render_fwd: shared memory need exceeds 227 KB");
   static int cached_sms = 0;
   if (!cached_sms) {
@@ -615,7 +868,34 @@ extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes
   }
   const long long strips = (long long)d.batch * ((d.res + nwarps - 1) / nwarps) * d.res;
   const int blocks = (int)(strips < cached_sms ? strips : cached_sms);   // persistent: one CTA per SM
-  render_fwd_kernel<<<blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(p);
-  HFAGP_CHECK_LAUNCH("render_fwd_kernel");
+  render_kernel<false><<<blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(p);
+  HFAGP_CHECK_LAUNCH("render_kernel<fwd>");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                                const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
+                                float* dplanes, void* stream) {
+  HFAGP_CHECK_ARG(desc && planes && c && mlp && lin && jitter && dfeat && dplanes, "render_bwd: null pointer");
+  const HfagpRenderDesc& d = *desc;
+  HFAGP_CHECK_ARG(d.batch > 0 && d.res > 0 && d.plane_h > 0 && d.plane_w > 0, "render_bwd: bad dims");
+  HFAGP_CHECK_ARG(d.s_coarse >= 4 && d.s_coarse <= 64 && d.s_fine >= 0 && d.s_fine <= 64,
+                  "render_bwd: samples per ray must be 4..64 coarse, 0..64 fine");
+  HFAGP_CHECK_ARG(d.s_fine == 0 || u_fine, "render_bwd: u_fine required when s_fine > 0");
+  HFAGP_CHECK_ARG((long long)d.plane_h * d.plane_w * 96 < (1ll << 31), "render_bwd: plane too large for 32-bit tap offsets");
+  RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                 nullptr, dfeat, dplanes};
+  const int nwarps = 8;
+  const size_t smem = WEIGHT_BYTES_BWD + nwarps * render_warp_bytes(d.s_coarse, d.s_fine, true);
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  HFAGP_CHECK_ARG(smem <= 227 * 1024, "render_bwd: shared memory need exceeds 227 KB");
+  int dev = 0, sms = 148;
+  HFAGP_CUDA(cudaGetDevice(&dev));
+  HFAGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long strips = (long long)d.batch * ((d.res + nwarps - 1) / nwarps) * d.res;
+  const int blocks = (int)(strips < sms ? strips : sms);
+  render_kernel<true><<<blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(p);
+  HFAGP_CHECK_LAUNCH("render_kernel<bwd>");
   return HFAGP_OK;
 }

@@ -375,8 +375,10 @@ class TriPlaneGenerator(nn.Module):
         ``tap`` (tests only) collects channels-last intermediates.
         """
         cfg = self.cfg
-        if torch.is_grad_enabled() and (ws.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise HfagpError('generator backward is not implemented in this build; call under torch.no_grad()')
+        train = torch.is_grad_enabled() and ws.requires_grad
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise HfagpError('gradients w.r.t. the generator weights (the post-tune_iter regime, train_rgb.py:132-134) '
+                             'are not implemented in this build: keep the generator frozen (requires_grad_(False))')
         if not ws.is_cuda:
             raise HfagpError('TriPlaneGenerator.synthesis needs CUDA tensors (there is no CPU fallback)')
         if ws.dim() != 3 or ws.shape[1] != cfg.num_ws or ws.shape[2] != cfg.w_dim:
@@ -384,6 +386,8 @@ class TriPlaneGenerator(nn.Module):
         if c.dim() != 2 or c.shape[1] != cfg.c_dim or c.shape[0] != ws.shape[0]:
             raise HfagpError(f'c must be [B,{cfg.c_dim}], got {tuple(c.shape)}')
         res = neural_rendering_resolution or self.neural_rendering_resolution
+        if train:
+            return self._synthesis_train(ws, c, res, noise_mode, jitter_coarse, u_fine, tap)
         ws = ws.detach().float().contiguous()
         c = c.detach().float().contiguous()
         b = ws.shape[0]
@@ -446,6 +450,41 @@ class TriPlaneGenerator(nn.Module):
             t4 = mark()
             pe.extend([('backbone', t0, t1), ('render', t2, t3), ('superres', t3, t4), ('synthesis', t0, t4)])
         return out
+
+    def _render_inputs(self, b, res, device, jitter_coarse, u_fine, pk):
+        cfg = self.cfg
+        rays = res * res
+        s, sf = cfg.depth_res, cfg.depth_res_importance
+        if jitter_coarse is None and u_fine is None and self.fixed_draws is not None:
+            jitter_coarse, u_fine = self.fixed_draws
+        if jitter_coarse is None:
+            jitter_coarse = torch.rand((b, rays, s, 1), device=device)
+        if u_fine is None and sf > 0:
+            u_fine = torch.rand((b * rays, sf), device=device)
+        jitter = jitter_coarse.detach().reshape(b, rays, s).float().contiguous()
+        delta = (cfg.ray_end - cfg.ray_start) / (s - 1)
+        lin = pk['lin']
+        depth_range = torch.stack([lin[0] + jitter[:, :, 0].min() * delta, lin[-1] + jitter[:, :, -1].max() * delta]).float().contiguous()
+        kw = dict(res=res, s_coarse=s, s_fine=sf, delta=delta, box_scale=2.0 / cfg.box_warp)
+        return jitter, (u_fine.detach().float().contiguous() if sf > 0 else None), depth_range, kw
+
+    def _synthesis_train(self, ws, c, res, noise_mode, jitter_coarse, u_fine, tap):
+        """synthesis() with autograd: same kernels, each stage an autograd.Function (hfa_gp_b200/autograd.py)
+        that keeps the activations it produced and walks them backwards.  Gradient reaches ``ws`` only."""
+        from . import autograd as ag
+        b = ws.shape[0]
+        self._batch = b
+        pk = self._ensure_packed()
+        c = c.detach().float().contiguous()
+        styles_flat = ag.StylesFn.apply(ws.float().contiguous(), self)
+        planes = ag.BackboneFn.apply(styles_flat, self, noise_mode, b, tap)
+        if tap is not None:
+            tap['planes'] = planes
+        jitter, u, depth_range, kw = self._render_inputs(b, res, ws.device, jitter_coarse, u_fine, pk)
+        feat, depth, wsum = ag.RenderFn.apply(planes, self, c, jitter, u, depth_range, kw, False)
+        img = ag.SuperresFn.apply(feat, styles_flat, self, b, tap)
+        return {'image': img.permute(0, 3, 1, 2), 'image_raw': feat[..., :3].permute(0, 3, 1, 2),
+                'image_depth': depth.view(b, 1, res, res)}
 
     def forward(self, *a, **k):
         raise HfagpError('HFA-GP drives the generator through .synthesis(ws, c=..., noise_mode=...) only '

@@ -201,6 +201,16 @@ def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s
     return feat, depth, wsum, book
 
 
+def render_bwd(planes, c, mlp, lin, jitter, u_fine, dfeat, *, res, s_coarse, s_fine, delta, box_scale):
+    """d(feat) [N,res,res,32] -> d(planes) [N,PH,PW,96] (decoder frozen), see ``hfagp_render_bwd``."""
+    n, ph, pw, _ = planes.shape
+    dplanes = torch.zeros_like(planes)
+    d = RenderDesc(n, res, ph, pw, s_coarse, s_fine, delta, box_scale)
+    _ok(_cabi.lib().hfagp_render_bwd(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
+                                       ptr(dfeat), ptr(dplanes), stream()), 'hfagp_render_bwd')
+    return dplanes
+
+
 def blur(x, pad0, pad1, stride=1, split_out: bool = False, gain: float = 1.0):
     """gain * [1,3,3,1]^2/64 FIR of a channels-last activation (fp32 tensor or Split) -> fp32 or Split."""
     n, h, wd, c = x.shape

@@ -176,6 +176,16 @@ int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes, const flo
                      float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above, int32_t* sort_idx,
                      float* depths_sorted, void* stream);
 
+/* Backward of hfagp_render_fwd w.r.t. the planes (decoder frozen, trainer_rgb.py:59-60): per ray the forward is
+ * recomputed from the same inputs (jitter / u_fine make it deterministic), then d(feat) is pushed through the
+ * composite, the mid-point march (d sigma), the decoder MLP (tensor-pipe, split bf16) and the bilinear gather;
+ * dplanes[n][ph][pw][96] is ACCUMULATED with 16-byte red.global.add (caller zeroes it).  Sample positions carry
+ * no gradient (upstream's importance sampling runs under no_grad); depth / wsum are not differentiated.
+ * Replaces: autograd of ImportanceRenderer.forward + OSGDecoder + MipRayMarcher2 + grid_sample (eg3d). */
+int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                     const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
+                     float* dplanes, void* stream);
+
 /* [1,3,3,1]^2/64 FIR, zero-pad (pad0,pad1), optional output stride and gain:
  *   y[n][oy][ox][c] = gain * sum_{ky,kx} g[ky] g[kx] x[n][oy*stride + ky - pad0][ox*stride + kx - pad0][c]
  * with oh = (h + pad0 + pad1 - 4) / stride + 1.  Input is x (fp32) or the split-bf16 pair (x_hi, x_lo);

@@ -191,3 +191,62 @@ def test_superres_backward(precision):
     (img * nhwc(gi)).sum().backward()
     _check_grad(pu.to_nchw(feat_g.grad), feat_r.grad, precision, 'superres dfeat')
     _check_grad(ws_g.grad, ws_r.grad, precision, 'superres dws')
+
+
+# ------------------------------------------------------------------ renderer backward
+
+@pytest.mark.parametrize('res,s,sf,batch', [(8, 16, 0, 1), (8, 16, 16, 2), (8, 20, 9, 1), (16, 48, 48, 1)])
+def test_render_backward(res, s, sf, batch):
+    """d(feat) -> d(planes) through composite, march, decoder MLP and bilinear gather vs autograd of the oracle."""
+    ops = _ops()
+    plane_res = 32
+    cfg = eg3d_ref.GeneratorConfig(nrr=res, depth_res=s, depth_res_importance=sf, plane_res=plane_res)
+    g = torch.Generator().manual_seed(res + s)
+    planes = torch.randn(batch, 3, 32, plane_res, plane_res, generator=g).requires_grad_(True)
+    with torch.random.fork_rng():
+        torch.manual_seed(1)
+        dec = eg3d_ref.OSGDecoderRef(cfg)
+        with torch.no_grad():
+            dec.net[0].bias.normal_(0, 0.5)
+            dec.net[2].bias.normal_(0, 0.5)
+    dec.requires_grad_(False)
+    c = hfagp_ref.flip_label_(hfagp_ref.synthetic_labels(batch, seed=3))
+    rays = res * res
+    jitter = torch.rand(batch, rays, s, 1, generator=g)
+    u = torch.rand(batch * rays, max(sf, 1), generator=g)
+    ro, rd = eg3d_ref.ray_sampler_ref(c[:, :16].view(-1, 4, 4), c[:, 16:25].view(-1, 3, 3), res)
+    feat_ref, _, _ = eg3d_ref.render_ref(planes, dec, ro, rd, cfg, jitter, u if sf > 0 else None)
+    gf = torch.randn(feat_ref.shape, generator=g)
+    (feat_ref * gf).sum().backward()
+    d0, d2 = dec.net[0], dec.net[2]
+    mlp = torch.cat([(d0.weight * d0.weight_gain).reshape(-1), d0.bias * d0.bias_gain,
+                     (d2.weight * d2.weight_gain).reshape(-1), d2.bias * d2.bias_gain]).detach().cuda()
+    pl = planes.detach().reshape(batch, 96, plane_res, plane_res).permute(0, 2, 3, 1).contiguous().cuda()
+    lin = torch.linspace(cfg.ray_start, cfg.ray_end, s)
+    delta = (cfg.ray_end - cfg.ray_start) / (s - 1)
+    dpl = ops.render_bwd(pl, c.cuda(), mlp, lin.cuda(), jitter.reshape(batch, -1, s).contiguous().cuda(),
+                         u.cuda() if sf > 0 else None, gf.reshape(batch, res, res, 32).contiguous().cuda(),
+                         res=res, s_coarse=s, s_fine=sf, delta=delta, box_scale=2.0 / cfg.box_warp)
+    want = planes.grad.reshape(batch, 96, plane_res, plane_res)
+    e_max, e_l2 = pu.rel_err(pu.to_nchw(dpl), want), pu.rel_l2(pu.to_nchw(dpl), want)
+    print(f'render dplanes: max-rel {e_max:.3e} rel-L2 {e_l2:.3e}')
+    assert e_l2 < 1e-3 and e_max < 5e-3, (e_max, e_l2)
+
+
+@pytest.mark.parametrize('precision', ['tc', 'fp32'])
+def test_generator_backward_to_ws(precision):
+    """loss(image) -> d(ws) through super-resolution, renderer and backbone (generator frozen), vs the oracle."""
+    cfg = eg3d_ref.small14_config()
+    ref, prod = _pair(cfg, precision)
+    b = 2
+    ws, c, jitter, u = pu.make_inputs(cfg, b, seed=2)
+    g = torch.Generator().manual_seed(11)
+    ws_r = ws.clone().requires_grad_(True)
+    img_r = ref.synthesis(ws_r, c, jitter_coarse=jitter, u_fine=u)['image']
+    gi = torch.randn(img_r.shape, generator=g)
+    (img_r * gi).sum().backward()
+    ws_g = ws.clone().cuda().requires_grad_(True)
+    img = prod.synthesis(ws_g, c.cuda(), noise_mode='const', jitter_coarse=jitter.cuda(), u_fine=u.cuda())['image']
+    assert pu.rel_err(img, img_r) < pu.REL_TOL
+    (img * gi.cuda()).sum().backward()
+    _check_grad(ws_g.grad, ws_r.grad, precision, 'generator dws')
