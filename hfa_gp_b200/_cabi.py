@@ -23,7 +23,8 @@ SYMBOLS = [
     'hfagp_blur_fwd', 'hfagp_linear_fwd', 'hfagp_latent_fwd', 'hfagp_nchw_to_nhwc',
     'hfagp_nhwc_to_nchw', 'hfagp_conv2d_tc_fwd', 'hfagp_split_bf16', 'hfagp_modulate_split_fwd',
     'hfagp_blur_up', 'hfagp_act_bwd', 'hfagp_styles_bwd', 'hfagp_demod_bwd', 'hfagp_linear_bwd',
-    'hfagp_conv2d_wgrad', 'hfagp_render_bwd',
+    'hfagp_conv2d_wgrad', 'hfagp_render_bwd', 'hfagp_latent_bwd', 'hfagp_facepool_fwd', 'hfagp_facepool_bwd',
+    'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step',
 ]
 
 
@@ -93,6 +94,12 @@ def lib() -> C.CDLL:
     l.hfagp_conv2d_wgrad.argtypes = [C.POINTER(ConvDesc)] + [vp] * 6 + [f32, vp, vp]
     l.hfagp_linear_fwd.argtypes = [i32, i32, i32, vp, vp, vp, f32, f32, vp, vp]
     l.hfagp_latent_fwd.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
+    l.hfagp_latent_bwd.argtypes = [i32, i32, i32] + [vp] * 7
+    l.hfagp_facepool_fwd.argtypes = [i32] * 5 + [vp] * 3
+    l.hfagp_facepool_bwd.argtypes = [i32] * 5 + [vp] * 3
+    l.hfagp_mse_fwd.argtypes = [C.c_longlong, vp, vp, f32, vp, vp]
+    l.hfagp_mse_bwd.argtypes = [C.c_longlong, vp, vp, f32, vp, i32, vp, vp]
+    l.hfagp_adam_step.argtypes = [C.c_longlong, vp, vp, vp, vp, f32] + [C.c_double] * 5 + [C.c_longlong, vp]
     l.hfagp_nchw_to_nhwc.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     l.hfagp_nhwc_to_nchw.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     l.hfagp_conv2d_tc_fwd.argtypes = [C.POINTER(ConvDesc), vp, vp, vp, vp, i32] + [vp] * 9

@@ -202,3 +202,90 @@ class RenderFn(torch.autograd.Function):
         dplanes = ops.render_bwd(planes, c, pk['mlp'], pk['lin'], jitter, u_fine if u_fine.numel() else None,
                                  dfeat.contiguous(), **ctx.kw)
         return dplanes, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------ encoder / latent / loss (trainer_rgb.py:79-91)
+
+class LinearFn(torch.autograd.Function):
+    """EqualLinear with activation=None (encoder3d.py:128-136): y = x W^T * scale + b * lr_mul."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, scale, lr_mul):
+        w = weight.detach().contiguous()
+        ctx.save_for_backward(x, w)
+        ctx.scale, ctx.lr_mul, ctx.has_bias = scale, lr_mul, bias is not None
+        return ops.linear(x, w, None if bias is None else bias.detach(), scale, lr_mul)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dw = torch.zeros_like(w) if need_dw else None
+        db = torch.zeros(w.shape[0], device=w.device) if (need_dw and ctx.has_bias) else None
+        dx = ops.linear_bwd(dy, x, w, ctx.scale, ctx.lr_mul, need_dx=need_dx, dw=dw, db=db)
+        return dx, dw, db, None, None
+
+
+class EncoderAppFn(torch.autograd.Function):
+    """frame [B,3,S,S] -> [B, w_dim] through EncoderApp (encoder3d.py:231-239); gradients reach the convolution
+    weights and activation biases (``*params`` = ``net.parameters()``, in that order), not the frame."""
+
+    @staticmethod
+    def forward(ctx, x, net, *params):
+        tape = {}
+        out = net._forward_impl(x, tape)
+        ctx.net, ctx.tape, ctx.params = net, tape, params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.net._backward_impl(ctx.tape, dout.contiguous())
+        out = tuple(grads.get(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[2:]))
+        ctx.tape = None
+        return (None, None) + out
+
+
+class LatentFn(torch.autograd.Function):
+    """ws = weights . Q^T + delta (headnerf.py:96-100); Q comes from torch.linalg.qr, whose own autograd carries
+    d(Q) on to ``bases``."""
+
+    @staticmethod
+    def forward(ctx, weights, q, delta):
+        w, qc = weights.detach().float().contiguous(), q.detach().contiguous()
+        ctx.save_for_backward(w, qc)
+        return ops.latent(w, qc, delta.detach().contiguous(), qc.shape[0])
+
+    @staticmethod
+    def backward(ctx, dws):
+        w, q = ctx.saved_tensors
+        nw, nq, nd = ctx.needs_input_grad
+        return ops.latent_bwd(dws.contiguous(), w, q, nw, nq, nd)
+
+
+class FacePoolFn(torch.autograd.Function):
+    """face_pool (trainer_rgb.py:63,84): channels-last image -> AdaptiveAvgPool2d(size) in NCHW."""
+
+    @staticmethod
+    def forward(ctx, img_nhwc, size):
+        ctx.hw = img_nhwc.shape[1:3]
+        return ops.facepool(img_nhwc.contiguous(), size)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.facepool_bwd(dy.contiguous(), *ctx.hw), None
+
+
+class MseFn(torch.autograd.Function):
+    """MSELoss(reduction='mean')(real, generated) (trainer_rgb.py:15,85); gradient to ``generated`` only."""
+
+    @staticmethod
+    def forward(ctx, real, generated):
+        real, generated = real.detach().float().contiguous(), generated.contiguous()
+        ctx.save_for_backward(real, generated)
+        return ops.mse(generated, real)
+
+    @staticmethod
+    def backward(ctx, gout):
+        real, generated = ctx.saved_tensors
+        return None, ops.mse_bwd(generated, real, gout.contiguous())

@@ -212,7 +212,7 @@ class TriPlaneGenerator(nn.Module):
             dev = p.device
         for b in self.buffers():
             ver += b._version
-        return (str(dev), ver)
+        return (str(dev), ver, ops.param_epoch[0])
 
     def _layers_in_order(self):
         cfg = self.cfg

@@ -63,7 +63,7 @@ class EqualConv2d(nn.Module):
     def packed(self):
         """[k*k][O][I] with the equalised-lr scale folded in (what F.conv2d sees at :103); cached
         until the parameter is written again."""
-        key = (self.weight._version, self.weight.device, self.weight.data_ptr())
+        key = (self.weight._version, self.weight.device, self.weight.data_ptr(), ops.param_epoch[0])
         if self._pk is None or self._pk_key != key:
             o, i, kh, kw = self.weight.shape
             self._pk = (self.weight.detach() * self.scale).permute(2, 3, 0, 1).reshape(kh * kw, o, i).contiguous().float()
@@ -76,6 +76,17 @@ class EqualConv2d(nn.Module):
         if getattr(self, '_pks_src', None) is not pk:
             self._pks, self._pks_src = ops.split(pk), pk
         return self._pks
+
+    def packed_T(self, split=False):
+        """[k*k][I][O] (scale folded in): the operand of the data-gradient convolution; fp32 or split bf16."""
+        pk = self.packed()
+        if getattr(self, '_pkt_src', None) is not pk:
+            self._pkt, self._pkt_src, self._pkts = pk.transpose(1, 2).contiguous(), pk, None
+        if not split:
+            return self._pkt
+        if self._pkts is None:
+            self._pkts = ops.split(self._pkt)
+        return self._pkts
 
     def packed_linear(self):
         """[O][(ky,kx,ci)]: the kernel as one row per output channel, matching a channels-last flatten of the
@@ -99,6 +110,9 @@ class EqualLinear(nn.Module):
         self.lr_mul = lr_mul
 
     def forward(self, input):
+        if torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad):
+            from ..autograd import LinearFn
+            return LinearFn.apply(input.float().contiguous(), self.weight, self.bias, self.scale, self.lr_mul)
         x = input.detach().float().contiguous()
         return ops.linear(x, self.weight.detach().contiguous(), None if self.bias is None else self.bias.detach(),
                           self.scale, self.lr_mul)
@@ -123,9 +137,10 @@ class ConvLayer(nn.Sequential):
             layers.append(FusedLeakyReLU(out_channel))
         super().__init__(*layers)
 
-    def run(self, x, residual=None, tc=False, split_out=False):
+    def run(self, x, residual=None, tc=False, split_out=False, rec=None):
         """x channels-last [N,H,W,C] (fp32 tensor or ops.Split) -> channels-last output, epilogue fused.
-        ``tc``: tcgen05 split-bf16 kernel (fp32-class accuracy) instead of the exact-fp32 SIMT kernel."""
+        ``tc``: tcgen05 split-bf16 kernel (fp32-class accuracy) instead of the exact-fp32 SIMT kernel.
+        ``rec`` (training): dict receiving what backward() needs."""
         mods = list(self.children())
         conv = next(m for m in mods if isinstance(m, EqualConv2d))
         act = mods[-1] if isinstance(mods[-1], FusedLeakyReLU) else None
@@ -152,12 +167,67 @@ class ConvLayer(nn.Sequential):
                    residual_scale=INV_SQRT2 if residual is not None else 1.0)
         cout = conv.weight.shape[0]
         if tc:
-            xs = x if isinstance(x, ops.Split) else ops.split(x)
-            return ops.conv2d_tc(xs, conv.packed_split(), taps, cout, oh=oh, ow=ow, in_stride=stride,
-                                 split_out=split_out, **epi)
-        xf = x.float() if isinstance(x, ops.Split) else x
-        y = ops.conv2d(xf, conv.packed(), taps, cout, oh=oh, ow=ow, in_stride=stride, **epi)
-        return ops.split(y) if split_out else y
+            xin = x if isinstance(x, ops.Split) else ops.split(x)
+            y = ops.conv2d_tc(xin, conv.packed_split(), taps, cout, oh=oh, ow=ow, in_stride=stride,
+                              split_out=split_out, **epi)
+        else:
+            xin = x.float() if isinstance(x, ops.Split) else x
+            y = ops.conv2d(xin, conv.packed(), taps, cout, oh=oh, ow=ow, in_stride=stride, **epi)
+            y = ops.split(y) if split_out else y
+        if rec is not None:
+            rec.update(x_in=xin, y=y, residual=residual, taps=taps, stride=stride, oh=oh, ow=ow, hw=(h, w), tc=tc)
+        return y
+
+    def backward(self, rec, dy, grads, need_dx=True, post_scale=1.0):
+        """Gradient of run(): ``dy`` is one fp32 channels-last gradient of the output or a pair of them (summed
+        inside hfagp_act_bwd).  Fills ``grads[param]`` for the conv weight and the activation bias; returns the
+        fp32 gradient of the layer input (pre-blur geometry) or None."""
+        mods = list(self.children())
+        conv = next(m for m in mods if isinstance(m, EqualConv2d))
+        act = mods[-1] if isinstance(mods[-1], FusedLeakyReLU) else None
+        if conv.bias is not None:
+            raise HfagpError('backward of a biased non-activated ConvLayer is never needed on the HFA-GP path')
+        cout, cin, k = conv.weight.shape[0], conv.weight.shape[1], self.kernel_size
+        g0, g1 = (dy if isinstance(dy, tuple) else (dy, None))
+        tc = rec['tc'] and cout % 8 == 0
+        residual = rec['residual']
+        kw = dict(g0=g0, g1=g1, out='split' if (tc and need_dx) else 'f32')
+        if act is not None:
+            db = torch.zeros(cout, device=g0.device)
+            dz = ops.act_bwd(rec['y'], residual=residual, residual_scale=INV_SQRT2, act=ACT_LRELU, act_gain=SQRT2,
+                             post_scale=INV_SQRT2 if residual is not None else 1.0, dbias=db, **kw)
+            grads[act.bias] = db.view(1, -1, 1, 1)
+        else:
+            dz = ops.act_bwd(rec['y'], act=ACT_LINEAR, act_gain=1.0, post_scale=post_scale, **kw)
+        # ---- weight gradient (fp32 SIMT split-K); the equalised-lr scale is d(packed)/d(weight)
+        x_in = rec['x_in']
+        cin_p = (cin + 3) // 4 * 4
+        if cin_p != cin:
+            x_in = torch.nn.functional.pad(x_in, (0, cin_p - cin))
+        dwp = torch.zeros((k * k, cout, cin_p), device=g0.device)
+        ops.conv2d_wgrad(x_in, dz, rec['taps'], dwp, oh=rec['oh'], ow=rec['ow'], in_stride=rec['stride'],
+                         scale=conv.scale)
+        grads[conv.weight] = dwp[:, :, :cin].reshape(k, k, cout, cin).permute(2, 3, 0, 1)
+        if not need_dx:
+            return None
+        # ---- data gradient: the forward kernels on transposed weights, then the blur transpose
+        h, w = rec['hw']
+        wt = conv.packed_T(split=tc)
+
+        def conv_t(taps, oh, ow):
+            if tc:
+                return ops.conv2d_tc(dz, wt, taps, cin, oh=oh, ow=ow)
+            return ops.conv2d(dz, wt, taps, cin, oh=oh, ow=ow)
+
+        if not self.downsample:
+            return conv_t(tuple((-ty, -tx, t) for ty, tx, t in rec['taps']), h, w)
+        pad0, pad1 = mods[0].pad
+        if k == 1:
+            return ops.blur_up(conv_t(ops.TAPS_1X1, rec['oh'], rec['ow']), h, w, pad0, pad1, 2)
+        if k != 3:
+            raise HfagpError('backward of a down-sampling ConvLayer is implemented for k = 1 and k = 3')
+        t = ops.conv_transpose_s2_tc(dz, wt, cin) if tc else ops.conv_transpose_s2(dz, wt, cin, 0)
+        return ops.blur(t, 3 - pad0, 3 - pad1, stride=1)
 
 
 class ResBlock(nn.Module):
@@ -167,10 +237,21 @@ class ResBlock(nn.Module):
         self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True)
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
 
-    def run(self, x, tc=False):
-        skip = self.skip.run(x, tc=tc)                                # fp32: it is the residual operand
-        out = self.conv1.run(x, tc=tc, split_out=tc)
-        return self.conv2.run(out, residual=skip, tc=tc, split_out=tc)   # (conv2(out) + skip) / sqrt(2) in the epilogue
+    def run(self, x, tc=False, rec=None):
+        rs, r1, r2 = ({}, {}, {}) if rec is not None else (None, None, None)
+        skip = self.skip.run(x, tc=tc, rec=rs)                        # fp32: it is the residual operand
+        out = self.conv1.run(x, tc=tc, split_out=tc, rec=r1)
+        y = self.conv2.run(out, residual=skip, tc=tc, split_out=tc, rec=r2)   # (conv2(out) + skip) / sqrt(2) in the epilogue
+        if rec is not None:
+            rec.update(skip=rs, conv1=r1, conv2=r2)
+        return y
+
+    def backward(self, rec, dy, grads):
+        """-> (d input via conv1, d input via skip): the pair is summed by the consumer's hfagp_act_bwd."""
+        dout = self.conv2.backward(rec['conv2'], dy, grads)
+        dx_skip = self.skip.backward(rec['skip'], dy, grads, post_scale=INV_SQRT2)
+        dx_main = self.conv1.backward(rec['conv1'], dout, grads)
+        return dx_main, dx_skip
 
 
 class EncoderApp(nn.Module):
@@ -194,21 +275,44 @@ class EncoderApp(nn.Module):
         if not x.is_cuda:
             raise HfagpError('Encoder needs CUDA tensors (there is no CPU fallback)')
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise HfagpError('encoder backward is not implemented in this build; call under torch.no_grad()')
+            from ..autograd import EncoderAppFn
+            return EncoderAppFn.apply(x, self, *self.parameters())
+        return self._forward_impl(x, None)
+
+    def _forward_impl(self, x, tape):
         tc = self.precision == 'tc'
+        recs = [({} if tape is not None else None) for _ in self.convs[:-1]]
         h = ops.nchw_to_nhwc(x.detach().float().contiguous())
-        h = self.convs[0].run(h, split_out=tc)           # cin = 3: exact-fp32 SIMT kernel
-        for m in self.convs[1:-1]:
-            h = m.run(h, tc=tc)
+        h = self.convs[0].run(h, split_out=tc, rec=recs[0])           # cin = 3: exact-fp32 SIMT kernel
+        for m, r in zip(self.convs[1:-1], recs[1:]):
+            h = m.run(h, tc=tc, rec=r)
         last = self.convs[-1]
         k = last.weight.shape[-1]
         hf = h.float() if isinstance(h, ops.Split) else h
+        if tape is not None:
+            if hf.shape[1] != k or hf.shape[2] != k:
+                raise HfagpError('encoder backward needs the final k x k convolution to see exactly one window')
+            tape.update(recs=recs, flat=hf.reshape(hf.shape[0], -1), shape=hf.shape)
         if hf.shape[1] == k and hf.shape[2] == k:
             # one k x k window -> [B, w_dim]: a linear map over the channels-last flatten (weights-bandwidth bound)
             return ops.linear(hf.reshape(hf.shape[0], -1), last.packed_linear(), None, 1.0, 1.0)
         taps = tuple((ky, kx, ky * k + kx) for ky in range(k) for kx in range(k))
         hf = ops.conv2d(hf, last.packed(), taps, last.weight.shape[0], oh=hf.shape[1] - k + 1, ow=hf.shape[2] - k + 1)
         return hf.reshape(hf.shape[0], -1)                 # 1x1 spatial: channels-last == [B, w_dim]
+
+    def _backward_impl(self, tape, dout):
+        """dout [B, w_dim] -> {parameter: gradient} for every encoder convolution (the frame itself carries none)."""
+        grads = {}
+        last = self.convs[-1]
+        o, i, k, _ = last.weight.shape
+        dwl = torch.zeros((o, k * k * i), device=dout.device)
+        dflat = ops.linear_bwd(dout, tape['flat'], last.packed_linear(), 1.0, 1.0, dw=dwl)
+        grads[last.weight] = dwl.view(o, k, k, i).permute(0, 3, 1, 2) * last.scale
+        dy = dflat.view(tape['shape'])
+        for m, r in zip(reversed(self.convs[1:-1]), reversed(tape['recs'][1:])):
+            dy = m.backward(r, dy, grads)
+        self.convs[0].backward(tape['recs'][0], dy, grads, need_dx=False)
+        return grads
 
 
 class Encoder(nn.Module):

@@ -77,7 +77,7 @@ class _LatentSubspace:
     """get_latent shared by the three avatar classes (headnerf.py:81-102, :182-195, :242-255)."""
 
     def _q_factor(self, bases: torch.Tensor) -> torch.Tensor:
-        key = (bases._version, bases.data_ptr(), bases.device)
+        key = (bases._version, bases.data_ptr(), bases.device, ops.param_epoch[0])
         cache = self.__dict__.get('_q_cache')
         if cache is not None and cache[0] == key and not torch.is_grad_enabled():
             return cache[1]
@@ -89,9 +89,13 @@ class _LatentSubspace:
     def _latent_from(self, weights, bases, delta):
         if weights is None:
             return self._q_factor(bases)
-        if torch.is_grad_enabled() and (weights.requires_grad or bases.requires_grad):
-            raise HfagpError('get_latent backward is not implemented in this build; call under torch.no_grad()')
         b = weights.shape[0]
+        if torch.is_grad_enabled() and (weights.requires_grad or bases.requires_grad or delta.requires_grad):
+            # training (trainer_rgb.py:79-80): the QR factorisation is recomputed under autograd, as the
+            # reference does every call (headnerf.py:92), so d(Q) reaches ``bases`` through torch's QR backward
+            from ..autograd import LatentFn
+            q, _ = torch.linalg.qr((bases + 1e-8).T, mode='reduced')
+            return LatentFn.apply(weights, q, delta).view(b, -1, self.dim)
         q = self._q_factor(bases)
         out = ops.latent(weights.detach().float().contiguous(), q, delta.detach().contiguous(), q.shape[0])
         return out.view(b, -1, self.dim)

@@ -15,6 +15,9 @@ from ._cabi import ACT_LINEAR, ACT_LRELU, ActBwdDesc, ConvDesc, RenderDesc, chec
 
 _desc_cache = {}
 _launches = [0]
+# bumped by every optimiser step that writes parameters through the C ABI (raw device writes do not advance
+# torch's per-tensor version counters); part of the key of every packed-weight cache
+param_epoch = [0]
 
 
 def launch_count() -> int:
@@ -433,3 +436,69 @@ class StyleTableBwd:
         _ok(_cabi.lib().hfagp_styles_bwd(t.n, batch, num_ws, w_dim, t.aw, t.cin, t.widx, t.gain, off_arr,
                                            ptr(dstyles_flat), ptr(dws), stream()), 'hfagp_styles_bwd')
         return dws
+
+
+def conv_transpose_s2_tc(x: Split, w: Split, cout: int, w_batched: bool = False) -> torch.Tensor:
+    """conv_transpose_s2() on the tcgen05 path: four output-parity launches scattering into [N,2H+1,2W+1,Co]."""
+    n, h, wd, _ = x.shape
+    out = torch.empty((n, 2 * h + 1, 2 * wd + 1, cout), device=x.device, dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            conv2d_tc(x, w, _parity_taps(a, b), cout, oh=h + 1 - a, ow=wd + 1 - b, out=out,
+                      out_hw=(2 * h + 1, 2 * wd + 1), out_stride=2, out_off=(a, b), w_batched=w_batched)
+    return out
+
+
+# ------------------------------------------------------------------ training step: latent backward, loss, optimiser
+
+def latent_bwd(dws, weights, q, need_dweights=True, need_dq=True, need_ddelta=True):
+    """dws [B,dim] -> (dweights [B,K], dq [dim,K], ddelta [dim]), see ``hfagp_latent_bwd``."""
+    n, dim = dws.shape
+    k = q.shape[1]
+    dev = dws.device
+    dweights = torch.empty((n, k), device=dev, dtype=torch.float32) if need_dweights else None
+    dq = torch.empty((dim, k), device=dev, dtype=torch.float32) if need_dq else None
+    ddelta = torch.empty((dim,), device=dev, dtype=torch.float32) if need_ddelta else None
+    _ok(_cabi.lib().hfagp_latent_bwd(n, k, dim, ptr(dws), ptr(weights), ptr(q), ptr(dweights), ptr(dq), ptr(ddelta),
+                                       stream()), 'hfagp_latent_bwd')
+    return dweights, dq, ddelta
+
+
+def facepool(x_nhwc, size):
+    """AdaptiveAvgPool2d((size,size)) for an integer factor, channels-last in -> NCHW out."""
+    n, h, wd, c = x_nhwc.shape
+    if h % size or wd % size or h // size != wd // size:
+        raise _cabi.HfagpError(f'face_pool {h}x{wd} -> {size} is not an integer-factor average')
+    f = h // size
+    out = torch.empty((n, c, size, size), device=x_nhwc.device, dtype=torch.float32)
+    _ok(_cabi.lib().hfagp_facepool_fwd(n, h, wd, c, f, ptr(x_nhwc), ptr(out), stream()), 'hfagp_facepool_fwd')
+    return out
+
+
+def facepool_bwd(dy_nchw, h, wd):
+    n, c, oh, ow = dy_nchw.shape
+    dx = torch.empty((n, h, wd, c), device=dy_nchw.device, dtype=torch.float32)
+    _ok(_cabi.lib().hfagp_facepool_bwd(n, h, wd, c, h // oh, ptr(dy_nchw), ptr(dx), stream()), 'hfagp_facepool_bwd')
+    return dx
+
+
+def mse(a, b):
+    loss = torch.zeros((), device=a.device, dtype=torch.float32)
+    _ok(_cabi.lib().hfagp_mse_fwd(a.numel(), ptr(a), ptr(b), 1.0 / a.numel(), ptr(loss), stream()), 'hfagp_mse_fwd')
+    return loss
+
+
+def mse_bwd(a, b, gout, out=None):
+    """d(mse)/da * gout (device scalar); accumulated into ``out`` when given."""
+    acc = out is not None
+    if out is None:
+        out = torch.empty_like(a)
+    _ok(_cabi.lib().hfagp_mse_bwd(a.numel(), ptr(a), ptr(b), 1.0 / a.numel(), ptr(gout), int(acc), ptr(out), stream()),
+          'hfagp_mse_bwd')
+    return out
+
+
+def adam_step(p, g, m, v, *, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """In-place torch.optim.Adam update of the flat buffer ``p`` (see ``hfagp_adam_step``)."""
+    _ok(_cabi.lib().hfagp_adam_step(p.numel(), ptr(p), ptr(g), ptr(m), ptr(v), grad_scale, lr, beta1, beta2, eps,
+                                      weight_decay, int(step), stream()), 'hfagp_adam_step')

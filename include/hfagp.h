@@ -272,6 +272,37 @@ int hfagp_conv2d_wgrad(const HfagpConvDesc* desc, const float* x, const uint16_t
                        const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, float scale, float* dw,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Around the render path inside one training step (Trainer.gen_update, code/trainer_rgb.py:73-98).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Backward of hfagp_latent_fwd: dweights[n][k] = sum_j dws[n][j] q[j][k] ; dq[j][k] = sum_n dws[n][j] weights[n][k] ;
+ * ddelta[j] = sum_n dws[n][j].  Outputs are WRITTEN; each may be NULL.  d(bases) continues through the QR
+ * factorisation in the host framework (torch.linalg.qr autograd), as in the reference (headnerf.py:92-100). */
+int hfagp_latent_bwd(int batch, int k, int dim, const float* dws, const float* weights, const float* q,
+                     float* dweights, float* dq, float* ddelta, void* stream);
+
+/* face_pool = AdaptiveAvgPool2d((size,size)) of the generated image (code/trainer_rgb.py:63,84) for an integer
+ * factor f = h/size, fused with the layout change: x[n][h][w][c] channels-last -> y[n][c][h/f][w/f]; c <= 4.
+ * hfagp_facepool_bwd is its transpose: dy[n][c][h/f][w/f] -> dx[n][h][w][c] (written). */
+int hfagp_facepool_fwd(int batch, int h, int w_, int c, int f, const float* x, float* y, void* stream);
+int hfagp_facepool_bwd(int batch, int h, int w_, int c, int f, const float* dy, float* dx, void* stream);
+
+/* MSELoss(reduction='mean') (code/trainer_rgb.py:15,65-67,85): loss[0] += scale * sum_i (a[i]-b[i])^2 with
+ * scale = 1/count (caller zeroes loss); backward da[i] (+)= 2 * scale * gout[0] * (a[i]-b[i]), gout a device scalar. */
+int hfagp_mse_fwd(long long count, const float* a, const float* b, float scale, float* loss, void* stream);
+int hfagp_mse_bwd(long long count, const float* a, const float* b, float scale, const float* gout, int accumulate,
+                  float* da, void* stream);
+
+/* One torch.optim.Adam step (code/trainer_rgb.py:57,95; amsgrad off) over a flat fp32 buffer of `count` elements:
+ *   g' = g*grad_scale + weight_decay*p ; m = lerp(m, g', 1-beta1) ; v = beta2 v + (1-beta2) g'^2
+ *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)
+ * grad_scale carries the 1/world_size of the data-parallel gradient mean.  Hyper-parameters are doubles: the scalar
+ * terms are evaluated in double on the host (as torch evaluates them in Python) and rounded once.  Buffers must be
+ * 16-byte aligned. */
+int hfagp_adam_step(long long count, float* p, const float* g, float* m, float* v, float grad_scale, double lr,
+                    double beta1, double beta2, double eps, double weight_decay, long long step, void* stream);
+
 /* Layout helpers (elementwise, bandwidth-bound): NCHW <-> NHWC for the frame entering the encoder
  * and the image leaving the super-resolution head. */
 int hfagp_nchw_to_nhwc(int batch, int c, int h, int w_, const float* x, float* y, void* stream);
