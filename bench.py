@@ -149,6 +149,81 @@ def cpu_baseline_sample(frames=2):
             'sample': f'{frames} full 512x512 frames after 1 warm-up (encoder+latent+synthesis), PyTorch fp32 CPU oracle'}
 
 
+def train_bench(args, rank, world, local_rank):
+    """--workload train: BASELINE.json configs[2] (trainer_rgb.gen_update, size 256, latent_dim_shape 50, MSE + LPIPS,
+    generator frozen) and, at N > 1, the configs[3]-style data-parallel step: per-rank micro-batch, ONE flat NCCL
+    all-reduce of the encoder/bases/delta gradients per step.  Not the driver's headline line (that is configs[1]);
+    printed for the record with its own workload name."""
+    import torch
+    import torch.distributed as dist
+    from hfa_gp_b200 import _cabi, ops
+    from hfa_gp_b200 import trainer_rgb
+
+    _cabi.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    bs = args.frames_per_step if args.frames_per_step > 1 else 2          # train_rgb.py:164 default batch 2
+    ns = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='',
+                            synthetic_generator=True, generator_seed=0, batch_size=bs * world, size=ENC_SIZE,
+                            latent_dim_style=512, latent_dim_shape=DIM_SHAPE, run_id='bench', emb_dir='./', lr=3e-4)
+    torch.manual_seed(0)
+    tr = trainer_rgb.Trainer(ns, dev, local_rank)
+    g = torch.Generator().manual_seed(4321 + rank)
+    total = args.warmup + args.steps
+    host_frames = (torch.rand(total, bs, 3, ENC_SIZE, ENC_SIZE, generator=g) * 2 - 1).pin_memory()
+    host_labels = torch.stack([trainer_rgb.cam_sampler(bs, 'cpu') for _ in range(total)]).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        real = host_frames[i].to(dev, non_blocking=True)
+        label = host_labels[i].to(dev, non_blocking=True)
+        l2, lp, _ = tr.gen_update(real, label)
+        return l2, lp
+
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        l2, lp = step(args.warmup + i)
+    loss_host = float(l2.detach()) + float(lp.detach())                  # D2H read of the step's result inside the timed region
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    if rank == 0:
+        frames = args.steps * bs * world
+        v = frames / (ms / 1e3)
+        print(json.dumps({
+            'metric': 'training frames/sec (whole job), trainer_rgb.gen_update', 'value': v, 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[2]: trainer_rgb.gen_update, 512x512 render pooled to 256, latent_dim_shape=50, '
+                                   'MSE+LPIPS(alex, random-init), Adam, generator frozen', 'per_rank_batch': bs,
+                       'exchange': 'one flat all-reduce of %d gradient floats per step' % tr.g_optim.live_elements()
+                                   if world > 1 else 'none (1 rank)',
+                       'l2': 'per-step working set exceeds the 126 MB L2; no flush'},
+            'clocks': clocks,
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': bs * (3 * ENC_SIZE * ENC_SIZE + 25) * 4, 'd2h_bytes_per_step': 8},
+            'gpu_launches': ops.launch_count() - n0, 'final_loss': loss_host}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -158,6 +233,8 @@ def main():
     ap.add_argument('--frames-per-step', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='drive the frame loop eagerly instead of replaying the CUDA graph')
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train'],
+                    help="'infer' = configs[1] (the headline line); 'train' = configs[2]/[3] training step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', 0))
@@ -165,6 +242,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
         reference_arm(args, rank, world)
+        return
+    if args.workload == 'train':
+        train_bench(args, rank, world, local_rank)
         return
 
     import torch
