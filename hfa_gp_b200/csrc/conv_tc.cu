@@ -20,18 +20,40 @@ namespace hfagp {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                       // bf16 elements per K chunk = one 128 B swizzle row
-constexpr int TC_STAGES = 3;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB per (hi|lo) A tile
-constexpr int TC_THREADS = 192;                 // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 epilogue
-constexpr uint32_t SPIN_LIMIT = 1u << 22;       // a broken pipeline traps instead of hanging the GPU
+constexpr int TC_ROW = TC_BK * 2;               // bytes of one pixel row of a chunk (= the swizzle span)
+constexpr int TC_THREADS = 320;                 // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..9 epilogue
+constexpr int TC_MAX_CLASSES = 4;               // sub-problems of one launch (output parity classes)
+constexpr int TC_MAX_STAGES = 4;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;       // a broken pipeline traps instead of hanging the GPU
+
+// One sub-problem of a launch: its own output window and tap list, sharing operands and epilogue with the others.
+// Taps are ordered in GROUPS: the taps of a group read the same shared-memory input patch (loaded once per K chunk)
+// at different row offsets, so a 3x3 stride-1 convolution loads 3 patches instead of 9 tiles.
+struct TcClass {
+  int oh, ow, off_y, off_x;
+  int tiles_x, tiles_y, tile_begin;             // M tiles of this class inside one frame
+  int ntaps;
+  int8_t dx[HFAGP_MAX_TAPS];                    // patch origin (x) of the tap's group
+  int8_t dy0[HFAGP_MAX_TAPS];                   // patch origin (y) of the tap's group
+  int8_t row_off[HFAGP_MAX_TAPS];               // tap's first patch row (dy - dy0)
+  int8_t first[HFAGP_MAX_TAPS];                 // 1: first tap of its group (a new patch is loaded)
+  int8_t last[HFAGP_MAX_TAPS];                  // 1: last tap of its group (the patch slot is released)
+  int8_t wtap[HFAGP_MAX_TAPS];
+};
 
 struct TcParams {
-  ConvParams cp;          // epilogue operands + geometry (x / w pointers unused here)
-  int tile_w, tile_h;     // BW x BH = 128
+  ConvParams cp;          // epilogue operands + shared geometry (x / w pointers unused here)
+  TcClass cls[TC_MAX_CLASSES];
+  int ncls;
+  int tile_w, tile_h;     // BW x BH = 128, BW % 8 == 0
+  int patch_rows;         // rows of one A patch: BH + max dy-span of a group
   int bn;                 // N tile (multiple of 16, <= 128)
-  int tiles_x, tiles_y;   // M tiles per frame
+  int n_tiles;            // N tiles
+  int tiles_per_frame;    // M tiles of all classes
+  int total_tiles;        // batch * tiles_per_frame * n_tiles
   int taps_per_frame;     // weight taps stored per batch sample (B map z-coordinate stride)
   int w_batched;          // 1: weights are per sample
+  int a_stages, b_stages;
   __nv_bfloat16* y_hi;    // split output (or null -> cp.y fp32)
   __nv_bfloat16* y_lo;
 };
@@ -43,6 +65,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -104,39 +129,70 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// tile id -> (class, batch sample, tile origin, N offset).  N tiles are the fastest index so that the CTAs running
+// side by side read the same input patch (L2 hits), then M tiles, then classes, then batch samples.
+struct TileCoord { int c, n, y0, x0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+  TileCoord tc;
+  const int nt = t % p.n_tiles;
+  int r = t / p.n_tiles;
+  tc.n = r / p.tiles_per_frame;
+  r -= tc.n * p.tiles_per_frame;
+  int c = 0;
+  while (c + 1 < p.ncls && r >= p.cls[c + 1].tile_begin) ++c;
+  r -= p.cls[c].tile_begin;
+  const int ty = r / p.cls[c].tiles_x;
+  tc.c = c;
+  tc.y0 = ty * p.tile_h;
+  tc.x0 = (r - ty * p.cls[c].tiles_x) * p.tile_w;
+  tc.n0 = nt * p.bn;
+  return tc;
+}
+
+// Persistent kernel: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Two shared-memory rings (input
+// patches, weight tiles) run ahead across tile boundaries and the fp32 accumulator is double-buffered in TMEM, so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const TcParams p) {
+               const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stage][A_hi | A_lo | B_hi | B_lo] (each 1024-aligned), then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_bytes = p.bn * TC_BK * 2;
-  const int b_pad = (b_bytes + 1023) & ~1023;
-  const int stage_bytes = 2 * TC_A_BYTES + 2 * b_pad;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * stage_bytes);
-  uint64_t* empty = full + TC_STAGES;
-  uint64_t* acc_full = empty + TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int a_half = p.patch_rows * p.tile_w * TC_ROW;          // bytes of one (hi | lo) patch, multiple of 1024
+  const int a_stage = 2 * a_half;
+  const int b_bytes = p.bn * TC_ROW;
+  const int b_half = (b_bytes + 1023) & ~1023;
+  const int b_stage = 2 * b_half;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.a_stages * a_stage;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + p.b_stages * b_stage);
+  uint64_t* a_empty = a_full + TC_MAX_STAGES;
+  uint64_t* b_full = a_empty + TC_MAX_STAGES;
+  uint64_t* b_empty = b_full + TC_MAX_STAGES;
+  uint64_t* acc_full = b_empty + TC_MAX_STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  // per-channel epilogue scale / shift of the current N tile (512 B past the barrier block)
+  float* epi_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);
+  float* epi_sh = epi_sc + TC_BM;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const HfagpConvDesc& d = p.cp.d;
-  const int n = blockIdx.z;
-  const int tile = blockIdx.x;
-  const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-  const int y0 = ty * p.tile_h, x0 = tx * p.tile_w;
-  const int n0 = blockIdx.y * p.bn;
   const int kchunks = (d.cin + TC_BK - 1) / TC_BK;   // a partial last chunk is zero-filled by TMA (both operands)
-  const int iters = d.ntaps * kchunks;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.bn) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * p.bn) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < TC_MAX_STAGES; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);               // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -151,23 +207,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (one thread)
+    // ===== TMA producer (one thread): patches and weight tiles in the exact order the MMA issuer consumes them
     if (lane == 0) {
-      const int wz0 = p.w_batched ? n * p.taps_per_frame : 0;
-      const uint32_t tx_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        const int t = it / kchunks;
-        const int c0 = (it - t * kchunks) * TC_BK;
-        uint8_t* st = smem + s * stage_bytes;
-        mbar_expect_tx(&full[s], tx_bytes);
-        const int ax = x0 * d.in_stride + d.dx[t], ay = y0 * d.in_stride + d.dy[t];
-        tma_load_4d(&map_a_hi, st, &full[s], c0, ax, ay, n);
-        tma_load_4d(&map_a_lo, st + TC_A_BYTES, &full[s], c0, ax, ay, n);
-        tma_load_3d(&map_b_hi, st + 2 * TC_A_BYTES, &full[s], c0, n0, wz0 + d.wtap[t]);
-        tma_load_3d(&map_b_lo, st + 2 * TC_A_BYTES + b_pad, &full[s], c0, n0, wz0 + d.wtap[t]);
+      uint32_t ia = 0, ib = 0;                     // running slot counters of the two rings
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const TcClass& c = p.cls[tc.c];
+        const int wz0 = p.w_batched ? tc.n * p.taps_per_frame : 0;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const int c0 = kc * TC_BK;
+          for (int tp = 0; tp < c.ntaps; ++tp) {
+            if (c.first[tp]) {
+              const int s = ia % p.a_stages;
+              mbar_wait(&a_empty[s], ((ia / p.a_stages) & 1) ^ 1);
+              mbar_expect_tx(&a_full[s], 2 * a_half);
+              const int ax = tc.x0 * d.in_stride + c.dx[tp], ay = tc.y0 * d.in_stride + c.dy0[tp];
+              tma_load_4d(&map_a_hi, smem_a + s * a_stage, &a_full[s], c0, ax, ay, tc.n);
+              tma_load_4d(&map_a_lo, smem_a + s * a_stage + a_half, &a_full[s], c0, ax, ay, tc.n);
+              ++ia;
+            }
+            const int s = ib % p.b_stages;
+            mbar_wait(&b_empty[s], ((ib / p.b_stages) & 1) ^ 1);
+            mbar_expect_tx(&b_full[s], 2 * b_bytes);
+            tma_load_3d(&map_b_hi, smem_b + s * b_stage, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
+            tma_load_3d(&map_b_lo, smem_b + s * b_stage + b_half, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
+            ++ib;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -175,76 +241,160 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((TC_BM >> 4) << 24);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      const int row_bytes = p.tile_w * TC_ROW;     // one patch row of pixels (multiple of 1024: BW % 8 == 0)
+      uint32_t ia = 0, ib = 0, j = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+        const TileCoord tc = decode_tile(p, t);
+        const TcClass& c = p.cls[tc.c];
+        const uint32_t buf = j & 1;
+        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * stage_bytes);
-        const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + b_pad;
+        const uint32_t acc = tmem_base + buf * p.bn;
+        uint32_t a_addr = 0, sa = 0;
+        bool started = false;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          for (int tp = 0; tp < c.ntaps; ++tp) {
+            if (c.first[tp]) {
+              sa = ia % p.a_stages;
+              mbar_wait(&a_full[sa], (ia / p.a_stages) & 1);
+              a_addr = smem_u32(smem_a + sa * a_stage);
+              ++ia;
+            }
+            const uint32_t sb = ib % p.b_stages;
+            mbar_wait(&b_full[sb], (ib / p.b_stages) & 1);
+            ++ib;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = a_addr + c.row_off[tp] * row_bytes, a_lo = a_hi + a_half;
+            const uint32_t b_hi = smem_u32(smem_b + sb * b_stage), b_lo = b_hi + b_half;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
-          umma_bf16(tmem_base, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, (it | k) ? 1u : 0u);
-          umma_bf16(tmem_base, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, 1u);
-          umma_bf16(tmem_base, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1u);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
+              umma_bf16(acc, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, (started || k) ? 1u : 0u);
+              umma_bf16(acc, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, 1u);
+              umma_bf16(acc, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1u);
+            }
+            started = true;
+            umma_commit(&b_empty[sb]);               // frees the weight slot once these MMAs have read it
+            if (c.last[tp]) umma_commit(&a_empty[sa]);  // ... and the patch slot after its last tap
+          }
         }
-        umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+        umma_commit(&acc_full[buf]);                 // accumulator complete
       }
-      umma_commit(acc_full);     // accumulator complete
     }
   } else {
-    // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
-    const int q = warp & 3;
+    // ===== epilogue: 8 warps; warp w may touch TMEM lanes [32*(w%4), +32), the two warps of a quadrant split the
+    // accumulator columns in 32-wide chunks.  Per-channel scale/shift (demodulation, bias) are staged in shared
+    // memory once per (sample, N tile); the common epilogue is branch-free.
+    const int ew = warp - 2;
+    const int q = warp & 3, half = ew >> 2;
     const int r = q * 32 + lane;                     // accumulator row = pixel inside the tile
     const int ly = r / p.tile_w, lx = r - ly * p.tile_w;
-    const int my = y0 + ly, mx = x0 + lx;
-    const bool valid = my < d.oh && mx < d.ow;
-    mbar_wait(acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    EpiCtx ec;
-    epi_setup(ec, p.cp, n, valid ? my : 0, valid ? mx : 0);
-    for (int cb = 0; cb < p.bn; cb += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb, v);   // warp-collective: no early exit before this
-      if (!valid) continue;
-      const int co0 = n0 + cb;
+    const int et = threadIdx.x - 64;                 // 0..255
+    const bool generic = p.cp.residual != nullptr || p.cp.up_img != nullptr;
+    const float slope = d.act == HFAGP_ACT_LRELU ? 0.2f : 1.f;
+    const float gain = d.act_gain;
+    const float cl = d.clamp > 0.f ? d.clamp : __int_as_float(0x7f800000);
+    int staged_n = -1, staged_n0 = -1;
+    uint32_t j = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+      const TileCoord tc = decode_tile(p, t);
+      const TcClass& c = p.cls[tc.c];
+      const uint32_t buf = j & 1;
+      if (tc.n != staged_n || tc.n0 != staged_n0) {  // uniform over the epilogue threads
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone is done reading the previous vectors
+        if (et < p.bn) {
+          const int co = tc.n0 + et;
+          const bool in = co < d.cout;
+          epi_sc[et] = (in && p.cp.dcoef) ? __ldg(p.cp.dcoef + (size_t)tc.n * d.cout + co) : 1.f;
+          epi_sh[et] = (in && p.cp.bias) ? __ldg(p.cp.bias + co) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        staged_n = tc.n;
+        staged_n0 = tc.n0;
+      }
+      const int my = tc.y0 + ly, mx = tc.x0 + lx;
+      const bool valid = my < c.oh && mx < c.ow;
+      EpiCtx ec;
+      epi_setup_at(ec, p.cp, tc.n, valid ? my : 0, valid ? mx : 0, c.off_y, c.off_x);
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.bn;
+      bool arrived = false;
+      for (int cb = half * 32; cb < p.bn; cb += 64) {
+        float v[32];
+        tmem_ld32(acc + cb, v);                        // warp-collective: no early exit before this
+        if (cb + 64 >= p.bn) {
+          // last read of this accumulator by this warp: hand it back to the MMA issuer before the stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          arrived = true;
+        }
+        if (!valid) continue;
+        const int co0 = tc.n0 + cb;
+        if (co0 >= d.cout) continue;
+        const bool full = co0 + 32 <= d.cout;
+        if (!generic && full) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (co0 + j < d.cout) v[j] = epi_apply(ec, p.cp, v[j], co0 + j);
-      if (p.y_hi) {
-        __nv_bfloat16* oh = p.y_hi + ec.out_base + co0;
-        __nv_bfloat16* ol = p.y_lo + ec.out_base + co0;
-        if (co0 + 32 <= d.cout && (d.cout & 7) == 0) {
+          for (int jj = 0; jj < 32; jj += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(&epi_sc[cb + jj]);
+            const float4 sh = *reinterpret_cast<const float4*>(&epi_sh[cb + jj]);
+            float a0 = fmaf(v[jj], sc.x, sh.x + ec.nz), a1 = fmaf(v[jj + 1], sc.y, sh.y + ec.nz);
+            float a2 = fmaf(v[jj + 2], sc.z, sh.z + ec.nz), a3 = fmaf(v[jj + 3], sc.w, sh.w + ec.nz);
+            a0 = fmaxf(a0, slope * a0) * gain; a1 = fmaxf(a1, slope * a1) * gain;
+            a2 = fmaxf(a2, slope * a2) * gain; a3 = fmaxf(a3, slope * a3) * gain;
+            v[jj] = fminf(fmaxf(a0, -cl), cl); v[jj + 1] = fminf(fmaxf(a1, -cl), cl);
+            v[jj + 2] = fminf(fmaxf(a2, -cl), cl); v[jj + 3] = fminf(fmaxf(a3, -cl), cl);
+          }
+        } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t hw[4], lw[4];
+          for (int jj = 0; jj < 32; ++jj)
+            if (co0 + jj < d.cout) v[jj] = epi_apply(ec, p.cp, v[jj], co0 + jj);
+        }
+        if (p.y_hi) {
+          __nv_bfloat16* oh = p.y_hi + ec.out_base + co0;
+          __nv_bfloat16* ol = p.y_lo + ec.out_base + co0;
+          if (full && (d.cout & 7) == 0) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat16 h0 = __float2bfloat16_rn(v[j + 2 * e]), h1 = __float2bfloat16_rn(v[j + 2 * e + 1]);
-              __nv_bfloat16 l0 = __float2bfloat16_rn(v[j + 2 * e] - __bfloat162float(h0));
-              __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 2 * e + 1] - __bfloat162float(h1));
-              hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            for (int jj = 0; jj < 32; jj += 8) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat16 h0 = __float2bfloat16_rn(v[jj + 2 * e]), h1 = __float2bfloat16_rn(v[jj + 2 * e + 1]);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(v[jj + 2 * e] - __bfloat162float(h0));
+                __nv_bfloat16 l1 = __float2bfloat16_rn(v[jj + 2 * e + 1] - __bfloat162float(h1));
+                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              *reinterpret_cast<uint4*>(oh + jj) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(ol + jj) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
-            *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        } else {
-          for (int j = 0; j < 32 && co0 + j < d.cout; ++j) {
-            __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-            oh[j] = h;
-            ol[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
-          }
-        }
-      } else {
-        float* o = p.cp.y + ec.out_base + co0;
-        if (co0 + 32 <= d.cout && (d.cout & 3) == 0) {
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int jj = 0; jj < 32; ++jj)
+              if (co0 + jj < d.cout) {
+                __nv_bfloat16 h = __float2bfloat16_rn(v[jj]);
+                oh[jj] = h;
+                ol[jj] = __float2bfloat16_rn(v[jj] - __bfloat162float(h));
+              }
+          }
         } else {
-          for (int j = 0; j < 32 && co0 + j < d.cout; ++j) o[j] = v[j];
+          float* o = p.cp.y + ec.out_base + co0;
+          if (full && (d.cout & 3) == 0) {
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4)
+              *reinterpret_cast<float4*>(o + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (co0 + jj < d.cout) o[jj] = v[jj];
+          }
         }
+      }
+      if (!arrived) {                                  // this warp had no column chunk (bn <= 32)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -327,48 +477,135 @@ static int get_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, 
 
 using namespace hfagp;
 
-extern "C" int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_hi, const uint16_t* x_lo,
-                                   const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
-                                   const float* noise, const float* bias, const float* residual, const float* up_img,
-                                   float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream) {
-  HFAGP_CHECK_ARG(desc && x_hi && x_lo && w_hi && w_lo, "conv2d_tc_fwd: null pointer");
-  HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "conv2d_tc_fwd: give y or (y_hi, y_lo)");
-  const HfagpConvDesc& d = *desc;
-  HFAGP_CHECK_ARG(d.batch > 0 && d.batch <= 65535 && d.oh > 0 && d.ow > 0 && d.cout > 0, "conv2d_tc_fwd: bad dims");
-  HFAGP_CHECK_ARG(d.cin % 8 == 0, "conv2d_tc_fwd: cin must be a multiple of 8 (got %d)", d.cin);
-  HFAGP_CHECK_ARG(d.ntaps > 0 && d.ntaps <= HFAGP_MAX_TAPS, "conv2d_tc_fwd: ntaps out of range");
-  HFAGP_CHECK_ARG(d.in_stride == 1 || d.in_stride == 2, "conv2d_tc_fwd: in_stride must be 1 or 2");
-  HFAGP_CHECK_ARG((d.oh - 1) * d.out_stride + d.out_off_y < d.out_h && (d.ow - 1) * d.out_stride + d.out_off_x < d.out_w,
-                  "conv2d_tc_fwd: output window exceeds out_h/out_w");
-  HFAGP_CHECK_ARG(!up_img || (d.up_h * 2 == d.out_h && d.up_w * 2 == d.out_w), "conv2d_tc_fwd: up_img must be out/2");
-  HFAGP_CHECK_ARG(w_taps_total > 0, "conv2d_tc_fwd: w_taps_total");
+// ---------------------------------------------------------------- host: problem setup
+namespace hfagp {
+
+// Tap list of one desc -> grouped class.  patch mode (in_stride == 1): taps that share dx read one input patch.
+static void build_class(const HfagpConvDesc& d, bool patch_mode, TcClass& c, int& max_span) {
+  c.oh = d.oh; c.ow = d.ow; c.off_y = d.out_off_y; c.off_x = d.out_off_x;
+  int order[HFAGP_MAX_TAPS];
+  for (int t = 0; t < d.ntaps; ++t) order[t] = t;
+  if (patch_mode) {   // sort by (dx, dy): insertion sort, <= 16 entries
+    for (int i = 1; i < d.ntaps; ++i)
+      for (int j = i; j > 0; --j) {
+        const int a = order[j - 1], b = order[j];
+        if (d.dx[a] > d.dx[b] || (d.dx[a] == d.dx[b] && d.dy[a] > d.dy[b])) { order[j - 1] = b; order[j] = a; } else break;
+      }
+  }
+  c.ntaps = d.ntaps;
+  int i = 0;
+  while (i < d.ntaps) {
+    int j = i;
+    if (patch_mode) while (j + 1 < d.ntaps && d.dx[order[j + 1]] == d.dx[order[i]]) ++j;
+    const int dy0 = d.dy[order[i]];
+    const int span = d.dy[order[j]] - dy0;
+    if (span > max_span) max_span = span;
+    for (int k = i; k <= j; ++k) {
+      const int t = order[k];
+      c.dx[k] = (int8_t)d.dx[t];
+      c.dy0[k] = (int8_t)dy0;
+      c.row_off[k] = (int8_t)(d.dy[t] - dy0);
+      c.first[k] = k == i;
+      c.last[k] = k == j;
+      c.wtap[k] = (int8_t)d.wtap[t];
+    }
+    i = j + 1;
+  }
+}
+
+static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi, const uint16_t* x_lo,
+                     const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
+                     const float* noise, const float* bias, const float* residual, const float* up_img, float* y,
+                     uint16_t* y_hi, uint16_t* y_lo, void* stream, const char* who) {
+  HFAGP_CHECK_ARG(descs && ndesc >= 1 && ndesc <= TC_MAX_CLASSES, "%s: 1..%d descs", who, TC_MAX_CLASSES);
+  HFAGP_CHECK_ARG(x_hi && x_lo && w_hi && w_lo, "%s: null pointer", who);
+  HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "%s: give y or (y_hi, y_lo)", who);
+  const HfagpConvDesc& d = descs[0];
+  HFAGP_CHECK_ARG(d.batch > 0 && d.batch <= 65535 && d.cout > 0, "%s: bad dims", who);
+  HFAGP_CHECK_ARG(d.cin % 8 == 0, "%s: cin must be a multiple of 8 (got %d)", who, d.cin);
+  HFAGP_CHECK_ARG(d.in_stride == 1 || d.in_stride == 2, "%s: in_stride must be 1 or 2", who);
+  HFAGP_CHECK_ARG(!up_img || (d.up_h * 2 == d.out_h && d.up_w * 2 == d.out_w), "%s: up_img must be out/2", who);
+  HFAGP_CHECK_ARG(w_taps_total > 0 && w_taps_total <= 127, "%s: w_taps_total", who);
+  for (int i = 0; i < ndesc; ++i) {
+    const HfagpConvDesc& e = descs[i];
+    HFAGP_CHECK_ARG(e.oh > 0 && e.ow > 0 && e.ntaps > 0 && e.ntaps <= HFAGP_MAX_TAPS, "%s: desc %d: empty window / taps", who, i);
+    HFAGP_CHECK_ARG((e.oh - 1) * e.out_stride + e.out_off_y < e.out_h && (e.ow - 1) * e.out_stride + e.out_off_x < e.out_w,
+                    "%s: desc %d: output window exceeds out_h/out_w", who, i);
+    HFAGP_CHECK_ARG(e.batch == d.batch && e.in_h == d.in_h && e.in_w == d.in_w && e.cin == d.cin && e.cout == d.cout &&
+                        e.in_stride == d.in_stride && e.out_h == d.out_h && e.out_w == d.out_w &&
+                        e.out_stride == d.out_stride && e.w_batch_stride == d.w_batch_stride && e.act == d.act &&
+                        e.act_gain == d.act_gain && e.clamp == d.clamp && e.noise_gain == d.noise_gain &&
+                        e.residual_scale == d.residual_scale && e.up_h == d.up_h && e.up_w == d.up_w,
+                    "%s: desc %d differs from desc 0 in more than its window and taps", who, i);
+    for (int t = 0; t < e.ntaps; ++t)
+      HFAGP_CHECK_ARG(e.dy[t] >= -64 && e.dy[t] <= 63 && e.dx[t] >= -64 && e.dx[t] <= 63 && e.wtap[t] >= 0 &&
+                          e.wtap[t] < w_taps_total, "%s: desc %d: tap %d out of range", who, i, t);
+  }
 
   TcParams p;
   p.cp = ConvParams{d, nullptr, nullptr, dcoef, noise, bias, residual, up_img, y};
   p.y_hi = reinterpret_cast<__nv_bfloat16*>(y_hi);
   p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
-  // M tile shape: the BW x BH (=128) rectangle that wastes the fewest pixels
-  long long best = -1;
+  p.ncls = ndesc;
+  const bool patch_mode = d.in_stride == 1;
+  int max_span = 0;
+  for (int i = 0; i < ndesc; ++i) build_class(descs[i], patch_mode, p.cls[i], max_span);
+  p.bn = d.cout >= 128 ? 128 : ((d.cout + 15) / 16) * 16;
+  p.n_tiles = cdiv(d.cout, p.bn);
+  // M tile shape BW x BH (= 128 pixels, BW % 8 == 0): least operand traffic = padded tiles x (patch rows + weight rows)
+  double best = -1;
   for (int bw = 128; bw >= 8; bw >>= 1) {
-    int bh = 128 / bw;
-    long long padded = (long long)cdiv(d.ow, bw) * bw * cdiv(d.oh, bh) * bh;
-    if (best < 0 || padded < best) {
-      best = padded;
+    const int bh = 128 / bw;
+    double cost = 0;
+    for (int i = 0; i < ndesc; ++i) {
+      const TcClass& c = p.cls[i];
+      int groups = 0;
+      for (int t = 0; t < c.ntaps; ++t) groups += c.first[t];
+      const double tiles = (double)cdiv(c.ow, bw) * cdiv(c.oh, bh);
+      cost += tiles * (groups * (double)(bh + max_span) * bw + (double)c.ntaps * p.bn);
+    }
+    if (best < 0 || cost < best) {
+      best = cost;
       p.tile_w = bw;
       p.tile_h = bh;
     }
   }
-  p.tiles_x = cdiv(d.ow, p.tile_w);
-  p.tiles_y = cdiv(d.oh, p.tile_h);
-  p.bn = d.cout >= 128 ? 128 : ((d.cout + 15) / 16) * 16;
+  p.patch_rows = p.tile_h + max_span;
+  int tiles = 0;
+  for (int i = 0; i < ndesc; ++i) {
+    TcClass& c = p.cls[i];
+    c.tiles_x = cdiv(c.ow, p.tile_w);
+    c.tiles_y = cdiv(c.oh, p.tile_h);
+    c.tile_begin = tiles;
+    tiles += c.tiles_x * c.tiles_y;
+  }
+  p.tiles_per_frame = tiles;
+  p.total_tiles = tiles * p.n_tiles * d.batch;
   p.w_batched = d.w_batch_stride != 0;
   p.taps_per_frame = w_taps_total;
+
+  // shared-memory rings: as deep as 225 KB allows
+  const int a_stage = 2 * p.patch_rows * p.tile_w * TC_ROW;
+  const int b_stage = 2 * ((p.bn * TC_ROW + 1023) & ~1023);
+  const int extra = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * TC_BM * 4 /*epilogue vectors*/;
+  const int budget = 227 * 1024 - extra;
+  static const int choices[][2] = {{3, 4}, {2, 4}, {3, 3}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
+  p.a_stages = p.b_stages = 0;
+  for (const auto& ch : choices)
+    if (ch[0] * a_stage + ch[1] * b_stage <= budget) {
+      p.a_stages = ch[0];
+      p.b_stages = ch[1];
+      break;
+    }
+  HFAGP_CHECK_ARG(p.a_stages > 0, "%s: tile does not fit shared memory", who);
+  const size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + extra;
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   const uint32_t es = (uint32_t)d.in_stride;
   // box extents are given in un-strided coordinates: a stride-2 traversal of BW outputs spans 2*BW-1 inputs
   const uint32_t box_w = (uint32_t)(p.tile_w * d.in_stride - (d.in_stride - 1));
-  const uint32_t box_h = (uint32_t)(p.tile_h * d.in_stride - (d.in_stride - 1));
+  const uint32_t box_h = (uint32_t)(p.patch_rows * d.in_stride - (d.in_stride - 1));
+  HFAGP_CHECK_ARG(box_w <= 256 && box_h <= 256, "%s: TMA box too large", who);
   int rc;
   if ((rc = get_map(&ma_hi, x_hi, d.cin, d.in_w, d.in_h, d.batch, TC_BK, box_w, box_h, 1, es, 4))) return rc;
   if ((rc = get_map(&ma_lo, x_lo, d.cin, d.in_w, d.in_h, d.batch, TC_BK, box_w, box_h, 1, es, 4))) return rc;
@@ -376,14 +613,38 @@ extern "C" int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_
   if ((rc = get_map(&mb_hi, w_hi, d.cin, d.cout, wz, 1, TC_BK, p.bn, 1, 1, 1, 3))) return rc;
   if ((rc = get_map(&mb_lo, w_lo, d.cin, d.cout, wz, 1, TC_BK, p.bn, 1, 1, 1, 3))) return rc;
 
-  const int b_pad = (p.bn * TC_BK * 2 + 1023) & ~1023;
-  const size_t smem = (size_t)TC_STAGES * (2 * TC_A_BYTES + 2 * b_pad) + 1024 + 128;
   static std::once_flag attr_once;
+  static int num_sms = 148;
+  static cudaError_t attr_rc = cudaSuccess;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_rc = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      num_sms = n;
   });
-  dim3 grid(p.tiles_x * p.tiles_y, cdiv(d.cout, p.bn), d.batch);
+  if (attr_rc != cudaSuccess) return fail(HFAGP_E_CUDA, "%s: cudaFuncSetAttribute(max dynamic smem) failed: %s", who, cudaGetErrorString(attr_rc));
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   HFAGP_CHECK_LAUNCH("conv_tc_kernel");
   return HFAGP_OK;
+}
+
+}  // namespace hfagp
+
+extern "C" int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_hi, const uint16_t* x_lo,
+                                   const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
+                                   const float* noise, const float* bias, const float* residual, const float* up_img,
+                                   float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream) {
+  return launch_tc(desc, 1, x_hi, x_lo, w_hi, w_lo, w_taps_total, dcoef, noise, bias, residual, up_img, y, y_hi, y_lo,
+                   stream, "conv2d_tc_fwd");
+}
+
+extern "C" int hfagp_conv2d_tc_multi_fwd(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi,
+                                         const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                                         int w_taps_total, const float* dcoef, const float* noise, const float* bias,
+                                         const float* residual, const float* up_img, float* y, uint16_t* y_hi,
+                                         uint16_t* y_lo, void* stream) {
+  return launch_tc(descs, ndesc, x_hi, x_lo, w_hi, w_lo, w_taps_total, dcoef, noise, bias, residual, up_img, y, y_hi,
+                   y_lo, stream, "conv2d_tc_multi_fwd");
 }

@@ -46,15 +46,20 @@ struct EpiCtx {
   const float* up;       // low-res skip image of sample n (or null)
 };
 
-__device__ __forceinline__ void epi_setup(EpiCtx& e, const ConvParams& p, int n, int my, int mx) {
+// (off_y, off_x): output offset of the sub-problem (an output parity class of a merged launch)
+__device__ __forceinline__ void epi_setup_at(EpiCtx& e, const ConvParams& p, int n, int my, int mx, int off_y, int off_x) {
   const HfagpConvDesc& d = p.d;
-  e.oy = my * d.out_stride + d.out_off_y;
-  e.ox = mx * d.out_stride + d.out_off_x;
+  e.oy = my * d.out_stride + off_y;
+  e.ox = mx * d.out_stride + off_x;
   e.nz = p.noise ? __ldg(p.noise + (size_t)e.oy * d.out_w + e.ox) * d.noise_gain : 0.f;
   e.out_base = (((size_t)n * d.out_h + e.oy) * d.out_w + e.ox) * d.cout;
   e.dco = p.dcoef ? p.dcoef + (size_t)n * d.cout : nullptr;
   e.res = p.residual ? p.residual + e.out_base : nullptr;
   e.up = p.up_img ? p.up_img + (size_t)n * d.up_h * d.up_w * d.cout : nullptr;
+}
+
+__device__ __forceinline__ void epi_setup(EpiCtx& e, const ConvParams& p, int n, int my, int mx) {
+  epi_setup_at(e, p, n, my, mx, p.d.out_off_y, p.d.out_off_x);
 }
 
 __device__ __forceinline__ float epi_apply(const EpiCtx& e, const ConvParams& p, float v, int co) {

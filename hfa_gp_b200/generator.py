@@ -294,11 +294,7 @@ class TriPlaneGenerator(nn.Module):
                 y = ops.conv2d_tc(xs, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batched=True,
                                   split_out=split_out, **epi)
             else:
-                t = torch.empty((x.shape[0], 2 * h + 1, 2 * w + 1, pl.cout), device=xs.device, dtype=torch.float32)
-                for a in (0, 1):
-                    for b in (0, 1):
-                        ops.conv2d_tc(xs, wmod, ops._parity_taps(a, b), pl.cout, oh=h + 1 - a, ow=w + 1 - b, out=t,
-                                      out_hw=(2 * h + 1, 2 * w + 1), out_stride=2, out_off=(a, b), w_batched=True)
+                t = ops.conv_transpose_s2_tc(xs, wmod, pl.cout, w_batched=True)
                 y = ops.upfir_act(t, split_out=split_out, **epi)
         else:
             xs = self._as_f32(x)

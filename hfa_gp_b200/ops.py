@@ -439,13 +439,37 @@ class StyleTableBwd:
 
 
 def conv_transpose_s2_tc(x: Split, w: Split, cout: int, w_batched: bool = False) -> torch.Tensor:
-    """conv_transpose_s2() on the tcgen05 path: four output-parity launches scattering into [N,2H+1,2W+1,Co]."""
-    n, h, wd, _ = x.shape
+    """conv_transpose_s2() on the tcgen05 path: the four output-parity classes as ONE persistent launch
+    (``hfagp_conv2d_tc_multi_fwd``) scattering into [N,2H+1,2W+1,Co]."""
+    n, h, wd, cin = x.shape
     out = torch.empty((n, 2 * h + 1, 2 * wd + 1, cout), device=x.device, dtype=torch.float32)
-    for a in (0, 1):
-        for b in (0, 1):
-            conv2d_tc(x, w, _parity_taps(a, b), cout, oh=h + 1 - a, ow=wd + 1 - b, out=out,
-                      out_hw=(2 * h + 1, 2 * wd + 1), out_stride=2, out_off=(a, b), w_batched=w_batched)
+    w_taps_total = w.shape[-3]
+    wbs = w_taps_total * cout * cin if w_batched else 0
+    key = ('tcup', n, h, wd, cin, cout, wbs)
+
+    def build():
+        arr = (ConvDesc * 4)()
+        i = 0
+        for a in (0, 1):
+            for b in (0, 1):
+                d = arr[i]
+                i += 1
+                d.batch, d.in_h, d.in_w, d.cin, d.cout = n, h, wd, cin, cout
+                d.oh, d.ow, d.in_stride = h + 1 - a, wd + 1 - b, 1
+                d.out_h, d.out_w, d.out_stride = 2 * h + 1, 2 * wd + 1, 2
+                d.out_off_y, d.out_off_x = a, b
+                taps = _parity_taps(a, b)
+                d.ntaps = len(taps)
+                for k, (dy, dx, wt) in enumerate(taps):
+                    d.dy[k], d.dx[k], d.wtap[k] = dy, dx, wt
+                d.w_batch_stride = wbs
+                d.act, d.act_gain, d.clamp, d.noise_gain, d.residual_scale = ACT_LINEAR, 1.0, 0.0, 0.0, 1.0
+        return arr
+
+    arr = _conv_desc(key, build)
+    _ok(_cabi.lib().hfagp_conv2d_tc_multi_fwd(arr, 4, ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total, None,
+                                              None, None, None, None, ptr(out), None, None, stream()),
+        'hfagp_conv2d_tc_multi_fwd')
     return out
 
 

@@ -103,6 +103,15 @@ int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_hi, const u
                         const float* noise, const float* bias, const float* residual, const float* up_img,
                         float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
 
+/* Several sub-problems in ONE launch: descs[0..ndesc) (ndesc <= 4) share operands, channel counts, strides, the
+ * output tensor and the epilogue, and differ only in their output window (oh, ow, out_off_*) and tap list — the
+ * four output-parity classes of the stride-2 transposed convolution (up-sampling layers; data gradient of the
+ * encoder's stride-2 convolutions) run as one persistent grid instead of four launches. */
+int hfagp_conv2d_tc_multi_fwd(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi, const uint16_t* x_lo,
+                              const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
+                              const float* noise, const float* bias, const float* residual, const float* up_img,
+                              float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
+
 /* fp32 -> split bf16 (elementwise). */
 int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, uint16_t* lo, void* stream);
 
