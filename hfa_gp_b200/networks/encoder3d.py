@@ -26,6 +26,11 @@ from .._cabi import ACT_LINEAR, ACT_LRELU, HfagpError
 SQRT2 = math.sqrt(2.0)
 INV_SQRT2 = 1.0 / SQRT2
 
+# None: the backward pass uses the kernel family the forward pass used.  True / False force the tcgen05 / SIMT
+# backward kernels on any tape (tests: run the tensor-core backward on an exact-fp32 forward so that both sides
+# take the same leaky-ReLU branches and the comparison isolates the backward arithmetic).
+BACKWARD_TC_OVERRIDE = None
+
 
 def make_kernel(k):
     k = torch.tensor(k, dtype=torch.float32)
@@ -189,7 +194,7 @@ class ConvLayer(nn.Sequential):
             raise HfagpError('backward of a biased non-activated ConvLayer is never needed on the HFA-GP path')
         cout, cin, k = conv.weight.shape[0], conv.weight.shape[1], self.kernel_size
         g0, g1 = (dy if isinstance(dy, tuple) else (dy, None))
-        tc = rec['tc'] and cout % 8 == 0
+        tc = (rec['tc'] if BACKWARD_TC_OVERRIDE is None else BACKWARD_TC_OVERRIDE) and cout % 8 == 0 and cin % 8 == 0
         residual = rec['residual']
         kw = dict(g0=g0, g1=g1, out='split' if (tc and need_dx) else 'f32')
         if act is not None:

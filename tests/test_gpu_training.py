@@ -15,7 +15,7 @@ from oracle import eg3d_ref, hfagp_ref, train_ref
 pytestmark = pytest.mark.gpu
 
 
-GRAD_TOL_L2 = {'fp32': 1e-3, 'tc': 1e-2}
+GRAD_TOL_L2 = {'fp32': 1e-3, 'tc': 3e-2, 'fp32fwd_tcbwd': 1e-3}
 
 
 def _check(got, want, precision, what, tol=None):
@@ -24,7 +24,12 @@ def _check(got, want, precision, what, tol=None):
     pre-activation lands within 4e-7 of the leaky-ReLU kink, the GPU's fp32 summation order puts it on the other
     side than the CPU's, and that single flipped slope moves every upstream gradient by ~2e-4 relative L2 (up to
     1e-2 on individual near-cancelling elements).  The bound still catches any real error (a wrong tap, scale or
-    missing term changes the L2 by >= 1e-2)."""
+    missing term changes the L2 by >= 1e-2).
+
+    On the tensor-core path the forward differs from fp32 by ~3e-5, so about 3e-5 of all activations (tens per
+    layer) take the other leaky-ReLU branch and the gradient's relative L2 moves by sqrt(flips/elements) ~ 5e-3 per
+    layer, chaotically in the summation order: 'tc' is therefore held to 3e-2, and the tensor-core BACKWARD kernels
+    are pinned separately at the fp32 bound by 'fp32fwd_tcbwd' (exact-fp32 forward tape, tcgen05 backward)."""
     e_max, e_l2 = pu.rel_err(got, want), pu.rel_l2(got, want)
     print(f'{what}: max-rel {e_max:.3e} rel-L2 {e_l2:.3e}')
     assert e_l2 < (tol or GRAD_TOL_L2[precision]), (what, e_l2)
@@ -149,9 +154,36 @@ def _args(size, k, cfg, **kw):
                               **kw)
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'tc'])
+class _BackwardOnTensorCores:
+    """fp32 forward, tcgen05 backward: flips the kernel family between trainer.gen_update's two halves."""
+
+    def __init__(self, gen):
+        self.gen = gen
+
+    def __enter__(self):
+        from hfa_gp_b200.networks import encoder3d
+        gen = self.gen
+        encoder3d.BACKWARD_TC_OVERRIDE = True
+        orig = gen.generator.synthesis
+
+        def synthesis(*a, **k):
+            gen.generator.precision = 'fp32'
+            out = orig(*a, **k)
+            gen.generator.precision = 'tc'          # read again by autograd.py when the tape is walked backwards
+            return out
+        gen.generator.synthesis = synthesis
+        return self
+
+    def __exit__(self, *exc):
+        from hfa_gp_b200.networks import encoder3d
+        encoder3d.BACKWARD_TC_OVERRIDE = None
+        del self.gen.generator.synthesis
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tc', 'fp32fwd_tcbwd'])
 def test_trainer_rgb_steps_match_oracle(precision):
     """Two gen_update steps of the RGB trainer: losses, pooled image, gradients and updated parameters."""
+    import contextlib
     from hfa_gp_b200.trainer_rgb import Trainer
     from hfa_gp_b200.lpips import LPIPS
     cfg = eg3d_ref.small14_config()
@@ -160,8 +192,8 @@ def test_trainer_rgb_steps_match_oracle(precision):
     tr = Trainer(_args(size, k, cfg), torch.device('cuda'), 0)
     gen = tr.gen.module
     gen.generator.load_state_dict(ref_gen.state_dict())
-    gen.generator.precision = gen.encoder.net_app.precision = precision
-    sd, enc = _encoder_pair(size, k, precision, seed=4)
+    gen.generator.precision = gen.encoder.net_app.precision = 'tc' if precision == 'tc' else 'fp32'
+    sd, enc = _encoder_pair(size, k, 'fp32', seed=4)
     with torch.no_grad():
         for n, p in gen.encoder.named_parameters():
             p.copy_(sd[n])
@@ -177,11 +209,12 @@ def test_trainer_rgb_steps_match_oracle(precision):
         l2_r, lp_r, img_r = oracle.step(real, label, jit, u)
         gen.generator.fixed_draws = (jit.cuda(), u.cuda())
         lab = label.clone().cuda()
-        l2, lpv, img = tr.gen_update(real.cuda(), lab)
+        with (_BackwardOnTensorCores(gen) if precision == 'fp32fwd_tcbwd' else contextlib.nullcontext()):
+            l2, lpv, img = tr.gen_update(real.cuda(), lab)
         assert torch.equal(lab.cpu(), hfagp_ref.flip_label_(label.clone()))       # in-place flip preserved
         assert pu.rel_err(img, img_r) < pu.REL_TOL
-        assert abs(float(l2) - float(l2_r)) < 1e-3 * abs(float(l2_r))
-        assert abs(float(lpv) - float(lp_r)) < 2e-3 * abs(float(lp_r))
+        assert abs(float(l2.detach()) - float(l2_r)) < 1e-3 * abs(float(l2_r))
+        assert abs(float(lpv.detach()) - float(lp_r)) < 2e-3 * abs(float(lp_r))
         if it == 0:
             names = dict(gen.encoder.named_parameters())
             for n in oracle.names:
@@ -193,7 +226,9 @@ def test_trainer_rgb_steps_match_oracle(precision):
         # Adam's first steps move every element by ~lr regardless of gradient size: compare the UPDATE
         upd_r = oracle.sd[n].detach() - sd[n]
         upd = names[n].detach().cpu() - sd[n]
-        assert pu.rel_l2(upd, upd_r) < 5e-2, (n, pu.rel_l2(upd, upd_r))
+        # (on the full tensor-core path the flipped-branch noise of the gradients reaches the SIGN of near-zero
+        # gradient elements, which Adam's first steps amplify to +-lr: only a loose bound is meaningful there)
+        assert pu.rel_l2(upd, upd_r) < (0.3 if precision == 'tc' else 5e-2), (n, pu.rel_l2(upd, upd_r))
     assert pu.rel_err(gen.bases, oracle.bases) < 1e-3
     assert tr.g_optim.steps == [2, 0]
 
@@ -219,7 +254,7 @@ def test_trainer_3dmm_step_matches_oracle():
     gen.generator.fixed_draws = (jit.cuda(), u.cuda())
     _, l2, lpv, img = tr.gen_update(real.cuda(), label.clone().cuda(), params.cuda())
     assert pu.rel_err(img, img_r) < pu.REL_TOL
-    assert abs(float(l2) - float(l2_r)) < 1e-3 * abs(float(l2_r))
+    assert abs(float(l2.detach()) - float(l2_r)) < 1e-3 * abs(float(l2_r))
     names = dict(gen.weights_3dmm.named_parameters())
     for n in oracle.names:
         _check(names[n].grad, oracle.sd[n].grad, 'tc', f'd {n}')
