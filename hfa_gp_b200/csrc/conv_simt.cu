@@ -160,6 +160,29 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvParams p) {
   }
 }
 
+// ---------------------------------------------------------------- epilogue of a split-K convolution
+// acc[n][oy][ox][c] holds the raw convolution sums (hfagp_conv2d_tc_acc_fwd); apply the fused epilogue elementwise.
+__global__ void conv_epilogue_kernel(const ConvParams p, const float* __restrict__ acc, __nv_bfloat16* __restrict__ y_hi,
+                                     __nv_bfloat16* __restrict__ y_lo) {
+  const HfagpConvDesc& d = p.d;
+  const int c4 = d.cout >> 2;
+  const size_t total = (size_t)d.batch * d.out_h * d.out_w * c4;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cq = idx % c4;
+  size_t pix = idx / c4;
+  const int ox = pix % d.out_w;
+  pix /= d.out_w;
+  const int oy = pix % d.out_h, n = pix / d.out_h;
+  EpiCtx ec;
+  epi_setup_at(ec, p, n, oy, ox, 0, 0);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(acc) + idx);
+  float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = epi_apply(ec, p, v[k], cq * 4 + k);
+  st4_any(p.y, y_hi, y_lo, idx, v);
+}
+
 // ---------------------------------------------------------------- FIR after transposed conv
 __global__ void upfir_act_kernel(int batch, int h2, int w2, int c, const float* __restrict__ t,
                                  const float* __restrict__ dcoef, const float* __restrict__ noise, float noise_gain,
@@ -371,6 +394,24 @@ extern "C" int hfagp_conv2d_fwd(const HfagpConvDesc* desc, const float* x, const
     conv_igemm_kernel<4, 4><<<grid, 256, 0, st>>>(p);
   }
   HFAGP_CHECK_LAUNCH("conv_igemm_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_conv_epilogue_fwd(const HfagpConvDesc* desc, const float* acc, const float* dcoef, const float* noise,
+                                       const float* bias, const float* residual, const float* up_img, float* y,
+                                       uint16_t* y_hi, uint16_t* y_lo, void* stream) {
+  HFAGP_CHECK_ARG(desc && acc && ((y != nullptr) != (y_hi != nullptr && y_lo != nullptr)),
+                  "conv_epilogue_fwd: give acc and either y or (y_hi, y_lo)");
+  const HfagpConvDesc& d = *desc;
+  HFAGP_CHECK_ARG(d.batch > 0 && d.cout > 0 && (d.cout & 3) == 0, "conv_epilogue_fwd: cout must be a multiple of 4");
+  HFAGP_CHECK_ARG(d.out_stride == 1 && d.out_off_y == 0 && d.out_off_x == 0 && d.oh == d.out_h && d.ow == d.out_w,
+                  "conv_epilogue_fwd: the output must be dense");
+  HFAGP_CHECK_ARG(!up_img || (d.up_h * 2 == d.out_h && d.up_w * 2 == d.out_w), "conv_epilogue_fwd: up_img must be out/2");
+  ConvParams p{d, nullptr, nullptr, dcoef, noise, bias, residual, up_img, y};
+  const size_t total = (size_t)d.batch * d.out_h * d.out_w * (d.cout >> 2);
+  conv_epilogue_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(p, acc, reinterpret_cast<__nv_bfloat16*>(y_hi),
+                                                                          reinterpret_cast<__nv_bfloat16*>(y_lo));
+  HFAGP_CHECK_LAUNCH("conv_epilogue_kernel");
   return HFAGP_OK;
 }
 

@@ -31,8 +31,12 @@ constexpr uint32_t SPIN_LIMIT = 1u << 24;       // a broken pipeline traps inste
 // at different row offsets, so a 3x3 stride-1 convolution loads 3 patches instead of 9 tiles.
 struct TcClass {
   int oh, ow, off_y, off_x;
-  int tiles_x, tiles_y, tile_begin;             // M tiles of this class inside one frame
+  int tiles_x, tiles_y, tile_begin;             // M tiles of this class inside one frame (x splits = work items)
   int ntaps;
+  int ngroups;                                  // tap groups (patches) per K chunk
+  int splits;                                   // split-K factor of this class: its kchunks*ngroups units are dealt
+                                                // out to `splits` CTAs per tile (1 = no split)
+  int8_t gstart[HFAGP_MAX_TAPS + 1];            // taps of group g: [gstart[g], gstart[g+1])
   int8_t dx[HFAGP_MAX_TAPS];                    // patch origin (x) of the tap's group
   int8_t dy0[HFAGP_MAX_TAPS];                   // patch origin (y) of the tap's group
   int8_t row_off[HFAGP_MAX_TAPS];               // tap's first patch row (dy - dy0)
@@ -54,6 +58,7 @@ struct TcParams {
   int taps_per_frame;     // weight taps stored per batch sample (B map z-coordinate stride)
   int w_batched;          // 1: weights are per sample
   int a_stages, b_stages;
+  int accumulate;         // 1: split-K mode — raw fp32 partial sums are atomically added to cp.y, no epilogue
   __nv_bfloat16* y_hi;    // split output (or null -> cp.y fp32)
   __nv_bfloat16* y_lo;
 };
@@ -131,8 +136,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 
 // tile id -> (class, batch sample, tile origin, N offset).  N tiles are the fastest index so that the CTAs running
 // side by side read the same input patch (L2 hits), then M tiles, then classes, then batch samples.
-struct TileCoord { int c, n, y0, x0, n0; };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+struct TileCoord { int c, n, y0, x0, n0, u0, u1; };   // [u0, u1): (K chunk, tap group) units of this work item
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int kchunks) {
   TileCoord tc;
   const int nt = t % p.n_tiles;
   int r = t / p.n_tiles;
@@ -141,6 +146,12 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   int c = 0;
   while (c + 1 < p.ncls && r >= p.cls[c + 1].tile_begin) ++c;
   r -= p.cls[c].tile_begin;
+  const int splits = p.cls[c].splits;
+  const int ks = r % splits;
+  r /= splits;
+  const int units = kchunks * p.cls[c].ngroups;
+  tc.u0 = (int)((long long)units * ks / splits);
+  tc.u1 = (int)((long long)units * (ks + 1) / splits);
   const int ty = r / p.cls[c].tiles_x;
   tc.c = c;
   tc.y0 = ty * p.tile_h;
@@ -211,12 +222,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       uint32_t ia = 0, ib = 0;                     // running slot counters of the two rings
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+        const TileCoord tc = decode_tile(p, t, kchunks);
         const TcClass& c = p.cls[tc.c];
         const int wz0 = p.w_batched ? tc.n * p.taps_per_frame : 0;
-        for (int kc = 0; kc < kchunks; ++kc) {
+        for (int u = tc.u0; u < tc.u1; ++u) {
+          const int kc = u / c.ngroups, g = u - kc * c.ngroups;
           const int c0 = kc * TC_BK;
-          for (int tp = 0; tp < c.ntaps; ++tp) {
+          for (int tp = c.gstart[g]; tp < c.gstart[g + 1]; ++tp) {
             if (c.first[tp]) {
               const int s = ia % p.a_stages;
               mbar_wait(&a_empty[s], ((ia / p.a_stages) & 1) ^ 1);
@@ -244,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const int row_bytes = p.tile_w * TC_ROW;     // one patch row of pixels (multiple of 1024: BW % 8 == 0)
       uint32_t ia = 0, ib = 0, j = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
-        const TileCoord tc = decode_tile(p, t);
+        const TileCoord tc = decode_tile(p, t, kchunks);
         const TcClass& c = p.cls[tc.c];
         const uint32_t buf = j & 1;
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
@@ -252,8 +264,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t acc = tmem_base + buf * p.bn;
         uint32_t a_addr = 0, sa = 0;
         bool started = false;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          for (int tp = 0; tp < c.ntaps; ++tp) {
+        for (int u = tc.u0; u < tc.u1; ++u) {
+          const int g = u % c.ngroups;
+          for (int tp = c.gstart[g]; tp < c.gstart[g + 1]; ++tp) {
             if (c.first[tp]) {
               sa = ia % p.a_stages;
               mbar_wait(&a_full[sa], (ia / p.a_stages) & 1);
@@ -297,7 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     int staged_n = -1, staged_n0 = -1;
     uint32_t j = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
-      const TileCoord tc = decode_tile(p, t);
+      const TileCoord tc = decode_tile(p, t, kchunks);
       const TcClass& c = p.cls[tc.c];
       const uint32_t buf = j & 1;
       if (tc.n != staged_n || tc.n0 != staged_n0) {  // uniform over the epilogue threads
@@ -334,6 +347,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int co0 = tc.n0 + cb;
         if (co0 >= d.cout) continue;
         const bool full = co0 + 32 <= d.cout;
+        if (p.accumulate) {
+          float* o = p.cp.y + ec.out_base + co0;
+          if (full && (d.cout & 3) == 0) {
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4)
+              atomicAdd(reinterpret_cast<float4*>(o + jj), make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]));
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (co0 + jj < d.cout) atomicAdd(o + jj, v[jj]);
+          }
+          continue;
+        }
         if (!generic && full) {
 #pragma unroll
           for (int jj = 0; jj < 32; jj += 4) {
@@ -493,6 +519,8 @@ static void build_class(const HfagpConvDesc& d, bool patch_mode, TcClass& c, int
       }
   }
   c.ntaps = d.ntaps;
+  c.ngroups = 0;
+  c.splits = 1;
   int i = 0;
   while (i < d.ntaps) {
     int j = i;
@@ -509,14 +537,16 @@ static void build_class(const HfagpConvDesc& d, bool patch_mode, TcClass& c, int
       c.last[k] = k == j;
       c.wtap[k] = (int8_t)d.wtap[t];
     }
+    c.gstart[c.ngroups++] = (int8_t)i;
     i = j + 1;
   }
+  c.gstart[c.ngroups] = (int8_t)d.ntaps;
 }
 
 static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi, const uint16_t* x_lo,
                      const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
                      const float* noise, const float* bias, const float* residual, const float* up_img, float* y,
-                     uint16_t* y_hi, uint16_t* y_lo, void* stream, const char* who) {
+                     uint16_t* y_hi, uint16_t* y_lo, int ksplit, void* stream, const char* who) {
   HFAGP_CHECK_ARG(descs && ndesc >= 1 && ndesc <= TC_MAX_CLASSES, "%s: 1..%d descs", who, TC_MAX_CLASSES);
   HFAGP_CHECK_ARG(x_hi && x_lo && w_hi && w_lo, "%s: null pointer", who);
   HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "%s: give y or (y_hi, y_lo)", who);
@@ -547,6 +577,7 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   p.y_hi = reinterpret_cast<__nv_bfloat16*>(y_hi);
   p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
   p.ncls = ndesc;
+  p.accumulate = ksplit > 0;
   const bool patch_mode = d.in_stride == 1;
   int max_span = 0;
   for (int i = 0; i < ndesc; ++i) build_class(descs[i], patch_mode, p.cls[i], max_span);
@@ -572,12 +603,15 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   }
   p.patch_rows = p.tile_h + max_span;
   int tiles = 0;
+  const int kchunks_h = cdiv(d.cin, TC_BK);
   for (int i = 0; i < ndesc; ++i) {
     TcClass& c = p.cls[i];
     c.tiles_x = cdiv(c.ow, p.tile_w);
     c.tiles_y = cdiv(c.oh, p.tile_h);
     c.tile_begin = tiles;
-    tiles += c.tiles_x * c.tiles_y;
+    const int units = kchunks_h * c.ngroups;
+    c.splits = ksplit > 1 ? (ksplit < units ? ksplit : units) : 1;
+    tiles += c.tiles_x * c.tiles_y * c.splits;
   }
   p.tiles_per_frame = tiles;
   p.total_tiles = tiles * p.n_tiles * d.batch;
@@ -637,7 +671,7 @@ extern "C" int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_
                                    const float* noise, const float* bias, const float* residual, const float* up_img,
                                    float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream) {
   return launch_tc(desc, 1, x_hi, x_lo, w_hi, w_lo, w_taps_total, dcoef, noise, bias, residual, up_img, y, y_hi, y_lo,
-                   stream, "conv2d_tc_fwd");
+                   0, stream, "conv2d_tc_fwd");
 }
 
 extern "C" int hfagp_conv2d_tc_multi_fwd(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi,
@@ -646,5 +680,13 @@ extern "C" int hfagp_conv2d_tc_multi_fwd(const HfagpConvDesc* descs, int ndesc, 
                                          const float* residual, const float* up_img, float* y, uint16_t* y_hi,
                                          uint16_t* y_lo, void* stream) {
   return launch_tc(descs, ndesc, x_hi, x_lo, w_hi, w_lo, w_taps_total, dcoef, noise, bias, residual, up_img, y, y_hi,
-                   y_lo, stream, "conv2d_tc_multi_fwd");
+                   y_lo, 0, stream, "conv2d_tc_multi_fwd");
+}
+
+extern "C" int hfagp_conv2d_tc_acc_fwd(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi, const uint16_t* x_lo,
+                                       const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, int ksplit,
+                                       float* acc, void* stream) {
+  HFAGP_CHECK_ARG(ksplit >= 1 && acc, "conv2d_tc_acc_fwd: ksplit >= 1 and an accumulator are required");
+  return launch_tc(descs, ndesc, x_hi, x_lo, w_hi, w_lo, w_taps_total, nullptr, nullptr, nullptr, nullptr, nullptr, acc,
+                   nullptr, nullptr, ksplit, stream, "conv2d_tc_acc_fwd");
 }

@@ -311,6 +311,19 @@ def modulate_split(w: torch.Tensor, styles: torch.Tensor, demodulate: bool):
     return Split(hi, lo), dcoef
 
 
+NUM_SMS = 148
+
+
+def _ksplit(tiles: int, cin: int, taps, in_stride: int) -> int:
+    """Split-K factor for a tensor-core convolution with ``tiles`` output tiles: 1 unless the tiles would leave
+    three quarters of the SMs idle.  Units of K = 64-channel chunks x tap groups (taps sharing dx at stride 1)."""
+    groups = len({t[1] for t in taps}) if in_stride == 1 else len(taps)
+    units = -(-cin // 64) * groups
+    if tiles * 4 > NUM_SMS or units < 4:
+        return 1
+    return max(1, min(units, NUM_SMS // tiles))
+
+
 def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_stride: int = 1, out=None,
               out_hw=None, out_stride: int = 1, out_off=(0, 0), w_batched: bool = False, split_out: bool = False,
               dcoef=None, noise=None, noise_gain: float = 0.0, bias=None, act: int = ACT_LINEAR,
@@ -347,6 +360,17 @@ def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_strid
 
     d = _conv_desc(key, build)
     is_split = isinstance(out, Split)
+    ksplit = _ksplit(n * -(-oh * ow // 128) * -(-cout // 128), cin, taps, in_stride)
+    if ksplit > 1 and out_stride == 1 and (oh, ow) == (out_h, out_w) and cout % 4 == 0:
+        # few output tiles, long K (the 4^2..32^2 layers): split K over the idle SMs, then one elementwise epilogue
+        acc = torch.zeros((n, out_h, out_w, cout), device=x.device, dtype=torch.float32)
+        _ok(_cabi.lib().hfagp_conv2d_tc_acc_fwd(C.byref(d), 1, ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total,
+                                                ksplit, ptr(acc), stream()), 'hfagp_conv2d_tc_acc_fwd')
+        y = None if is_split else out
+        _ok(_cabi.lib().hfagp_conv_epilogue_fwd(C.byref(d), ptr(acc), ptr(dcoef), ptr(noise), ptr(bias), ptr(residual),
+                                                ptr(up_img), ptr(y), ptr(out.hi) if is_split else None,
+                                                ptr(out.lo) if is_split else None, stream()), 'hfagp_conv_epilogue_fwd')
+        return out
     _ok(_cabi.lib().hfagp_conv2d_tc_fwd(C.byref(d), ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total,
                                         ptr(dcoef), ptr(noise), ptr(bias), ptr(residual), ptr(up_img),
                                         None if is_split else ptr(out), ptr(out.hi) if is_split else None,
@@ -467,6 +491,13 @@ def conv_transpose_s2_tc(x: Split, w: Split, cout: int, w_batched: bool = False)
         return arr
 
     arr = _conv_desc(key, build)
+    tiles = n * -(-cout // 128) * sum(-(-(h + 1 - a) * (wd + 1 - b) // 128) for a in (0, 1) for b in (0, 1))
+    ksplit = _ksplit(tiles, cin, ((0, 0, 0),), 1)          # the smallest class has one tap group: units = K chunks
+    if ksplit > 1:
+        out.zero_()
+        _ok(_cabi.lib().hfagp_conv2d_tc_acc_fwd(arr, 4, ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total,
+                                                ksplit, ptr(out), stream()), 'hfagp_conv2d_tc_acc_fwd')
+        return out
     _ok(_cabi.lib().hfagp_conv2d_tc_multi_fwd(arr, 4, ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total, None,
                                               None, None, None, None, ptr(out), None, None, stream()),
         'hfagp_conv2d_tc_multi_fwd')

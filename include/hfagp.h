@@ -112,6 +112,22 @@ int hfagp_conv2d_tc_multi_fwd(const HfagpConvDesc* descs, int ndesc, const uint1
                               const float* noise, const float* bias, const float* residual, const float* up_img,
                               float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
 
+/* Split-K form for layers with few output tiles (the 4^2..32^2 blocks: a handful of 128-pixel tiles would leave
+ * most SMs idle while each CTA streams megabytes of weights): every tile's K range (K chunks x tap groups) is dealt
+ * out to up to `ksplit` CTAs, which ADD their raw fp32 partial sums into acc[n][out_h][out_w][cout] with 16-byte
+ * atomics (caller zeroes acc).  No epilogue is applied: follow with hfagp_conv_epilogue_fwd (or, for the
+ * up-sampling layers, hfagp_upfir_act_fwd, which reads the raw sums anyway). */
+int hfagp_conv2d_tc_acc_fwd(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi, const uint16_t* x_lo,
+                            const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, int ksplit, float* acc,
+                            void* stream);
+
+/* The epilogue of hfagp_conv2d_fwd (demod, noise, bias, leaky-ReLU, gain, clamp, residual merge, skip-image add)
+ * applied elementwise to raw sums acc[n][out_h][out_w][cout] of a dense output (out_stride 1); writes y (fp32, may
+ * alias acc) or the split pair. */
+int hfagp_conv_epilogue_fwd(const HfagpConvDesc* desc, const float* acc, const float* dcoef, const float* noise,
+                            const float* bias, const float* residual, const float* up_img, float* y, uint16_t* y_hi,
+                            uint16_t* y_lo, void* stream);
+
 /* fp32 -> split bf16 (elementwise). */
 int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, uint16_t* lo, void* stream);
 

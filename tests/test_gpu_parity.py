@@ -410,7 +410,7 @@ def test_conv_transpose_tc_parity_classes():
 
 
 def test_frame_loop_graph_matches_eager():
-    """hfa_gp_b200.frame_loop.FrameLoop: the captured CUDA graph replays exactly what the eager
+    """hfa_gp_b200.frame_loop.FrameLoop: the captured CUDA graph replays what the eager
     get_weights -> get_latent -> get_image sequence computes (random draws pinned)."""
     import argparse
     from hfa_gp_b200.frame_loop import FrameLoop
@@ -432,5 +432,6 @@ def test_frame_loop_graph_matches_eager():
         with torch.no_grad():
             want = model.get_image(model.get_latent(model.get_weights(img)), lab_e).clone()
         got = loop(img, lab_g).clone()
-        assert torch.equal(got, want)
+        # not bit-equal: the split-K layers add fp32 partial sums with atomics, whose order varies run to run
+        assert pu.rel_err(got, want) < 1e-5
         assert torch.equal(lab_g, lab_e)            # the in-place GL flip is visible to the caller
