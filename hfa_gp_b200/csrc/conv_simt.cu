@@ -184,96 +184,157 @@ __global__ void conv_epilogue_kernel(const ConvParams p, const float* __restrict
 }
 
 // ---------------------------------------------------------------- FIR after transposed conv
-__global__ void upfir_act_kernel(int batch, int h2, int w2, int c, const float* __restrict__ t,
-                                 const float* __restrict__ dcoef, const float* __restrict__ noise, float noise_gain,
-                                 const float* __restrict__ bias, int act, float act_gain, float clamp,
-                                 float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
-                                 __nv_bfloat16* __restrict__ y_lo) {
+// y[oy][ox] = sum_{ky,kx} g[ky] g[kx] t[oy+ky-1][ox+kx-1]  (g = [1,3,3,1]/4: the 4x4 filter with its gain of 4),
+// evaluated separably in registers: a thread owns 4 channels of TWO adjacent output columns and UPFIR_R output rows;
+// it walks the R+3 input rows once (5 float4 loads per row), forms the two horizontal sums and scatters them into
+// the vertical accumulators.  3.4 loads per output instead of 16; the epilogue is branch-free.
+constexpr int UPFIR_R = 8;
+
+__global__ void __launch_bounds__(256) upfir_act_kernel(int batch, int h2, int w2, int c, const float* __restrict__ t,
+                                                       const float* __restrict__ dcoef,
+                                                       const float* __restrict__ noise, float noise_gain,
+                                                       const float* __restrict__ bias, int act, float act_gain,
+                                                       float clamp, float* __restrict__ y,
+                                                       __nv_bfloat16* __restrict__ y_hi,
+                                                       __nv_bfloat16* __restrict__ y_lo) {
   const int c4 = c >> 2;
-  size_t total = (size_t)batch * h2 * w2 * c4;
+  const int wp = (w2 + 1) >> 1;                       // column pairs
+  const int hb = (h2 + UPFIR_R - 1) / UPFIR_R;        // row bands
+  const size_t total = (size_t)batch * hb * wp * c4;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  int cq = idx % c4;
-  size_t pix = idx / c4;
-  int ox = pix % w2;
-  size_t r = pix / w2;
-  int oy = r % h2;
-  int n = r / h2;
+  const int cq = idx % c4;
+  size_t r = idx / c4;
+  const int px = r % wp;
+  r /= wp;
+  const int band = r % hb, n = r / hb;
+  const int ox0 = px * 2, oy0 = band * UPFIR_R;
   const int th = h2 + 1, tw = w2 + 1;
+  const float4* tn = reinterpret_cast<const float4*>(t) + (size_t)n * th * tw * c4 + cq;
   const float g[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-  const float4* tn = reinterpret_cast<const float4*>(t + (size_t)n * th * tw * c);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc[UPFIR_R][2][4];
 #pragma unroll
-  for (int ky = 0; ky < 4; ++ky) {
-    int iy = oy + ky - 1;
-    if (iy < 0 || iy >= th) continue;
+  for (int i = 0; i < UPFIR_R; ++i)
 #pragma unroll
-    for (int kx = 0; kx < 4; ++kx) {
-      int ix = ox + kx - 1;
-      if (ix < 0 || ix >= tw) continue;
-      float wgt = g[ky] * g[kx];
-      float4 v = __ldg(tn + ((size_t)iy * tw + ix) * c4 + cq);
-      s.x = fmaf(wgt, v.x, s.x);
-      s.y = fmaf(wgt, v.y, s.y);
-      s.z = fmaf(wgt, v.z, s.z);
-      s.w = fmaf(wgt, v.w, s.w);
-    }
-  }
-  float nz = noise ? __ldg(noise + (size_t)oy * w2 + ox) * noise_gain : 0.f;
-  float vals[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    int co = cq * 4 + k;
-    float v = vals[k];
-    if (dcoef) v *= __ldg(dcoef + (size_t)n * c + co);
-    v += nz;
-    if (bias) v += __ldg(bias + co);
-    if (act == HFAGP_ACT_LRELU) v = lrelu02(v);
-    v *= act_gain;
-    if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
-    vals[k] = v;
-  }
-  st4_any(y, y_hi, y_lo, idx, vals);
-}
+    for (int k = 0; k < 4; ++k) acc[i][0][k] = acc[i][1][k] = 0.f;
 
-// ---------------------------------------------------------------- small-N ToRGB (cout <= 4)
-__global__ void torgb_small_kernel(int batch, int h, int w_, int cin, int cout, const float* __restrict__ x,
-                                   const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
-                                   const float* __restrict__ w, const float* __restrict__ bias, float clamp,
-                                   const float* __restrict__ up_img, float* __restrict__ y) {
-  const int lane = threadIdx.x & 31;
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t npix = (size_t)batch * h * w_;
-  if (warp >= npix) return;
-  const int n = warp / ((size_t)h * w_);
-  const size_t rem = warp - (size_t)n * h * w_;
-  const int oy = rem / w_, ox = rem - (size_t)oy * w_;
-  const float4* xp = x ? reinterpret_cast<const float4*>(x + warp * cin) : nullptr;
-  const size_t xq = warp * (size_t)(cin >> 2);
-  const float4* wp = reinterpret_cast<const float4*>(w + (size_t)n * cout * cin);
-  const int c4 = cin >> 2;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int q = lane; q < c4; q += 32) {
-    float4 xv = xp ? __ldg(xp + q) : bf16x4_sum(x_hi, x_lo, xq + q);
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      if (o < cout) {
-        float4 wv = __ldg(wp + (size_t)o * c4 + q);
-        acc[o] = fmaf(xv.x, wv.x, acc[o]);
-        acc[o] = fmaf(xv.y, wv.y, acc[o]);
-        acc[o] = fmaf(xv.z, wv.z, acc[o]);
-        acc[o] = fmaf(xv.w, wv.w, acc[o]);
+  for (int rr = 0; rr < UPFIR_R + 3; ++rr) {
+    const int iy = oy0 + rr - 1;
+    if (iy < 0 || iy >= th) continue;
+    float4 v[5];
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) {
+      const int ix = ox0 + kx - 1;
+      v[kx] = (ix >= 0 && ix < tw) ? __ldg(tn + ((size_t)iy * tw + ix) * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float ha[4], hb2[4];
+    ha[0] = g[0] * v[0].x + g[1] * v[1].x + g[2] * v[2].x + g[3] * v[3].x;
+    ha[1] = g[0] * v[0].y + g[1] * v[1].y + g[2] * v[2].y + g[3] * v[3].y;
+    ha[2] = g[0] * v[0].z + g[1] * v[1].z + g[2] * v[2].z + g[3] * v[3].z;
+    ha[3] = g[0] * v[0].w + g[1] * v[1].w + g[2] * v[2].w + g[3] * v[3].w;
+    hb2[0] = g[0] * v[1].x + g[1] * v[2].x + g[2] * v[3].x + g[3] * v[4].x;
+    hb2[1] = g[0] * v[1].y + g[1] * v[2].y + g[2] * v[3].y + g[3] * v[4].y;
+    hb2[2] = g[0] * v[1].z + g[1] * v[2].z + g[2] * v[3].z + g[3] * v[4].z;
+    hb2[3] = g[0] * v[1].w + g[1] * v[2].w + g[2] * v[3].w + g[3] * v[4].w;
+    // input row rr (iy = oy0 + rr - 1) feeds output rows i = rr - ky, ky = 0..3
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int i = rr - ky;
+      if (i < 0 || i >= UPFIR_R) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[i][0][k] = fmaf(g[ky], ha[k], acc[i][0][k]);
+        acc[i][1][k] = fmaf(g[ky], hb2[k], acc[i][1][k]);
       }
     }
   }
+  float sc[4], sh[4];
 #pragma unroll
-  for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
-  if (lane < cout) {
-    float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-    if (bias) v += __ldg(bias + lane);
-    if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
-    if (up_img) v += upsample_tap(up_img + (size_t)n * (h / 2) * (w_ / 2) * cout, h / 2, w_ / 2, cout, oy, ox, lane);
-    y[warp * cout + lane] = v;
+  for (int k = 0; k < 4; ++k) {
+    sc[k] = dcoef ? __ldg(dcoef + (size_t)n * c + cq * 4 + k) : 1.f;
+    sh[k] = bias ? __ldg(bias + cq * 4 + k) : 0.f;
+  }
+  const float slope = act == HFAGP_ACT_LRELU ? 0.2f : 1.f;
+  const float cl = clamp > 0.f ? clamp : __int_as_float(0x7f800000);
+#pragma unroll
+  for (int i = 0; i < UPFIR_R; ++i) {
+    const int oy = oy0 + i;
+    if (oy >= h2) break;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ox = ox0 + j;
+      if (ox >= w2) continue;
+      const float nz = noise ? __ldg(noise + (size_t)oy * w2 + ox) * noise_gain : 0.f;
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a = fmaf(acc[i][j][k], sc[k], sh[k] + nz);
+        a = fmaxf(a, slope * a) * act_gain;
+        o[k] = fminf(fmaxf(a, -cl), cl);
+      }
+      st4_any(y, y_hi, y_lo, (((size_t)n * h2 + oy) * w2 + ox) * c4 + cq, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- small-N ToRGB (cout <= 4)
+// 8 lanes per pixel (4 pixels per warp pass, TORGB_PASSES passes per warp); the per-sample weights sit in shared
+// memory (every pixel group reads the same addresses: broadcast); 16-byte activation loads, 3-step shuffle reduce.
+constexpr int TORGB_PASSES = 8;
+
+__global__ void __launch_bounds__(256) torgb_small_kernel(int batch, int h, int w_, int cin, int cout,
+                                                         const float* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ x_hi,
+                                                         const __nv_bfloat16* __restrict__ x_lo,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float clamp, const float* __restrict__ up_img,
+                                                         float* __restrict__ y) {
+  extern __shared__ __align__(16) float wsm[];          // [cout][cin] of sample n
+  const int n = blockIdx.y;
+  const int c4 = cin >> 2;
+  for (int i = threadIdx.x; i < cout * c4; i += blockDim.x)
+    reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * cout * cin) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int hw = h * w_;
+  const int pix0 = (blockIdx.x * 8 + warp_in_block) * (4 * TORGB_PASSES);
+#pragma unroll 2
+  for (int ps = 0; ps < TORGB_PASSES; ++ps) {
+    const int pix = pix0 + ps * 4 + grp;
+    const bool valid = pix < hw;
+    const size_t gp = (size_t)n * hw + (valid ? pix : 0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = l8; q < c4; q += 8) {
+      const float4 xv = x ? __ldg(reinterpret_cast<const float4*>(x) + gp * c4 + q) : bf16x4_sum(x_hi, x_lo, gp * c4 + q);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (o < cout) {
+          const float4 wv = reinterpret_cast<const float4*>(wsm)[o * c4 + q];
+          acc[o] = fmaf(xv.x, wv.x, acc[o]);
+          acc[o] = fmaf(xv.y, wv.y, acc[o]);
+          acc[o] = fmaf(xv.z, wv.z, acc[o]);
+          acc[o] = fmaf(xv.w, wv.w, acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+    }
+    if (valid && l8 < cout) {
+      float v = l8 == 0 ? acc[0] : l8 == 1 ? acc[1] : l8 == 2 ? acc[2] : acc[3];
+      if (bias) v += __ldg(bias + l8);
+      if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
+      if (up_img) {
+        const int oy = pix / w_, ox = pix - oy * w_;
+        v += upsample_tap(up_img + (size_t)n * (h / 2) * (w_ / 2) * cout, h / 2, w_ / 2, cout, oy, ox, l8);
+      }
+      y[gp * cout + l8] = v;
+    }
   }
 }
 
@@ -421,7 +482,7 @@ extern "C" int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float
   HFAGP_CHECK_ARG(t && ((y != nullptr) != (y_hi != nullptr && y_lo != nullptr)),
                   "upfir_act_fwd: give t and either y or (y_hi, y_lo)");
   HFAGP_CHECK_ARG(batch > 0 && h2 > 0 && w2 > 0 && c > 0 && (c & 3) == 0, "upfir_act_fwd: c must be a multiple of 4");
-  size_t total = (size_t)batch * h2 * w2 * (c >> 2);
+  size_t total = (size_t)batch * cdiv(h2, UPFIR_R) * cdiv(w2, 2) * (c >> 2);
   upfir_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain,
                                                                       bias, act, act_gain, clamp, y,
                                                                       reinterpret_cast<__nv_bfloat16*>(y_hi),
@@ -437,8 +498,10 @@ extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout
                   "torgb_small_fwd: give w, y and either x or (x_hi, x_lo)");
   HFAGP_CHECK_ARG(cout >= 1 && cout <= 4 && (cin & 3) == 0, "torgb_small_fwd: cout<=4 and cin%%4==0 required");
   HFAGP_CHECK_ARG(!up_img || ((h & 1) == 0 && (w_ & 1) == 0), "torgb_small_fwd: odd size with up_img");
-  size_t warps = (size_t)batch * h * w_;
-  torgb_small_kernel<<<cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+  HFAGP_CHECK_ARG(batch > 0 && batch <= 65535 && (size_t)cout * cin * 4 <= 48 * 1024, "torgb_small_fwd: bad dims");
+  const int pix_per_block = 8 * 4 * TORGB_PASSES;
+  dim3 grid(cdiv((long long)h * w_, pix_per_block), batch);
+  torgb_small_kernel<<<grid, 256, (size_t)cout * cin * 4, (cudaStream_t)stream>>>(
       batch, h, w_, cin, cout, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
       reinterpret_cast<const __nv_bfloat16*>(x_lo), w, bias, clamp, up_img, y);
   HFAGP_CHECK_LAUNCH("torgb_small_kernel");

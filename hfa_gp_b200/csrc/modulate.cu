@@ -66,6 +66,32 @@ __global__ void modulate_kernel(int ntaps, int cout, int cin, const float* __res
   }
 }
 
+// block per (n, o) for long rows (the encoder's final 4x4 convolution as a linear map: cin = 8192): 16-byte loads,
+// block reduction
+__global__ void __launch_bounds__(128) linear_long_kernel(int batch, int cin, int cout, const float* __restrict__ x,
+                                                         const float* __restrict__ w, const float* __restrict__ b,
+                                                         float w_gain, float b_gain, float* __restrict__ y) {
+  const int o = blockIdx.x, n = blockIdx.y;
+  const float4* xv = reinterpret_cast<const float4*>(x + (size_t)n * cin);
+  const float4* wv = reinterpret_cast<const float4*>(w + (size_t)o * cin);
+  float s = 0.f;
+  for (int k = threadIdx.x; k < (cin >> 2); k += blockDim.x) {
+    const float4 a = __ldg(xv + k), c = __ldg(wv + k);
+    s = fmaf(a.x, c.x * w_gain, s);
+    s = fmaf(a.y, c.y * w_gain, s);
+    s = fmaf(a.z, c.z * w_gain, s);
+    s = fmaf(a.w, c.w * w_gain, s);
+  }
+  __shared__ float red[4];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = red[0] + red[1] + red[2] + red[3];
+    y[(size_t)n * cout + o] = s + (b ? __ldg(b + o) * b_gain : 0.f);
+  }
+}
+
 // warp per (n, o)
 __global__ void linear_kernel(int batch, int cin, int cout, const float* __restrict__ x, const float* __restrict__ w,
                               const float* __restrict__ b, float w_gain, float b_gain, float* __restrict__ y) {
@@ -137,6 +163,11 @@ extern "C" int hfagp_modulate_fwd(int batch, int ntaps, int cout, int cin, const
 extern "C" int hfagp_linear_fwd(int batch, int cin, int cout, const float* x, const float* w, const float* b,
                                 float w_gain, float b_gain, float* y, void* stream) {
   HFAGP_CHECK_ARG(x && w && y && batch > 0 && cin > 0 && cout > 0, "linear_fwd: bad args");
+  if (cin >= 2048 && (cin & 3) == 0 && batch <= 65535 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0) {
+    linear_long_kernel<<<dim3(cout, batch), 128, 0, (cudaStream_t)stream>>>(batch, cin, cout, x, w, b, w_gain, b_gain, y);
+    HFAGP_CHECK_LAUNCH("linear_long_kernel");
+    return HFAGP_OK;
+  }
   linear_kernel<<<cdiv((long long)batch * cout * 32, 256), 256, 0, (cudaStream_t)stream>>>(batch, cin, cout, x, w, b,
                                                                                           w_gain, b_gain, y);
   HFAGP_CHECK_LAUNCH("linear_kernel");

