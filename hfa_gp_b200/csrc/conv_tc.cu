@@ -303,7 +303,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int r = q * 32 + lane;                     // accumulator row = pixel inside the tile
     const int ly = r / p.tile_w, lx = r - ly * p.tile_w;
     const int et = threadIdx.x - 64;                 // 0..255
-    const bool generic = p.cp.residual != nullptr || p.cp.up_img != nullptr;
+    const bool generic = p.cp.residual != nullptr || (p.cp.up_img != nullptr && (d.cout & 3) != 0);
+    const bool add_up = p.cp.up_img != nullptr && !generic;
     const float slope = d.act == HFAGP_ACT_LRELU ? 0.2f : 1.f;
     const float gain = d.act_gain;
     const float cl = d.clamp > 0.f ? d.clamp : __int_as_float(0x7f800000);
@@ -371,6 +372,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             a2 = fmaxf(a2, slope * a2) * gain; a3 = fmaxf(a3, slope * a3) * gain;
             v[jj] = fminf(fmaxf(a0, -cl), cl); v[jj + 1] = fminf(fmaxf(a1, -cl), cl);
             v[jj + 2] = fminf(fmaxf(a2, -cl), cl); v[jj + 3] = fminf(fmaxf(a3, -cl), cl);
+          }
+          if (add_up) {                                // + upsample2d(previous skip image): 4 taps x 16-byte loads
+            const UpTaps ut = upsample_taps(d.up_h, d.up_w, ec.oy, ec.ox);
+            const float* ub = ec.up + co0;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+#pragma unroll
+              for (int tp = 0; tp < 4; ++tp) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(ub + (size_t)ut.off[tp] * d.cout + jj));
+                v[jj] = fmaf(ut.w[tp], u.x, v[jj]); v[jj + 1] = fmaf(ut.w[tp], u.y, v[jj + 1]);
+                v[jj + 2] = fmaf(ut.w[tp], u.z, v[jj + 2]); v[jj + 3] = fmaf(ut.w[tp], u.w, v[jj + 3]);
+              }
+            }
           }
         } else {
 #pragma unroll

@@ -36,6 +36,28 @@ __device__ __forceinline__ float upsample_tap(const float* __restrict__ img, int
   return v;
 }
 
+// The same interpolation prepared once per pixel: four tap offsets (in pixels of the low-res image) and weights
+// (0 for taps outside the image), so the per-channel work is 4 vector loads + FMAs.
+struct UpTaps {
+  int off[4];
+  float w[4];
+};
+__device__ __forceinline__ UpTaps upsample_taps(int uh, int uw, int oy, int ox) {
+  const int my = oy >> 1, mx = ox >> 1;
+  int y0, y1, x0, x1;
+  float wy0, wy1, wx0, wx1;
+  if (oy & 1) { y0 = my; y1 = my + 1; wy0 = 0.75f; wy1 = 0.25f; } else { y0 = my - 1; y1 = my; wy0 = 0.25f; wy1 = 0.75f; }
+  if (ox & 1) { x0 = mx; x1 = mx + 1; wx0 = 0.75f; wx1 = 0.25f; } else { x0 = mx - 1; x1 = mx; wx0 = 0.25f; wx1 = 0.75f; }
+  const bool vy0 = y0 >= 0 && y0 < uh, vy1 = y1 >= 0 && y1 < uh;
+  const bool vx0 = x0 >= 0 && x0 < uw, vx1 = x1 >= 0 && x1 < uw;
+  UpTaps t;
+  t.off[0] = (vy0 && vx0) ? y0 * uw + x0 : 0; t.w[0] = (vy0 && vx0) ? wy0 * wx0 : 0.f;
+  t.off[1] = (vy0 && vx1) ? y0 * uw + x1 : 0; t.w[1] = (vy0 && vx1) ? wy0 * wx1 : 0.f;
+  t.off[2] = (vy1 && vx0) ? y1 * uw + x0 : 0; t.w[2] = (vy1 && vx0) ? wy1 * wx0 : 0.f;
+  t.off[3] = (vy1 && vx1) ? y1 * uw + x1 : 0; t.w[3] = (vy1 && vx1) ? wy1 * wx1 : 0.f;
+  return t;
+}
+
 // per-output-pixel state
 struct EpiCtx {
   int oy, ox;
