@@ -101,6 +101,13 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* smem, 
       ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a TMA box (no shared-memory destination): issued one tile ahead for the input patches
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row x 128 B atoms, 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -132,6 +139,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+#ifdef HFAGP_TC_TIMING
+// per-CTA cycle counters (debug builds only): [0] MMA loop total, [1] wait acc_empty, [2] wait a_full, [3] wait b_full,
+// [4] epilogue warp 2 total, [5] its wait on acc_full, [6] tiles
+__device__ unsigned long long tc_dbg[256][8];
+#define TC_T0(var) const long long var = clock64()
+#define TC_ADD(slot, var) dbg_local[slot] += clock64() - var
+#else
+#define TC_T0(var)
+#define TC_ADD(slot, var)
+#endif
+
+// One lane of a converged warp (elect.sync).  The producer and MMA warps run their loops warp-uniformly and only the
+// issuing instruction is predicated on the elected lane: addresses, descriptors and coordinates then live in UNIFORM
+// registers.  Inside an `if (lane == 0)` region every tcgen05.mma / TMA operand costs an R2UR round trip — measured
+// 119 cycles per MMA issue against 64 cycles of tensor-pipe time, i.e. the issuing thread, not the pipe, paced the
+// kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // tile id -> (class, batch sample, tile origin, N offset).  N tiles are the fastest index so that the CTAs running
@@ -191,7 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const HfagpConvDesc& d = p.cp.d;
   const int kchunks = (d.cin + TC_BK - 1) / TC_BK;   // a partial last chunk is zero-filled by TMA (both operands)
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.bn) tmem_cols <<= 1;
+  while ((int)tmem_cols < 4 * p.bn) tmem_cols <<= 1;   // 2 buffers x (hi|lo weight halves: 2*bn columns)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_MAX_STAGES; ++s) {
@@ -218,13 +251,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (one thread): patches and weight tiles in the exact order the MMA issuer consumes them
-    if (lane == 0) {
+    // ===== TMA producer (warp-uniform loop, elected lane issues): patches and weight tiles in the exact order the
+    // MMA issuer consumes them
+    {
       uint32_t ia = 0, ib = 0;                     // running slot counters of the two rings
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t, kchunks);
         const TcClass& c = p.cls[tc.c];
         const int wz0 = p.w_batched ? tc.n * p.taps_per_frame : 0;
+        if (t + (int)gridDim.x < p.total_tiles) {
+          // pull the NEXT work item's input patches into L2 while this one streams (they are first-touch data)
+          const TileCoord nx = decode_tile(p, t + gridDim.x, kchunks);
+          const TcClass& cn = p.cls[nx.c];
+          for (int u = nx.u0; u < nx.u1; ++u) {
+            const int kc = u / cn.ngroups, g = u - kc * cn.ngroups;
+            const int tp = cn.gstart[g];
+            const int ax = nx.x0 * d.in_stride + cn.dx[tp], ay = nx.y0 * d.in_stride + cn.dy0[tp];
+            if (elect_one()) {
+              tma_prefetch_4d(&map_a_hi, kc * TC_BK, ax, ay, nx.n);
+              tma_prefetch_4d(&map_a_lo, kc * TC_BK, ax, ay, nx.n);
+            }
+          }
+        }
         for (int u = tc.u0; u < tc.u1; ++u) {
           const int kc = u / c.ngroups, g = u - kc * c.ngroups;
           const int c0 = kc * TC_BK;
@@ -232,67 +280,105 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             if (c.first[tp]) {
               const int s = ia % p.a_stages;
               mbar_wait(&a_empty[s], ((ia / p.a_stages) & 1) ^ 1);
-              mbar_expect_tx(&a_full[s], 2 * a_half);
               const int ax = tc.x0 * d.in_stride + c.dx[tp], ay = tc.y0 * d.in_stride + c.dy0[tp];
-              tma_load_4d(&map_a_hi, smem_a + s * a_stage, &a_full[s], c0, ax, ay, tc.n);
-              tma_load_4d(&map_a_lo, smem_a + s * a_stage + a_half, &a_full[s], c0, ax, ay, tc.n);
+              if (elect_one()) {
+                mbar_expect_tx(&a_full[s], 2 * a_half);
+                tma_load_4d(&map_a_hi, smem_a + s * a_stage, &a_full[s], c0, ax, ay, tc.n);
+                tma_load_4d(&map_a_lo, smem_a + s * a_stage + a_half, &a_full[s], c0, ax, ay, tc.n);
+              }
               ++ia;
             }
             const int s = ib % p.b_stages;
             mbar_wait(&b_empty[s], ((ib / p.b_stages) & 1) ^ 1);
-            mbar_expect_tx(&b_full[s], 2 * b_bytes);
-            tma_load_3d(&map_b_hi, smem_b + s * b_stage, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
-            tma_load_3d(&map_b_lo, smem_b + s * b_stage + b_half, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[s], 2 * b_bytes);
+              tma_load_3d(&map_b_hi, smem_b + s * b_stage, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
+              tma_load_3d(&map_b_lo, smem_b + s * b_stage + b_half, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
+            }
             ++ib;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===== MMA issuer (warp-uniform loop, elected lane issues)
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((TC_BM >> 4) << 24);
+      // the same with N = 2*bn: the hi and lo halves of a weight tile are adjacent in shared memory, so
+      // x_hi * [w_hi ; w_lo] is ONE instruction writing accumulator columns [0,bn) and [bn,2bn) — x_hi is read from
+      // shared memory once instead of twice (SS-mode MMAs at N=128 are shared-memory-read bound: 8 KB per 64 cycles)
+      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 2) << 17) | ((TC_BM >> 4) << 24);
+      const bool wide = b_half == b_bytes;         // halves contiguous (bn*128 B is a multiple of 1024: bn % 8 == 0)
       const int row_bytes = p.tile_w * TC_ROW;     // one patch row of pixels (multiple of 1024: BW % 8 == 0)
       uint32_t ia = 0, ib = 0, j = 0;
+#ifdef HFAGP_TC_TIMING
+      long long dbg_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+      TC_T0(t_loop);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
         const TileCoord tc = decode_tile(p, t, kchunks);
         const TcClass& c = p.cls[tc.c];
         const uint32_t buf = j & 1;
+        TC_T0(t_ae);
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+        TC_ADD(1, t_ae);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem_base + buf * p.bn;
+        const uint32_t acc = tmem_base + buf * 2 * p.bn;
         uint32_t a_addr = 0, sa = 0;
-        bool started = false;
+        uint32_t started = 0;
         for (int u = tc.u0; u < tc.u1; ++u) {
           const int g = u % c.ngroups;
           for (int tp = c.gstart[g]; tp < c.gstart[g + 1]; ++tp) {
             if (c.first[tp]) {
               sa = ia % p.a_stages;
+              TC_T0(t_af);
               mbar_wait(&a_full[sa], (ia / p.a_stages) & 1);
+              TC_ADD(2, t_af);
               a_addr = smem_u32(smem_a + sa * a_stage);
               ++ia;
             }
             const uint32_t sb = ib % p.b_stages;
+            TC_T0(t_bf);
             mbar_wait(&b_full[sb], (ib / p.b_stages) & 1);
+            TC_ADD(3, t_bf);
             ++ib;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = a_addr + c.row_off[tp] * row_bytes, a_lo = a_hi + a_half;
-            const uint32_t b_hi = smem_u32(smem_b + sb * b_stage), b_lo = b_hi + b_half;
+            // descriptors of k-step 0; a k-step advances the start-address field by 32 B >> 4 = 2
+            const uint64_t da_hi = umma_desc(a_addr + c.row_off[tp] * row_bytes);
+            const uint64_t da_lo = umma_desc(a_addr + c.row_off[tp] * row_bytes + a_half);
+            const uint64_t db_hi = umma_desc(smem_u32(smem_b + sb * b_stage));
+            const uint64_t db_lo = umma_desc(smem_u32(smem_b + sb * b_stage) + b_half);
+            const bool last = c.last[tp] != 0;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
-              umma_bf16(acc, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, (started || k) ? 1u : 0u);
-              umma_bf16(acc, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, 1u);
-              umma_bf16(acc, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1u);
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint32_t first = (k == 0) ? started : 1u;
+                if (wide) {
+                  umma_bf16(acc, da_hi + 2 * k, db_hi + 2 * k, idesc2, first);         // cols [0,bn) += hi*hi, [bn,2bn) += hi*lo
+                } else {
+                  umma_bf16(acc, da_hi + 2 * k, db_hi + 2 * k, idesc, first);
+                  umma_bf16(acc + p.bn, da_hi + 2 * k, db_lo + 2 * k, idesc, first);
+                }
+                umma_bf16(acc, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);               // cols [0,bn) += lo*hi
+              }
+              umma_commit(&b_empty[sb]);               // frees the weight slot once these MMAs have read it
+              if (last) umma_commit(&a_empty[sa]);     // ... and the patch slot after its last tap
             }
-            started = true;
-            umma_commit(&b_empty[sb]);               // frees the weight slot once these MMAs have read it
-            if (c.last[tp]) umma_commit(&a_empty[sa]);  // ... and the patch slot after its last tap
+            __syncwarp();
+            started = 1;
           }
         }
-        umma_commit(&acc_full[buf]);                 // accumulator complete
+        if (elect_one()) umma_commit(&acc_full[buf]);  // accumulator complete
+        __syncwarp();
       }
+#ifdef HFAGP_TC_TIMING
+      TC_ADD(0, t_loop);
+      if (lane == 0) {
+        for (int i = 0; i < 4; ++i) tc_dbg[blockIdx.x][i] = dbg_local[i];
+        tc_dbg[blockIdx.x][6] = j;
+      }
+#endif
     }
   } else {
     // ===== epilogue: 8 warps; warp w may touch TMEM lanes [32*(w%4), +32), the two warps of a quadrant split the
@@ -310,6 +396,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const float cl = d.clamp > 0.f ? d.clamp : __int_as_float(0x7f800000);
     int staged_n = -1, staged_n0 = -1;
     uint32_t j = 0;
+#ifdef HFAGP_TC_TIMING
+    long long dbg_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    TC_T0(t_epi);
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
       const TileCoord tc = decode_tile(p, t, kchunks);
       const TcClass& c = p.cls[tc.c];
@@ -330,13 +420,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const bool valid = my < c.oh && mx < c.ow;
       EpiCtx ec;
       epi_setup_at(ec, p.cp, tc.n, valid ? my : 0, valid ? mx : 0, c.off_y, c.off_x);
+      TC_T0(t_afl);
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      TC_ADD(5, t_afl);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.bn;
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * p.bn;
       bool arrived = false;
       for (int cb = half * 32; cb < p.bn; cb += 64) {
         float v[32];
-        tmem_ld32(acc + cb, v);                        // warp-collective: no early exit before this
+        {
+          float v2[32];
+          tmem_ld32(acc + cb, v);                      // warp-collective: no early exit before this
+          tmem_ld32(acc + p.bn + cb, v2);              // the x_hi * w_lo partial sums
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] += v2[jj];
+        }
         if (cb + 64 >= p.bn) {
           // last read of this accumulator by this warp: hand it back to the MMA issuer before the stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -437,6 +535,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
     }
+#ifdef HFAGP_TC_TIMING
+    TC_ADD(4, t_epi);
+    if (warp == 2 && lane == 0) { tc_dbg[blockIdx.x][4] = dbg_local[4]; tc_dbg[blockIdx.x][5] = dbg_local[5]; }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -637,7 +739,8 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   const int b_stage = 2 * ((p.bn * TC_ROW + 1023) & ~1023);
   const int extra = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * TC_BM * 4 /*epilogue vectors*/;
   const int budget = 227 * 1024 - extra;
-  static const int choices[][2] = {{3, 4}, {2, 4}, {3, 3}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
+  // the input patches of a tile are first-touch (HBM latency), the weights are L2 hits: favour patch depth
+  static const int choices[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
   p.a_stages = p.b_stages = 0;
   for (const auto& ch : choices)
     if (ch[0] * a_stage + ch[1] * b_stage <= budget) {
@@ -704,3 +807,9 @@ extern "C" int hfagp_conv2d_tc_acc_fwd(const HfagpConvDesc* descs, int ndesc, co
   return launch_tc(descs, ndesc, x_hi, x_lo, w_hi, w_lo, w_taps_total, nullptr, nullptr, nullptr, nullptr, nullptr, acc,
                    nullptr, nullptr, ksplit, stream, "conv2d_tc_acc_fwd");
 }
+
+#ifdef HFAGP_TC_TIMING
+extern "C" int hfagp_debug_tc_timing(unsigned long long* host_out /* [256][8] */) {
+  return cudaMemcpyFromSymbol(host_out, hfagp::tc_dbg, sizeof(unsigned long long) * 256 * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
