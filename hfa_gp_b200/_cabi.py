@@ -69,6 +69,8 @@ _lib: Optional[C.CDLL] = None
 def lib() -> C.CDLL:
     """Load the library once.  Raises (never falls back) when it has not been built."""
     global _lib
+    if _timed is not None:
+        return _timed
     if _lib is not None:
         return _lib
     if not os.path.isfile(LIB_PATH):
@@ -118,9 +120,48 @@ def lib() -> C.CDLL:
     return l
 
 
+class _TimedLib:
+    """Wraps the CDLL so that every entry point is bracketed by CUDA events on torch's current stream (the stream
+    the kernels are enqueued on).  bench.py uses it for per-kernel durations measured live, outside any profiler."""
+
+    def __init__(self, cdll, sink):
+        self._cdll, self._sink = cdll, sink
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if name in ('hfagp_last_error', 'hfagp_abi_version') or not name.startswith('hfagp_'):
+            return fn
+        sink = self._sink
+
+        def call(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            sink.append((name, e0, e1))
+            return rc
+        return call
+
+
+_timed: Optional[_TimedLib] = None
+
+
+def start_timing() -> list:
+    """Every C-ABI call from now on appends (entry point, start event, end event) to the returned list."""
+    global _timed
+    sink = []
+    _timed = _TimedLib(lib(), sink)
+    return sink
+
+
+def stop_timing():
+    global _timed
+    _timed = None
+
+
 def check(rc: int, what: str):
     if rc != 0:
-        msg = lib().hfagp_last_error()
+        msg = (_lib or lib()).hfagp_last_error()
         raise HfagpError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}')
 
 

@@ -375,6 +375,7 @@ __global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int strid
   st4_any(y, y_hi, y_lo, idx, s);
 }
 
+
 // any channel count (3-channel images of the super-resolution skip path), fp32 only
 __global__ void blur_scalar_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow, float gain,
                                    const float* __restrict__ x, float* __restrict__ y) {
