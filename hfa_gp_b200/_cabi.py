@@ -24,7 +24,7 @@ SYMBOLS = [
     'hfagp_nhwc_to_nchw', 'hfagp_conv2d_tc_fwd', 'hfagp_split_bf16', 'hfagp_modulate_split_fwd',
     'hfagp_blur_up', 'hfagp_act_bwd', 'hfagp_styles_bwd', 'hfagp_demod_bwd', 'hfagp_linear_bwd',
     'hfagp_conv2d_wgrad', 'hfagp_render_bwd', 'hfagp_latent_bwd', 'hfagp_facepool_fwd', 'hfagp_facepool_bwd',
-    'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd',
+    'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8',
 ]
 
 
@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
     l.hfagp_conv2d_tc_multi_fwd.argtypes = [vp, i32, vp, vp, vp, vp, i32] + [vp] * 9
     l.hfagp_conv2d_tc_acc_fwd.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, vp, vp]
     l.hfagp_conv_epilogue_fwd.argtypes = [C.POINTER(ConvDesc)] + [vp] * 10
+    l.hfagp_frame_to_uint8.argtypes = [C.c_longlong, vp, i32, vp, vp]
+    l.hfagp_frame_from_uint8.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     l.hfagp_split_bf16.argtypes = [C.c_longlong, vp, vp, vp, vp]
     l.hfagp_modulate_split_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     for s in SYMBOLS:

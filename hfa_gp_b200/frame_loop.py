@@ -22,8 +22,13 @@ from ._cabi import HfagpError
 
 
 class FrameLoop:
-    def __init__(self, model, batch: int = 1, size: int = 256, device=None, use_graph: bool = True, warmup: int = 3):
+    def __init__(self, model, batch: int = 1, size: int = 256, device=None, use_graph: bool = True, warmup: int = 3,
+                 egress: str = None):
+        """``egress``: None -> the fp32 image of ``get_image``; 'save_image' | 'layout_grid' -> additionally convert to the
+        uint8 [B,H,W,3] frame the reference writes out (hfa_gp_b200.frameio.to_uint8, inside the graph), in ``out_u8``."""
         self.model = model
+        self.egress = egress
+        self.out_u8 = None
         dev = torch.device(device) if device is not None else next(model.parameters()).device
         if dev.type != 'cuda':
             raise HfagpError('FrameLoop needs a CUDA model (there is no CPU fallback)')
@@ -45,7 +50,11 @@ class FrameLoop:
         if isinstance(w, tuple):          # out_pose models return (weights, pose)
             w = w[0]
         lat = m.get_latent(w)
-        return m.get_image(lat, self.label)
+        img = m.get_image(lat, self.label)
+        if self.egress is not None:
+            from . import frameio
+            self.out_u8 = frameio.to_uint8(img, self.egress, out=self.out_u8)
+        return img
 
     def _capture(self, warmup):
         side = torch.cuda.Stream(device=self.device)

@@ -328,6 +328,22 @@ int hfagp_mse_bwd(long long count, const float* a, const float* b, float scale, 
 int hfagp_adam_step(long long count, float* p, const float* g, float* m, float* v, float grad_scale, double lr,
                     double beta1, double beta2, double eps, double weight_decay, long long step, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Frame egress / ingress: the pixel-format conversions either side of the render path.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Generated image (fp32, any layout, `count` values, nominally in [-1,1]) -> uint8, BIT-EXACT with torch:
+ *   mode 0: torchvision.utils.save_image(img, normalize=True, range=(-1,1))  (code/run_recon_video_rgb.py:233-234)
+ *           v = clamp(x,-1,1); v = (v+1)/2; u8 = trunc(clamp(v*255 + 0.5, 0, 255))
+ *   mode 1: layout_grid(float_to_uint8=True)                                  (code/run_recon_video_rgb.py:34)
+ *           u8 = trunc(clamp(x*127.5 + 128, 0, 255))
+ * Applied to the channels-last image it yields the [h][w][3] bytes an image / video encoder takes. */
+int hfagp_frame_to_uint8(long long count, const float* x, int mode, unsigned char* y, void* stream);
+
+/* Decoded frame uint8 [n][h][w][c] -> fp32 NCHW in [-1,1]: ToTensor() + Normalize(0.5, 0.5) of the reference's
+ * loader (code/train_rgb.py:78-81; code/dataset.py:205-214), bit-exact: v = u8/255 ; y = (v - 0.5) / 0.5. */
+int hfagp_frame_from_uint8(int batch, int h, int w_, int c, const unsigned char* x, float* y, void* stream);
+
 /* Layout helpers (elementwise, bandwidth-bound): NCHW <-> NHWC for the frame entering the encoder
  * and the image leaving the super-resolution head. */
 int hfagp_nchw_to_nhwc(int batch, int c, int h, int w_, const float* x, float* y, void* stream);

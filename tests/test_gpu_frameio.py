@@ -1,0 +1,74 @@
+"""Frame egress / ingress kernels against the CPU oracle (oracle/frameio_ref.py, itself pinned to torchvision):
+integer outputs bit-exact, float outputs bit-exact (same separately-rounded fp32 steps)."""
+import pytest
+import torch
+
+from oracle import frameio_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _img(seed, n, h, w):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 3, h, w, generator=g) * 0.8
+    m = min(8, x.numel())
+    x.view(-1)[:m] = torch.tensor([-1.0, 1.0, 0.0, -1.5, 1.5, 0.999999, -0.999999, 1e-8])[:m]
+    return x
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 512, 512), (2, 37, 53), (1, 1, 1)])
+def test_to_uint8_bit_exact(n, h, w):
+    from hfa_gp_b200 import frameio
+    x = _img(3, n, h, w)
+    # every multiple of 1/255 and 1/127.5 and its fp32 neighbours: the rounding boundaries of both conventions
+    k = torch.arange(0, 256, dtype=torch.float32)
+    edges = torch.cat([k / 127.5 - 1, (k - 128) / 127.5, (k + 0.5) / 127.5 - 1])
+    edges = torch.cat([edges, torch.nextafter(edges, torch.tensor(9.0)), torch.nextafter(edges, torch.tensor(-9.0))])
+    flat = x.view(-1)
+    m = min(flat.numel(), edges.numel())
+    flat[-m:] = edges[:m]
+    for mode, ref in (('save_image', frameio_ref.save_image_uint8), ('layout_grid', frameio_ref.layout_grid_uint8)):
+        want = ref(x)
+        got_nchw = frameio.to_uint8(x.cuda(), mode)                                   # NCHW input
+        got_view = frameio.to_uint8(x.permute(0, 2, 3, 1).contiguous().cuda().permute(0, 3, 1, 2), mode)   # get_image's view
+        assert got_nchw.dtype == torch.uint8 and tuple(got_nchw.shape) == (n, h, w, 3)
+        assert torch.equal(got_nchw.cpu(), want), mode
+        assert torch.equal(got_view.cpu(), want), mode
+
+
+def test_from_uint8_bit_exact_all_byte_values():
+    from hfa_gp_b200 import frameio
+    g = torch.Generator().manual_seed(4)
+    u8 = torch.randint(0, 256, (2, 31, 45, 3), generator=g, dtype=torch.uint8)
+    u8.view(-1)[:256] = torch.arange(256, dtype=torch.uint8)
+    got = frameio.from_uint8(u8.cuda())
+    assert torch.equal(got.cpu(), frameio_ref.to_tensor_normalize(u8))
+
+
+def test_sink_and_feeder_round_trip():
+    """Asynchronous rings: frames come back in order, bit-equal to the synchronous conversion; the feeder's output
+    drives the encoder-side layout ([N,3,H,W] fp32)."""
+    from hfa_gp_b200 import frameio
+    sink = frameio.FrameSink(64, 48, depth=3, mode='layout_grid')
+    imgs = [_img(10 + i, 1, 64, 48) for i in range(7)]
+    got = []
+    for i, im in enumerate(imgs):
+        if i >= 3:
+            got.append(sink.pop().copy())
+        sink.push(im.cuda())
+    got += sink.drain()
+    assert len(got) == 7 and sink.pop() is None
+    for im, g_ in zip(imgs, got):
+        assert (torch.from_numpy(g_) == frameio_ref.layout_grid_uint8(im)).all()
+    with pytest.raises(Exception):
+        for im in imgs:
+            sink.push(im.cuda())
+    feeder = frameio.FrameFeeder(64, 48, depth=2)
+    frames = [torch.from_numpy(g_) for g_ in got[:4]]
+    outs = []
+    for f in frames:
+        feeder.push(f.numpy())
+        outs.append(feeder.next())
+    assert feeder.next() is None
+    for f, o in zip(frames, outs):
+        assert torch.equal(o.cpu(), frameio_ref.to_tensor_normalize(f))

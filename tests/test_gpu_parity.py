@@ -409,6 +409,53 @@ def test_conv_transpose_tc_parity_classes():
     assert pu.rel_err(pu.to_nchw(out), ref) < 1e-4
 
 
+@pytest.mark.parametrize('n,cin,cout,h,batched', [
+    (1, 512, 512, 8, True),       # low-res up layer: 4 classes x 1 tile, split-K accumulate path (hfagp_conv2d_tc_acc_fwd)
+    (2, 64, 128, 40, True),       # 4 classes x several tiles x 2 samples in one persistent launch (..._multi_fwd)
+    (1, 32, 48, 130, False),      # more tiles than SMs: every CTA walks several tiles of different classes
+])
+def test_conv_transpose_tc_merged_launch(n, cin, cout, h, batched):
+    """ops.conv_transpose_s2_tc: the four output-parity classes as ONE launch vs torch's conv_transpose2d (fp64)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(n, cin, h, h, generator=g)
+    wt = torch.randn(n if batched else 1, cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    ref = torch.cat([F.conv_transpose2d(x[i:i + 1].double(), wt[i if batched else 0].double().transpose(0, 1), stride=2)
+                     for i in range(n)]).float()
+    wp = wt.permute(0, 3, 4, 1, 2).reshape(wt.shape[0], 9, cout, cin).contiguous().cuda()
+    t = ops.conv_transpose_s2_tc(ops.split(nhwc(x)), ops.split(wp), cout, w_batched=batched)
+    assert tuple(t.shape) == (n, 2 * h + 1, 2 * h + 1, cout)
+    assert pu.rel_err(pu.to_nchw(t), ref) < 1e-4
+
+
+def test_conv2d_tc_persistent_many_tiles_and_epilogues():
+    """More output tiles than SMs (each CTA loops: ring wrap-around across tiles, both TMEM accumulators) with every
+    epilogue term: demodulation, noise, bias, leaky-ReLU, gain, clamp, skip-image upsample-add; then the residual
+    merge (the generic epilogue path)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(22)
+    n, cin, cout, h, w = 2, 64, 96, 120, 104            # 2 * ceil(120*104/128) = 196 tiles
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    d = torch.rand(n, cout, generator=g) + 0.5
+    noise = torch.randn(h, w, generator=g)
+    b = torch.randn(cout, generator=g) * 0.1
+    up = torch.randn(n, cout, h // 2, w // 2, generator=g)
+    res = torch.randn(n, cout, h, w, generator=g)
+    v = F.conv2d(x.double(), wt.double(), padding=1) * d.double()[:, :, None, None] + noise.double() * 0.3
+    v = F.leaky_relu(v + b.double()[None, :, None, None], 0.2) * 1.3
+    v = v.clamp(-1.0, 1.0)
+    want_up = (v + eg3d_ref.upsample2d_ref(up.double(), eg3d_ref.setup_filter().double())).float()
+    want_res = ((v + res.double()) * 0.7).float()
+    xs, ws = ops.split(nhwc(x)), ops.split(pack(wt)[None].contiguous())
+    common = dict(oh=h, ow=w, dcoef=d.cuda(), noise=noise.cuda(), noise_gain=0.3, bias=b.cuda(), act=1, act_gain=1.3,
+                  clamp=1.0)
+    y = ops.conv2d_tc(xs, ws, ops.TAPS_3X3, cout, up_img=nhwc(up), **common)
+    assert pu.rel_err(pu.to_nchw(y), want_up) < 1e-4
+    y = ops.conv2d_tc(xs, ws, ops.TAPS_3X3, cout, residual=nhwc(res), residual_scale=0.7, split_out=True, **common)
+    assert pu.rel_err(pu.to_nchw(y.float()), want_res) < 1e-4
+
+
 def test_frame_loop_graph_matches_eager():
     """hfa_gp_b200.frame_loop.FrameLoop: the captured CUDA graph replays what the eager
     get_weights -> get_latent -> get_image sequence computes (random draws pinned)."""
