@@ -13,8 +13,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhfagp_sm100.so')
-MAX_TAPS = 16
-ACT_LINEAR, ACT_LRELU = 0, 1
+MAX_TAPS = 32
+ACT_LINEAR, ACT_LRELU, ACT_RELU = 0, 1, 2
 
 # every symbol include/hfagp.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -25,6 +25,8 @@ SYMBOLS = [
     'hfagp_blur_up', 'hfagp_act_bwd', 'hfagp_styles_bwd', 'hfagp_demod_bwd', 'hfagp_linear_bwd',
     'hfagp_conv2d_wgrad', 'hfagp_render_bwd', 'hfagp_latent_bwd', 'hfagp_facepool_fwd', 'hfagp_facepool_bwd',
     'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8',
+    'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
+    'hfagp_lpips_head_bwd',
 ]
 
 
@@ -110,6 +112,12 @@ def lib() -> C.CDLL:
     l.hfagp_conv_epilogue_fwd.argtypes = [C.POINTER(ConvDesc)] + [vp] * 10
     l.hfagp_frame_to_uint8.argtypes = [C.c_longlong, vp, i32, vp, vp]
     l.hfagp_frame_from_uint8.argtypes = [i32, i32, i32, i32, vp, vp, vp]
+    l.hfagp_lpips_stem_fwd.argtypes = [i32, i32, i32] + [vp] * 6
+    l.hfagp_lpips_stem_bwd.argtypes = [i32, i32, i32] + [vp] * 4
+    l.hfagp_maxpool3s2_fwd.argtypes = [i32] * 4 + [vp] * 7
+    l.hfagp_maxpool3s2_bwd.argtypes = [i32] * 4 + [vp] * 6
+    l.hfagp_lpips_head_fwd.argtypes = [i32, i32, i32] + [vp] * 6
+    l.hfagp_lpips_head_bwd.argtypes = [i32, i32, i32] + [vp] * 7
     l.hfagp_split_bf16.argtypes = [C.c_longlong, vp, vp, vp, vp]
     l.hfagp_modulate_split_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     for s in SYMBOLS:

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
 #pragma unroll
     for (int o = 0; o < 4; ++o) wr[o][k] = (p.dimg && o < d.rgb_k) ? __ldg(p.wrgb + (size_t)o * d.c + c0 + k) : 0.f;
   }
-  const float slope_pos = d.act_gain, slope_neg = d.act == HFAGP_ACT_LRELU ? 0.2f * d.act_gain : d.act_gain;
+  const float slope_pos = d.act_gain, slope_neg = act_slope(d.act) * d.act_gain;
   const float inv_rs = d.residual_scale != 0.f ? 1.f / d.residual_scale : 1.f;
 
   float r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f}, rr[4] = {0.f, 0.f, 0.f, 0.f};

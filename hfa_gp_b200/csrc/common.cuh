@@ -34,6 +34,8 @@ int fail(int code, const char* fmt, ...);
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+// negative-side slope of an HFAGP_ACT_* activation (linear 1, leaky-ReLU 0.2, ReLU 0): act(v) = max(v, slope*v)
+__host__ __device__ __forceinline__ float act_slope(int act) { return act == HFAGP_ACT_LRELU ? 0.2f : (act == HFAGP_ACT_RELU ? 0.f : 1.f); }
 
 // softplus with torch semantics (beta=1, threshold=20)
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }

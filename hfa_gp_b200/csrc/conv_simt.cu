@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) upfir_act_kernel(int batch, int h2, int w
     sc[k] = dcoef ? __ldg(dcoef + (size_t)n * c + cq * 4 + k) : 1.f;
     sh[k] = bias ? __ldg(bias + cq * 4 + k) : 0.f;
   }
-  const float slope = act == HFAGP_ACT_LRELU ? 0.2f : 1.f;
+  const float slope = act_slope(act);
   const float cl = clamp > 0.f ? clamp : __int_as_float(0x7f800000);
 #pragma unroll
   for (int i = 0; i < UPFIR_R; ++i) {

@@ -391,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int et = threadIdx.x - 64;                 // 0..255
     const bool generic = p.cp.residual != nullptr || (p.cp.up_img != nullptr && (d.cout & 3) != 0);
     const bool add_up = p.cp.up_img != nullptr && !generic;
-    const float slope = d.act == HFAGP_ACT_LRELU ? 0.2f : 1.f;
+    const float slope = act_slope(d.act);
     const float gain = d.act_gain;
     const float cl = d.clamp > 0.f ? d.clamp : __int_as_float(0x7f800000);
     int staged_n = -1, staged_n0 = -1;

@@ -89,7 +89,7 @@ __device__ __forceinline__ float epi_apply(const EpiCtx& e, const ConvParams& p,
   if (e.dco) v *= __ldg(e.dco + co);
   v += e.nz;
   if (p.bias) v += __ldg(p.bias + co);
-  if (d.act == HFAGP_ACT_LRELU) v = lrelu02(v);
+  if (d.act != HFAGP_ACT_LINEAR) v = fmaxf(v, act_slope(d.act) * v);
   v *= d.act_gain;
   if (d.clamp > 0.f) v = fminf(fmaxf(v, -d.clamp), d.clamp);
   if (e.res) v = (v + __ldg(e.res + co)) * d.residual_scale;

@@ -37,9 +37,9 @@ enum {
   HFAGP_E_WORKSPACE = -3  /* caller workspace too small */
 };
 
-enum { HFAGP_ACT_LINEAR = 0, HFAGP_ACT_LRELU = 1 };
+enum { HFAGP_ACT_LINEAR = 0, HFAGP_ACT_LRELU = 1 /* slope 0.2 */, HFAGP_ACT_RELU = 2 /* LPIPS AlexNet */ };
 
-#define HFAGP_MAX_TAPS 16
+#define HFAGP_MAX_TAPS 32          /* 5x5 = 25 taps (LPIPS AlexNet conv2) is the largest tap list on the path */
 
 int hfagp_abi_version(void);
 const char* hfagp_last_error(void);
@@ -54,7 +54,7 @@ const char* hfagp_last_error(void);
  *   v = acc * dcoef[n][co]           (if dcoef)        demodulation      eg3d modulated_conv2d
  *   v += noise[oy][ox] * noise_gain  (if noise)        per-pixel noise   SynthesisLayer 'const'
  *   v += bias[co]                    (if bias)
- *   v = lrelu_0.2(v)                 (if act==LRELU)
+ *   v = lrelu_0.2(v) | relu(v)       (if act==LRELU | RELU)
  *   v *= act_gain ; clamp to +-clamp (if clamp > 0)                      bias_act
  *   v = (v + residual[n][oy][ox][co]) * residual_scale   (if residual)   ResBlock (out+skip)/sqrt2
  *   v += upsample2d(up_img)[n][oy][ox][co]               (if up_img)     'skip' image path
@@ -327,6 +327,34 @@ int hfagp_mse_bwd(long long count, const float* a, const float* b, float scale, 
  * 16-byte aligned. */
 int hfagp_adam_step(long long count, float* p, const float* g, float* m, float* v, float grad_scale, double lr,
                     double beta1, double beta2, double eps, double weight_decay, long long step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LPIPS(net='alex') (code/trainer_rgb.py:10,62,86-87 -> pip package `lpips`): what sits between its five AlexNet
+ * convolutions, which run on hfagp_conv2d_tc_fwd with the bias + HFAGP_ACT_RELU epilogue.
+ * ------------------------------------------------------------------------------------------- */
+
+/* ScalingLayer + zero-pad 2 + space-to-depth by 4 + split-bf16, x[n][3][h][w] (NCHW fp32, sides % 4 == 0) ->
+ * y[n][(h+4)/4][(w+4)/4][48] with channel (py*4+px)*3+c = (x[c][4Y+py-2][4X+px-2] - shift[c]) / scale[c]: the 11x11
+ * stride-4 first convolution becomes a 3x3 stride-1 convolution over 48 channels.  shift/scale: 3 host floats. */
+int hfagp_lpips_stem_fwd(int batch, int h, int w_, const float* x, const float* shift3_host, const float* scale3_host,
+                         uint16_t* y_hi, uint16_t* y_lo, void* stream);
+/* its transpose: dx48[n][(h+4)/4][(w+4)/4][48] -> dimg[n][3][h][w] (written) */
+int hfagp_lpips_stem_bwd(int batch, int h, int w_, const float* dx48, const float* scale3_host, float* dimg, void* stream);
+
+/* nn.MaxPool2d(3, stride=2), channels-last (c % 4 == 0); input / output fp32 or split bf16.  Backward routes each
+ * window's gradient to its FIRST maximum (row-major scan, as ATen) in gather form: dx is written, no atomics. */
+int hfagp_maxpool3s2_fwd(int batch, int h, int w_, int c, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
+                         float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
+int hfagp_maxpool3s2_bwd(int batch, int h, int w_, int c, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
+                         const float* dy, float* dx, void* stream);
+
+/* One LPIPS layer: features f[2*batch][hw][c] (first half: image 0, second half: image 1), lin[c] ->
+ *   out[b] += mean_pix sum_c lin[c] * (f0/(|f0|+1e-10) - f1/(|f1|+1e-10))^2        (caller zeroes out)
+ * Backward: df1[batch][hw][c] = gout[b] * d out[b] / d f1 (written); image 0 carries no gradient. */
+int hfagp_lpips_head_fwd(int batch, int hw, int c, const float* f, const uint16_t* f_hi, const uint16_t* f_lo,
+                         const float* lin, float* out, void* stream);
+int hfagp_lpips_head_bwd(int batch, int hw, int c, const float* f, const uint16_t* f_hi, const uint16_t* f_lo,
+                         const float* lin, const float* gout, float* df1, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Frame egress / ingress: the pixel-format conversions either side of the render path.

@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 import parity_utils as pu
-from oracle import eg3d_ref, hfagp_ref, train_ref
+from oracle import eg3d_ref, hfagp_ref, lpips_ref, train_ref
 
 pytestmark = pytest.mark.gpu
 
@@ -147,6 +147,41 @@ def test_flat_adam_matches_torch_adam():
     assert pu.rel_err(opt2.exp_avg, opt.exp_avg) < 1e-5
 
 
+def _oracle_lpips(native):
+    lp = lpips_ref.LPIPS(net='alex').eval()
+    lp.load_state_dict(native.state_dict())
+    return lp
+
+
+@pytest.mark.parametrize('b,size', [(2, 64), (1, 256), (3, 32)])
+def test_lpips_value_and_gradient_match_oracle(b, size):
+    """hfa_gp_b200.lpips.LPIPS (stem / tcgen05 convs / max-pools / heads and their backward) vs the torch oracle."""
+    from hfa_gp_b200.lpips import LPIPS
+    native = LPIPS(net='alex', seed=3).cuda().eval()
+    with torch.no_grad():                                   # exercise the biases (torch inits them non-zero already)
+        for c in native.net.convs():
+            c.bias.mul_(3.0)
+    oracle = _oracle_lpips(native)
+    g = torch.Generator().manual_seed(b * 100 + size)
+    real = torch.rand(b, 3, size, size, generator=g) * 2 - 1
+    gen = (real + 0.3 * torch.randn(b, 3, size, size, generator=g)).clamp(-1.2, 1.2)
+    wts = torch.rand(b, generator=g) + 0.5
+    gen_r = gen.clone().requires_grad_(True)
+    val_r = oracle(real, gen_r)
+    (val_r.reshape(b) * wts).sum().backward()
+    gen_g = gen.clone().cuda().requires_grad_(True)
+    val = native(real.cuda(), gen_g)
+    assert tuple(val.shape) == (b, 1, 1, 1)
+    (val.reshape(b) * wts.cuda()).sum().backward()
+    assert pu.rel_err(val, val_r) < 1e-3
+    # ReLU / max-pool routing decisions flip for features within rounding distance of a tie: relative-L2 bound
+    _check(gen_g.grad, gen_r.grad, 'tc', f'lpips d(generated) b={b} size={size}')
+    with pytest.raises(Exception):
+        native.train()(real.cuda(), gen_g)                  # train-mode Dropout is not on the path
+    with pytest.raises(Exception):
+        native.eval()(real, gen)                            # no CPU fallback
+
+
 def _args(size, k, cfg, **kw):
     return argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, batch_size=2, size=size,
                               latent_dim_style=512, latent_dim_shape=k, run_id='synthetic', emb_dir='./none/',
@@ -185,7 +220,6 @@ def test_trainer_rgb_steps_match_oracle(precision):
     """Two gen_update steps of the RGB trainer: losses, pooled image, gradients and updated parameters."""
     import contextlib
     from hfa_gp_b200.trainer_rgb import Trainer
-    from hfa_gp_b200.lpips import LPIPS
     cfg = eg3d_ref.small14_config()
     size, k, b = 32, 10, 2
     ref_gen, _ = pu.make_pair(cfg, seed=0)
@@ -198,7 +232,8 @@ def test_trainer_rgb_steps_match_oracle(precision):
         for n, p in gen.encoder.named_parameters():
             p.copy_(sd[n])
     bases, delta = gen.bases.detach().cpu().clone(), gen.delta.detach().cpu().clone()
-    lp = LPIPS(net='alex').eval()
+    lp = lpips_ref.LPIPS(net='alex').eval()
+    lp.load_state_dict(tr.lpips_loss.state_dict())
     oracle = train_ref.TrainStepRef(sd, bases, delta, ref_gen, size, 3e-4, lpips=lp)
     g = torch.Generator().manual_seed(9)
     for it in range(2):
@@ -243,7 +278,7 @@ def test_trainer_3dmm_step_matches_oracle():
     gen.generator.load_state_dict(ref_gen.state_dict())
     sd = {n: p.detach().cpu().clone() for n, p in gen.weights_3dmm.named_parameters()}
     oracle = train_ref.TrainStepRef(sd, gen.bases.detach().cpu(), gen.delta.detach().cpu(), ref_gen, size, 3e-4,
-                                    lpips=copy.deepcopy(tr.lpips_loss).cpu(), head='3dmm')
+                                    lpips=_oracle_lpips(tr.lpips_loss), head='3dmm')
     g = torch.Generator().manual_seed(5)
     real = torch.rand(b, 3, size, size, generator=g) * 2 - 1
     params = torch.randn(b, 76, generator=g)
