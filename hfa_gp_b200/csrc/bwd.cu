@@ -194,29 +194,44 @@ __global__ void styles_bwd_kernel(const StyleBwdTable tb, int num_ws, int w_dim,
 }
 
 // ds[n][i] -= s[n][i] * sum_o ddcoef[n][o] * dcoef[n][o]^3 * w2[o][i]      (w2 = sum_taps w^2)
-__global__ void demod_bwd_kernel(int cout, int cin, const float* __restrict__ w2, const float* __restrict__ styles,
-                                 const float* __restrict__ dcoef, const float* __restrict__ ddcoef,
-                                 float* __restrict__ dstyles) {
+// block = 32 input channels x 8 slices of the output channels (coalesced w2 rows), shared-memory reduce over slices
+__global__ void __launch_bounds__(256) demod_bwd_kernel(int cout, int cin, const float* __restrict__ w2,
+                                                       const float* __restrict__ styles,
+                                                       const float* __restrict__ dcoef, const float* __restrict__ ddcoef,
+                                                       float* __restrict__ dstyles) {
   const int n = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cin) return;
+  const int ix = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ix;
   float acc = 0.f;
-  for (int o = 0; o < cout; ++o) {
-    const float dc = __ldg(dcoef + (size_t)n * cout + o);
-    acc = fmaf(__ldg(ddcoef + (size_t)n * cout + o) * dc * dc * dc, __ldg(w2 + (size_t)o * cin + i), acc);
+  if (i < cin)
+    for (int o = slice; o < cout; o += 8) {
+      const float dc = __ldg(dcoef + (size_t)n * cout + o);
+      acc = fmaf(__ldg(ddcoef + (size_t)n * cout + o) * dc * dc * dc, __ldg(w2 + (size_t)o * cin + i), acc);
+    }
+  __shared__ float red[8][33];
+  red[slice][ix] = acc;
+  __syncthreads();
+  if (slice == 0 && i < cin) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][ix];
+    dstyles[(size_t)n * cin + i] -= __ldg(styles + (size_t)n * cin + i) * t;
   }
-  dstyles[(size_t)n * cin + i] -= __ldg(styles + (size_t)n * cin + i) * acc;
 }
 
 // ---------------------------------------------------------------- EqualLinear backward
+// gridDim.y slices of the output channels (1 slice: dx is written; more: atomically added into a zeroed dx)
 __global__ void linear_bwd_dx_kernel(int batch, int cin, int cout, const float* __restrict__ dy,
                                      const float* __restrict__ w, float w_gain, float* __restrict__ dx) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= batch * cin) return;
   int n = idx / cin, i = idx - n * cin;
+  const int per = (cout + gridDim.y - 1) / gridDim.y;
+  const int o0 = blockIdx.y * per, o1 = min(cout, o0 + per);
   float acc = 0.f;
-  for (int o = 0; o < cout; ++o) acc = fmaf(__ldg(dy + (size_t)n * cout + o), __ldg(w + (size_t)o * cin + i), acc);
-  dx[idx] = acc * w_gain;
+  for (int o = o0; o < o1; ++o) acc = fmaf(__ldg(dy + (size_t)n * cout + o), __ldg(w + (size_t)o * cin + i), acc);
+  if (gridDim.y == 1) dx[idx] = acc * w_gain;
+  else atomicAdd(dx + idx, acc * w_gain);
 }
 __global__ void linear_bwd_dw_kernel(int batch, int cin, int cout, const float* __restrict__ dy,
                                      const float* __restrict__ x, float w_gain, float b_gain, float* __restrict__ dw,
@@ -394,7 +409,7 @@ extern "C" int hfagp_styles_bwd(int nlayers, int batch, int num_ws, int w_dim, c
 extern "C" int hfagp_demod_bwd(int batch, int cout, int cin, const float* w2, const float* styles, const float* dcoef,
                                const float* ddcoef, float* dstyles, void* stream) {
   HFAGP_CHECK_ARG(w2 && styles && dcoef && ddcoef && dstyles && batch > 0 && batch <= 65535, "demod_bwd: bad args");
-  demod_bwd_kernel<<<dim3(cdiv(cin, 128), batch), 128, 0, (cudaStream_t)stream>>>(cout, cin, w2, styles, dcoef, ddcoef, dstyles);
+  demod_bwd_kernel<<<dim3(cdiv(cin, 32), batch), 256, 0, (cudaStream_t)stream>>>(cout, cin, w2, styles, dcoef, ddcoef, dstyles);
   HFAGP_CHECK_LAUNCH("demod_bwd_kernel");
   return HFAGP_OK;
 }
@@ -404,7 +419,10 @@ extern "C" int hfagp_linear_bwd(int batch, int cin, int cout, const float* dy, c
   HFAGP_CHECK_ARG(dy && w && batch > 0 && cin > 0 && cout > 0, "linear_bwd: bad args");
   HFAGP_CHECK_ARG(!dw || x, "linear_bwd: dw needs x");
   if (dx) {
-    linear_bwd_dx_kernel<<<cdiv((long long)batch * cin, 256), 256, 0, (cudaStream_t)stream>>>(batch, cin, cout, dy, w, w_gain, dx);
+    // few long rows (the encoder's 8192-wide final map): slice the output channels over more CTAs
+    const int slices = ((long long)batch * cin < 148 * 256 * 2 && cout >= 64) ? 8 : 1;
+    if (slices > 1) HFAGP_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)batch * cin, (cudaStream_t)stream));
+    linear_bwd_dx_kernel<<<dim3(cdiv((long long)batch * cin, 256), slices), 256, 0, (cudaStream_t)stream>>>(batch, cin, cout, dy, w, w_gain, dx);
     HFAGP_CHECK_LAUNCH("linear_bwd_dx_kernel");
   }
   if (dw) {

@@ -25,16 +25,17 @@ from . import ops
 MODES = {'save_image': 0, 'layout_grid': 1}
 
 
-def to_uint8(image: torch.Tensor, mode: str = 'save_image', out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """image [N,3,H,W] (as ``get_image`` returns it: an NCHW tensor or an NCHW view of the channels-last image) or
-    channels-last [N,H,W,3] -> uint8 [N,H,W,3] on the device."""
+def to_uint8(image: torch.Tensor, mode: str = 'save_image', out: Optional[torch.Tensor] = None,
+             layout: str = 'nchw') -> torch.Tensor:
+    """image [N,3,H,W] (``layout='nchw'``, as ``get_image`` returns it: an NCHW tensor or an NCHW view of the
+    channels-last image) or channels-last [N,H,W,3] (``layout='nhwc'``) -> uint8 [N,H,W,3] on the device."""
     if mode not in MODES:
         raise HfagpError(f'unknown uint8 convention {mode!r}; use one of {sorted(MODES)}')
-    if image.dim() != 4:
-        raise HfagpError('to_uint8 expects a 4-D image batch')
-    if image.shape[1] in (1, 3, 4) and image.shape[-1] not in (1, 3, 4):
+    if image.dim() != 4 or layout not in ('nchw', 'nhwc'):
+        raise HfagpError("to_uint8 expects a 4-D image batch and layout 'nchw' | 'nhwc'")
+    if layout == 'nchw':
         nhwc = image.permute(0, 2, 3, 1)
-        if not nhwc.is_contiguous():
+        if not nhwc.is_contiguous() or image.shape[2] * image.shape[3] == 1:
             nhwc = ops.nchw_to_nhwc(image.detach().float().contiguous())
     else:
         nhwc = image

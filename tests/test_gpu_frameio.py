@@ -31,6 +31,8 @@ def test_to_uint8_bit_exact(n, h, w):
         want = ref(x)
         got_nchw = frameio.to_uint8(x.cuda(), mode)                                   # NCHW input
         got_view = frameio.to_uint8(x.permute(0, 2, 3, 1).contiguous().cuda().permute(0, 3, 1, 2), mode)   # get_image's view
+        got_nhwc = frameio.to_uint8(x.permute(0, 2, 3, 1).contiguous().cuda(), mode, layout='nhwc')
+        assert torch.equal(got_nhwc.cpu(), want), mode
         assert got_nchw.dtype == torch.uint8 and tuple(got_nchw.shape) == (n, h, w, 3)
         assert torch.equal(got_nchw.cpu(), want), mode
         assert torch.equal(got_view.cpu(), want), mode
