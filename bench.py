@@ -405,10 +405,11 @@ def main():
         if render_ms:
             ach = RENDER_ALG_BYTES * fps_ / (render_ms * 1e-3) / 1e9
             render_roof = {'kernel': 'render_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                           'frac': ach / hbm_peak, 'traffic': 27_700_000, 'ms_per_launch': render_ms,
+                           'frac': ach / hbm_peak, 'traffic': 22_568_960, 'ms_per_launch': render_ms,
                            'peak_source': peak_src,
-                           'note': 'algorithmic bytes 27 394 048 B/frame (SURVEY 8d); ncu dram read+write 27.7 MB/launch '
-                                   '(profiles/): no wasted HBM re-reads; the kernel is bound by on-chip gathers '
+                           'note': 'algorithmic bytes 27 394 048 B/frame (SURVEY 8d); traffic = ncu dram read+write per launch '
+                                   '(profiles/r1_ncu_render_final.txt: 22.6 MB read, the 2.2 MB of outputs are still in L2 at '
+                                   'kernel end): no wasted HBM re-reads; the kernel is bound by on-chip gathers '
                                    '(2.4 GB L1/L2->RF per frame) and the decoder MLP, see DESIGN.md'}
         # dominant kernel: conv_tc_kernel (tcgen05) — all its launches of one frame together
         tc_ms = sum(kernel_ms.get(k, 0.0) for k in TC_ENTRY_POINTS)
@@ -418,7 +419,7 @@ def main():
         if tc_ms:
             ach_tf = tc_flops / (tc_ms * 1e-3) / 1e12
             roof = {'kernel': 'conv_tc_kernel', 'bound': 'tensor', 'achieved': ach_tf, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                    'frac': ach_tf / tf_peak, 'traffic': None, 'ms_per_frame': tc_ms, 'launches_per_frame': tc_launches,
+                    'frac': ach_tf / tf_peak, 'traffic': None,   # tensor-bound; the largest launch moves 222 MB (ncu) vs 201 MB algorithmic 'ms_per_frame': tc_ms, 'launches_per_frame': tc_launches,
                     'share_of_step': tc_ms / (ms / args.steps),
                     'tensor_pipe_frac': 3.0 * ach_tf / tf_peak, 'peak_source': peak_src + ', sustained bf16',
                     'note': 'achieved = algorithmic fp32 FLOPs of the tensor-core convolutions (%.1f GFLOP/frame) / summed '
