@@ -52,9 +52,83 @@ __global__ void modulate_split_kernel(int ntaps, int cout, int cin, const float*
   }
 }
 
+// All layers of a network in ONE launch: a block per (layer, output channel, sample).  The weights of a frame are
+// modulated by styles that are all known before the first convolution runs, so the 24 per-layer launches of the
+// inference path collapse into one HBM-streaming pass over the 113 MB of generator weights.
+constexpr int MAX_MOD_LAYERS = 40;
+struct ModTable {
+  const float* w[MAX_MOD_LAYERS];
+  __nv_bfloat16* hi[MAX_MOD_LAYERS];
+  __nv_bfloat16* lo[MAX_MOD_LAYERS];
+  float* dcoef[MAX_MOD_LAYERS];          // null: no demodulation (ToRGB)
+  long long soff[MAX_MOD_LAYERS];        // offset of the layer's styles [batch][cin] in the flat styles buffer
+  int ntaps[MAX_MOD_LAYERS], cout[MAX_MOD_LAYERS], cin[MAX_MOD_LAYERS];
+  int row_start[MAX_MOD_LAYERS + 1];     // prefix sum of cout
+  int nlayers;
+};
+
+__global__ void __launch_bounds__(128) modulate_split_multi_kernel(const __grid_constant__ ModTable tb,
+                                                                  const float* __restrict__ styles) {
+  const int row = blockIdx.x, n = blockIdx.y;
+  int l = 0;
+  while (row >= tb.row_start[l + 1]) ++l;
+  const int o = row - tb.row_start[l];
+  const int ntaps = tb.ntaps[l], cout = tb.cout[l], cin = tb.cin[l], c4 = cin >> 2;
+  const float* w = tb.w[l];
+  __nv_bfloat16* whi = tb.hi[l];
+  __nv_bfloat16* wlo = tb.lo[l];
+  const float* sn = styles + tb.soff[l] + (size_t)n * cin;
+  float ss = 0.f;
+  for (int q = threadIdx.x; q < c4; q += blockDim.x) {
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn) + q);
+    for (int t = 0; t < ntaps; ++t) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + ((size_t)t * cout + o) * cin) + q);
+      const float v[4] = {w4.x * s4.x, w4.y * s4.y, w4.z * s4.z, w4.w * s4.w};
+      st4_split(whi, wlo, ((((size_t)n * ntaps + t) * cout + o) * cin >> 2) + q, v);
+      ss = fmaf(v[0], v[0], ss); ss = fmaf(v[1], v[1], ss); ss = fmaf(v[2], v[2], ss); ss = fmaf(v[3], v[3], ss);
+    }
+  }
+  if (tb.dcoef[l]) {
+    __shared__ float red[4];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) tb.dcoef[l][(size_t)n * cout + o] = rsqrtf(red[0] + red[1] + red[2] + red[3] + 1e-8f);
+  }
+}
+
 }  // namespace hfagp
 
 using namespace hfagp;
+
+extern "C" int hfagp_modulate_split_multi_fwd(int nlayers, int batch, const float* const* w_host, const int32_t* ntaps_host,
+                                              const int32_t* cout_host, const int32_t* cin_host,
+                                              const int64_t* styles_off_host, const float* styles,
+                                              uint16_t* const* hi_host, uint16_t* const* lo_host,
+                                              float* const* dcoef_host, void* stream) {
+  HFAGP_CHECK_ARG(nlayers > 0 && nlayers <= MAX_MOD_LAYERS && batch > 0 && batch <= 65535, "modulate_split_multi_fwd: bad dims");
+  HFAGP_CHECK_ARG(w_host && ntaps_host && cout_host && cin_host && styles_off_host && styles && hi_host && lo_host && dcoef_host,
+                  "modulate_split_multi_fwd: null pointer");
+  ModTable tb;
+  int rows = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    HFAGP_CHECK_ARG(w_host[l] && hi_host[l] && lo_host[l] && ntaps_host[l] > 0 && cout_host[l] > 0 && cin_host[l] > 0 &&
+                        (cin_host[l] & 3) == 0, "modulate_split_multi_fwd: layer %d: bad entry (cin must be a multiple of 4)", l);
+    tb.w[l] = w_host[l];
+    tb.hi[l] = reinterpret_cast<__nv_bfloat16*>(hi_host[l]);
+    tb.lo[l] = reinterpret_cast<__nv_bfloat16*>(lo_host[l]);
+    tb.dcoef[l] = dcoef_host[l];
+    tb.soff[l] = styles_off_host[l];
+    tb.ntaps[l] = ntaps_host[l]; tb.cout[l] = cout_host[l]; tb.cin[l] = cin_host[l];
+    tb.row_start[l] = rows;
+    rows += cout_host[l];
+  }
+  tb.row_start[nlayers] = rows;
+  tb.nlayers = nlayers;
+  modulate_split_multi_kernel<<<dim3(rows, batch), 128, 0, (cudaStream_t)stream>>>(tb, styles);
+  HFAGP_CHECK_LAUNCH("modulate_split_multi_kernel");
+  return HFAGP_OK;
+}
 
 extern "C" int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, uint16_t* lo, void* stream) {
   HFAGP_CHECK_ARG(x && hi && lo && count > 0, "split_bf16: bad args");

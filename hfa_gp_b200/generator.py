@@ -198,6 +198,7 @@ class TriPlaneGenerator(nn.Module):
         self._packed_key = None
         self.fixed_draws = None    # (jitter_coarse, u_fine) used instead of torch.rand when synthesis() gets none
         self.precision = 'tc'      # 'tc': tcgen05 split-bf16 convolutions (fp32-class); 'fp32': SIMT kernels only
+        self._premod = None        # inference: per-layer (modulated weights, dcoef) of the current synthesis() call
 
     @property
     def num_ws(self) -> int:
@@ -289,7 +290,8 @@ class TriPlaneGenerator(nn.Module):
         h, w = x.shape[1], x.shape[2]
         if self._use_tc(pl.cin):
             xs = x if isinstance(x, ops.Split) else ops.split(x)
-            wmod, epi['dcoef'] = ops.modulate_split(pl.w, styles, True)
+            pre = self._premod.get(id(m)) if self._premod else None
+            wmod, epi['dcoef'] = pre if pre is not None else ops.modulate_split(pl.w, styles, True)
             if pl.up == 1:
                 y = ops.conv2d_tc(xs, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batched=True,
                                   split_out=split_out, **epi)
@@ -325,7 +327,8 @@ class TriPlaneGenerator(nn.Module):
             raise HfagpError('backward of a clamped wide ToRGB is not implemented (EG3D clamps only the 3-channel SR ToRGB)')
         if self._use_tc(pl.cin):
             xs = x if isinstance(x, ops.Split) else ops.split(x)
-            wmod, _ = ops.modulate_split(pl.w, styles, False)
+            pre = self._premod.get(id(m)) if self._premod else None
+            wmod, _ = pre if pre is not None else ops.modulate_split(pl.w, styles, False)
             return ops.conv2d_tc(xs, wmod, ops.TAPS_1X1, pl.cout, oh=h, ow=w, w_batched=True, bias=pl.bias,
                                  clamp=pl.clamp, up_img=img)
         wmod, _ = ops.modulate(pl.w, styles, False)
@@ -399,7 +402,9 @@ class TriPlaneGenerator(nn.Module):
             return e
 
         t0 = mark()
-        styles = iter(pk['styles'].run(ws))
+        flat, offs = pk['styles'].run_flat(ws)
+        styles = iter(pk['styles'].views(flat, offs, b))
+        self._premod = self._modulate_all(pk, flat, offs, b)
 
         x = img = None
         for r in cfg.block_resolutions:
@@ -442,10 +447,26 @@ class TriPlaneGenerator(nn.Module):
         out = {'image': ops.nhwc_to_nchw(img),
                'image_raw': ops.nhwc_to_nchw(rgb_lo),
                'image_depth': depth.view(b, 1, res, res)}
+        self._premod = None
         if pe is not None:
             t4 = mark()
             pe.extend([('backbone', t0, t1), ('render', t2, t3), ('superres', t3, t4), ('synthesis', t0, t4)])
         return out
+
+    def _modulate_all(self, pk, flat, offs, batch):
+        """Inference: every tensor-core layer's weights modulated (and demodulation coefficients computed) in one
+        launch, before the first convolution — all styles of a frame are known up front."""
+        if self.precision != 'tc':
+            return None
+        sel = []
+        for (kind, m, _), off in zip(pk['order'], offs):
+            pl = pk['layers'][id(m)]
+            if self._use_tc(pl.cin) and not (kind == 'torgb' and pl.cout <= 4):
+                sel.append((m, (pl.w, off, kind == 'conv')))
+        if not sel:
+            return None
+        outs = ops.modulate_split_multi([e for _, e in sel], flat, batch)
+        return {id(m): o for (m, _), o in zip(sel, outs)}
 
     def _render_inputs(self, b, res, device, jitter_coarse, u_fine, pk):
         cfg = self.cfg

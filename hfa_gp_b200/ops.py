@@ -324,6 +324,28 @@ def _ksplit(tiles: int, cin: int, taps, in_stride: int) -> int:
     return max(1, min(units, NUM_SMS // tiles))
 
 
+def modulate_split_multi(entries, styles_flat, batch):
+    """entries: list of (w [taps][O][I] fp32, styles offset, demodulate) -> list of (Split wmod [B][taps][O][I], dcoef
+    [B][O] or None), all layers in ONE launch (``hfagp_modulate_split_multi_fwd``)."""
+    n = len(entries)
+    dev = styles_flat.device
+    outs, his, los, dcs = [], [], [], []
+    for w, off, demod in entries:
+        taps, cout, cin = w.shape
+        hi = torch.empty((batch, taps, cout, cin), device=dev, dtype=torch.bfloat16)
+        lo = torch.empty((batch, taps, cout, cin), device=dev, dtype=torch.bfloat16)
+        dc = torch.empty((batch, cout), device=dev, dtype=torch.float32) if demod else None
+        outs.append((Split(hi, lo), dc))
+        his.append(hi.data_ptr()); los.append(lo.data_ptr()); dcs.append(dc.data_ptr() if demod else None)
+    vp = C.c_void_p
+    _ok(_cabi.lib().hfagp_modulate_split_multi_fwd(
+        n, batch, (vp * n)(*[e[0].data_ptr() for e in entries]), (C.c_int32 * n)(*[e[0].shape[0] for e in entries]),
+        (C.c_int32 * n)(*[e[0].shape[1] for e in entries]), (C.c_int32 * n)(*[e[0].shape[2] for e in entries]),
+        (C.c_int64 * n)(*[e[1] for e in entries]), ptr(styles_flat), (vp * n)(*his), (vp * n)(*los), (vp * n)(*dcs),
+        stream()), 'hfagp_modulate_split_multi_fwd')
+    return outs
+
+
 def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_stride: int = 1, out=None,
               out_hw=None, out_stride: int = 1, out_off=(0, 0), w_batched: bool = False, split_out: bool = False,
               dcoef=None, noise=None, noise_gain: float = 0.0, bias=None, act: int = ACT_LINEAR,

@@ -135,6 +135,15 @@ int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, uint16_t* lo
 int hfagp_modulate_split_fwd(int batch, int ntaps, int cout, int cin, const float* w, const float* styles,
                              uint16_t* wmod_hi, uint16_t* wmod_lo, float* dcoef, void* stream);
 
+/* hfagp_modulate_split_fwd for every layer of a network in ONE launch (host arrays of length nlayers: packed weight
+ * pointer, taps, cout, cin, offset of the layer's styles inside the flat styles buffer of hfagp_styles_fwd, output
+ * pointers; dcoef_host[l] may be NULL = no demodulation).  All styles of a frame exist before its first convolution,
+ * so the inference path modulates the whole generator in one pass. */
+int hfagp_modulate_split_multi_fwd(int nlayers, int batch, const float* const* w_host, const int32_t* ntaps_host,
+                                   const int32_t* cout_host, const int32_t* cin_host, const int64_t* styles_off_host,
+                                   const float* styles, uint16_t* const* hi_host, uint16_t* const* lo_host,
+                                   float* const* dcoef_host, void* stream);
+
 /* 4x4 [1,3,3,1]x[1,3,3,1]/64 FIR (gain 4, pad 1) over the (2H+1)x(2W+1) output of the stride-2
  * transposed convolution, fused with demodulation, noise, bias, leaky-ReLU, gain and clamp.
  * t[n][2H+1][2W+1][c] -> y[n][2H][2W][c] (fp32), or the split-bf16 pair (y_hi, y_lo) when y is NULL.
