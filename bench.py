@@ -73,14 +73,47 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (the timed
+    region of a 2.6 ms/frame loop is tens of milliseconds, too short for `nvidia-smi -lms`); falls back to nvidia-smi."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+               0x80: 'hw_power_brake_slowdown'}
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.nvml, self.handle, self.samples, self.mask, self.stop_flag = None, None, [], 0, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                try:
+                    idx = int(vis.split(',')[gpu_index])
+                except (ValueError, IndexError):
+                    idx = gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.stop_flag = False
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.Q}',
                                           '--format=csv,noheader,nounits', '-lms', '100'],
@@ -91,6 +124,17 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            n = self.nvml
+            try:
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            except Exception:
+                mx = None
+            reasons = sorted(v for k, v in self.REASONS.items() if self.mask & k)
+            return {'sm_mhz': statistics.median(self.samples) if self.samples else None, 'sm_max_mhz': mx,
+                    'samples': len(self.samples), 'reasons': reasons, 'source': 'nvml, 2 ms poll'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -110,7 +154,7 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(nm)
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'reasons': sorted(reasons), 'source': 'nvidia-smi -lms 100'}
 
 
 def reference_arm(args, rank, world):
