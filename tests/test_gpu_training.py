@@ -316,3 +316,53 @@ def test_trainer_checkpoint_round_trip(tmp_path):
     with pytest.raises(Exception):
         tr2.tune_generator()
         tr2.gen_update(real, hfagp_ref.synthetic_labels(2, seed=0).cuda())
+
+
+@pytest.mark.parametrize('smooth', [False, True])
+def test_trainer_audio_step_matches_oracle(smooth):
+    """trainer_audio.gen_update, both branches of trainer_audio.py:66-93 (single frame / 8-frame attention smoothing with
+    zero padding at the sequence start): image, losses and the gradients reaching AudioNet, AudioAttNet, Weights_3DMM
+    and the latent basis."""
+    from hfa_gp_b200.trainer_audio import Trainer
+    cfg = eg3d_ref.small14_config()
+    size, k = 32, 10
+    ref_gen, _ = pu.make_pair(cfg, seed=2)
+    g = torch.Generator().manual_seed(17)
+    auds = torch.randn(40, 16, 29, generator=g)
+    args = _args(size, k, cfg, params_len=64, dim_aud=64, win_size=16, smo_size=8, nosmo_iters=100)
+    tr = Trainer(auds.numpy(), 30, args, torch.device('cuda'), 0)
+    gen = tr.gen.module
+    gen.generator.load_state_dict(ref_gen.state_dict())
+    cpu = lambda m: {n: p.detach().cpu().clone().requires_grad_(True) for n, p in m.named_parameters()}
+    sd_w, sd_a, sd_t = cpu(gen.weights_3dmm), cpu(tr.AudNet.module), cpu(tr.AudAttNet.module)
+    oracle = train_ref.TrainStepRef({n: p.detach() for n, p in sd_w.items()}, gen.bases.detach().cpu(),
+                                    gen.delta.detach().cpu(), ref_gen, size, 3e-4, lpips=_oracle_lpips(tr.lpips_loss),
+                                    head='3dmm')
+    real = torch.rand(1, 3, size, size, generator=g) * 2 - 1
+    label = hfagp_ref.synthetic_labels(1, seed=5)
+    jit = torch.rand(1, cfg.nrr ** 2, cfg.depth_res, 1, generator=g)
+    u = torch.rand(cfg.nrr ** 2, cfg.depth_res_importance, generator=g)
+    img_i = 2                                              # window [-2, 6): two zero-padded rows on the left
+    step = 200 if smooth else 0
+    if smooth:
+        win = torch.cat((torch.zeros(2, 16, 29), auds[0:6]), dim=0)
+        feats = hfagp_ref.audionet_ref(sd_a, win)
+        feat = hfagp_ref.audioattnet_ref(sd_t, feats).unsqueeze(0)
+    else:
+        feat = hfagp_ref.audionet_ref(sd_a, auds[torch.tensor([img_i])]).unsqueeze(0)
+    l2_r, lp_r, img_r = oracle.step(real, label, jit, u, params=feat)
+    gen.generator.fixed_draws = (jit.cuda(), u.cuda())
+    idx = img_i if smooth else torch.tensor([img_i], device='cuda')
+    _, l2, lpv, img = tr.gen_update(real.cuda(), label.clone().cuda(), None, step, idx)
+    assert pu.rel_err(img, img_r) < pu.REL_TOL
+    assert abs(float(l2.detach()) - float(l2_r)) < 1e-3 * abs(float(l2_r))
+    assert abs(float(lpv.detach()) - float(lp_r)) < 2e-3 * abs(float(lp_r))
+    for n, p in tr.AudNet.module.named_parameters():
+        _check(p.grad, sd_a[n].grad, 'tc', f'd AudNet.{n}')
+    if smooth:
+        for n, p in tr.AudAttNet.module.named_parameters():
+            _check(p.grad, sd_t[n].grad, 'tc', f'd AudAttNet.{n}')
+    names = dict(gen.weights_3dmm.named_parameters())
+    for n in oracle.names:
+        _check(names[n].grad, oracle.sd[n].grad, 'tc', f'd weights_3dmm.{n}')
+    assert tr.optimizer_Aud.steps[0] == 1 and tr.optimizer_AudAtt.steps[0] == (1 if smooth else 0)
