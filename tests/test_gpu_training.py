@@ -366,3 +366,42 @@ def test_trainer_audio_step_matches_oracle(smooth):
     for n in oracle.names:
         _check(names[n].grad, oracle.sd[n].grad, 'tc', f'd weights_3dmm.{n}')
     assert tr.optimizer_Aud.steps[0] == 1 and tr.optimizer_AudAtt.steps[0] == (1 if smooth else 0)
+
+
+@pytest.mark.parametrize('same_bases', [False, True])
+def test_trainer_rgb_person_2_and_out_pose(same_bases):
+    """--person_2 (second identity: bases_2 / delta_2, optionally sharing bases, headnerf.py:58-73,84-90) with an
+    --out_pose encoder (get_weights returns (weights, pose), encoder3d.py:257-263,288-290): the step trains the second
+    identity's tensors and leaves the first one's delta untouched."""
+    from hfa_gp_b200.trainer_rgb import Trainer
+    cfg = eg3d_ref.small14_config()
+    size, k, b = 32, 10, 2
+    ref_gen, _ = pu.make_pair(cfg, seed=3)
+    args = _args(size, k, cfg)
+    args.person_2, args.same_bases, args.out_pose = True, same_bases, True
+    tr = Trainer(args, torch.device('cuda'), 0)
+    gen = tr.gen.module
+    gen.generator.load_state_dict(ref_gen.state_dict())
+    assert hasattr(gen, 'delta_2') and hasattr(gen, 'bases_2') == (not same_bases)
+    sd = {n: p.detach().cpu().clone() for n, p in gen.encoder.state_dict().items()}     # parameters + blur kernels
+    bases2 = (gen.bases if same_bases else gen.bases_2).detach().cpu()
+    oracle = train_ref.TrainStepRef({n: v for n, v in sd.items() if not n.startswith('pose.')}, bases2,
+                                    gen.delta_2.detach().cpu(), ref_gen, size, 3e-4, lpips=_oracle_lpips(tr.lpips_loss))
+    g = torch.Generator().manual_seed(23)
+    real = torch.rand(b, 3, size, size, generator=g) * 2 - 1
+    label = hfagp_ref.synthetic_labels(b, seed=7)
+    jit = torch.rand(b, cfg.nrr ** 2, cfg.depth_res, 1, generator=g)
+    u = torch.rand(b * cfg.nrr ** 2, cfg.depth_res_importance, generator=g)
+    l2_r, lp_r, img_r = oracle.step(real, label, jit, u)
+    gen.generator.fixed_draws = (jit.cuda(), u.cuda())
+    delta1 = gen.delta.detach().clone()
+    l2, lpv, img = tr.gen_update(real.cuda(), label.clone().cuda(), person_2=True)
+    assert pu.rel_err(img, img_r) < pu.REL_TOL
+    assert abs(float(l2.detach()) - float(l2_r)) < 1e-3 * abs(float(l2_r))
+    _check(gen.delta_2.grad, oracle.delta.grad, 'tc', 'd delta_2')
+    _check((gen.bases if same_bases else gen.bases_2).grad, oracle.bases.grad, 'tc', 'd bases(_2)')
+    assert float(gen.delta.grad.abs().max()) == 0.0 and torch.equal(gen.delta.detach(), delta1)
+    w, pose = gen.get_weights(real.cuda())
+    assert tuple(w.shape) == (b, k) and tuple(pose.shape) == (b, 25)
+    assert pu.rel_err(pose, hfagp_ref.encoder_ref({n: p.detach().cpu() for n, p in gen.encoder.state_dict().items()},
+                                                  real, out_pose=True)[1]) < 1e-3
