@@ -11,6 +11,7 @@
 // (c0, x0+dx, y0+dy, n): out-of-range coordinates are zero-filled by the TMA unit, which *is* the conv padding.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include "common.cuh"
@@ -152,6 +153,56 @@ __device__ unsigned long long tc_dbg[256][8];
 #define TC_ADD(slot, var)
 #endif
 
+// ---- CTA-pair (cta_group::2) forms.  A shared::cta address of the executing CTA is a valid shared::cluster address;
+// bit 24 of it is the CTA's rank inside the pair, so clearing it names the same object in the LEADER (rank 0) CTA.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2cta(const CUtensorMap* map, void* smem, uint32_t bar_addr, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(const CUtensorMap* map, void* smem, uint32_t bar_addr, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this address in BOTH CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // One lane of a converged warp (elect.sync).  The producer and MMA warps run their loops warp-uniformly and only the
 // issuing instruction is predicated on the elected lane: addresses, descriptors and coordinates then live in UNIFORM
 // registers.  Inside an `if (lane == 0)` region every tcgen05.mma / TMA operand costs an R2UR round trip — measured
@@ -170,7 +221,7 @@ __device__ __forceinline__ bool elect_one() {
 // tile id -> (class, batch sample, tile origin, N offset).  N tiles are the fastest index so that the CTAs running
 // side by side read the same input patch (L2 hits), then M tiles, then classes, then batch samples.
 struct TileCoord { int c, n, y0, x0, n0, u0, u1; };   // [u0, u1): (K chunk, tap group) units of this work item
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int kchunks) {
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int kchunks, int pair_rank = -1) {
   TileCoord tc;
   const int nt = t % p.n_tiles;
   int r = t / p.n_tiles;
@@ -188,7 +239,10 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int k
   const int ty = r / p.cls[c].tiles_x;
   tc.c = c;
   tc.y0 = ty * p.tile_h;
-  tc.x0 = (r - ty * p.cls[c].tiles_x) * p.tile_w;
+  // pair mode (cta_group::2): tiles_x counts PAIRS of horizontally adjacent tiles; this CTA takes tile 2*px + rank
+  // (a tile beyond the image is harmless: TMA zero-fills its patches and the epilogue finds no valid pixel)
+  const int px = r - ty * p.cls[c].tiles_x;
+  tc.x0 = (pair_rank < 0 ? px : 2 * px + pair_rank) * p.tile_w;
   tc.n0 = nt * p.bn;
   return tc;
 }
@@ -196,17 +250,32 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int k
 // Persistent kernel: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Two shared-memory rings (input
 // patches, weight tiles) run ahead across tile boundaries and the fp32 accumulator is double-buffered in TMEM, so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// TWO = true is the CTA-pair form (cluster of 2, tcgen05 cta_group::2): the pair computes two horizontally adjacent
+// M tiles as ONE M=256 MMA issued by the leader CTA.  Each CTA stages its own input patches and only part of every
+// weight tile — rank 0 the hi half (x_hi*w_hi columns), rank 1 the lo half (x_hi*w_lo columns), and each one half of
+// the w_hi rows for the x_lo*w_hi MMA: 24 KB per tap instead of 32 KB written by TMA and 14 KB instead of 20 KB read
+// by the MMAs per K step and SM.  SS-mode MMAs at this tile size are shared-memory-bandwidth bound
+// (profiles/r1_conv_tc_notes.md), so that is what buys speed.  TMA completions of both CTAs land on the leader's
+// full barriers; the leader's commits are multicast to both CTAs' empty / accumulator-full barriers; both CTAs'
+// epilogue warps arrive on the leader's accumulator-empty barrier.
+template <bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const __grid_constant__ TcParams p) {
+               const __grid_constant__ CUtensorMap map_b_half, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int a_half = p.patch_rows * p.tile_w * TC_ROW;          // bytes of one (hi | lo) patch, multiple of 1024
   const int a_stage = 2 * a_half;
   const int b_bytes = p.bn * TC_ROW;
   const int b_half = (b_bytes + 1023) & ~1023;
-  const int b_stage = 2 * b_half;
+  // pair form: [bn rows: this CTA's half of (w_hi ; w_lo)] [bn/2 rows: this CTA's half of w_hi]
+  const int b_stage = TWO ? b_bytes + b_bytes / 2 : 2 * b_half;
+  const int rank = TWO ? (int)cluster_ctarank() : 0;
+  const int pair_rank = TWO ? rank : -1;
+  const int wid = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // work-item lane: cluster or CTA index
+  const int wstride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.a_stages * a_stage;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + p.b_stages * b_stage);
@@ -228,25 +297,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_MAX_STAGES; ++s) {
-      mbar_init(&a_full[s], 1);
+      mbar_init(&a_full[s], TWO ? 2 : 1);        // pair form: one expect_tx arrival per CTA of the pair
       mbar_init(&a_empty[s], 1);
-      mbar_init(&b_full[s], 1);
+      mbar_init(&b_full[s], TWO ? 2 : 1);
       mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8);               // one arrival per epilogue warp
+      mbar_init(&acc_empty[s], TWO ? 16 : 8);    // one arrival per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote arrival
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -255,13 +331,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // MMA issuer consumes them
     {
       uint32_t ia = 0, ib = 0;                     // running slot counters of the two rings
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t, kchunks);
+      for (int t = wid; t < p.total_tiles; t += wstride) {
+        const TileCoord tc = decode_tile(p, t, kchunks, pair_rank);
         const TcClass& c = p.cls[tc.c];
         const int wz0 = p.w_batched ? tc.n * p.taps_per_frame : 0;
-        if (t + (int)gridDim.x < p.total_tiles) {
+        if (t + wstride < p.total_tiles) {
           // pull the NEXT work item's input patches into L2 while this one streams (they are first-touch data)
-          const TileCoord nx = decode_tile(p, t + gridDim.x, kchunks);
+          const TileCoord nx = decode_tile(p, t + wstride, kchunks, pair_rank);
           const TcClass& cn = p.cls[nx.c];
           for (int u = nx.u0; u < nx.u1; ++u) {
             const int kc = u / cn.ngroups, g = u - kc * cn.ngroups;
@@ -282,18 +358,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               mbar_wait(&a_empty[s], ((ia / p.a_stages) & 1) ^ 1);
               const int ax = tc.x0 * d.in_stride + c.dx[tp], ay = tc.y0 * d.in_stride + c.dy0[tp];
               if (elect_one()) {
-                mbar_expect_tx(&a_full[s], 2 * a_half);
-                tma_load_4d(&map_a_hi, smem_a + s * a_stage, &a_full[s], c0, ax, ay, tc.n);
-                tma_load_4d(&map_a_lo, smem_a + s * a_stage + a_half, &a_full[s], c0, ax, ay, tc.n);
+                if (TWO) {
+                  const uint32_t bar = smem_u32(&a_full[s]) & PEER_BIT_MASK;       // the LEADER's barrier
+                  mbar_expect_tx_cluster(bar, 2 * a_half);
+                  tma_load_4d_2cta(&map_a_hi, smem_a + s * a_stage, bar, c0, ax, ay, tc.n);
+                  tma_load_4d_2cta(&map_a_lo, smem_a + s * a_stage + a_half, bar, c0, ax, ay, tc.n);
+                } else {
+                  mbar_expect_tx(&a_full[s], 2 * a_half);
+                  tma_load_4d(&map_a_hi, smem_a + s * a_stage, &a_full[s], c0, ax, ay, tc.n);
+                  tma_load_4d(&map_a_lo, smem_a + s * a_stage + a_half, &a_full[s], c0, ax, ay, tc.n);
+                }
               }
               ++ia;
             }
             const int s = ib % p.b_stages;
             mbar_wait(&b_empty[s], ((ib / p.b_stages) & 1) ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&b_full[s], 2 * b_bytes);
-              tma_load_3d(&map_b_hi, smem_b + s * b_stage, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
-              tma_load_3d(&map_b_lo, smem_b + s * b_stage + b_half, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
+              if (TWO) {
+                const uint32_t bar = smem_u32(&b_full[s]) & PEER_BIT_MASK;         // the LEADER's barrier
+                mbar_expect_tx_cluster(bar, b_bytes + b_bytes / 2);
+                tma_load_3d_2cta(rank == 0 ? &map_b_hi : &map_b_lo, smem_b + s * b_stage, bar, c0, tc.n0, wz0 + c.wtap[tp]);
+                tma_load_3d_2cta(&map_b_half, smem_b + s * b_stage + b_bytes, bar, c0, tc.n0 + rank * (p.bn / 2),
+                                 wz0 + c.wtap[tp]);
+              } else {
+                mbar_expect_tx(&b_full[s], 2 * b_bytes);
+                tma_load_3d(&map_b_hi, smem_b + s * b_stage, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
+                tma_load_3d(&map_b_lo, smem_b + s * b_stage + b_half, &b_full[s], c0, tc.n0, wz0 + c.wtap[tp]);
+              }
             }
             ++ib;
           }
@@ -301,14 +392,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform loop, elected lane issues)
-    {
+    // ===== MMA issuer (warp-uniform loop, elected lane issues); pair form: the leader CTA only
+    if (!TWO || rank == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((TC_BM >> 4) << 24);
       // the same with N = 2*bn: the hi and lo halves of a weight tile are adjacent in shared memory, so
       // x_hi * [w_hi ; w_lo] is ONE instruction writing accumulator columns [0,bn) and [bn,2bn) — x_hi is read from
       // shared memory once instead of twice (SS-mode MMAs at N=128 are shared-memory-read bound: 8 KB per 64 cycles)
       const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 2) << 17) | ((TC_BM >> 4) << 24);
+      // pair form: M = 256 across the two CTAs
+      const uint32_t idesc_p = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((2 * TC_BM >> 4) << 24);
+      const uint32_t idesc2_p = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 2) << 17) | ((2 * TC_BM >> 4) << 24);
       const bool wide = b_half == b_bytes;         // halves contiguous (bn*128 B is a multiple of 1024: bn % 8 == 0)
       const int row_bytes = p.tile_w * TC_ROW;     // one patch row of pixels (multiple of 1024: BW % 8 == 0)
       uint32_t ia = 0, ib = 0, j = 0;
@@ -316,8 +410,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       long long dbg_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
       TC_T0(t_loop);
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
-        const TileCoord tc = decode_tile(p, t, kchunks);
+      for (int t = wid; t < p.total_tiles; t += wstride, ++j) {
+        const TileCoord tc = decode_tile(p, t, kchunks, pair_rank);
         const TcClass& c = p.cls[tc.c];
         const uint32_t buf = j & 1;
         TC_T0(t_ae);
@@ -348,9 +442,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint64_t da_hi = umma_desc(a_addr + c.row_off[tp] * row_bytes);
             const uint64_t da_lo = umma_desc(a_addr + c.row_off[tp] * row_bytes + a_half);
             const uint64_t db_hi = umma_desc(smem_u32(smem_b + sb * b_stage));
-            const uint64_t db_lo = umma_desc(smem_u32(smem_b + sb * b_stage) + b_half);
+            const uint64_t db_lo = umma_desc(smem_u32(smem_b + sb * b_stage) + (TWO ? b_bytes : b_half));
             const bool last = c.last[tp] != 0;
-            if (elect_one()) {
+            if (TWO) {
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  // cols [0,bn) += x_hi*w_hi (rank 0's rows), [bn,2bn) += x_hi*w_lo (rank 1's rows)
+                  umma_bf16_2cta(acc, da_hi + 2 * k, db_hi + 2 * k, idesc2_p, (k == 0) ? started : 1u);
+                  // cols [0,bn) += x_lo*w_hi: each CTA holds bn/2 of the w_hi rows behind its hi|lo block
+                  umma_bf16_2cta(acc, da_lo + 2 * k, db_lo + 2 * k, idesc_p, 1u);
+                }
+                umma_commit_2cta(&b_empty[sb]);
+                if (last) umma_commit_2cta(&a_empty[sa]);
+              }
+            } else if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {
                 const uint32_t first = (k == 0) ? started : 1u;
@@ -369,7 +475,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             started = 1;
           }
         }
-        if (elect_one()) umma_commit(&acc_full[buf]);  // accumulator complete
+        if (elect_one()) {                             // accumulator complete
+          if (TWO) umma_commit_2cta(&acc_full[buf]); else umma_commit(&acc_full[buf]);
+        }
         __syncwarp();
       }
 #ifdef HFAGP_TC_TIMING
@@ -400,8 +508,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     long long dbg_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     TC_T0(t_epi);
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
-      const TileCoord tc = decode_tile(p, t, kchunks);
+    for (int t = wid; t < p.total_tiles; t += wstride, ++j) {
+      const TileCoord tc = decode_tile(p, t, kchunks, pair_rank);
       const TcClass& c = p.cls[tc.c];
       const uint32_t buf = j & 1;
       if (tc.n != staged_n || tc.n0 != staged_n0) {  // uniform over the epilogue threads
@@ -439,7 +547,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           // last read of this accumulator by this warp: hand it back to the MMA issuer before the stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          if (lane == 0) {
+            if (TWO) mbar_arrive_cluster(smem_u32(&acc_empty[buf]) & PEER_BIT_MASK); else mbar_arrive(&acc_empty[buf]);
+          }
           arrived = true;
         }
         if (!valid) continue;
@@ -532,7 +642,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (!arrived) {                                  // this warp had no column chunk (bn <= 32)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) {
+          if (TWO) mbar_arrive_cluster(smem_u32(&acc_empty[buf]) & PEER_BIT_MASK); else mbar_arrive(&acc_empty[buf]);
+        }
       }
     }
 #ifdef HFAGP_TC_TIMING
@@ -541,10 +653,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer may still touch its smem / TMEM
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if (TWO)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -718,11 +833,17 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
     }
   }
   p.patch_rows = p.tile_h + max_span;
+  // CTA-pair form (cta_group::2) for the big layers: at least one pair of M tiles per pair of SMs, no split-K
+  int m_tiles = 0;
+  for (int i = 0; i < ndesc; ++i) m_tiles += cdiv(p.cls[i].ow, p.tile_w) * cdiv(p.cls[i].oh, p.tile_h);
+  static const bool pair_off = getenv("HFAGP_TC_NO_PAIR") != nullptr;      // debugging aid: force the single-CTA form
+  const bool two = !pair_off && ksplit == 0 && (long long)m_tiles * d.batch * p.n_tiles >= 148 && p.bn % 16 == 0;
   int tiles = 0;
   const int kchunks_h = cdiv(d.cin, TC_BK);
   for (int i = 0; i < ndesc; ++i) {
     TcClass& c = p.cls[i];
     c.tiles_x = cdiv(c.ow, p.tile_w);
+    if (two) c.tiles_x = cdiv(c.tiles_x, 2);       // pairs of horizontally adjacent tiles
     c.tiles_y = cdiv(c.oh, p.tile_h);
     c.tile_begin = tiles;
     const int units = kchunks_h * c.ngroups;
@@ -736,7 +857,7 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
 
   // shared-memory rings: as deep as 225 KB allows
   const int a_stage = 2 * p.patch_rows * p.tile_w * TC_ROW;
-  const int b_stage = 2 * ((p.bn * TC_ROW + 1023) & ~1023);
+  const int b_stage = two ? p.bn * TC_ROW * 3 / 2 : 2 * ((p.bn * TC_ROW + 1023) & ~1023);
   const int extra = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * TC_BM * 4 /*epilogue vectors*/;
   const int budget = 227 * 1024 - extra;
   // the input patches of a tile are first-touch (HBM latency), the weights are L2 hits: favour patch depth
@@ -751,7 +872,7 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   HFAGP_CHECK_ARG(p.a_stages > 0, "%s: tile does not fit shared memory", who);
   const size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + extra;
 
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mb_half;
   const uint32_t es = (uint32_t)d.in_stride;
   // box extents are given in un-strided coordinates: a stride-2 traversal of BW outputs spans 2*BW-1 inputs
   const uint32_t box_w = (uint32_t)(p.tile_w * d.in_stride - (d.in_stride - 1));
@@ -763,20 +884,42 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   const uint64_t wz = (uint64_t)w_taps_total * (p.w_batched ? d.batch : 1);
   if ((rc = get_map(&mb_hi, w_hi, d.cin, d.cout, wz, 1, TC_BK, p.bn, 1, 1, 1, 3))) return rc;
   if ((rc = get_map(&mb_lo, w_lo, d.cin, d.cout, wz, 1, TC_BK, p.bn, 1, 1, 1, 3))) return rc;
+  mb_half = mb_hi;
+  if (two && (rc = get_map(&mb_half, w_hi, d.cin, d.cout, wz, 1, TC_BK, p.bn / 2, 1, 1, 1, 3))) return rc;
 
   static std::once_flag attr_once;
   static int num_sms = 148;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_rc = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_rc = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_rc == cudaSuccess)
+      attr_rc = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
       num_sms = n;
   });
   if (attr_rc != cudaSuccess) return fail(HFAGP_E_CUDA, "%s: cudaFuncSetAttribute(max dynamic smem) failed: %s", who, cudaGetErrorString(attr_rc));
+  if (two) {
+    const int pairs = p.total_tiles < num_sms / 2 ? p.total_tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, ma_hi, ma_lo, mb_hi, mb_lo, mb_half, p);
+    if (e != cudaSuccess) return fail(HFAGP_E_CUDA, "%s: cluster launch failed: %s", who, cudaGetErrorString(e));
+    return HFAGP_OK;
+  }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  conv_tc_kernel<false><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mb_half, p);
   HFAGP_CHECK_LAUNCH("conv_tc_kernel");
   return HFAGP_OK;
 }
