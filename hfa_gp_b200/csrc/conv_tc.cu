@@ -837,7 +837,7 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   int m_tiles = 0;
   for (int i = 0; i < ndesc; ++i) m_tiles += cdiv(p.cls[i].ow, p.tile_w) * cdiv(p.cls[i].oh, p.tile_h);
   static const bool pair_off = getenv("HFAGP_TC_NO_PAIR") != nullptr;      // debugging aid: force the single-CTA form
-  const bool two = !pair_off && ksplit == 0 && (long long)m_tiles * d.batch * p.n_tiles >= 148 && p.bn % 16 == 0;
+  const bool two = !pair_off && ksplit == 0 && (long long)m_tiles * d.batch * p.n_tiles >= 100 && p.bn % 16 == 0;
   int tiles = 0;
   const int kchunks_h = cdiv(d.cin, TC_BK);
   for (int i = 0; i < ndesc; ++i) {
