@@ -2,6 +2,7 @@
 // plus the small bandwidth-bound companions (FIR after the transposed conv, small-N ToRGB, blur).
 // This is the exact-fp32 path; see conv_tc.cu for the tcgen05 tensor-core path.
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "splitio.cuh"
@@ -185,11 +186,10 @@ __global__ void conv_epilogue_kernel(const ConvParams p, const float* __restrict
 
 // ---------------------------------------------------------------- FIR after transposed conv
 // y[oy][ox] = sum_{ky,kx} g[ky] g[kx] t[oy+ky-1][ox+kx-1]  (g = [1,3,3,1]/4: the 4x4 filter with its gain of 4),
-// evaluated separably in registers: a thread owns 4 channels of TWO adjacent output columns and UPFIR_R output rows;
+// evaluated separably in registers: a thread owns 4 channels of TWO adjacent output columns and UPFIR_R (4) output rows;
 // it walks the R+3 input rows once (5 float4 loads per row), forms the two horizontal sums and scatters them into
 // the vertical accumulators.  3.4 loads per output instead of 16; the epilogue is branch-free.
-constexpr int UPFIR_R = 8;
-
+template <int UPFIR_R>
 __global__ void __launch_bounds__(256) upfir_act_kernel(int batch, int h2, int w2, int c, const float* __restrict__ t,
                                                        const float* __restrict__ dcoef,
                                                        const float* __restrict__ noise, float noise_gain,
@@ -218,15 +218,26 @@ __global__ void __launch_bounds__(256) upfir_act_kernel(int batch, int h2, int w
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[i][0][k] = acc[i][1][k] = 0.f;
 
+  // the five input columns ox0-1 .. ox0+3 are all inside the row except for the first and the last column pair:
+  // interior threads walk a pointer, no per-load index arithmetic or bounds tests
+  const bool interior_x = ox0 >= 1 && ox0 + 3 < tw;
+  const long long rstride = (long long)tw * c4;
+  const float4* rowp = tn + ((long long)(oy0 - 1) * tw + (ox0 - 1)) * c4;     // (row oy0-1, column ox0-1); may lie outside
 #pragma unroll
   for (int rr = 0; rr < UPFIR_R + 3; ++rr) {
     const int iy = oy0 + rr - 1;
     if (iy < 0 || iy >= th) continue;
+    const float4* rp = rowp + rr * rstride;
     float4 v[5];
+    if (interior_x) {
 #pragma unroll
-    for (int kx = 0; kx < 5; ++kx) {
-      const int ix = ox0 + kx - 1;
-      v[kx] = (ix >= 0 && ix < tw) ? __ldg(tn + ((size_t)iy * tw + ix) * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kx = 0; kx < 5; ++kx) v[kx] = __ldg(rp + kx * c4);
+    } else {
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const int ix = ox0 + kx - 1;
+        v[kx] = (ix >= 0 && ix < tw) ? __ldg(rp + kx * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     float ha[4], hb2[4];
     ha[0] = g[0] * v[0].x + g[1] * v[1].x + g[2] * v[2].x + g[3] * v[3].x;
@@ -483,11 +494,19 @@ extern "C" int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float
   HFAGP_CHECK_ARG(t && ((y != nullptr) != (y_hi != nullptr && y_lo != nullptr)),
                   "upfir_act_fwd: give t and either y or (y_hi, y_lo)");
   HFAGP_CHECK_ARG(batch > 0 && h2 > 0 && w2 > 0 && c > 0 && (c & 3) == 0, "upfir_act_fwd: c must be a multiple of 4");
-  size_t total = (size_t)batch * cdiv(h2, UPFIR_R) * cdiv(w2, 2) * (c >> 2);
-  upfir_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain,
-                                                                      bias, act, act_gain, clamp, y,
-                                                                      reinterpret_cast<__nv_bfloat16*>(y_hi),
-                                                                      reinterpret_cast<__nv_bfloat16*>(y_lo));
+  static const int r_env = getenv("HFAGP_UPFIR_R") ? atoi(getenv("HFAGP_UPFIR_R")) : 0;
+  const int R = r_env ? r_env : 4;     // measured on B200 (tools/prof_upfir.py): 2: 100 us, 4: 85 us, 8: 91 us, 16: 142 us (512^2 x 128)
+  size_t total = (size_t)batch * cdiv(h2, R) * cdiv(w2, 2) * (c >> 2);
+  auto* hi_ = reinterpret_cast<__nv_bfloat16*>(y_hi);
+  auto* lo_ = reinterpret_cast<__nv_bfloat16*>(y_lo);
+  if (R == 4)
+    upfir_act_kernel<4><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_);
+  else if (R == 2)
+    upfir_act_kernel<2><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_);
+  else if (R == 16)
+    upfir_act_kernel<16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_);
+  else
+    upfir_act_kernel<8><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_);
   HFAGP_CHECK_LAUNCH("upfir_act_kernel");
   return HFAGP_OK;
 }
