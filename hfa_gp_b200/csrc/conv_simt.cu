@@ -349,6 +349,26 @@ __global__ void __launch_bounds__(256) torgb_small_kernel(int batch, int h, int 
   }
 }
 
+// img[n][oy][ox][o] = clamp(acc + bias[o]) + upsample2d(prev)[..][o]: the tail of a ToRGB whose channel sums were
+// accumulated by the producing convolution's epilogue (hfagp_conv2d_tc_rgb_fwd)
+__global__ void torgb_finalize_kernel(int batch, int h, int w_, int k, const float* __restrict__ acc,
+                                      const float* __restrict__ bias, float clamp, const float* __restrict__ up_img,
+                                      float* __restrict__ y) {
+  const size_t total = (size_t)batch * h * w_ * k;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int o = idx % k;
+  size_t pix = idx / k;
+  const int ox = pix % w_;
+  pix /= w_;
+  const int oy = pix % h, n = pix / h;
+  float v = __ldg(acc + idx);
+  if (bias) v += __ldg(bias + o);
+  if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
+  if (up_img) v += upsample_tap(up_img + (size_t)n * (h / 2) * (w_ / 2) * k, h / 2, w_ / 2, k, oy, ox, o);
+  y[idx] = v;
+}
+
 // ---------------------------------------------------------------- encoder blur
 __global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow, float gain,
                             const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi,
@@ -525,6 +545,16 @@ extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout
       batch, h, w_, cin, cout, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
       reinterpret_cast<const __nv_bfloat16*>(x_lo), w, bias, clamp, up_img, y);
   HFAGP_CHECK_LAUNCH("torgb_small_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_torgb_finalize_fwd(int batch, int h, int w_, int k, const float* acc, const float* bias, float clamp,
+                                        const float* up_img, float* y, void* stream) {
+  HFAGP_CHECK_ARG(acc && y && batch > 0 && h > 0 && w_ > 0 && k >= 1 && k <= 4, "torgb_finalize_fwd: bad args");
+  HFAGP_CHECK_ARG(!up_img || ((h & 1) == 0 && (w_ & 1) == 0), "torgb_finalize_fwd: odd size with up_img");
+  torgb_finalize_kernel<<<cdiv((long long)batch * h * w_ * k, 256), 256, 0, (cudaStream_t)stream>>>(batch, h, w_, k, acc, bias,
+                                                                                               clamp, up_img, y);
+  HFAGP_CHECK_LAUNCH("torgb_finalize_kernel");
   return HFAGP_OK;
 }
 

@@ -62,6 +62,11 @@ struct TcParams {
   int accumulate;         // 1: split-K mode — raw fp32 partial sums are atomically added to cp.y, no epilogue
   __nv_bfloat16* y_hi;    // split output (or null -> cp.y fp32)
   __nv_bfloat16* y_lo;
+  // fused small ToRGB (super-resolution blocks): rgb_acc[n][oy][ox][o] += sum_co y[..][co] * rgb_w[n][o][co], o < rgb_k,
+  // taken from the finished activations while they are still in registers (saves re-reading the layer output)
+  const float* rgb_w;
+  float* rgb_acc;
+  int rgb_k;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -288,6 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   // per-channel epilogue scale / shift of the current N tile (512 B past the barrier block)
   float* epi_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);
   float* epi_sh = epi_sc + TC_BM;
+  float* epi_rgb = epi_sh + TC_BM;          // [4][TC_BM] ToRGB weights of the current (sample, N tile)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const HfagpConvDesc& d = p.cp.d;
@@ -519,6 +525,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const bool in = co < d.cout;
           epi_sc[et] = (in && p.cp.dcoef) ? __ldg(p.cp.dcoef + (size_t)tc.n * d.cout + co) : 1.f;
           epi_sh[et] = (in && p.cp.bias) ? __ldg(p.cp.bias + co) : 0.f;
+          if (p.rgb_acc)
+            for (int o = 0; o < p.rgb_k; ++o)
+              epi_rgb[o * TC_BM + et] = in ? __ldg(p.rgb_w + ((size_t)tc.n * p.rgb_k + o) * d.cout + co) : 0.f;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         staged_n = tc.n;
@@ -598,6 +607,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj)
             if (co0 + jj < d.cout) v[jj] = epi_apply(ec, p.cp, v[jj], co0 + jj);
+        }
+        if (p.rgb_acc) {
+          float pr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (o < p.rgb_k) {
+                const float4 w4 = *reinterpret_cast<const float4*>(&epi_rgb[o * TC_BM + cb + jj]);
+                pr[o] = fmaf(v[jj], w4.x, fmaf(v[jj + 1], w4.y, fmaf(v[jj + 2], w4.z, fmaf(v[jj + 3], w4.w, pr[o]))));
+              }
+            }
+          }
+          float* ra = p.rgb_acc + (ec.out_base / d.cout) * p.rgb_k;
+          for (int o = 0; o < p.rgb_k; ++o) atomicAdd(ra + o, pr[o]);
         }
         if (p.y_hi) {
           __nv_bfloat16* oh = p.y_hi + ec.out_base + co0;
@@ -777,7 +801,8 @@ static void build_class(const HfagpConvDesc& d, bool patch_mode, TcClass& c, int
 static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi, const uint16_t* x_lo,
                      const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
                      const float* noise, const float* bias, const float* residual, const float* up_img, float* y,
-                     uint16_t* y_hi, uint16_t* y_lo, int ksplit, void* stream, const char* who) {
+                     uint16_t* y_hi, uint16_t* y_lo, int ksplit, void* stream, const char* who,
+                     const float* rgb_w = nullptr, int rgb_k = 0, float* rgb_acc = nullptr) {
   HFAGP_CHECK_ARG(descs && ndesc >= 1 && ndesc <= TC_MAX_CLASSES, "%s: 1..%d descs", who, TC_MAX_CLASSES);
   HFAGP_CHECK_ARG(x_hi && x_lo && w_hi && w_lo, "%s: null pointer", who);
   HFAGP_CHECK_ARG((y != nullptr) != (y_hi != nullptr && y_lo != nullptr), "%s: give y or (y_hi, y_lo)", who);
@@ -809,6 +834,12 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
   p.ncls = ndesc;
   p.accumulate = ksplit > 0;
+  p.rgb_w = rgb_w;
+  p.rgb_acc = rgb_acc;
+  p.rgb_k = rgb_k;
+  HFAGP_CHECK_ARG(!rgb_acc || (rgb_w && rgb_k >= 1 && rgb_k <= 4 && ksplit == 0 && !residual && !(up_img && (d.cout & 3)) &&
+                               d.cout % 32 == 0 && d.out_stride == 1),
+                  "%s: fused ToRGB needs rgb_w, 1..4 outputs, a dense non-split-K layer with cout %% 32 == 0", who);
   const bool patch_mode = d.in_stride == 1;
   int max_span = 0;
   for (int i = 0; i < ndesc; ++i) build_class(descs[i], patch_mode, p.cls[i], max_span);
@@ -858,7 +889,7 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   // shared-memory rings: as deep as 225 KB allows
   const int a_stage = 2 * p.patch_rows * p.tile_w * TC_ROW;
   const int b_stage = two ? p.bn * TC_ROW * 3 / 2 : 2 * ((p.bn * TC_ROW + 1023) & ~1023);
-  const int extra = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * TC_BM * 4 /*epilogue vectors*/;
+  const int extra = 1024 /*alignment*/ + 512 /*barriers*/ + 6 * TC_BM * 4 /*epilogue vectors + ToRGB weights*/;
   const int budget = 227 * 1024 - extra;
   // the input patches of a tile are first-touch (HBM latency), the weights are L2 hits: favour patch depth
   static const int choices[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
@@ -932,6 +963,15 @@ extern "C" int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_
                                    float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream) {
   return launch_tc(desc, 1, x_hi, x_lo, w_hi, w_lo, w_taps_total, dcoef, noise, bias, residual, up_img, y, y_hi, y_lo,
                    0, stream, "conv2d_tc_fwd");
+}
+
+extern "C" int hfagp_conv2d_tc_rgb_fwd(const HfagpConvDesc* desc, const uint16_t* x_hi, const uint16_t* x_lo,
+                                       const uint16_t* w_hi, const uint16_t* w_lo, int w_taps_total, const float* dcoef,
+                                       const float* noise, const float* bias, float* y, uint16_t* y_hi, uint16_t* y_lo,
+                                       const float* rgb_w, int rgb_k, float* rgb_acc, void* stream) {
+  HFAGP_CHECK_ARG(rgb_w && rgb_acc, "conv2d_tc_rgb_fwd: null ToRGB operands");
+  return launch_tc(desc, 1, x_hi, x_lo, w_hi, w_lo, w_taps_total, dcoef, noise, bias, nullptr, nullptr, y, y_hi, y_lo, 0,
+                   stream, "conv2d_tc_rgb_fwd", rgb_w, rgb_k, rgb_acc);
 }
 
 extern "C" int hfagp_conv2d_tc_multi_fwd(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi,

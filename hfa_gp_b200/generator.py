@@ -278,7 +278,7 @@ class TriPlaneGenerator(nn.Module):
     def _as_f32(x):
         return x.float() if isinstance(x, ops.Split) else x
 
-    def _conv_layer(self, x, m, styles, noise_mode, pk, split_out, rec=None):
+    def _conv_layer(self, x, m, styles, noise_mode, pk, split_out, rec=None, rgb=None):
         pl: _PackedLayer = pk['layers'][id(m)]
         noise = None
         if pl.use_noise and noise_mode == 'const' and pl.noise_gain != 0.0:
@@ -293,8 +293,9 @@ class TriPlaneGenerator(nn.Module):
             pre = self._premod.get(id(m)) if self._premod else None
             wmod, epi['dcoef'] = pre if pre is not None else ops.modulate_split(pl.w, styles, True)
             if pl.up == 1:
+                extra = dict(rgb_w=rgb[0], rgb_acc=rgb[1]) if rgb is not None else {}
                 y = ops.conv2d_tc(xs, wmod, ops.TAPS_3X3, pl.cout, oh=h, ow=w, w_batched=True,
-                                  split_out=split_out, **epi)
+                                  split_out=split_out, **epi, **extra)
             else:
                 t = ops.conv_transpose_s2_tc(xs, wmod, pl.cout, w_batched=True)
                 y = ops.upfir_act(t, split_out=split_out, **epi)
@@ -355,10 +356,24 @@ class TriPlaneGenerator(nn.Module):
             x = self._conv_layer(x, blk.conv0, next(styles_iter), noise_mode, pk, split_out=tc_next, rec=r0)
             if tap is not None:
                 tap[name + '.conv0'] = self._as_f32(x)
-        x = self._conv_layer(x, blk.conv1, next(styles_iter), noise_mode, pk, split_out=tc_next, rec=r1)
+        s1, st = next(styles_iter), next(styles_iter)
+        plt = pk['layers'][id(blk.torgb)]
+        if rec is None and plt.cout <= 4 and self._use_tc(blk.cout) and blk.cout % 32 == 0:
+            # super-resolution blocks: the 3-channel ToRGB rides on conv1's epilogue (its activations are still in
+            # registers there) instead of re-reading the whole layer output
+            wrgb, _ = ops.modulate(plt.w, st, False)                       # [n][1][k][cout]
+            acc = torch.zeros((x.shape[0], blk.res, blk.res, plt.cout), device=wrgb.device, dtype=torch.float32)
+            x = self._conv_layer(x, blk.conv1, s1, noise_mode, pk, split_out=tc_next, rgb=(wrgb[:, 0], acc))
+            if tap is not None:
+                tap[name + '.conv1'] = self._as_f32(x)
+            img = ops.torgb_finalize(acc, plt.bias, plt.clamp, img)
+            if tap is not None:
+                tap[name + '.img'] = img
+            return x, img
+        x = self._conv_layer(x, blk.conv1, s1, noise_mode, pk, split_out=tc_next, rec=r1)
         if tap is not None:
             tap[name + '.conv1'] = self._as_f32(x)
-        img = self._torgb_layer(x, blk.torgb, next(styles_iter), img, pk, rec=rt)
+        img = self._torgb_layer(x, blk.torgb, st, img, pk, rec=rt)
         if tap is not None:
             tap[name + '.img'] = img
         return x, img

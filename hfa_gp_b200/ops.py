@@ -128,6 +128,15 @@ def torgb_small(x, wmod, bias, clamp, up_img, cout):
     return out
 
 
+def torgb_finalize(acc, bias, clamp, up_img):
+    """acc [n][h][w][k] (channel sums from conv2d_tc(..., rgb_acc=)) -> clamp(acc + bias) + upsample2d(up_img)."""
+    n, h, wd, k = acc.shape
+    out = torch.empty_like(acc)
+    _ok(_cabi.lib().hfagp_torgb_finalize_fwd(n, h, wd, k, ptr(acc), ptr(bias), clamp, ptr(up_img), ptr(out), stream()),
+        'hfagp_torgb_finalize_fwd')
+    return out
+
+
 class StyleTable:
     """Host-side layer table for ``hfagp_styles_fwd`` (built once per packed generator)."""
 
@@ -349,8 +358,11 @@ def modulate_split_multi(entries, styles_flat, batch):
 def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_stride: int = 1, out=None,
               out_hw=None, out_stride: int = 1, out_off=(0, 0), w_batched: bool = False, split_out: bool = False,
               dcoef=None, noise=None, noise_gain: float = 0.0, bias=None, act: int = ACT_LINEAR,
-              act_gain: float = 1.0, clamp: float = 0.0, residual=None, residual_scale: float = 1.0, up_img=None):
-    """tcgen05 implicit-GEMM convolution on split-bf16 operands; same semantics as conv2d()."""
+              act_gain: float = 1.0, clamp: float = 0.0, residual=None, residual_scale: float = 1.0, up_img=None,
+              rgb_w=None, rgb_acc=None):
+    """tcgen05 implicit-GEMM convolution on split-bf16 operands; same semantics as conv2d().
+    ``rgb_w [n][k][cout]`` / ``rgb_acc [n][oh][ow][k]`` (zeroed): also accumulate the block's small ToRGB from the
+    finished activations (``hfagp_conv2d_tc_rgb_fwd``)."""
     n, h, wd, cin = x.shape
     out_h, out_w = out_hw if out_hw is not None else (oh, ow)
     w_taps_total = w.shape[-3]
@@ -382,6 +394,13 @@ def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_strid
 
     d = _conv_desc(key, build)
     is_split = isinstance(out, Split)
+    if rgb_acc is not None:
+        _ok(_cabi.lib().hfagp_conv2d_tc_rgb_fwd(C.byref(d), ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total,
+                                                ptr(dcoef), ptr(noise), ptr(bias), None if is_split else ptr(out),
+                                                ptr(out.hi) if is_split else None, ptr(out.lo) if is_split else None,
+                                                ptr(rgb_w), rgb_w.shape[-2], ptr(rgb_acc), stream()),
+            'hfagp_conv2d_tc_rgb_fwd')
+        return out
     ksplit = _ksplit(n * -(-oh * ow // 128) * -(-cout // 128), cin, taps, in_stride)
     if ksplit > 1 and out_stride == 1 and (oh, ow) == (out_h, out_w) and cout % 4 == 0:
         # few output tiles, long K (the 4^2..32^2 layers): split K over the idle SMs, then one elementwise epilogue

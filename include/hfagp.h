@@ -103,6 +103,17 @@ int hfagp_conv2d_tc_fwd(const HfagpConvDesc* desc, const uint16_t* x_hi, const u
                         const float* noise, const float* bias, const float* residual, const float* up_img,
                         float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
 
+/* hfagp_conv2d_tc_fwd that ALSO feeds the block's small ToRGB (cout <= 4, the super-resolution blocks): the finished
+ * activations of a pixel are multiplied with the per-sample modulated ToRGB weights rgb_w[n][rgb_k][cout] while they
+ * are still in registers and ADDED to rgb_acc[n][out_h][out_w][rgb_k] (caller zeroes it), so the layer output is not
+ * read a second time; hfagp_torgb_finalize_fwd then applies bias, clamp and "+ upsample2d(previous image)". */
+int hfagp_conv2d_tc_rgb_fwd(const HfagpConvDesc* desc, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi,
+                            const uint16_t* w_lo, int w_taps_total, const float* dcoef, const float* noise,
+                            const float* bias, float* y, uint16_t* y_hi, uint16_t* y_lo, const float* rgb_w, int rgb_k,
+                            float* rgb_acc, void* stream);
+int hfagp_torgb_finalize_fwd(int batch, int h, int w_, int k, const float* acc, const float* bias, float clamp,
+                             const float* up_img, float* y, void* stream);
+
 /* Several sub-problems in ONE launch: descs[0..ndesc) (ndesc <= 4) share operands, channel counts, strides, the
  * output tensor and the epilogue, and differ only in their output window (oh, ow, out_off_*) and tap list — the
  * four output-parity classes of the stride-2 transposed convolution (up-sampling layers; data gradient of the
