@@ -199,6 +199,9 @@ class TriPlaneGenerator(nn.Module):
         self.fixed_draws = None    # (jitter_coarse, u_fine) used instead of torch.rand when synthesis() gets none
         self.precision = 'tc'      # 'tc': tcgen05 split-bf16 convolutions (fp32-class); 'fp32': SIMT kernels only
         self._premod = None        # inference: per-layer (modulated weights, dcoef) of the current synthesis() call
+        self.overlap_streams = True   # inference: the ToRGB / skip-image chain of the backbone on a second CUDA stream
+        self._side = None
+        self._keep = None
 
     @property
     def num_ws(self) -> int:
@@ -373,7 +376,16 @@ class TriPlaneGenerator(nn.Module):
         x = self._conv_layer(x, blk.conv1, s1, noise_mode, pk, split_out=tc_next, rec=r1)
         if tap is not None:
             tap[name + '.conv1'] = self._as_f32(x)
-        img = self._torgb_layer(x, blk.torgb, st, img, pk, rec=rt)
+        if self._keep is not None and rec is None:
+            # inference: ToRGB_b and the skip-image chain only meet the main chain again at the planes, so they run
+            # on the side stream next to block b+1's convolutions (small, latency-bound launches at batch 1)
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            self._keep.append(x)                      # x must outlive the side stream's read of it
+            with torch.cuda.stream(self._side):
+                img = self._torgb_layer(x, blk.torgb, st, img, pk)
+        else:
+            img = self._torgb_layer(x, blk.torgb, st, img, pk, rec=rt)
         if tap is not None:
             tap[name + '.img'] = img
         return x, img
@@ -422,9 +434,16 @@ class TriPlaneGenerator(nn.Module):
         self._premod = self._modulate_all(pk, flat, offs, b)
 
         x = img = None
+        if self.overlap_streams and tap is None and pe is None:
+            if self._side is None or self._side.device != ws.device:
+                self._side = torch.cuda.Stream(device=ws.device)
+            self._keep = []
         for r in cfg.block_resolutions:
             blk = getattr(self.backbone.synthesis, f'b{r}')
             x, img = self._run_block(blk, x, img, styles, noise_mode, pk, tap, f'b{r}')
+        if self._keep is not None:
+            torch.cuda.current_stream().wait_stream(self._side)     # join: the renderer reads the planes
+            self._keep = None
         planes = img                                             # [B,256,256,96] channels-last
         t1 = mark()
         if tap is not None:

@@ -242,8 +242,18 @@ class ResBlock(nn.Module):
         self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True)
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
 
-    def run(self, x, tc=False, rec=None):
+    def run(self, x, tc=False, rec=None, side=None):
         rs, r1, r2 = ({}, {}, {}) if rec is not None else (None, None, None)
+        if side is not None and rec is None:
+            # inference: the skip branch (blur + 1x1) is independent of conv1 — both are small, latency-bound
+            # launches at batch 1, so they run side by side on two streams and join before conv2 merges them
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                skip = self.skip.run(x, tc=tc)
+            out = self.conv1.run(x, tc=tc, split_out=tc)
+            cur.wait_stream(side)
+            return self.conv2.run(out, residual=skip, tc=tc, split_out=tc)
         skip = self.skip.run(x, tc=tc, rec=rs)                        # fp32: it is the residual operand
         out = self.conv1.run(x, tc=tc, split_out=tc, rec=r1)
         y = self.conv2.run(out, residual=skip, tc=tc, split_out=tc, rec=r2)   # (conv2(out) + skip) / sqrt(2) in the epilogue
@@ -265,6 +275,7 @@ class EncoderApp(nn.Module):
         channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256, 128: 128, 256: 64, 512: 32, 1024: 16}
         self.w_dim = w_dim
         self.precision = 'tc'      # 'tc': tcgen05 split-bf16 convolutions (fp32-class); 'fp32': SIMT kernels only
+        self.overlap_streams = True   # inference: independent branches of a ResBlock on two CUDA streams
         log_size = int(math.log(size, 2))
         self.convs = nn.ModuleList()
         self.convs.append(ConvLayer(3, channels[size], 1))
@@ -289,8 +300,13 @@ class EncoderApp(nn.Module):
         recs = [({} if tape is not None else None) for _ in self.convs[:-1]]
         h = ops.nchw_to_nhwc(x.detach().float().contiguous())
         h = self.convs[0].run(h, split_out=tc, rec=recs[0])           # cin = 3: exact-fp32 SIMT kernel
+        side = None
+        if tape is None and self.overlap_streams:
+            side = self.__dict__.get('_side')
+            if side is None or side.device != h.device:
+                side = self.__dict__['_side'] = torch.cuda.Stream(device=h.device)
         for m, r in zip(self.convs[1:-1], recs[1:]):
-            h = m.run(h, tc=tc, rec=r)
+            h = m.run(h, tc=tc, rec=r, side=side)
         last = self.convs[-1]
         k = last.weight.shape[-1]
         hf = h.float() if isinstance(h, ops.Split) else h
