@@ -438,6 +438,12 @@ class TriPlaneGenerator(nn.Module):
             if self._side is None or self._side.device != ws.device:
                 self._side = torch.cuda.Stream(device=ws.device)
             self._keep = []
+        ri = None
+        if self._keep is not None:
+            # the renderer's random draws and depth range depend on nothing: first work of the side stream
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                ri = self._render_inputs(b, res, ws.device, jitter_coarse, u_fine, pk)
         for r in cfg.block_resolutions:
             blk = getattr(self.backbone.synthesis, f'b{r}')
             x, img = self._run_block(blk, x, img, styles, noise_mode, pk, tap, f'b{r}')
@@ -449,26 +455,13 @@ class TriPlaneGenerator(nn.Module):
         if tap is not None:
             tap['planes'] = planes
 
-        rays = res * res
+        if ri is None:
+            ri = self._render_inputs(b, res, ws.device, jitter_coarse, u_fine, pk)
+        jitter, u_f, depth_range, rkw = ri
         s, sf = cfg.depth_res, cfg.depth_res_importance
-        if jitter_coarse is None and u_fine is None and self.fixed_draws is not None:
-            jitter_coarse, u_fine = self.fixed_draws          # tests: pin upstream's two random tensors
-        if jitter_coarse is None:
-            jitter_coarse = torch.rand((b, rays, s, 1), device=ws.device)
-        if u_fine is None and sf > 0:
-            u_fine = torch.rand((b * rays, sf), device=ws.device)
-        jitter = jitter_coarse.reshape(b, rays, s).float().contiguous()
-        delta = (cfg.ray_end - cfg.ray_start) / (s - 1)
-        lin = pk['lin']
-        # global clamp range of the composite depth: min/max over every sample depth (coarse ends bound the fine ones)
-        dmin = (lin[0] + jitter[:, :, 0].min() * delta)
-        dmax = (lin[-1] + jitter[:, :, -1].max() * delta)
-        depth_range = torch.stack([dmin, dmax]).float().contiguous()
         t2 = mark()
-        feat, depth, wsum, book = ops.render(planes, c, pk['mlp'], lin, jitter,
-                                             u_fine.float().contiguous() if sf > 0 else None, depth_range, res=res,
-                                             s_coarse=s, s_fine=sf, delta=delta, box_scale=2.0 / cfg.box_warp,
-                                             bookkeeping=tap is not None)
+        feat, depth, wsum, book = ops.render(planes, c, pk['mlp'], pk['lin'], jitter, u_f, depth_range,
+                                             bookkeeping=tap is not None, **rkw)
         t3 = mark()
         if tap is not None:
             tap.update(book)

@@ -350,8 +350,34 @@ class Encoder(nn.Module):
     def enc_app(self, x):
         return self.net_app(x)
 
+    def _folded(self, stack, name):
+        """The EqualLinear stacks have no activation (encoder3d.py:250-263): at inference five layers are ONE affine
+        map.  Composed in float64 on the host side once per parameter version, applied with one hfagp_linear_fwd."""
+        key = (tuple(p._version for p in stack.parameters()), str(next(stack.parameters()).device), ops.param_epoch[0])
+        cache = self.__dict__.setdefault('_fold_cache', {})
+        hit = cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        a = c = None
+        for lin in stack:
+            w = lin.weight.detach().double() * lin.scale
+            b = lin.bias.detach().double() * lin.lr_mul if lin.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64, device=w.device)
+            a, c = (w, b) if a is None else (w @ a, w @ c + b)
+        a, c = a.float().contiguous(), c.float().contiguous()
+        cache[name] = (key, a, c)
+        return a, c
+
     def get_weights(self, x):
         h = self.net_app(x)
+        if not torch.is_grad_enabled() and not self.training:
+            a, c = self._folded(self.fc, 'fc')
+            h_weights = ops.linear(h, a, c, 1.0, 1.0)
+            if self.use_softmax:
+                h_weights = self.softmax(h_weights)
+            if self.out_pose:
+                a, c = self._folded(self.pose, 'pose')
+                return h_weights, ops.linear(h, a, c, 1.0, 1.0)
+            return h_weights
         h_weights = self.fc(h)
         if self.use_softmax:
             h_weights = self.softmax(h_weights)
