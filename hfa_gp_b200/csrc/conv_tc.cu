@@ -503,7 +503,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int r = q * 32 + lane;                     // accumulator row = pixel inside the tile
     const int ly = r / p.tile_w, lx = r - ly * p.tile_w;
     const int et = threadIdx.x - 64;                 // 0..255
-    const bool generic = p.cp.residual != nullptr || (p.cp.up_img != nullptr && (d.cout & 3) != 0);
+    const bool generic = (p.cp.residual != nullptr || p.cp.up_img != nullptr) && (d.cout & 3) != 0;
+    const bool add_res = p.cp.residual != nullptr && !generic;
     const bool add_up = p.cp.up_img != nullptr && !generic;
     const float slope = act_slope(d.act);
     const float gain = d.act_gain;
@@ -589,6 +590,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             a2 = fmaxf(a2, slope * a2) * gain; a3 = fmaxf(a3, slope * a3) * gain;
             v[jj] = fminf(fmaxf(a0, -cl), cl); v[jj + 1] = fminf(fmaxf(a1, -cl), cl);
             v[jj + 2] = fminf(fmaxf(a2, -cl), cl); v[jj + 3] = fminf(fmaxf(a3, -cl), cl);
+          }
+          if (add_res) {                               // ResBlock merge (v + skip) * 1/sqrt2: 16-byte loads
+            const float rs = d.residual_scale;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(ec.res + co0 + jj));
+              v[jj] = (v[jj] + r4.x) * rs; v[jj + 1] = (v[jj + 1] + r4.y) * rs;
+              v[jj + 2] = (v[jj + 2] + r4.z) * rs; v[jj + 3] = (v[jj + 3] + r4.w) * rs;
+            }
           }
           if (add_up) {                                // + upsample2d(previous skip image): 4 taps x 16-byte loads
             const UpTaps ut = upsample_taps(d.up_h, d.up_w, ec.oy, ec.ox);
@@ -837,7 +847,7 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   p.rgb_w = rgb_w;
   p.rgb_acc = rgb_acc;
   p.rgb_k = rgb_k;
-  HFAGP_CHECK_ARG(!rgb_acc || (rgb_w && rgb_k >= 1 && rgb_k <= 4 && ksplit == 0 && !residual && !(up_img && (d.cout & 3)) &&
+  HFAGP_CHECK_ARG(!rgb_acc || (rgb_w && rgb_k >= 1 && rgb_k <= 4 && ksplit == 0 && !((residual || up_img) && (d.cout & 3)) &&
                                d.cout % 32 == 0 && d.out_stride == 1),
                   "%s: fused ToRGB needs rgb_w, 1..4 outputs, a dense non-split-K layer with cout %% 32 == 0", who);
   const bool patch_mode = d.in_stride == 1;
