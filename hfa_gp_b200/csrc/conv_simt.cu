@@ -548,6 +548,50 @@ extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout
   return HFAGP_OK;
 }
 
+// stride-1 blur, two adjacent output columns per thread: the 4x5 input window is loaded once (10 loads per output
+// instead of 16) and both horizontal sums are formed per row
+__global__ void blur2_kernel(int batch, int h, int w_, int c, int pad0, int oh, int ow, float gain,
+                             const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi,
+                             const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
+                             __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+  const int c4 = c >> 2, wp = (ow + 1) >> 1;
+  const size_t total = (size_t)batch * oh * wp * c4;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cq = idx % c4;
+  size_t r = idx / c4;
+  const int px = r % wp;
+  r /= wp;
+  const int oy = r % oh, n = r / oh;
+  const int ox0 = px * 2;
+  const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  const size_t nb = (size_t)n * h * w_ * c4 + cq;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    const int iy = oy + ky - pad0;
+    if (iy < 0 || iy >= h) continue;
+    float4 v[5];
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) {
+      const int ix = ox0 + kx - pad0;
+      v[kx] = (ix >= 0 && ix < w_) ? ld4_any(x, x_hi, x_lo, nb + ((size_t)iy * w_ + ix) * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float wy = g[ky] * gain;
+    a[0] = fmaf(wy, g[0] * v[0].x + g[1] * v[1].x + g[2] * v[2].x + g[3] * v[3].x, a[0]);
+    a[1] = fmaf(wy, g[0] * v[0].y + g[1] * v[1].y + g[2] * v[2].y + g[3] * v[3].y, a[1]);
+    a[2] = fmaf(wy, g[0] * v[0].z + g[1] * v[1].z + g[2] * v[2].z + g[3] * v[3].z, a[2]);
+    a[3] = fmaf(wy, g[0] * v[0].w + g[1] * v[1].w + g[2] * v[2].w + g[3] * v[3].w, a[3]);
+    b[0] = fmaf(wy, g[0] * v[1].x + g[1] * v[2].x + g[2] * v[3].x + g[3] * v[4].x, b[0]);
+    b[1] = fmaf(wy, g[0] * v[1].y + g[1] * v[2].y + g[2] * v[3].y + g[3] * v[4].y, b[1]);
+    b[2] = fmaf(wy, g[0] * v[1].z + g[1] * v[2].z + g[2] * v[3].z + g[3] * v[4].z, b[2]);
+    b[3] = fmaf(wy, g[0] * v[1].w + g[1] * v[2].w + g[2] * v[3].w + g[3] * v[4].w, b[3]);
+  }
+  const size_t o = (((size_t)n * oh + oy) * ow + ox0) * c4 + cq;
+  st4_any(y, y_hi, y_lo, o, a);
+  if (ox0 + 1 < ow) st4_any(y, y_hi, y_lo, o + c4, b);
+}
+
 extern "C" int hfagp_torgb_finalize_fwd(int batch, int h, int w_, int k, const float* acc, const float* bias, float clamp,
                                         const float* up_img, float* y, void* stream) {
   HFAGP_CHECK_ARG(acc && y && batch > 0 && h > 0 && w_ > 0 && k >= 1 && k <= 4, "torgb_finalize_fwd: bad args");
@@ -567,7 +611,13 @@ extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad
   int oh = (h + pad0 + pad1 - 4) / stride + 1;
   int ow = (w_ + pad0 + pad1 - 4) / stride + 1;
   HFAGP_CHECK_ARG(oh > 0 && ow > 0, "blur_fwd: empty output");
-  if ((c & 3) == 0) {
+  if ((c & 3) == 0 && stride == 1) {
+    size_t total = (size_t)batch * oh * cdiv(ow, 2) * (c >> 2);
+    blur2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        batch, h, w_, c, pad0, oh, ow, gain, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
+        reinterpret_cast<const __nv_bfloat16*>(x_lo), y, reinterpret_cast<__nv_bfloat16*>(y_hi),
+        reinterpret_cast<__nv_bfloat16*>(y_lo));
+  } else if ((c & 3) == 0) {
     size_t total = (size_t)batch * oh * ow * (c >> 2);
     blur_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         batch, h, w_, c, pad0, stride, oh, ow, gain, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
