@@ -64,6 +64,15 @@ def _mirror(taps):
     return tuple((-dy, -dx, t) for dy, dx, t in taps)
 
 
+def pack_stem_weight(w1: torch.Tensor) -> torch.Tensor:
+    """AlexNet conv1 weight [64,3,11,11] (stride 4, pad 2) -> [9 taps][64][48]: the same convolution as a 3x3 stride-1
+    VALID convolution over the space-to-depth(4) image of hfagp_lpips_stem_fwd, whose channel (py*4+px)*3+c holds
+    pixel (4Y+py-2, 4X+px-2) of input channel c; kernel row/column 11 is zero padding."""
+    o = w1.shape[0]
+    w = torch.nn.functional.pad(w1.detach().float(), (0, 1, 0, 1)).reshape(o, 3, 3, 4, 3, 4)       # o, c, ty, py, tx, px
+    return w.permute(2, 4, 0, 3, 5, 1).reshape(9, o, 48).contiguous()
+
+
 TAPS_STEM = _taps(3, 0)          # valid 3x3 over the space-to-depth grid
 TAPS_5X5 = _taps(5, 2)
 
@@ -94,9 +103,7 @@ class LPIPS(nn.Module):
             return self._pk
         convs = self.net.convs()
         pk = {'w': [], 'wT': [], 'b': [], 'lin': [], 'taps': [TAPS_STEM, TAPS_5X5, ops.TAPS_3X3, ops.TAPS_3X3, ops.TAPS_3X3]}
-        w1 = convs[0].weight.detach().float()                                  # [64,3,11,11] -> [9][64][48]
-        w1 = torch.nn.functional.pad(w1, (0, 1, 0, 1)).reshape(64, 3, 3, 4, 3, 4)       # o, c, ty, py, tx, px
-        w1 = w1.permute(2, 4, 0, 3, 5, 1).reshape(9, 64, 48).contiguous()
+        w1 = pack_stem_weight(convs[0].weight)                                 # [64,3,11,11] -> [9][64][48]
         packed = [w1] + [c.weight.detach().float().permute(2, 3, 0, 1).reshape(-1, c.weight.shape[0], c.weight.shape[1]).contiguous()
                          for c in convs[1:]]
         for w, c in zip(packed, convs):

@@ -1,0 +1,132 @@
+"""CPU: host-side arithmetic that decides what the kernels are asked to do — tap lists, split-K / tile heuristics,
+weight re-packings and the FLOP accounting of bench.py.  No compute call through the C ABI happens here."""
+import importlib.util
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hfa_gp_b200 import ops
+from hfa_gp_b200.generator import GeneratorConfig, TriPlaneGenerator, _pack_conv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _conv_by_taps(x, w_packed, taps, oh, ow, in_stride=1, out_stride=1, out_off=(0, 0), out_hw=None):
+    """Literal evaluation of the hfagp_conv2d_fwd contract (include/hfagp.h) in torch: x [C,H,W], w [taps][O][I]."""
+    cin, h, w = x.shape
+    cout = w_packed.shape[1]
+    out_h, out_w = out_hw or (oh, ow)
+    y = torch.zeros(cout, out_h, out_w, dtype=x.dtype)
+    for my in range(oh):
+        for mx in range(ow):
+            acc = torch.zeros(cout, dtype=x.dtype)
+            for dy, dx, t in taps:
+                iy, ix = my * in_stride + dy, mx * in_stride + dx
+                if 0 <= iy < h and 0 <= ix < w:
+                    acc += w_packed[t] @ x[:, iy, ix]
+            y[:, my * out_stride + out_off[0], mx * out_stride + out_off[1]] = acc
+    return y
+
+
+def test_parity_taps_reproduce_the_stride2_transposed_conv():
+    """The four output-parity tap lists (ops._parity_taps) cover each of the 9 taps once and, evaluated by the
+    conv contract with out_stride 2, equal F.conv_transpose2d(stride=2)."""
+    seen = sorted(t for a in (0, 1) for b in (0, 1) for _, _, t in ops._parity_taps(a, b))
+    assert seen == list(range(9))
+    g = torch.Generator().manual_seed(0)
+    cin, cout, h = 3, 2, 4
+    x = torch.randn(cin, h, h, generator=g, dtype=torch.float64)
+    wt = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv_transpose2d(x[None], wt.transpose(0, 1), stride=2)[0]
+    packed = wt.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    out = torch.zeros(cout, 2 * h + 1, 2 * h + 1, dtype=torch.float64)
+    for a in (0, 1):
+        for b in (0, 1):
+            out += _conv_by_taps(x, packed, ops._parity_taps(a, b), h + 1 - a, h + 1 - b, out_stride=2, out_off=(a, b),
+                                 out_hw=(2 * h + 1, 2 * h + 1))
+    assert torch.allclose(out, ref, atol=1e-12)
+
+
+def test_pack_conv_and_3x3_taps_equal_conv2d():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4, 5, 6, generator=g, dtype=torch.float64)
+    wt = torch.randn(3, 4, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x[None], wt, padding=1)[0]
+    packed = wt.permute(2, 3, 0, 1).reshape(9, 3, 4)
+    got = _conv_by_taps(x, packed, ops.TAPS_3X3, 5, 6)
+    assert torch.allclose(got, ref, atol=1e-12)
+    assert torch.equal(_pack_conv(wt.float()), packed.float())
+    assert torch.equal(_pack_conv(wt.float())[5], wt.float()[:, :, 1, 2])        # tap = ky*3 + kx, [O][I]
+
+
+def test_lpips_stem_packing_equals_the_11x11_stride4_conv():
+    """pack_stem_weight + the space-to-depth layout of hfagp_lpips_stem_fwd reproduce AlexNet's first convolution."""
+    from hfa_gp_b200 import lpips
+    g = torch.Generator().manual_seed(2)
+    h = w = 32
+    x = torch.randn(1, 3, h, w, generator=g, dtype=torch.float64)
+    w1 = torch.randn(8, 3, 11, 11, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w1, stride=4, padding=2)[0]
+    # the stem's layout, restated: out[Y][X][(py*4+px)*3+c] = x[c][4Y+py-2][4X+px-2] (zero outside)
+    xp = F.pad(x[0], (2, 2, 2, 2))                                               # [3, h+4, w+4]
+    s2d = xp.reshape(3, (h + 4) // 4, 4, (w + 4) // 4, 4).permute(2, 4, 0, 1, 3).reshape(48, (h + 4) // 4, (w + 4) // 4)
+    packed = lpips.pack_stem_weight(w1.float()).double()
+    # pack_stem_weight works in fp32; rebuild in fp64 with the same index map for an exact comparison
+    wd = F.pad(w1, (0, 1, 0, 1)).reshape(8, 3, 3, 4, 3, 4).permute(2, 4, 0, 3, 5, 1).reshape(9, 8, 48)
+    assert torch.allclose(packed, wd, atol=1e-6)
+    got = _conv_by_taps(s2d, wd, lpips.TAPS_STEM, ref.shape[1], ref.shape[2])
+    assert got.shape == ref.shape and torch.allclose(got, ref, atol=1e-10)
+    assert lpips._mirror(lpips.TAPS_5X5)[0] == (2, 2, 0) and len(lpips.TAPS_5X5) == 25
+
+
+def test_ksplit_heuristic():
+    assert ops._ksplit(4, 512, ops.TAPS_3X3, 1) == 24              # b4/b8 conv1: 8 chunks x 3 tap groups
+    assert ops._ksplit(32, 512, ops.TAPS_3X3, 1) == 4              # 32 tiles -> 128 CTAs
+    assert ops._ksplit(128, 512, ops.TAPS_3X3, 1) == 1             # enough tiles already
+    assert ops._ksplit(1, 64, ops.TAPS_1X1, 1) == 1                # a single K unit cannot be split
+    assert ops._ksplit(2, 512, ops.TAPS_3X3, 2) == 72              # stride 2: every tap is its own group
+    for tiles in range(1, 40):
+        k = ops._ksplit(tiles, 512, ops.TAPS_3X3, 1)
+        assert k >= 1 and k * tiles <= ops.NUM_SMS
+
+
+def test_bench_flop_accounting_matches_the_layer_table():
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cfg = GeneratorConfig()
+    gen = TriPlaneGenerator(cfg)
+    total = 0.0
+    for kind, m, _ in gen._layers_in_order():
+        k = m.weight.shape[-1]
+        if m.cin % 8:
+            continue
+        if kind == 'torgb':
+            if m.cout > 4:
+                blk_res = next(getattr(gen.backbone.synthesis, f'b{r}').res for r in cfg.block_resolutions
+                               if getattr(gen.backbone.synthesis, f'b{r}').torgb is m)
+                total += 2.0 * blk_res ** 2 * m.cin * m.cout
+            continue
+        pixels = (m.res // 2) ** 2 if m.up == 2 else m.res ** 2        # the transposed conv does 9 MACs per INPUT pixel
+        total += 2.0 * pixels * m.cin * m.cout * k * k
+    # + encoder ResBlocks (size 256), as bench.py counts them
+    channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256, 128: 128, 256: 64}
+    r, c = 256, 64
+    while r > 4:
+        c2 = channels[r // 2]
+        total += 2.0 * r * r * c * c * 9 + 2.0 * (r // 2) ** 2 * c * c2 * 10
+        r, c = r // 2, c2
+    assert math.isclose(bench.tensor_core_conv_flops(cfg, 256), total, rel_tol=1e-12)
+    assert 300e9 < total < 340e9                                      # 302 G generator + 31 G encoder - SIMT bits
+
+
+def test_frameio_modes_and_errors():
+    from hfa_gp_b200 import frameio
+    assert frameio.MODES == {'save_image': 0, 'layout_grid': 1}
+    with pytest.raises(Exception):
+        frameio.to_uint8(torch.zeros(1, 3, 4, 4), 'png')
+    with pytest.raises(Exception):
+        frameio.to_uint8(torch.zeros(1, 3, 4, 4), 'save_image')      # CPU tensor: no fallback
