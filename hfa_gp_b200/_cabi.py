@@ -26,7 +26,7 @@ SYMBOLS = [
     'hfagp_conv2d_wgrad', 'hfagp_render_bwd', 'hfagp_latent_bwd', 'hfagp_facepool_fwd', 'hfagp_facepool_bwd',
     'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8',
     'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
-    'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd',
+    'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd', 'hfagp_conv2d_wgrad_mod',
 ]
 
 
@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
     l.hfagp_modulate_split_multi_fwd.argtypes = [i32, i32] + [vp] * 10
     l.hfagp_conv2d_tc_rgb_fwd.argtypes = [C.POINTER(ConvDesc), vp, vp, vp, vp, i32] + [vp] * 7 + [i32, vp, vp]
     l.hfagp_torgb_finalize_fwd.argtypes = [i32, i32, i32, i32, vp, vp, f32, vp, vp, vp]
+    l.hfagp_conv2d_wgrad_mod.argtypes = [C.POINTER(ConvDesc)] + [vp] * 8 + [f32, vp, vp]
     l.hfagp_split_bf16.argtypes = [C.c_longlong, vp, vp, vp, vp]
     l.hfagp_modulate_split_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     for s in SYMBOLS:

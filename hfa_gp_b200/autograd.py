@@ -41,11 +41,73 @@ def _dgrad(gen, dz, pl, taps, *, oh, ow, in_stride=1):
     return ops.conv2d(dzf, bw['wT'], taps, pl.cin, oh=oh, ow=ow, in_stride=in_stride)
 
 
-def blocks_backward(gen, recs, dimg, dviews):
+def _acc(param, g):
+    """param.grad += g (shape of the parameter); the way loss.backward() would leave it."""
+    g = g.reshape(param.shape).to(param.dtype)
+    if param.grad is None:
+        param.grad = g.clone()
+    else:
+        param.grad.add_(g)
+
+
+def _unpack_conv(dw, k):
+    """packed [k*k][O][I] -> parameter layout [O][I][k][k]"""
+    t, o, i = dw.shape
+    return dw.view(k, k, o, i).permute(2, 3, 0, 1)
+
+
+def _demod_term(pl, styles, dcoef, ddc):
+    """d(dcoef)/dW folded back: -W[t][o][i] * sum_n ddcoef[n][o] dcoef[n][o]^3 styles[n][i]^2   (tiny tensors)"""
+    coef = torch.einsum('no,ni->oi', ddc * dcoef * dcoef * dcoef, styles * styles)
+    return -pl.w * coef[None]
+
+
+def _layer_param_grads(m, rec, dz, ddc, db, h, w, up):
+    """Gradients of one modulated SynthesisLayer's own parameters (the post-tune_iter regime, train_rgb.py:132-134):
+    weight (style-scaled wgrad + demodulation term), bias, noise_strength."""
+    pl, styles, dcoef = rec['pl'], rec['styles'], rec['dcoef']
+    x = rec['x']
+    dwp = torch.zeros_like(pl.w)
+    if up:
+        # transposed conv: dW[(ky,kx)][o][i] = sum dt[2m+k][o] * x[m][i] * s[i]  — wgrad with the roles swapped
+        # (dense operand = layer input, strided operand = gradient), result [t][i][o]
+        hin, win = x.shape[1], x.shape[2]
+        dwt = torch.zeros((9, pl.cin, pl.cout), device=dwp.device)
+        ops.conv2d_wgrad(dz, x, TAPS_UP_T, dwt, oh=hin, ow=win, in_stride=2, dzscale=styles)
+        dwp += dwt.transpose(1, 2)
+    else:
+        ops.conv2d_wgrad(x, dz, ops.TAPS_3X3, dwp, oh=h, ow=w, xscale=styles)
+    dwp += _demod_term(pl, styles, dcoef, ddc)
+    _acc(m.weight, _unpack_conv(dwp, 3))
+    _acc(m.bias, db)
+    if rec.get('noise_buf') is not None:
+        dzf = dz.float() if isinstance(dz, ops.Split) else dz
+        if up:
+            raise HfagpError('internal: noise gradient of an up layer must be taken from the post-FIR gradient')
+        dpre_sum = (dzf / dcoef[:, None, None, :]).sum(-1)
+        _acc(m.noise_strength, (dpre_sum * rec['noise_buf'][None]).sum())
+
+
+def _torgb_param_grads(m, rt, dimg_t, h, w):
+    pl = rt['pl']
+    x = rt['x']
+    k = pl.cout
+    kp = (k + 3) // 4 * 4
+    dz = dimg_t.contiguous()
+    if kp != k:
+        dz = torch.nn.functional.pad(dz, (0, kp - k))
+    dwp = torch.zeros((1, kp, pl.cin), device=dz.device)
+    ops.conv2d_wgrad(x, dz, ops.TAPS_1X1, dwp, oh=h, ow=w, xscale=rt['styles'])
+    _acc(m.weight, dwp[0, :k])
+    _acc(m.bias, dimg_t.sum((0, 1, 2)))
+
+
+def blocks_backward(gen, recs, dimg, dviews, wgrads=False):
     """Walk the recorded blocks in reverse.  ``dimg``: gradient of the last block's output image (fp32 NHWC).
     ``dviews[i]``: [B,cin] accumulator of d(styles) of layer i.  Returns (gx, dimg_in): the unscaled data gradient
     into the first block's input with its style scale / d(styles) view (or None), and the gradient of the first
-    block's input image (or None)."""
+    block's input image (or None).  ``wgrads``: also accumulate the gradients of the blocks' own parameters into
+    their ``.grad`` (generator unfrozen by tune_generator())."""
     gx = None
     tc = gen.precision == 'tc'
     for blk in reversed(recs):
@@ -62,34 +124,48 @@ def blocks_backward(gen, recs, dimg, dviews):
         else:
             dxu_rgb = _dgrad(gen, dimg_t, plt, ops.TAPS_1X1, oh=h, ow=w)
             kw = dict(g1=dxu_rgb, s1=rt['styles'], ds1=dviews[plt.index])
+        if wgrads:
+            _torgb_param_grads(blk['mods'][2], rt, dimg_t, h, w)
         if gx is not None:
             kw.update(g0=gx[0], s0=gx[1], ds0=gx[2])
         # ---- conv1: activation / demodulation backward, then its data gradient
         ddc = torch.zeros((b, pl1.cout), device=dev)
+        db1 = torch.zeros(pl1.cout, device=dev) if wgrads else None
         use_tc1 = tc and pl1.bwd()['wT_split'] is not None
         dz1 = ops.act_bwd(y1, dcoef=r1['dcoef'], noise=r1['noise'], noise_gain=pl1.noise_gain, bias=pl1.bias,
                           act=ACT_LRELU, act_gain=SQRT2, clamp=pl1.clamp, out='split' if use_tc1 else 'f32',
-                          ddcoef=ddc, **kw)
+                          ddcoef=ddc, dbias=db1, **kw)
         ops.demod_bwd(pl1.bwd()['w2'], r1['styles'], r1['dcoef'], ddc, dviews[pl1.index])
+        if wgrads:
+            _layer_param_grads(blk['mods'][1], r1, dz1, ddc, db1, h, w, up=False)
         dxu1 = _dgrad(gen, dz1, pl1, TAPS_3X3_T, oh=h, ow=w)
         # ---- skip image path: img_out = upsample2d(img_prev) + torgb
         dimg = ops.blur(dimg, 1, 1, stride=2, gain=4.0) if blk['has_img_prev'] else None
         if r0 is None:
             # first backbone block: conv1 reads the learned constant; only its d(styles) is needed
             ops.act_bwd(blk['x_in'], g0=dxu1, ds0=dviews[pl1.index], act=ACT_LINEAR, act_gain=1.0, out='none')
+            if wgrads:      # the learned constant input: d const[c][y][x] = sum_n dxu[n][y][x][c] * styles[n][c]
+                _acc(blk['const'], (dxu1 * r1['styles'][:, None, None, :]).sum(0).permute(2, 0, 1))
             gx = None
             continue
         # ---- conv0 (x2 up): act/demod backward at 2H, FIR transpose, then the stride-2 data gradient
         pl0 = r0['pl']
         ddc0 = torch.zeros((b, pl0.cout), device=dev)
+        db0 = torch.zeros(pl0.cout, device=dev) if wgrads else None
         dz0 = ops.act_bwd(r0['y'], g0=dxu1, s0=r1['styles'], ds0=dviews[pl1.index], dcoef=r0['dcoef'],
                           noise=r0['noise'], noise_gain=pl0.noise_gain, bias=pl0.bias, act=ACT_LRELU, act_gain=SQRT2,
-                          clamp=pl0.clamp, out='f32', ddcoef=ddc0)
+                          clamp=pl0.clamp, out='f32', ddcoef=ddc0, dbias=db0)
         ops.demod_bwd(pl0.bwd()['w2'], r0['styles'], r0['dcoef'], ddc0, dviews[pl0.index])
         use_tc0 = tc and pl0.bwd()['wT_split'] is not None
         dt = ops.blur(dz0, 2, 2, stride=1, gain=4.0, split_out=use_tc0)          # [B,2H+1,2W+1,cout]
         hin, win = h // 2, w // 2
         dxu0 = _dgrad(gen, dt, pl0, TAPS_UP_T, oh=hin, ow=win, in_stride=2)
+        if wgrads:
+            m0 = blk['mods'][0]
+            nb0, r0['noise_buf'] = r0.get('noise_buf'), None           # noise enters after the FIR: use dz0, not dt
+            _layer_param_grads(m0, r0, dt, ddc0, db0, h, w, up=True)
+            if nb0 is not None:
+                _acc(m0.noise_strength, ((dz0 / r0['dcoef'][:, None, None, :]).sum(-1) * nb0[None]).sum())
         gx = (dxu0, r0['styles'], dviews[pl0.index])
     return gx, dimg
 
@@ -101,14 +177,29 @@ class StylesFn(torch.autograd.Function):
     def forward(ctx, ws, gen):
         pk = gen._ensure_packed()
         flat, offs = pk['styles'].run_flat(ws)
-        ctx.gen, ctx.offs, ctx.shape = gen, offs, ws.shape
+        ctx.gen, ctx.offs, ctx.shape, ctx.ws = gen, offs, ws.shape, ws.detach()
         return flat
 
     @staticmethod
     def backward(ctx, dflat):
-        pk = ctx.gen._ensure_packed()
+        gen = ctx.gen
+        pk = gen._ensure_packed()
         b, num_ws, w_dim = ctx.shape
-        dws = ops.StyleTableBwd(pk['styles']).run(dflat.contiguous(), ctx.offs, b, num_ws, w_dim)
+        dflat = dflat.contiguous()
+        dws = ops.StyleTableBwd(pk['styles']).run(dflat, ctx.offs, b, num_ws, w_dim)
+        if any(p.requires_grad for p in gen.parameters()):
+            # affine layers of the unfrozen generator: styles_l = (ws[widx] A^T / sqrt(D) + b) * gain_l
+            ws = ctx.ws
+            views = pk['styles'].views(dflat, ctx.offs, b)
+            for (kind, m, widx), ds in zip(pk['order'], views):
+                gain = 1.0 if kind == 'conv' else 1.0 / math.sqrt(m.cin)
+                a = m.affine
+                dw = torch.zeros_like(a.weight)
+                db = torch.zeros_like(a.bias)
+                ops.linear_bwd(ds.contiguous(), ws[:, widx].contiguous(), a.weight.detach().contiguous(),
+                               gain / math.sqrt(w_dim), gain, need_dx=False, dw=dw, db=db)
+                _acc(a.weight, dw)
+                _acc(a.bias, db)
         return dws, None
 
 
@@ -144,7 +235,8 @@ class BackboneFn(torch.autograd.Function):
         gen = ctx.gen
         pk = gen._ensure_packed()
         dflat = torch.zeros(ctx.total, device=dplanes.device)
-        blocks_backward(gen, ctx.recs, dplanes.contiguous(), _dviews(pk, dflat, ctx.batch))
+        blocks_backward(gen, ctx.recs, dplanes.contiguous(), _dviews(pk, dflat, ctx.batch),
+                        wgrads=any(p.requires_grad for p in gen.parameters()))
         ctx.recs = None
         return dflat, None, None, None, None
 
@@ -173,7 +265,8 @@ class SuperresFn(torch.autograd.Function):
         gen = ctx.gen
         pk = gen._ensure_packed()
         dflat = torch.zeros(ctx.total, device=dimg.device)
-        gx, drgb_lo = blocks_backward(gen, ctx.recs, dimg.contiguous(), _dviews(pk, dflat, ctx.batch))
+        gx, drgb_lo = blocks_backward(gen, ctx.recs, dimg.contiguous(), _dviews(pk, dflat, ctx.batch),
+                                      wgrads=any(p.requires_grad for p in gen.parameters()))
         # first SR layer reads the feature image itself: dfeat = dxu * styles, d(styles) += sum dxu * feat
         dfeat = ops.act_bwd(ctx.feat, g0=gx[0], s0=gx[1], ds0=gx[2], act=ACT_LINEAR, act_gain=1.0, out='f32')
         dfeat[..., :3] += drgb_lo

@@ -259,6 +259,8 @@ struct WgradParams {
   float* dw;
   float scale;
   int k_per_split;
+  const float* xscale;    // optional [batch][cin]: x is multiplied per (sample, channel) — the style of a modulated conv
+  const float* dzscale;   // optional [batch][cout]: the same for dz (transposed-role use: the dense operand is x)
 };
 
 constexpr int WG_T = 64, WG_K = 16, WG_LD = WG_T + 4;
@@ -294,10 +296,21 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
       const int rem = (int)(k - (long long)n * ohw);
       const int my = rem / p.ow, mx = rem - my * p.ow;
       const int co = o0 + quad * 4;
-      if (co < p.cout) ra = ld4_any(p.dz, p.dz_hi, p.dz_lo, ((size_t)k * p.cout + co) >> 2);
+      if (co < p.cout) {
+        ra = ld4_any(p.dz, p.dz_hi, p.dz_lo, ((size_t)k * p.cout + co) >> 2);
+        if (p.dzscale) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.dzscale + (size_t)n * p.cout + co));
+          ra.x *= s4.x; ra.y *= s4.y; ra.z *= s4.z; ra.w *= s4.w;
+        }
+      }
       const int iy = my * p.in_stride + tdy, ix = mx * p.in_stride + tdx, ci = i0 + quad * 4;
-      if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w && ci < p.cin)
+      if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w && ci < p.cin) {
         rb = ld4_any(p.x, p.x_hi, p.x_lo, ((((size_t)n * p.in_h + iy) * p.in_w + ix) * p.cin + ci) >> 2);
+        if (p.xscale) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.xscale + (size_t)n * p.cin + ci));
+          rb.x *= s4.x; rb.y *= s4.y; rb.z *= s4.z; rb.w *= s4.w;
+        }
+      }
     }
   };
   auto store = [&](int buf) {
@@ -433,9 +446,9 @@ extern "C" int hfagp_linear_bwd(int batch, int cin, int cout, const float* dy, c
   return HFAGP_OK;
 }
 
-extern "C" int hfagp_conv2d_wgrad(const HfagpConvDesc* desc, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
-                                  const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, float scale, float* dw,
-                                  void* stream) {
+static int wgrad_impl(const HfagpConvDesc* desc, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
+                      const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, const float* xscale,
+                      const float* dzscale, float scale, float* dw, void* stream) {
   HFAGP_CHECK_ARG(desc && dw, "conv2d_wgrad: null pointer");
   HFAGP_CHECK_ARG((x != nullptr) != (x_hi != nullptr && x_lo != nullptr), "conv2d_wgrad: give x or (x_hi, x_lo)");
   HFAGP_CHECK_ARG((dz != nullptr) != (dz_hi != nullptr && dz_lo != nullptr), "conv2d_wgrad: give dz or (dz_hi, dz_lo)");
@@ -451,6 +464,7 @@ extern "C" int hfagp_conv2d_wgrad(const HfagpConvDesc* desc, const float* x, con
   p.x = x; p.x_hi = reinterpret_cast<const __nv_bfloat16*>(x_hi); p.x_lo = reinterpret_cast<const __nv_bfloat16*>(x_lo);
   p.dz = dz; p.dz_hi = reinterpret_cast<const __nv_bfloat16*>(dz_hi); p.dz_lo = reinterpret_cast<const __nv_bfloat16*>(dz_lo);
   p.dw = dw; p.scale = scale;
+  p.xscale = xscale; p.dzscale = dzscale;
   const long long K = (long long)d.batch * d.oh * d.ow;
   const int tiles = cdiv(d.cout, WG_T) * cdiv(d.cin, WG_T);
   int splits = cdiv(148 * 6, (long long)tiles * d.ntaps);
@@ -463,4 +477,16 @@ extern "C" int hfagp_conv2d_wgrad(const HfagpConvDesc* desc, const float* x, con
   wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   HFAGP_CHECK_LAUNCH("wgrad_kernel");
   return HFAGP_OK;
+}
+
+extern "C" int hfagp_conv2d_wgrad(const HfagpConvDesc* desc, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
+                                  const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, float scale, float* dw,
+                                  void* stream) {
+  return wgrad_impl(desc, x, x_hi, x_lo, dz, dz_hi, dz_lo, nullptr, nullptr, scale, dw, stream);
+}
+
+extern "C" int hfagp_conv2d_wgrad_mod(const HfagpConvDesc* desc, const float* x, const uint16_t* x_hi,
+                                      const uint16_t* x_lo, const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo,
+                                      const float* xscale, const float* dzscale, float scale, float* dw, void* stream) {
+  return wgrad_impl(desc, x, x_hi, x_lo, dz, dz_hi, dz_lo, xscale, dzscale, scale, dw, stream);
 }

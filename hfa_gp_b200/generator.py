@@ -313,7 +313,8 @@ class TriPlaneGenerator(nn.Module):
                 t = ops.conv_transpose_s2(xs, wmod, pl.cout, wbs)
                 y = ops.upfir_act(t, split_out=split_out, **epi)
         if rec is not None:
-            rec.update(pl=pl, x=xs, y=y, styles=styles, dcoef=epi['dcoef'], noise=noise)
+            rec.update(pl=pl, x=xs, y=y, styles=styles, dcoef=epi['dcoef'], noise=noise,
+                       noise_buf=pl.noise if (pl.use_noise and noise_mode == 'const') else None)
         return y
 
     def _torgb_layer(self, x, m, styles, img, pk, rec=None):
@@ -345,7 +346,8 @@ class TriPlaneGenerator(nn.Module):
         r0 = r1 = rt = None
         if rec is not None:
             r0, r1, rt = ({} if blk.cin != 0 else None), {}, {}
-            rec.update(conv0=r0, conv1=r1, torgb=rt, has_img_prev=img is not None, x_in=x)
+            rec.update(conv0=r0, conv1=r1, torgb=rt, has_img_prev=img is not None, x_in=x,
+                       mods=(getattr(blk, 'conv0', None), blk.conv1, blk.torgb), const=getattr(blk, 'const', None))
         if blk.cin == 0:
             c = pk['const_split'] if tc_next else pk['const']
             if tc_next:
@@ -401,10 +403,11 @@ class TriPlaneGenerator(nn.Module):
         ``tap`` (tests only) collects channels-last intermediates.
         """
         cfg = self.cfg
-        train = torch.is_grad_enabled() and ws.requires_grad
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise HfagpError('gradients w.r.t. the generator weights (the post-tune_iter regime, train_rgb.py:132-134) '
-                             'are not implemented in this build: keep the generator frozen (requires_grad_(False))')
+        wgrads = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        train = torch.is_grad_enabled() and (ws.requires_grad or wgrads)
+        if wgrads and any(p.requires_grad for p in self.decoder.parameters()):
+            raise HfagpError('gradients w.r.t. the decoder MLP (part of the post-tune_iter regime, train_rgb.py:132-134) '
+                             'are not implemented in this build: keep generator.decoder frozen')
         if not ws.is_cuda:
             raise HfagpError('TriPlaneGenerator.synthesis needs CUDA tensors (there is no CPU fallback)')
         if ws.dim() != 3 or ws.shape[1] != cfg.num_ws or ws.shape[2] != cfg.w_dim:
@@ -520,6 +523,9 @@ class TriPlaneGenerator(nn.Module):
         self._batch = b
         pk = self._ensure_packed()
         c = c.detach().float().contiguous()
+        if not ws.requires_grad:
+            # only generator parameters are being trained: the stage Functions carry the graph through ws
+            ws = ws.detach().requires_grad_(True)
         styles_flat = ag.StylesFn.apply(ws.float().contiguous(), self)
         planes = ag.BackboneFn.apply(styles_flat, self, noise_mode, b, tap)
         if tap is not None:

@@ -465,8 +465,9 @@ def linear_bwd(dy, x, w, w_gain, b_gain, need_dx=True, dw=None, db=None):
     return dx
 
 
-def conv2d_wgrad(x, dz, taps, dw, *, oh, ow, in_stride=1, scale=1.0):
-    """dw [taps_total][cout][cin] += scale * sum dz (x) x, see ``hfagp_conv2d_wgrad``."""
+def conv2d_wgrad(x, dz, taps, dw, *, oh, ow, in_stride=1, scale=1.0, xscale=None, dzscale=None):
+    """dw [taps_total][cout][cin] += scale * sum dz (x) x, see ``hfagp_conv2d_wgrad`` (``xscale`` [n][cin] / ``dzscale``
+    [n][cout]: per-sample style factors of a modulated convolution, ``hfagp_conv2d_wgrad_mod``)."""
     n, h, wd, cin = x.shape
     cout = dz.shape[-1]
     taps = tuple(taps)
@@ -483,6 +484,10 @@ def conv2d_wgrad(x, dz, taps, dw, *, oh, ow, in_stride=1, scale=1.0):
         return d
 
     d = _conv_desc(key, build)
+    if xscale is not None or dzscale is not None:
+        _ok(_cabi.lib().hfagp_conv2d_wgrad_mod(C.byref(d), *_act_in(x), *_act_in(dz), ptr(xscale), ptr(dzscale), scale,
+                                               ptr(dw), stream()), 'hfagp_conv2d_wgrad_mod')
+        return dw
     _ok(_cabi.lib().hfagp_conv2d_wgrad(C.byref(d), *_act_in(x), *_act_in(dz), scale, ptr(dw), stream()),
           'hfagp_conv2d_wgrad')
     return dw

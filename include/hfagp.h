@@ -317,6 +317,15 @@ int hfagp_conv2d_wgrad(const HfagpConvDesc* desc, const float* x, const uint16_t
                        const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, float scale, float* dw,
                        void* stream);
 
+/* hfagp_conv2d_wgrad for a style-MODULATED convolution (the generator's layers once tune_generator() has unfrozen
+ * them, code/train_rgb.py:132-134): the per-sample style multiplies one operand inside the sum over samples,
+ *   dw[t][co][ci] += scale * sum_{n,pix} (dz[n][pix][co] * dzscale[n][co]) * (x[n][pix+t][ci] * xscale[n][ci])
+ * xscale [batch][cin] / dzscale [batch][cout] may each be NULL.  (The up-sampling layers use it with the roles of x
+ * and dz swapped: the dense operand is the layer input, the strided one the gradient of the transposed conv.) */
+int hfagp_conv2d_wgrad_mod(const HfagpConvDesc* desc, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
+                           const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, const float* xscale,
+                           const float* dzscale, float scale, float* dw, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Around the render path inside one training step (Trainer.gen_update, code/trainer_rgb.py:73-98).
  * ------------------------------------------------------------------------------------------- */

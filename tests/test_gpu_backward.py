@@ -252,3 +252,42 @@ def test_generator_backward_to_ws(precision):
     assert pu.rel_err(img, img_r) < pu.REL_TOL
     (img * gi.cuda()).sum().backward()
     _check_grad(ws_g.grad, ws_r.grad, precision, 'generator dws')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tc'])
+def test_generator_weight_gradients(precision):
+    """The post-tune_iter regime (train_rgb.py:132-134, trainer_rgb.py:69-71): gradients of the generator's own
+    parameters — modulated-conv weights (style-scaled wgrad + demodulation term), biases, noise strengths, affine
+    layers, ToRGB layers, the learned constant — against autograd of the oracle.  (Decoder MLP: next test.)"""
+    cfg = eg3d_ref.small14_config()
+    ref, prod = _pair(cfg, precision)
+    b = 2
+    ws, c, jitter, u = pu.make_inputs(cfg, b, seed=4)
+    g = torch.Generator().manual_seed(13)
+    skip = ('decoder.', 'backbone.mapping.')
+    for n, p in ref.named_parameters():
+        p.requires_grad_(not n.startswith(skip))
+    for n, p in prod.named_parameters():
+        p.requires_grad_(not n.startswith(skip))
+    img_r = ref.synthesis(ws, c, jitter_coarse=jitter, u_fine=u)['image']
+    gi = torch.randn(img_r.shape, generator=g)
+    (img_r * gi).sum().backward()
+    img = prod.synthesis(ws.cuda(), c.cuda(), noise_mode='const', jitter_coarse=jitter.cuda(), u_fine=u.cuda())['image']
+    assert pu.rel_err(img, img_r) < pu.REL_TOL
+    (img * gi.cuda()).sum().backward()
+    want = dict(ref.named_parameters())
+    checked = 0
+    for n, p in prod.named_parameters():
+        if n.startswith(skip):
+            assert p.grad is None
+            continue
+        wr = want[n].grad
+        if wr is None:                       # e.g. noise strengths of the SR blocks (noise_mode 'none' there)
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        assert p.grad is not None, n
+        e_max, e_l2 = pu.rel_err(p.grad, wr), pu.rel_l2(p.grad, wr)
+        print(f'{n}: max-rel {e_max:.2e} rel-L2 {e_l2:.2e}')
+        assert e_l2 < (GRAD_TOL_TC_L2 if precision == 'tc' else GRAD_TOL) * 2, (n, e_l2)
+        checked += 1
+    assert checked > 100
