@@ -274,6 +274,30 @@ class SuperresFn(torch.autograd.Function):
         return dfeat, dflat, None, None, None
 
 
+def _decoder_param_grads(gen, f, do, chunk=1 << 20):
+    """Weight gradient of the OSG decoder (32 -> 64 softplus -> 1+32) from the per-sample operands the render
+    backward kernel wrote: features f [S,32] and d(raw output) do [S,33].  The hidden layer is recomputed in fp32;
+    the four reductions over S = batch * rays * samples are plain GEMMs (torch, fp32), chunked to bound memory."""
+    d0, d2 = gen.decoder.net[0], gen.decoder.net[2]
+    w0 = (d0.weight.detach() * d0.weight_gain).float()
+    b0 = (d0.bias.detach() * d0.bias_gain).float()
+    w1 = (d2.weight.detach() * d2.weight_gain).float()
+    dw0 = torch.zeros_like(w0); db0 = torch.zeros_like(b0); dw1 = torch.zeros_like(w1); db1 = torch.zeros(w1.shape[0], device=w1.device)
+    for s0 in range(0, f.shape[0], chunk):
+        fc, dc = f[s0:s0 + chunk], do[s0:s0 + chunk]
+        pre = torch.addmm(b0, fc, w0.t())
+        h = torch.nn.functional.softplus(pre)
+        dw1 += dc.t() @ h
+        db1 += dc.sum(0)
+        dpre = (dc @ w1) * torch.sigmoid(pre)
+        dw0 += dpre.t() @ fc
+        db0 += dpre.sum(0)
+    _acc(d0.weight, dw0 * d0.weight_gain)
+    _acc(d0.bias, db0 * d0.bias_gain)
+    _acc(d2.weight, dw1 * d2.weight_gain)
+    _acc(d2.bias, db1 * d2.bias_gain)
+
+
 class RenderFn(torch.autograd.Function):
     """tri-planes [B,R,R,96] -> (feature image [B,r,r,32], depth [B,r*r], weight sum [B,r*r]); gradient to the
     planes only (camera, depths and the frozen decoder carry none)."""
@@ -291,9 +315,15 @@ class RenderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat, _ddepth, _dwsum):
         planes, c, jitter, u_fine = ctx.saved_tensors
-        pk = ctx.gen._ensure_packed()
-        dplanes = ops.render_bwd(planes, c, pk['mlp'], pk['lin'], jitter, u_fine if u_fine.numel() else None,
-                                 dfeat.contiguous(), **ctx.kw)
+        gen = ctx.gen
+        pk = gen._ensure_packed()
+        dec = any(p.requires_grad for p in gen.decoder.parameters())
+        out = ops.render_bwd(planes, c, pk['mlp'], pk['lin'], jitter, u_fine if u_fine.numel() else None,
+                             dfeat.contiguous(), decoder=dec, **ctx.kw)
+        if not dec:
+            return out, None, None, None, None, None, None, None
+        dplanes, f, do = out
+        _decoder_param_grads(gen, f, do)
         return dplanes, None, None, None, None, None, None, None
 
 

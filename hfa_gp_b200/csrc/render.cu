@@ -60,6 +60,11 @@ struct RenderParams {
   float* depths_sorted;
   const float* dfeat;     // backward only: gradient of feat [n][res][res][32]
   float* dplanes;         // backward only: gradient of planes (accumulated with red.global.add)
+  // backward only, optional: per-sample operands of the decoder-MLP weight gradient, in storage order
+  // (coarse samples first): dump_f[(ray*T + j)][32] mean tri-plane features, dump_do[(ray*T + j)][33] gradient of the
+  // decoder's raw outputs (column 0 = sigma, 1 + c = colour c)
+  float* dump_f;
+  float* dump_do;
 };
 
 struct Tap {
@@ -656,6 +661,11 @@ __global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(con
           const int crow0 = crow_begin + (base - s_begin);
           const int cnt = min(TILE, s_end - base);
           gather_tile(base, cnt);
+          if (p.dump_f) {
+            // lane = channel: row r of the tile is sample base + r of this ray
+            float* fd = p.dump_f + ((size_t)ray * T + base) * RC;
+            for (int r = 0; r < cnt; ++r) fd[(size_t)r * RC + lane] = ftile[r * RC + colx(r, lane)];
+          }
           uint32_t ah[2][4], al[2][4];
           feature_frags(ah, al);
           // layer 1 forward again: h = softplus(pre), all 8 n-tiles stay in registers
@@ -700,6 +710,18 @@ __global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(con
 #pragma unroll
               for (int e = 0; e < 8; ++e) av[e] = 0.f;
               if (t4 == 0) { av[0] = ds0; av[2] = ds1; }
+            }
+            if (p.dump_do) {
+              float* d0 = p.dump_do + ((size_t)ray * T + base + g) * 33;
+              float* d1 = d0 + 8 * 33;
+              if (ks < 2) {
+                const int c0 = 1 + 16 * ks + 2 * t4;
+                if (v0) { d0[c0] = av[0]; d0[c0 + 1] = av[1]; d0[c0 + 8] = av[4]; d0[c0 + 9] = av[5]; }
+                if (v1) { d1[c0] = av[2]; d1[c0 + 1] = av[3]; d1[c0 + 8] = av[6]; d1[c0 + 9] = av[7]; }
+              } else if (t4 == 0) {
+                if (v0) d0[0] = av[0];
+                if (v1) d1[0] = av[2];
+              }
             }
             uint32_t a2h[4], a2l[4];
             split_pair(av[0], av[1], a2h[0], a2l[0]);
@@ -873,9 +895,9 @@ extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes
   return HFAGP_OK;
 }
 
-extern "C" int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
-                                const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
-                                float* dplanes, void* stream) {
+static int render_bwd_impl(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                           const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
+                           float* dplanes, float* dump_f, float* dump_do, void* stream) {
   HFAGP_CHECK_ARG(desc && planes && c && mlp && lin && jitter && dfeat && dplanes, "render_bwd: null pointer");
   const HfagpRenderDesc& d = *desc;
   HFAGP_CHECK_ARG(d.batch > 0 && d.res > 0 && d.plane_h > 0 && d.plane_w > 0, "render_bwd: bad dims");
@@ -884,7 +906,7 @@ extern "C" int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes
   HFAGP_CHECK_ARG(d.s_fine == 0 || u_fine, "render_bwd: u_fine required when s_fine > 0");
   HFAGP_CHECK_ARG((long long)d.plane_h * d.plane_w * 96 < (1ll << 31), "render_bwd: plane too large for 32-bit tap offsets");
   RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                 nullptr, dfeat, dplanes};
+                 nullptr, dfeat, dplanes, dump_f, dump_do};
   const int nwarps = 8;
   const size_t smem = WEIGHT_BYTES_BWD + nwarps * render_warp_bytes(d.s_coarse, d.s_fine, true);
   static std::once_flag attr_once;
@@ -898,4 +920,17 @@ extern "C" int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes
   render_kernel<true><<<blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(p);
   HFAGP_CHECK_LAUNCH("render_kernel<bwd>");
   return HFAGP_OK;
+}
+
+extern "C" int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                                const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
+                                float* dplanes, void* stream) {
+  return render_bwd_impl(desc, planes, c, mlp, lin, jitter, u_fine, dfeat, dplanes, nullptr, nullptr, stream);
+}
+
+extern "C" int hfagp_render_bwd_dec(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                                    const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
+                                    float* dplanes, float* dump_f, float* dump_do, void* stream) {
+  HFAGP_CHECK_ARG(dump_f && dump_do, "render_bwd_dec: null dump buffers");
+  return render_bwd_impl(desc, planes, c, mlp, lin, jitter, u_fine, dfeat, dplanes, dump_f, dump_do, stream);
 }

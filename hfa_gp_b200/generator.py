@@ -405,9 +405,6 @@ class TriPlaneGenerator(nn.Module):
         cfg = self.cfg
         wgrads = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         train = torch.is_grad_enabled() and (ws.requires_grad or wgrads)
-        if wgrads and any(p.requires_grad for p in self.decoder.parameters()):
-            raise HfagpError('gradients w.r.t. the decoder MLP (part of the post-tune_iter regime, train_rgb.py:132-134) '
-                             'are not implemented in this build: keep generator.decoder frozen')
         if not ws.is_cuda:
             raise HfagpError('TriPlaneGenerator.synthesis needs CUDA tensors (there is no CPU fallback)')
         if ws.dim() != 3 or ws.shape[1] != cfg.num_ws or ws.shape[2] != cfg.w_dim:

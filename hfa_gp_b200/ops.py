@@ -213,11 +213,19 @@ def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s
     return feat, depth, wsum, book
 
 
-def render_bwd(planes, c, mlp, lin, jitter, u_fine, dfeat, *, res, s_coarse, s_fine, delta, box_scale):
-    """d(feat) [N,res,res,32] -> d(planes) [N,PH,PW,96] (decoder frozen), see ``hfagp_render_bwd``."""
+def render_bwd(planes, c, mlp, lin, jitter, u_fine, dfeat, *, res, s_coarse, s_fine, delta, box_scale, decoder=False):
+    """d(feat) [N,res,res,32] -> d(planes) [N,PH,PW,96], see ``hfagp_render_bwd``.  ``decoder=True`` also returns the
+    per-sample (features [S,32], d(raw decoder output) [S,33]) pair for the decoder's weight gradient."""
     n, ph, pw, _ = planes.shape
     dplanes = torch.zeros_like(planes)
     d = RenderDesc(n, res, ph, pw, s_coarse, s_fine, delta, box_scale)
+    if decoder:
+        total = n * res * res * (s_coarse + s_fine)
+        f = torch.zeros((total, 32), device=planes.device, dtype=torch.float32)
+        do = torch.zeros((total, 33), device=planes.device, dtype=torch.float32)
+        _ok(_cabi.lib().hfagp_render_bwd_dec(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
+                                             ptr(dfeat), ptr(dplanes), ptr(f), ptr(do), stream()), 'hfagp_render_bwd_dec')
+        return dplanes, f, do
     _ok(_cabi.lib().hfagp_render_bwd(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
                                        ptr(dfeat), ptr(dplanes), stream()), 'hfagp_render_bwd')
     return dplanes

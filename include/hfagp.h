@@ -231,6 +231,14 @@ int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes, const flo
                      const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
                      float* dplanes, void* stream);
 
+/* hfagp_render_bwd that additionally writes, per sample in storage order (coarse samples first, index
+ * (n*rays + ray)*(s_coarse+s_fine) + j), the two operands of the decoder-MLP weight gradient: dump_f[...][32] the mean
+ * tri-plane features fed to the decoder and dump_do[...][33] the gradient of its raw outputs (column 0 = sigma,
+ * 1+c = colour c).  Used when tune_generator() has unfrozen the decoder (code/train_rgb.py:132-134). */
+int hfagp_render_bwd_dec(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                         const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
+                         float* dplanes, float* dump_f, float* dump_do, void* stream);
+
 /* [1,3,3,1]^2/64 FIR, zero-pad (pad0,pad1), optional output stride and gain:
  *   y[n][oy][ox][c] = gain * sum_{ky,kx} g[ky] g[kx] x[n][oy*stride + ky - pad0][ox*stride + kx - pad0][c]
  * with oh = (h + pad0 + pad1 - 4) / stride + 1.  Input is x (fp32) or the split-bf16 pair (x_hi, x_lo);

@@ -258,13 +258,13 @@ def test_generator_backward_to_ws(precision):
 def test_generator_weight_gradients(precision):
     """The post-tune_iter regime (train_rgb.py:132-134, trainer_rgb.py:69-71): gradients of the generator's own
     parameters — modulated-conv weights (style-scaled wgrad + demodulation term), biases, noise strengths, affine
-    layers, ToRGB layers, the learned constant — against autograd of the oracle.  (Decoder MLP: next test.)"""
+    layers, ToRGB layers, the learned constant, the decoder MLP — against autograd of the oracle."""
     cfg = eg3d_ref.small14_config()
     ref, prod = _pair(cfg, precision)
     b = 2
     ws, c, jitter, u = pu.make_inputs(cfg, b, seed=4)
     g = torch.Generator().manual_seed(13)
-    skip = ('decoder.', 'backbone.mapping.')
+    skip = ('backbone.mapping.',)
     for n, p in ref.named_parameters():
         p.requires_grad_(not n.startswith(skip))
     for n, p in prod.named_parameters():
