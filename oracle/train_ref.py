@@ -30,19 +30,22 @@ from . import hfagp_ref
 
 class TrainStepRef:
     """Trainable tensors: every encoder (or Weights_3DMM) weight/bias in ``sd``, ``bases`` and ``delta``; the
-    generator is frozen (trainer_rgb.py:59-60)."""
+    generator is frozen (trainer_rgb.py:59-60) unless ``tune`` (after ``tune_generator()``, :69-71)."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], bases, delta, generator, size: int, lr: float,
-                 lpips: Optional[Callable] = None, head: str = 'encoder', dim: int = 512):
+                 lpips: Optional[Callable] = None, head: str = 'encoder', dim: int = 512, tune: bool = False):
         self.sd = {k: v.clone() for k, v in sd.items()}
         self.names = [k for k in self.sd if not k.endswith('.kernel')]
         for k in self.names:
             self.sd[k].requires_grad_(True)
         self.bases = bases.clone().requires_grad_(True)
         self.delta = delta.clone().requires_grad_(True)
-        self.generator = generator.requires_grad_(False)
+        # tune=True: the state after Trainer.tune_generator() (trainer_rgb.py:69-71) — every generator parameter
+        # requires grad and is already in the optimiser (it was built over gen.parameters(), :57)
+        self.generator = generator.requires_grad_(tune)
         self.size, self.lpips, self.head, self.dim = size, lpips, head, dim
-        self.opt = torch.optim.Adam([self.sd[k] for k in self.names] + [self.bases, self.delta], lr=lr)
+        self.opt = torch.optim.Adam([self.sd[k] for k in self.names] + [self.bases, self.delta]
+                                    + list(self.generator.parameters()), lr=lr)
 
     def forward(self, real, label, jitter_coarse=None, u_fine=None, params=None):
         if self.head == 'encoder':

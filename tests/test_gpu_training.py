@@ -313,9 +313,6 @@ def test_trainer_checkpoint_round_trip(tmp_path):
         assert torch.equal(a, b), n
     imgs = tr2.sample_bases()
     assert len(imgs) == 10 and imgs[0].shape == (1, 3, cfg.img_resolution, cfg.img_resolution)
-    with pytest.raises(Exception):
-        tr2.tune_generator()
-        tr2.gen_update(real, hfagp_ref.synthetic_labels(2, seed=0).cuda())
 
 
 @pytest.mark.parametrize('smooth', [False, True])
@@ -405,3 +402,51 @@ def test_trainer_rgb_person_2_and_out_pose(same_bases):
     assert tuple(w.shape) == (b, k) and tuple(pose.shape) == (b, 25)
     assert pu.rel_err(pose, hfagp_ref.encoder_ref({n: p.detach().cpu() for n, p in gen.encoder.state_dict().items()},
                                                   real, out_pose=True)[1]) < 1e-3
+
+
+def test_trainer_rgb_tune_generator_steps_match_oracle():
+    """After Trainer.tune_generator() (train_rgb.py:132-134) the generator's own parameters train too: two steps,
+    image / losses each step, first-step gradients of representative generator tensors, updated parameters."""
+    from hfa_gp_b200.trainer_rgb import Trainer
+    cfg = eg3d_ref.small14_config()
+    size, k, b = 32, 10, 2
+    ref_gen, _ = pu.make_pair(cfg, seed=5)
+    tr = Trainer(_args(size, k, cfg), torch.device('cuda'), 0)
+    gen = tr.gen.module
+    gen.generator.load_state_dict(ref_gen.state_dict())
+    gen.generator.precision = gen.encoder.net_app.precision = 'fp32'
+    sd = {n: p.detach().cpu().clone() for n, p in gen.encoder.state_dict().items()}
+    gen0 = {n: p.detach().clone() for n, p in ref_gen.named_parameters()}
+    oracle = train_ref.TrainStepRef(sd, gen.bases.detach().cpu(), gen.delta.detach().cpu(), ref_gen, size, 3e-4,
+                                    lpips=_oracle_lpips(tr.lpips_loss), tune=True)
+    tr.tune_generator()
+    assert all(p.requires_grad for p in gen.generator.parameters())
+    g = torch.Generator().manual_seed(31)
+    probes = ['backbone.synthesis.b4.const', 'backbone.synthesis.b8.conv0.weight', 'backbone.synthesis.b16.conv1.affine.weight',
+              'backbone.synthesis.b32.conv1.noise_strength', 'backbone.synthesis.b256.torgb.weight',
+              'superresolution.block1.conv1.bias', 'superresolution.block1.torgb.weight', 'decoder.net.0.weight',
+              'decoder.net.2.bias']
+    for it in range(2):
+        real = torch.rand(b, 3, size, size, generator=g) * 2 - 1
+        label = hfagp_ref.synthetic_labels(b, seed=40 + it)
+        jit = torch.rand(b, cfg.nrr ** 2, cfg.depth_res, 1, generator=g)
+        u = torch.rand(b * cfg.nrr ** 2, cfg.depth_res_importance, generator=g)
+        l2_r, lp_r, img_r = oracle.step(real, label, jit, u)
+        gen.generator.fixed_draws = (jit.cuda(), u.cuda())
+        l2, lpv, img = tr.gen_update(real.cuda(), label.clone().cuda())
+        assert pu.rel_err(img, img_r) < pu.REL_TOL, it
+        assert abs(float(l2.detach()) - float(l2_r)) < 1e-3 * abs(float(l2_r))
+        assert abs(float(lpv.detach()) - float(lp_r)) < 2e-3 * abs(float(lp_r))
+        if it == 0:
+            ours, theirs = dict(gen.generator.named_parameters()), dict(ref_gen.named_parameters())
+            for n in probes:
+                _check(ours[n].grad, theirs[n].grad, 'fp32', f'step0 d generator.{n}')
+    assert tr.g_optim.steps == [2, 2]
+    ours, theirs = dict(gen.generator.named_parameters()), dict(ref_gen.named_parameters())
+    for n in probes:
+        upd_r = theirs[n].detach() - gen0[n]
+        upd = ours[n].detach().cpu() - gen0[n]
+        assert float(upd_r.abs().max()) > 0, n
+        assert pu.rel_l2(upd, upd_r) < 5e-2, (n, pu.rel_l2(upd, upd_r))
+    w_avg = dict(gen.generator.named_buffers()).get('backbone.mapping.w_avg')
+    assert torch.equal(ours['backbone.mapping.fc0.weight'].detach().cpu(), gen0['backbone.mapping.fc0.weight'])   # unused: untouched
