@@ -245,6 +245,8 @@ def train_bench(args, rank, world, local_rank):
                             latent_dim_style=512, latent_dim_shape=DIM_SHAPE, run_id='bench', emb_dir='./', lr=3e-4)
     torch.manual_seed(0)
     tr = trainer_rgb.Trainer(ns, dev, local_rank)
+    if args.tune_generator:
+        tr.tune_generator()
     g = torch.Generator().manual_seed(4321 + rank)
     total = args.warmup + args.steps
     host_frames = (torch.rand(total, bs, 3, ENC_SIZE, ENC_SIZE, generator=g) * 2 - 1).pin_memory()
@@ -288,7 +290,8 @@ def train_bench(args, rank, world, local_rank):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'configs[2]: trainer_rgb.gen_update, 512x512 render pooled to 256, latent_dim_shape=50, '
-                                   'MSE+LPIPS(alex, random-init), Adam, generator frozen', 'per_rank_batch': bs,
+                                   'MSE+LPIPS(alex, random-init), Adam, generator ' + ('unfrozen (tune_generator)' if args.tune_generator else 'frozen'),
+                       'per_rank_batch': bs,
                        'exchange': 'one flat all-reduce of %d gradient floats per step' % tr.g_optim.live_elements()
                                    if world > 1 else 'none (1 rank)',
                        'l2': 'per-step working set exceeds the 126 MB L2; no flush'},
@@ -308,6 +311,8 @@ def main():
     ap.add_argument('--frames-per-step', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='drive the frame loop eagerly instead of replaying the CUDA graph')
+    ap.add_argument('--tune-generator', action='store_true',
+                    help="with --workload train: the post-tune_iter regime (generator unfrozen, train_rgb.py:132-134)")
     ap.add_argument('--workload', default='infer', choices=['infer', 'train'],
                     help="'infer' = configs[1] (the headline line); 'train' = configs[2]/[3] training step")
     args = ap.parse_args()
