@@ -434,6 +434,7 @@ class TriPlaneGenerator(nn.Module):
         self._premod = self._modulate_all(pk, flat, offs, b)
 
         x = img = None
+        self._keep = None                     # (a previous call may have been aborted by an exception)
         if self.overlap_streams and tap is None and pe is None:
             if self._side is None or self._side.device != ws.device:
                 self._side = torch.cuda.Stream(device=ws.device)
