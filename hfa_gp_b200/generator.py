@@ -519,6 +519,7 @@ class TriPlaneGenerator(nn.Module):
         from . import autograd as ag
         b = ws.shape[0]
         self._batch = b
+        self._premod = self._keep = None      # inference-only state (a previous call may have been aborted)
         pk = self._ensure_packed()
         c = c.detach().float().contiguous()
         if not ws.requires_grad:
