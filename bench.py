@@ -31,7 +31,10 @@ UNIT = 'frames/s'
 WORKLOAD = 'configs[1]: run_recon_video_rgb frame loop, 512x512, 48+48 samples/ray, random-init EG3D generator, encoder 256x256'
 RENDER_ALG_BYTES = 27_394_048        # planes 25 165 824 B read once + feat/depth/wsum 2 228 224 B written
 ENC_SIZE, DIM_SHAPE = 256, 50
-TC_ENTRY_POINTS = ('hfagp_conv2d_tc_fwd', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd')
+# every C-ABI entry point that launches conv_tc_kernel (tests/test_host_logic.py checks this list against conv_tc.cu)
+TC_ENTRY_POINTS = ('hfagp_conv2d_tc_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd')
+CONV_TC_DRAM_BYTES_PER_FRAME = None   # ncu dram__bytes_read+write summed over one frame's conv_tc_kernel launches (profiles/)
+DTYPE = 'bf16x3-split operands (hi*hi + lo*hi + hi*lo), fp32 accumulate'
 
 
 def tensor_core_conv_flops(cfg, enc_size):
@@ -463,7 +466,8 @@ def main():
         if tc_ms:
             ach_tf = tc_flops / (tc_ms * 1e-3) / 1e12
             roof = {'kernel': 'conv_tc_kernel', 'bound': 'tensor', 'achieved': ach_tf, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                    'frac': ach_tf / tf_peak, 'traffic': None,   # tensor-bound; the largest launch moves 222 MB (ncu) vs 201 MB algorithmic 'ms_per_frame': tc_ms, 'launches_per_frame': tc_launches,
+                    'frac': ach_tf / tf_peak, 'traffic': CONV_TC_DRAM_BYTES_PER_FRAME,
+                    'ms_per_frame': tc_ms, 'launches_per_frame': tc_launches,
                     'share_of_step': tc_ms / (ms / args.steps),
                     'tensor_pipe_frac': 3.0 * ach_tf / tf_peak, 'peak_source': peak_src + ', sustained bf16',
                     'note': 'achieved = algorithmic fp32 FLOPs of the tensor-core convolutions (%.1f GFLOP/frame) / summed '
@@ -472,7 +476,7 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'frames_per_step': fps_, 'sharding': 'frame i -> rank i mod N, no collective',
                        'l2': 'per-frame working set ~1.25 GB (weights 113 MB + activations) exceeds the 126 MB L2; no flush',
                        'launch': 'eager' if args.no_graph else 'one CUDA graph replay per frame (hfa_gp_b200.frame_loop.FrameLoop)'},

@@ -60,6 +60,34 @@ def reference_encoder(seed=5):
     np.savez_compressed(os.path.join(OUT, 'reference_encoder.npz'), **z)
 
 
+def reference_cameras(seed=11):
+    """Seeded outputs of the REFERENCE's cam_utils.py:12-80 in the three sampling modes HFA-GP uses and of the
+    trainer_rgb.py:27-42 samplers (restated on the reference's own functions: trainer_rgb.py itself needs lpips)."""
+    mods = ref_bridge.load()
+    assert mods is not None, 'needs /root/reference'
+    cam = mods[2]
+    z = dict(seed=np.int64(seed))
+    intr = torch.tensor([4.2647, 0, 0.5, 0, 4.2647, 0.5, 0, 0, 1])
+    for mode in ('gaussian', 'uniform', None):
+        torch.manual_seed(seed)
+        pts, phi, theta = cam.sample_camera_positions('cpu', n=5, r=2.7, horizontal_stddev=0.3, vertical_stddev=0.155,
+                                                      horizontal_mean=0.5 * math.pi, vertical_mean=0.5 * math.pi, mode=mode)
+        z[f'pts_{mode}'], z[f'phi_{mode}'], z[f'theta_{mode}'] = pts.numpy(), phi.numpy(), theta.numpy()
+        z[f'c2w_{mode}'] = cam.create_cam2world_matrix(-pts, pts, device='cpu').numpy()
+
+    def sampler(batch, hm, vm, hs):
+        pts, _, _ = cam.sample_camera_positions('cpu', n=batch, r=2.7, horizontal_mean=hm * math.pi, vertical_mean=vm * math.pi,
+                                                horizontal_stddev=hs, vertical_stddev=0.155, mode='gaussian')
+        c = cam.create_cam2world_matrix(-pts, pts, device='cpu').reshape(batch, -1)
+        return torch.cat((c, intr.reshape(1, -1).repeat(batch, 1).to(c)), -1)
+
+    torch.manual_seed(seed + 1)
+    z['cam_sampler'] = sampler(4, 0.5, 0.5, 0.3).numpy()                 # trainer_rgb.py:27-33
+    torch.manual_seed(seed + 2)
+    z['cam_sampler_pose'] = sampler(4, 0.4, 0.55, 0.15).numpy()          # trainer_rgb.py:36-42 (0.4, 0.55)
+    np.savez_compressed(os.path.join(OUT, 'reference_cameras.npz'), **z)
+
+
 def oracle_generator_tiny(seed=0):
     cfg = E.tiny_config()
     gen = E.make_generator(cfg, seed=seed, noise_strength=0.1)
@@ -81,5 +109,6 @@ def oracle_generator_tiny(seed=0):
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     reference_encoder()
+    reference_cameras()
     oracle_generator_tiny()
     print(sorted(os.listdir(OUT)), [os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))])

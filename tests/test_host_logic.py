@@ -130,3 +130,20 @@ def test_frameio_modes_and_errors():
         frameio.to_uint8(torch.zeros(1, 3, 4, 4), 'png')
     with pytest.raises(Exception):
         frameio.to_uint8(torch.zeros(1, 3, 4, 4), 'save_image')      # CPU tensor: no fallback
+
+
+def test_bench_counts_every_conv_tc_entry_point():
+    """bench.py's roofline divides the tensor-core FLOPs by the summed time of TC_ENTRY_POINTS: the list must hold
+    every C-ABI entry point of conv_tc.cu that launches conv_tc_kernel (round-1 bug: the _rgb_ entry was missing,
+    which dropped the two largest launches from the denominator), and each must be declared in include/hfagp.h."""
+    import re
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    src = open(os.path.join(ROOT, 'hfa_gp_b200', 'csrc', 'conv_tc.cu')).read()
+    entries = set(re.findall(r'extern "C" int (hfagp_conv2d_tc\w*_fwd)\s*\(', src))
+    assert entries, 'no tensor-core entry points found in conv_tc.cu'
+    assert entries == set(bench.TC_ENTRY_POINTS)
+    header = open(os.path.join(ROOT, 'include', 'hfagp.h')).read()
+    for e in entries:
+        assert e in header
