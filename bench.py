@@ -33,7 +33,9 @@ RENDER_ALG_BYTES = 27_394_048        # planes 25 165 824 B read 
 ENC_SIZE, DIM_SHAPE = 256, 50
 # every C-ABI entry point that launches conv_tc_kernel (tests/test_host_logic.py checks this list against conv_tc.cu)
 TC_ENTRY_POINTS = ('hfagp_conv2d_tc_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd')
-CONV_TC_DRAM_BYTES_PER_FRAME = None   # ncu dram__bytes_read+write summed over one frame's conv_tc_kernel launches (profiles/)
+# ncu dram__bytes_read.sum + dram__bytes_write.sum over the 42 conv_tc_kernel launches of one frame (profiles/r2_launches_start.csv:
+# 803.6 MB read + 211.1 MB written back before kernel end; the frame's algorithmic weight + activation bytes are ~1 250 MB)
+CONV_TC_DRAM_BYTES_PER_FRAME = 1_014_700_000
 DTYPE = 'bf16x3-split operands (hi*hi + lo*hi + hi*lo), fp32 accumulate'
 
 
