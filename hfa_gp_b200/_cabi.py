@@ -27,6 +27,7 @@ SYMBOLS = [
     'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8',
     'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
     'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd', 'hfagp_conv2d_wgrad_mod', 'hfagp_render_bwd_dec',
+    'hfagp_render_fwd_simt',
 ]
 
 
@@ -88,6 +89,7 @@ def lib() -> C.CDLL:
     l.hfagp_styles_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     l.hfagp_modulate_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_render_fwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
+    l.hfagp_render_fwd_simt.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
     l.hfagp_render_bwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 9
     l.hfagp_render_bwd_dec.argtypes = [C.POINTER(RenderDesc)] + [vp] * 11
     l.hfagp_blur_fwd.argtypes = [i32] * 7 + [f32] + [vp] * 7

@@ -22,140 +22,9 @@
 #include <mutex>
 #include <type_traits>
 #include "common.cuh"
+#include "render_common.cuh"
 
 namespace hfagp {
-
-constexpr int RC = 32;        // channels per plane == decoder input width
-constexpr int RH = 64;        // decoder hidden width
-constexpr int RO = 33;        // 1 sigma + 32 colour features
-constexpr int R_WARPS = 16;   // rays per strip / warps per CTA (8 when 16 rays' scratch does not fit in 227 KB)
-constexpr int TILE = 16;      // samples per MMA tile and per gather batch
-constexpr int MLP_FLOATS = RH * RC + RH + RO * RH + RO;  // 4257
-
-// shared-memory weight image (per CTA): B fragments of both layers as split bf16 + fp32 biases
-constexpr int W0F_U2 = 8 * 2 * 2 * 32;   // [ntile 8][kstep 2][hi|lo][lane] uint2
-constexpr int W1F_U2 = 5 * 4 * 2 * 32;   // [ntile 5][kstep 4][hi|lo][lane] uint2
-constexpr int WEIGHT_BYTES = (W0F_U2 + W1F_U2) * 8 + (RH + 40) * 4;
-// backward adds the transposed operands: dh = dout . W1 (K = 48 padded outputs, N = 64) and df = dpre . W0 (K = 64, N = 32)
-constexpr int W1T_U2 = 8 * 3 * 2 * 32;   // [ntile 8][kstep 3][hi|lo][lane] uint2
-constexpr int W0T_U2 = 4 * 4 * 2 * 32;   // [ntile 4][kstep 4][hi|lo][lane] uint2
-constexpr int WEIGHT_BYTES_BWD = ((WEIGHT_BYTES + 15) & ~15) + (W1T_U2 + W0T_U2) * 8;
-
-struct RenderParams {
-  HfagpRenderDesc d;
-  const float* planes;
-  const float* cam;
-  const float* mlp;
-  const float* lin;
-  const float* jitter;
-  const float* u_fine;
-  const float* depth_range;
-  float* feat;
-  float* depth;
-  float* wsum;
-  int32_t* inds;
-  int32_t* below;
-  int32_t* above;
-  int32_t* sort_idx;
-  float* depths_sorted;
-  const float* dfeat;     // backward only: gradient of feat [n][res][res][32]
-  float* dplanes;         // backward only: gradient of planes (accumulated with red.global.add)
-  // backward only, optional: per-sample operands of the decoder-MLP weight gradient, in storage order
-  // (coarse samples first): dump_f[(ray*T + j)][32] mean tri-plane features, dump_do[(ray*T + j)][33] gradient of the
-  // decoder's raw outputs (column 0 = sigma, 1 + c = colour c)
-  float* dump_f;
-  float* dump_do;
-};
-
-struct Tap {
-  uint32_t off;   // byte offset of the texel's channel 0 inside this sample's frame (0 when outside)
-  float w;        // bilinear weight (0 when outside: grid_sample padding_mode='zeros')
-};
-
-__host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
-
-// Per-warp shared memory:
-//   colq  [round16(S) + round16(SF)] rows x 32 u16   decoded colours as 16-bit fixed point (see quantise note)
-//   ftile [16][32] fp32                               features of the tile being decoded (MMA A operand)
-//   dep, sig, sdep, ssig [Tp] fp32 ; order [Tp] u8 ; cdf [S+2], zmid [S] fp32 ; taps [16*12]
-// wts (march weights) aliases sdep during the coarse pass (sdep is first written by the sort) and dep during the
-// final pass (unsorted depths are dead after the sort).
-__host__ __device__ inline size_t render_warp_bytes(int S, int SF, bool bwd = false) {
-  const size_t Tp = (size_t)(S + SF + 3) & ~(size_t)3;   // per-sample arrays padded so each stays 16 B aligned
-  size_t b = (size_t)(round16(S) + round16(SF)) * RC * 2 + TILE * RC * 4 + 4 * Tp * 4 + Tp + (size_t)(2 * S + 2) * 4;
-  if (bwd) b += 5 * Tp * 4 + 32 * 4;     // tarr (T_k), aarr (alpha_k), dsg (d sigma), pj (dfeat . colour), final weights + dfeat row
-  b = (b + 15) & ~(size_t)15;
-  return b + TILE * 12 * sizeof(Tap);
-}
-
-// exclusive product scan over n values held as v(k) for k = lane + 32q; returns weights into wts[k] = alpha*T
-// and the sum of weights.  alpha(k) supplied through a lambda.
-template <typename FA>
-__device__ __forceinline__ float march_weights(int nint, int lane, float* wts, FA alpha_of, float* tarr = nullptr,
-                                               float* aarr = nullptr) {
-  float carry = 1.f, wsum = 0.f;
-  for (int base = 0; base < nint; base += 32) {
-    int k = base + lane;
-    float a = k < nint ? alpha_of(k) : 0.f;
-    float v = k < nint ? (1.f - a + 1e-10f) : 1.f;
-    float incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      float t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl *= t;
-    }
-    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 1.f;
-    float w = a * (carry * excl);
-    if (k < nint) wts[k] = w;
-    if (tarr && k < nint) { tarr[k] = carry * excl; aarr[k] = a; }
-    wsum += k < nint ? w : 0.f;
-    carry *= __shfl_sync(0xffffffffu, incl, 31);
-  }
-  return warp_sum(wsum);
-}
-
-// ---- split-bf16 helpers (packed pairs: element 0 in the low half)
-__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));   // first source -> upper half
-  return r;
-}
-// (a, b) -> hi pair and residual lo pair
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  hi = pack_bf16x2(a, b);
-  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
-  lo = pack_bf16x2(a - ah, b - bh);
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
-}
-// softplus(x) = max(x,0) + ln2 * log2(1 + 2^(-|x| log2e)); equals torch's (beta 1, threshold 20) to fp32 rounding
-__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float softplus_fast(float x) {
-  return fmaf(lg2f(1.f + ex2f(-1.4426950408889634f * fabsf(x))), 0.6931471805599453f, fmaxf(x, 0.f));
-}
-__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigmoid01(float x) { return rcpf(1.f + ex2f(-1.4426950408889634f * x)); }
-
-// physical column of logical channel c in row r of the feature tile (row stride 32 floats): XOR-ing bits 3..4
-// with the row keeps the gather's float4 stores and the MMA fragment float2 loads conflict-free
-__device__ __forceinline__ int colx(int r, int c) { return c ^ ((r & 3) << 3); }
-// physical 32-bit word (2 channels) of channel pair cw = c/2 in row r of the colour buffer (row stride 16 words)
-__device__ __forceinline__ int colqx(int r, int cw) { return cw ^ (((r >> 1) & 3) << 2); }
-// Quantise note: colour = sigmoid*1.002 - 0.001 is stored between decode and composite as q = round(65535*sigmoid)
-// (step 1.53e-5, |error| <= 7.7e-6 per colour, <= 1.6e-5 on the composited feature): half the bytes per row lets
-// 16 instead of 8 rays live on an SM, which is what hides the gather latency.
-constexpr float QSCALE = 65535.f;
-constexpr float QSTEP = 1.002f / 65535.f;
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // BWD = false: the forward renderer.  BWD = true: recompute the forward per ray (same code), then back-propagate
 // d(feat) through the composite / march / decoder MLP / bilinear gather into d(planes) (8 rays per CTA).
@@ -858,10 +727,10 @@ __global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(con
 
 using namespace hfagp;
 
-extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
-                                const float* lin, const float* jitter, const float* u_fine, const float* depth_range,
-                                float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above, int32_t* sort_idx,
-                                float* depths_sorted, void* stream) {
+static int render_fwd_impl(bool allow_tc, const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                           const float* lin, const float* jitter, const float* u_fine, const float* depth_range,
+                           float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above, int32_t* sort_idx,
+                           float* depths_sorted, void* stream) {
   HFAGP_CHECK_ARG(desc && planes && c && mlp && lin && jitter && depth_range && feat && depth && wsum, "render_fwd: null pointer");
   const HfagpRenderDesc& d = *desc;
   HFAGP_CHECK_ARG(d.batch > 0 && d.res > 0 && d.plane_h > 0 && d.plane_w > 0, "render_fwd: bad dims");
@@ -872,6 +741,10 @@ extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes
   HFAGP_CHECK_ARG((long long)d.plane_h * d.plane_w * 96 < (1ll << 31), "render_fwd: plane too large for 32-bit tap offsets");
   RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, depth_range, feat, depth, wsum, inds, below, above, sort_idx, depths_sorted,
                  nullptr, nullptr};
+  int dev = 0, sms = 148;
+  HFAGP_CUDA(cudaGetDevice(&dev));
+  HFAGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (allow_tc && render_tc_supported(d)) return render_tc_launch(p, sms, (cudaStream_t)stream);
   int nwarps = R_WARPS;
   size_t smem = ((WEIGHT_BYTES + 15) & ~15) + nwarps * render_warp_bytes(d.s_coarse, d.s_fine);
   if (smem > 227 * 1024) {
@@ -881,18 +754,27 @@ extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes
   static std::once_flag attr_once;   // opt in to the full 227 KB once; not repeated on the (graph-captured) hot path
   std::call_once(attr_once, [] { cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   HFAGP_CHECK_ARG(smem <= 227 * 1024, "render_fwd: shared memory need exceeds 227 KB");
-  static int cached_sms = 0;
-  if (!cached_sms) {
-    int dev = 0, sms = 148;
-    HFAGP_CUDA(cudaGetDevice(&dev));
-    HFAGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    cached_sms = sms;
-  }
   const long long strips = (long long)d.batch * ((d.res + nwarps - 1) / nwarps) * d.res;
-  const int blocks = (int)(strips < cached_sms ? strips : cached_sms);   // persistent: one CTA per SM
+  const int blocks = (int)(strips < sms ? strips : sms);   // persistent: one CTA per SM
   render_kernel<false><<<blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(p);
   HFAGP_CHECK_LAUNCH("render_kernel<fwd>");
   return HFAGP_OK;
+}
+
+extern "C" int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                                const float* lin, const float* jitter, const float* u_fine, const float* depth_range,
+                                float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above, int32_t* sort_idx,
+                                float* depths_sorted, void* stream) {
+  return render_fwd_impl(true, desc, planes, c, mlp, lin, jitter, u_fine, depth_range, feat, depth, wsum, inds, below, above,
+                         sort_idx, depths_sorted, stream);
+}
+
+extern "C" int hfagp_render_fwd_simt(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                                     const float* lin, const float* jitter, const float* u_fine, const float* depth_range,
+                                     float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above,
+                                     int32_t* sort_idx, float* depths_sorted, void* stream) {
+  return render_fwd_impl(false, desc, planes, c, mlp, lin, jitter, u_fine, depth_range, feat, depth, wsum, inds, below, above,
+                         sort_idx, depths_sorted, stream);
 }
 
 static int render_bwd_impl(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,

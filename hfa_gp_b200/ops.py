@@ -189,8 +189,9 @@ def modulate(w: torch.Tensor, styles: torch.Tensor, demodulate: bool):
 
 
 def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s_fine, delta, box_scale,
-           bookkeeping: bool = False):
-    """planes [N,PH,PW,96] channels-last -> feat [N,res,res,32], depth [N,res*res], wsum [N,res*res]."""
+           bookkeeping: bool = False, simt: bool = False):
+    """planes [N,PH,PW,96] channels-last -> feat [N,res,res,32], depth [N,res*res], wsum [N,res*res].
+    ``simt=True`` forces the legacy mma.sync kernel (``hfagp_render_fwd_simt``; cross-checks only)."""
     n, ph, pw, _ = planes.shape
     dev = planes.device
     rays = res * res
@@ -206,10 +207,11 @@ def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s
         book['sort_idx'] = torch.empty((n, rays, t), device=dev, dtype=torch.int32)
         book['depths_sorted'] = torch.empty((n, rays, t), device=dev, dtype=torch.float32)
     d = RenderDesc(n, res, ph, pw, s_coarse, s_fine, delta, box_scale)
-    _ok(_cabi.lib().hfagp_render_fwd(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
-                                       ptr(depth_range), ptr(feat), ptr(depth), ptr(wsum), ptr(book.get('inds')), ptr(book.get('below')),
-                                       ptr(book.get('above')), ptr(book.get('sort_idx')),
-                                       ptr(book.get('depths_sorted')), stream()), 'hfagp_render_fwd')
+    name = 'hfagp_render_fwd_simt' if simt else 'hfagp_render_fwd'
+    _ok(getattr(_cabi.lib(), name)(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
+                                   ptr(depth_range), ptr(feat), ptr(depth), ptr(wsum), ptr(book.get('inds')), ptr(book.get('below')),
+                                   ptr(book.get('above')), ptr(book.get('sort_idx')),
+                                   ptr(book.get('depths_sorted')), stream()), name)
     return feat, depth, wsum, book
 
 

@@ -221,6 +221,15 @@ int hfagp_render_fwd(const HfagpRenderDesc* desc, const float* planes, const flo
                      float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above, int32_t* sort_idx,
                      float* depths_sorted, void* stream);
 
+/* Same contract as hfagp_render_fwd, but always on the legacy warp-per-ray kernel whose decoder MLP runs on mma.sync
+ * (csrc/render.cu).  hfagp_render_fwd itself dispatches to the tcgen05 renderer (csrc/render_tc.cu: 128-sample tiles,
+ * decoder layers as tcgen05.mma with TMEM accumulators) whenever its shared-memory plan fits; this entry point keeps the
+ * second implementation reachable for cross-checks (tests/test_gpu_parity.py::test_render_tc_equals_simt). */
+int hfagp_render_fwd_simt(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
+                          const float* lin, const float* jitter, const float* u_fine, const float* depth_range,
+                          float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above,
+                          int32_t* sort_idx, float* depths_sorted, void* stream);
+
 /* Backward of hfagp_render_fwd w.r.t. the planes (decoder frozen, trainer_rgb.py:59-60): per ray the forward is
  * recomputed from the same inputs (jitter / u_fine make it deterministic), then d(feat) is pushed through the
  * composite, the mid-point march (d sigma), the decoder MLP (tensor-pipe, split bf16) and the bilinear gather;

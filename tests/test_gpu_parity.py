@@ -171,7 +171,7 @@ def _render_case(res, s, sf, batch=1, seed=0, plane_res=64):
     return cfg, planes, dec, c, jitter, u
 
 
-def _run_render_gpu(cfg, planes, dec, c, jitter, u, book=True):
+def _run_render_gpu(cfg, planes, dec, c, jitter, u, book=True, simt=False):
     ops = _ops()
     d0, d2 = dec.net[0], dec.net[2]
     mlp = torch.cat([(d0.weight * d0.weight_gain).reshape(-1), d0.bias * d0.bias_gain,
@@ -185,7 +185,25 @@ def _run_render_gpu(cfg, planes, dec, c, jitter, u, book=True):
     rng = torch.stack([lin[0] + jit[:, :, 0].min() * delta, lin[-1] + jit[:, :, -1].max() * delta])
     return ops.render(pl, c.cuda(), mlp, lin.cuda(), jit.contiguous().cuda(), u.cuda() if sf > 0 else None,
                       rng.cuda(), res=cfg.nrr, s_coarse=s, s_fine=sf, delta=delta, box_scale=2.0 / cfg.box_warp,
-                      bookkeeping=book)
+                      bookkeeping=book, simt=simt)
+
+
+@pytest.mark.parametrize('res,s,sf,batch', [(16, 48, 48, 2), (8, 33, 20, 1), (24, 16, 16, 1), (16, 40, 0, 1)])
+def test_render_tc_equals_simt(res, s, sf, batch):
+    """The tcgen05 renderer (csrc/render_tc.cu, what hfagp_render_fwd dispatches to) against the legacy mma.sync
+    kernel (hfagp_render_fwd_simt) on identical inputs: two independent implementations of the same fp32-class
+    arithmetic, so they agree far inside the oracle tolerance; the integer bookkeeping is identical except where a
+    last-bit difference of a density moves u across a cdf knot."""
+    cfg, planes, dec, c, jitter, u = _render_case(res, s, sf, batch, seed=3)
+    a = _run_render_gpu(cfg, planes, dec, c, jitter, u)
+    b = _run_render_gpu(cfg, planes, dec, c, jitter, u, simt=True)
+    for x, y in zip(a[:3], b[:3]):
+        assert pu.rel_err(x, y.cpu()) < 1e-4
+    if sf > 0:
+        for k in ('inds', 'below', 'above', 'sort_idx'):
+            same = (a[3][k] == b[3][k]).float().mean()
+            assert float(same) > 0.999, f'{k}: only {float(same):.5f} equal'
+        assert pu.rel_err(a[3]['depths_sorted'], b[3]['depths_sorted'].cpu()) < 1e-5
 
 
 @pytest.mark.parametrize('res,s,sf,batch', [(16, 48, 0, 1), (16, 48, 48, 2), (8, 12, 12, 1), (8, 33, 20, 1),
