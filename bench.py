@@ -229,80 +229,176 @@ def cpu_baseline_sample(frames=2):
             'sample': f'{frames} full 512x512 frames after 1 warm-up (encoder+latent+synthesis), PyTorch fp32 CPU oracle'}
 
 
-def train_bench(args, rank, world, local_rank):
-    """--workload train: BASELINE.json configs[2] (trainer_rgb.gen_update, size 256, latent_dim_shape 50, MSE + LPIPS,
-    generator frozen) and, at N > 1, the configs[3]-style data-parallel step: per-rank micro-batch, ONE flat NCCL
-    all-reduce of the encoder/bases/delta gradients per step.  Not the driver's headline line (that is configs[1]);
-    printed for the record with its own workload name."""
+def _barrier(world):
     import torch
     import torch.distributed as dist
-    from hfa_gp_b200 import _cabi, ops
-    from hfa_gp_b200 import trainer_rgb
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def train_record(rank, world, dev, steps, warmup, trainer='rgb', per_rank_batch=2, tune_generator=False):
+    """One training workload through the reference's Trainer surface, timed on the device (max over ranks):
+    trainer='rgb'  BASELINE.json configs[2]: trainer_rgb.gen_update (encoder 256, latent_dim_shape 50, MSE + LPIPS-alex,
+                   Adam; generator frozen unless tune_generator), batch `per_rank_batch` per rank (train_rgb.py:164: 2)
+    trainer='3dmm' configs[3]: trainer_3dmm.gen_update driven by synthetic 3DMM coefficients [B,76], the global batch
+                   split over the ranks (train_3dmm.py:93), ONE flat NCCL all-reduce of the non-generator gradients per step.
+    Every step copies its inputs from pinned host memory and the last step's losses are read back inside the timed region."""
+    import torch
+    from hfa_gp_b200 import ops, trainer_3dmm, trainer_rgb
+
+    bs = per_rank_batch
+    ns = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='',
+                            synthetic_generator=True, generator_seed=0, batch_size=bs * world, size=ENC_SIZE,
+                            latent_dim_style=512, latent_dim_shape=DIM_SHAPE, run_id='bench', emb_dir='./', lr=3e-4,
+                            params_len=76)
+    os.environ.setdefault('HFAGP_SYNTHETIC_LPIPS', '1')          # no pretrained LPIPS weights offline: seeded random init
+    torch.manual_seed(0)
+    tr = (trainer_3dmm if trainer == '3dmm' else trainer_rgb).Trainer(ns, dev, rank)
+    if tune_generator:
+        tr.tune_generator()
+    optim = tr.w_optim if trainer == '3dmm' else tr.g_optim
+    g = torch.Generator().manual_seed(4321 + rank)
+    total = warmup + steps
+    host_frames = (torch.rand(total, bs, 3, ENC_SIZE, ENC_SIZE, generator=g) * 2 - 1).pin_memory()
+    host_labels = torch.stack([trainer_rgb.cam_sampler(bs, 'cpu') for _ in range(total)]).pin_memory()
+    host_params = torch.randn(total, bs, 76, generator=g).pin_memory()
+
+    def step(i):
+        real = host_frames[i].to(dev, non_blocking=True)
+        label = host_labels[i].to(dev, non_blocking=True)
+        if trainer == '3dmm':
+            out = tr.gen_update(real, label, host_params[i].to(dev, non_blocking=True))
+            return out[1], out[2]
+        out = tr.gen_update(real, label)
+        return out[0], out[1]
+
+    for i in range(warmup):
+        step(i)
+    _barrier(world)
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        l2, lp = step(warmup + i)
+    loss_host = float(l2.detach()) + float(lp.detach())          # D2H read of the step's result inside the timed region
+    e1.record()
+    _barrier(world)
+    ms, = _max_over_ranks([e0.elapsed_time(e1)], dev, world)
+    frames = steps * bs * world
+    h2d = bs * (3 * ENC_SIZE * ENC_SIZE + 25 + (76 if trainer == '3dmm' else 0)) * 4
+    rec = {
+        'workload': ('configs[3]: trainer_3dmm.gen_update, synthetic 3DMM coefficients [B,76], 512x512 render pooled to 256, '
+                     'MSE+LPIPS(alex, random-init), Adam, frame-sharded data parallel' if trainer == '3dmm' else
+                     'configs[2]: trainer_rgb.gen_update, 512x512 render pooled to 256, latent_dim_shape=50, MSE+LPIPS(alex, '
+                     'random-init), Adam') + ', generator ' + ('unfrozen (tune_generator)' if tune_generator else 'frozen'),
+        'value': frames / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps, 'warmup': warmup,
+        'per_rank_batch': bs, 'global_batch': bs * world, 'n_gpus': world,
+        'allreduce_floats_per_step': optim.live_elements() if world > 1 else 0,
+        'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8, 'gpu_launches_per_step': (ops.launch_count() - n0) / steps,
+        'dtype': DTYPE, 'final_loss': loss_host,
+    }
+    del tr, optim
+    torch.cuda.empty_cache()
+    return rec
+
+
+def reenact_record(rank, world, dev, frames_total=1000):
+    """BASELINE.json configs[4]: run_recon_video_audio.py — a `frames_total`-frame batch reenactment from synthetic aud.npy
+    features N(0,1) [F,16,29]: AudioNet -> AudioAttNet (8-frame window) -> HeadNeRF_Audio(aud_smo, label), frame i on rank
+    i mod N, no communication (every rank holds the tiny feature file).  `value` = frames/s of the whole job with
+    the features resident in HBM; `e2e` copies each frame's window + label from pinned host memory and reads the 512x512
+    image back inside the timed region."""
+    import torch
+    from hfa_gp_b200.frame_loop import FrameLoop, audio_windows
+    from hfa_gp_b200.networks.headnerf import AudioAttNet, AudioNet, HeadNeRF_Audio
+    from hfa_gp_b200 import cam_utils
+
+    ns = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='', params_len=64,
+                            synthetic_generator=True, generator_seed=0)
+    torch.manual_seed(0)
+    model = HeadNeRF_Audio(ns, ENC_SIZE, dev, 512, DIM_SHAPE, 'bench', './').to(dev).eval().requires_grad_(False)
+    aud_net, aud_att = AudioNet(64, 16).to(dev).eval(), AudioAttNet().to(dev).eval()
+    g = torch.Generator().manual_seed(99)                        # every rank draws the same "aud.npy"
+    auds = torch.randn(frames_total, 16, 29, generator=g)
+    labels = cam_utils.cam_sampler(frames_total, 'cpu', generator=g)
+    host_pad = audio_windows(auds, 8).pin_memory()
+    host_labels = labels.pin_memory()
+    dev_pad, dev_labels = host_pad.to(dev), host_labels.to(dev)
+    host_out = torch.empty(1, 3, 512, 512).pin_memory()
+    loop = FrameLoop(model, batch=1, size=ENC_SIZE, device=dev, drive='audio', aud_net=aud_net, aud_att=aud_att)
+    mine = list(range(rank, frames_total, world))
+    for i in mine[:5]:
+        loop(dev_pad[i:i + 8], dev_labels[i:i + 1], mutate_label=False)
+    _barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in mine:
+        loop(dev_pad[i:i + 8], dev_labels[i:i + 1], mutate_label=False)
+    e1.record()
+    _barrier(world)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in mine:
+        host_out.copy_(loop(host_pad[i:i + 8], host_labels[i:i + 1]), non_blocking=True)
+    f1.record()
+    _barrier(world)
+    ms, ms_e2e = _max_over_ranks([e0.elapsed_time(e1), f0.elapsed_time(f1)], dev, world)
+    rec = {
+        'workload': 'configs[4]: run_recon_video_audio, %d-frame reenactment from synthetic aud.npy [F,16,29], AudioNet + '
+                    'AudioAttNet(8-frame window) + HeadNeRF_Audio, 512x512, frame i -> rank i mod N' % frames_total,
+        'value': frames_total / (ms / 1e3), 'unit': UNIT, 'frames': frames_total, 'n_gpus': world,
+        'ms_per_frame_per_gpu': ms / len(mine), 'gpu_launches_per_frame': loop.launches_per_replay,
+        'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': (8 * 16 * 29 + 25) * 4,
+                'd2h_bytes_per_step': 3 * 512 * 512 * 4},
+        'dtype': DTYPE, 'scaling': 'strong (fixed clip, frames sharded)',
+    }
+    del loop, model
+    torch.cuda.empty_cache()
+    return rec
+
+
+def train_bench(args, rank, world, local_rank):
+    """--workload train: the training step as its own JSON line (configs[2] trainer_rgb at any N, or with
+    --trainer 3dmm configs[3]); the headline line carries the same record under "train"."""
+    import torch
+    import torch.distributed as dist
+    from hfa_gp_b200 import _cabi
 
     _cabi.lib()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    bs = args.frames_per_step if args.frames_per_step > 1 else 2          # train_rgb.py:164 default batch 2
-    ns = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='',
-                            synthetic_generator=True, generator_seed=0, batch_size=bs * world, size=ENC_SIZE,
-                            latent_dim_style=512, latent_dim_shape=DIM_SHAPE, run_id='bench', emb_dir='./', lr=3e-4)
-    torch.manual_seed(0)
-    tr = trainer_rgb.Trainer(ns, dev, local_rank)
-    if args.tune_generator:
-        tr.tune_generator()
-    g = torch.Generator().manual_seed(4321 + rank)
-    total = args.warmup + args.steps
-    host_frames = (torch.rand(total, bs, 3, ENC_SIZE, ENC_SIZE, generator=g) * 2 - 1).pin_memory()
-    host_labels = torch.stack([trainer_rgb.cam_sampler(bs, 'cpu') for _ in range(total)]).pin_memory()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step(i):
-        real = host_frames[i].to(dev, non_blocking=True)
-        label = host_labels[i].to(dev, non_blocking=True)
-        l2, lp, _ = tr.gen_update(real, label)
-        return l2, lp
-
-    for i in range(args.warmup):
-        step(i)
+    bs = args.frames_per_step if args.frames_per_step > 1 else (2 if args.trainer == 'rgb' else max(8 // world, 1))
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
-    n0 = ops.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        l2, lp = step(args.warmup + i)
-    loss_host = float(l2.detach()) + float(lp.detach())                  # D2H read of the step's result inside the timed region
-    e1.record()
-    barrier()
+    rec = train_record(rank, world, dev, args.steps, args.warmup, trainer=args.trainer, per_rank_batch=bs,
+                       tune_generator=args.tune_generator)
     clocks = sampler.stop()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t)
     if rank == 0:
-        frames = args.steps * bs * world
-        v = frames / (ms / 1e3)
         print(json.dumps({
-            'metric': 'training frames/sec (whole job), trainer_rgb.gen_update', 'value': v, 'unit': UNIT, 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'configs[2]: trainer_rgb.gen_update, 512x512 render pooled to 256, latent_dim_shape=50, '
-                                   'MSE+LPIPS(alex, random-init), Adam, generator ' + ('unfrozen (tune_generator)' if args.tune_generator else 'frozen'),
-                       'per_rank_batch': bs,
-                       'exchange': 'one flat all-reduce of %d gradient floats per step' % tr.g_optim.live_elements()
+            'metric': 'training frames/sec (whole job), trainer_%s.gen_update' % args.trainer, 'value': rec['value'], 'unit': UNIT,
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': rec['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak' if args.trainer == 'rgb' else 'strong', 'vs_baseline': None,
+            'dtype': DTYPE, 'data': 'synthetic',
+            'config': {'workload': rec['workload'], 'per_rank_batch': bs,
+                       'exchange': 'one flat all-reduce of %d gradient floats per step' % rec['allreduce_floats_per_step']
                                    if world > 1 else 'none (1 rank)',
                        'l2': 'per-step working set exceeds the 126 MB L2; no flush'},
             'clocks': clocks,
-            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': bs * (3 * ENC_SIZE * ENC_SIZE + 25) * 4, 'd2h_bytes_per_step': 8},
-            'gpu_launches': ops.launch_count() - n0, 'final_loss': loss_host}))
+            'e2e': {'value': rec['value'], 'unit': UNIT, 'h2d_bytes_per_step': rec['h2d_bytes_per_step'], 'd2h_bytes_per_step': 8},
+            'gpu_launches': int(rec['gpu_launches_per_step'] * args.steps), 'final_loss': rec['final_loss']}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -318,6 +414,9 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='drive the frame loop eagerly instead of replaying the CUDA graph')
     ap.add_argument('--tune-generator', action='store_true',
                     help="with --workload train: the post-tune_iter regime (generator unfrozen, train_rgb.py:132-134)")
+    ap.add_argument('--trainer', default='rgb', choices=['rgb', '3dmm'], help="with --workload train")
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the "train" (configs[2]/[3]) and "reenact" (configs[4]) sub-records of the headline line')
     ap.add_argument('--workload', default='infer', choices=['infer', 'train'],
                     help="'infer' = configs[1] (the headline line); 'train' = configs[2]/[3] training step")
     args = ap.parse_args()
@@ -444,6 +543,28 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
+
+    # ---- (d) a >= 1 s confirmation loop of the same replay (the K-step region above is tens of milliseconds)
+    n_confirm = max(int(1200.0 / max(ms / args.steps, 0.1)), args.steps)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(n_confirm):
+        loop(dev_frames[args.warmup + i % args.steps], dev_labels[args.warmup + i % args.steps], mutate_label=False)
+    c1.record()
+    barrier()
+    ms_confirm, = _max_over_ranks([c0.elapsed_time(c1)], dev, world)
+
+    # ---- (e) the other configs of BASELINE.json through the same launch: training step and audio reenactment
+    extras = {}
+    if not args.no_extras:
+        del loop
+        torch.cuda.empty_cache()
+        if world == 1:
+            extras['train'] = train_record(rank, world, dev, steps=5, warmup=3, trainer='rgb', per_rank_batch=2)
+        else:
+            extras['train'] = train_record(rank, world, dev, steps=5, warmup=3, trainer='3dmm', per_rank_batch=max(8 // world, 1))
+        extras['reenact'] = reenact_record(rank, world, dev, frames_total=1000)
     frames = args.steps * fps_ * world
     value = frames / (ms / 1e3)
     e2e = frames / (ms_e2e / 1e3)
@@ -492,7 +613,10 @@ def main():
             'kernel_ms_per_frame': {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])[:10]},
             'cabi_gpu_ms_per_frame': sum(kernel_ms.values()),
             'event_bracket_overhead_us': 1e3 * event_overhead_ms,
+            'confirm': {'frames_per_rank': n_confirm, 'ms_per_step': ms_confirm / n_confirm,
+                        'value': n_confirm * fps_ * world / (ms_confirm / 1e3)},
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_sample()
         print(json.dumps(line))

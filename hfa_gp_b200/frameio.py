@@ -60,8 +60,10 @@ def from_uint8(frames: torch.Tensor) -> torch.Tensor:
 
 class FrameSink:
     """Asynchronous egress: ``push(image)`` converts on the render stream, then copies device->pinned host on a side
-    stream; ``pop()`` hands back the oldest finished frame as a ``[H,W,3]`` uint8 numpy array (a view of the pinned
-    slot, valid until ``depth`` more frames have been pushed)."""
+    stream; ``pop()`` hands back the oldest finished frame as a ``[N,H,W,3]`` uint8 numpy array that OWNS its bytes (a
+    copy out of the pinned slot: the slot itself is reused by the next ``push`` that wraps onto it, by asynchronous DMA).
+    Slot reuse is ordered on the device as well: the conversion into a device slot waits for the previous device->host
+    copy out of it."""
 
     def __init__(self, height: int, width: int, channels: int = 3, batch: int = 1, depth: int = 4,
                  mode: str = 'save_image', device=None):
@@ -70,7 +72,7 @@ class FrameSink:
         shape = (batch, height, width, channels)
         self.dev = [torch.empty(shape, device=self.device, dtype=torch.uint8) for _ in range(depth)]
         self.host = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(depth)]
-        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [None] * depth                     # device->host copy of the slot's current frame
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.head = self.tail = 0
 
@@ -78,12 +80,15 @@ class FrameSink:
         if self.head - self.tail >= self.depth:
             raise HfagpError('FrameSink is full: pop() finished frames before pushing more')
         s = self.head % self.depth
+        if self.done[s] is not None:                   # the previous copy out of dev[s] must have read it
+            torch.cuda.current_stream(self.device).wait_event(self.done[s])
         to_uint8(image, self.mode, out=self.dev[s])
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(ready)
             self.host[s].copy_(self.dev[s], non_blocking=True)
+            self.done[s] = torch.cuda.Event()
             self.done[s].record()
         self.head += 1
 
@@ -92,19 +97,23 @@ class FrameSink:
             return None
         s = self.tail % self.depth
         self.done[s].synchronize()
+        frame = self.host[s].numpy().copy()            # the slot is free for the next push from here on
         self.tail += 1
-        return self.host[s].numpy()
+        return frame
 
     def drain(self) -> List:
         out = []
         while self.tail < self.head:
-            out.append(self.pop().copy())
+            out.append(self.pop())
         return out
 
 
 class FrameFeeder:
     """Asynchronous ingress: decoded uint8 frames ``[N,H,W,3]`` (numpy or CPU tensor) are staged in pinned memory,
-    copied host->device on a side stream and normalised on the device; ``next()`` returns fp32 ``[N,3,H,W]``."""
+    copied host->device on a side stream and normalised on the device; ``next()`` returns fp32 ``[N,3,H,W]``.
+    A slot is reused only when its previous occupants are done with it: the host write waits for the previous
+    host->device copy out of the pinned buffer, and the copy into the device buffer waits (on the device) for the
+    ``from_uint8`` kernel that last read it — a GPU that lags the host cannot see frames overwritten."""
 
     def __init__(self, height: int, width: int, channels: int = 3, batch: int = 1, depth: int = 4, device=None):
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
@@ -112,7 +121,8 @@ class FrameFeeder:
         self.depth = depth
         self.host = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(depth)]
         self.dev = [torch.empty(shape, device=self.device, dtype=torch.uint8) for _ in range(depth)]
-        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.ready = [None] * depth                    # host->device copy of the slot's current frame
+        self.consumed = [None] * depth                 # from_uint8 of the slot's previous frame (main stream)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.head = self.tail = 0
 
@@ -120,9 +130,14 @@ class FrameFeeder:
         if self.head - self.tail >= self.depth:
             raise HfagpError('FrameFeeder is full: consume frames with next() first')
         s = self.head % self.depth
+        if self.ready[s] is not None:
+            self.ready[s].synchronize()                # the DMA out of host[s] has finished: safe to overwrite it
         self.host[s].copy_(torch.as_tensor(frames).reshape(self.host[s].shape))
         with torch.cuda.stream(self.copy_stream):
+            if self.consumed[s] is not None:
+                self.copy_stream.wait_event(self.consumed[s])   # the kernel that read dev[s] has finished
             self.dev[s].copy_(self.host[s], non_blocking=True)
+            self.ready[s] = torch.cuda.Event()
             self.ready[s].record()
         self.head += 1
 
@@ -130,6 +145,10 @@ class FrameFeeder:
         if self.tail == self.head:
             return None
         s = self.tail % self.depth
-        torch.cuda.current_stream(self.device).wait_event(self.ready[s])
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[s])
+        out = from_uint8(self.dev[s])
+        self.consumed[s] = torch.cuda.Event()
+        self.consumed[s].record(cur)
         self.tail += 1
-        return from_uint8(self.dev[s])
+        return out

@@ -19,6 +19,8 @@ The LPIPS network itself is frozen (``.eval()``, ``requires_grad_(False)``), as 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -80,10 +82,23 @@ TAPS_5X5 = _taps(5, 2)
 class LPIPS(nn.Module):
     CHNS = (64, 192, 384, 256, 256)
 
-    def __init__(self, net='alex', seed=0, verbose=False):
+    def __init__(self, net='alex', seed=0, verbose=False, weights=None, synthetic=None):
+        """``weights``: path of a ``state_dict`` of the pip ``lpips`` package's ``LPIPS(net='alex')`` (its key names are kept
+        here: ``net.slice*.N.{weight,bias}``, ``lin*.model.1.weight``); default: env ``HFAGP_LPIPS_WEIGHTS``.
+        Without weights the constructor RAISES — a randomly initialised AlexNet is a different loss — unless
+        ``synthetic=True`` / env ``HFAGP_SYNTHETIC_LPIPS=1`` asks for the seeded random init of the synthetic benchmarks
+        (same policy as ``load_G_official`` for the generator pickle)."""
         super().__init__()
         if net != 'alex':
             raise ValueError("only LPIPS(net='alex') is on the HFA-GP path (trainer_rgb.py:62)")
+        weights = weights or os.environ.get('HFAGP_LPIPS_WEIGHTS')
+        if synthetic is None:
+            synthetic = os.environ.get('HFAGP_SYNTHETIC_LPIPS') == '1'
+        if not weights and not synthetic:
+            raise FileNotFoundError(
+                "LPIPS(net='alex') needs the pretrained weights of the pip `lpips` package: pass weights=<state_dict file> "
+                'or set HFAGP_LPIPS_WEIGHTS; for synthetic runs pass synthetic=True or set HFAGP_SYNTHETIC_LPIPS=1 '
+                '(seeded random init, NOT the perceptual loss the reference trains with)')
         with torch.random.fork_rng():
             torch.manual_seed(seed)
             self.scaling_layer = _ScalingLayer()
@@ -93,6 +108,10 @@ class LPIPS(nn.Module):
                 lin.model[1].weight.data.abs_()
         for k, lin in enumerate(self.lins):
             setattr(self, f'lin{k}', lin)
+        if weights:
+            sd = torch.load(weights, map_location='cpu', weights_only=True)
+            self.load_state_dict(sd.get('state_dict', sd) if isinstance(sd, dict) else sd)
+        self.synthetic = not weights
         self.requires_grad_(False)
         self._pk, self._pk_key = None, None
 

@@ -51,8 +51,10 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, int]
     if out is None:
         out = torch.empty((n, out_h, out_w, cout), device=x.device, dtype=torch.float32)
     taps = tuple(taps)
+    # per-call scalars that change during training (noise_strength after tune_generator) are NOT part of the key: they
+    # are written into the cached descriptor right before the call
     key = (n, h, wd, cin, cout, oh, ow, in_stride, out_h, out_w, out_stride, out_off, taps, w_batch_stride, act,
-           act_gain, clamp, noise_gain, residual_scale, up_img is not None)
+           act_gain, clamp, residual_scale, up_img is not None)
 
     def build():
         d = ConvDesc()
@@ -70,6 +72,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, int]
         return d
 
     d = _conv_desc(key, build)
+    d.noise_gain = noise_gain
     _ok(_cabi.lib().hfagp_conv2d_fwd(C.byref(d), ptr(x), ptr(w), ptr(dcoef), ptr(noise), ptr(bias), ptr(residual),
                                        ptr(up_img), ptr(out), stream()), 'hfagp_conv2d_fwd')
     return out
@@ -385,7 +388,7 @@ def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_strid
             out = torch.empty((n, out_h, out_w, cout), device=x.device, dtype=torch.float32)
     wbs = w_taps_total * cout * cin if w_batched else 0
     key = ('tc', n, h, wd, cin, cout, oh, ow, in_stride, out_h, out_w, out_stride, out_off, taps, wbs, act, act_gain,
-           clamp, noise_gain, residual_scale, up_img is not None)
+           clamp, residual_scale, up_img is not None)
 
     def build():
         d = ConvDesc()
@@ -403,6 +406,7 @@ def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_strid
         return d
 
     d = _conv_desc(key, build)
+    d.noise_gain = noise_gain
     is_split = isinstance(out, Split)
     if rgb_acc is not None:
         _ok(_cabi.lib().hfagp_conv2d_tc_rgb_fwd(C.byref(d), ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total,

@@ -14,7 +14,7 @@ One training step (``/root/reference/code/trainer_rgb.py:73-98``)::
 
 Differences kept on purpose: gradients are averaged over ranks every step (the reference's RGB trainer bypasses its
 DDP wrapper and lets replicas drift); ``tune_generator()`` flips ``requires_grad`` as upstream but
-generator-weight gradients (the post-``tune_iter`` regime) are not built yet, so the next step raises.
+every generator parameter then receives its gradient (hfa_gp_b200/autograd.py) and joins the flat Adam update.
 """
 from __future__ import annotations
 
@@ -88,7 +88,12 @@ class _TrainerBase(nn.Module):
         optim = FlatAdam(self.gen.parameters(), lr=args.lr, live_first=lambda p: id(p) not in gen_ids)
         for p in gen.generator.parameters():
             p.requires_grad = False
-        self.lpips_loss = LPIPS(net='alex').to(device).eval()
+        # pretrained LPIPS-alex weights: args.lpips_weights / HFAGP_LPIPS_WEIGHTS; the seeded random init only when the run
+        # is declared synthetic (args.synthetic_lpips, args.synthetic_generator or HFAGP_SYNTHETIC_LPIPS=1) — else it raises
+        synthetic = getattr(args, 'synthetic_lpips', None)
+        if synthetic is None and getattr(args, 'synthetic_generator', False):
+            synthetic = True
+        self.lpips_loss = LPIPS(net='alex', weights=getattr(args, 'lpips_weights', None), synthetic=synthetic).to(device).eval()
         self.face_pool = FacePool(args.size)
         return optim
 

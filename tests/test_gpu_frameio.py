@@ -74,3 +74,35 @@ def test_sink_and_feeder_round_trip():
     assert feeder.next() is None
     for f, o in zip(frames, outs):
         assert torch.equal(o.cpu(), frameio_ref.to_tensor_normalize(f))
+
+
+@pytest.mark.gpu
+def test_rings_survive_a_gpu_that_lags_the_host():
+    """with the GPU held busy (a long spin kernel in front) the host wraps the rings several times; no frame
+    may be corrupted or duplicated, and a popped frame must not change when later pushes reuse its slot."""
+    from hfa_gp_b200 import frameio
+    depth, n = 2, 9
+    feeder = frameio.FrameFeeder(32, 32, depth=depth)
+    g = torch.Generator().manual_seed(3)
+    frames = [torch.randint(0, 256, (1, 32, 32, 3), dtype=torch.uint8, generator=g) for _ in range(n)]
+    torch.cuda._sleep(int(2e8))                       # ~100 ms of GPU work queued ahead of everything below
+    outs = []
+    for f in frames:
+        feeder.push(f.numpy())
+        outs.append(feeder.next())                    # enqueued behind the spin: the GPU has consumed nothing yet
+    torch.cuda.synchronize()
+    for f, o in zip(frames, outs):
+        assert torch.equal(o.cpu(), frameio_ref.to_tensor_normalize(f))
+    sink = frameio.FrameSink(32, 32, depth=depth, mode='save_image')
+    imgs = [_img(40 + i, 1, 32, 32).cuda() for i in range(n)]
+    torch.cuda._sleep(int(2e8))
+    popped = []
+    for i, im in enumerate(imgs):
+        if i >= depth:
+            popped.append(sink.pop())
+        sink.push(im)
+    first = popped[0].copy()
+    popped += sink.drain()
+    assert (popped[0] == first).all()                 # later pushes wrapped onto its slot: the popped frame owns its bytes
+    for im, p_ in zip(imgs, popped):
+        assert (torch.from_numpy(p_) == frameio_ref.save_image_uint8(im.cpu())).all()

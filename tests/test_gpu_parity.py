@@ -546,3 +546,67 @@ def test_frame_loop_full_size_properties_and_egress():
     srt = tap['sort_idx'].long()
     assert bool((srt.sort(dim=-1).values == torch.arange(srt.shape[-1], device=srt.device)).all())   # a permutation
     assert pu.rel_err(out['image'], a) < 5e-4                           # eager synthesis == graph replay (same caveat)
+
+
+@pytest.mark.parametrize('drive', ['3dmm', 'audio'])
+def test_driven_frame_loops_match_oracle(drive):
+    """configs[4] / run_recon_video_{3dmm,audio}.py: the graph-captured frame loop of the driven avatars
+    (FrameLoop(drive=...)) against the oracle run end to end on the CPU — AudioNet -> AudioAttNet (8-frame window,
+    zero-padded at the clip ends exactly as run_recon_video_audio.py:323-339) -> Weights_3DMM -> get_latent ->
+    synthesis — at the first, an interior and the last frame of a short clip."""
+    import argparse
+    from hfa_gp_b200.frame_loop import FrameLoop, audio_windows
+    from hfa_gp_b200.networks.headnerf import AudioAttNet, AudioNet, HeadNeRF_3DMM, HeadNeRF_Audio
+    cfg = eg3d_ref.small14_config()
+    plen = 76 if drive == '3dmm' else 64
+    args = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='', params_len=plen,
+                              synthetic_generator=True, generator_seed=0, generator_config=pu.product_config(cfg))
+    torch.manual_seed(0)
+    cls = HeadNeRF_3DMM if drive == '3dmm' else HeadNeRF_Audio
+    model = cls(args, 64, 'cuda', 512, 50, 'x', './').cuda().eval().requires_grad_(False)
+    ref_gen = eg3d_ref.make_generator(cfg, seed=0)
+    ref_gen.load_state_dict({k: v.cpu() for k, v in model.generator.state_dict().items()})
+    g = torch.Generator().manual_seed(11)
+    rays = cfg.nrr ** 2
+    jit, u = torch.rand(1, rays, cfg.depth_res, 1, generator=g), torch.rand(rays, cfg.depth_res_importance, generator=g)
+    model.generator.fixed_draws = (jit.cuda(), u.cuda())
+    head_sd = {k: v.cpu() for k, v in model.weights_3dmm.state_dict().items()}
+    bases, delta = model.bases.detach().cpu(), model.delta.detach().cpu()
+
+    def oracle_image(weights_in, label):
+        with torch.no_grad():
+            w = hfagp_ref.weights_3dmm_ref(head_sd, weights_in)
+            lat = hfagp_ref.get_latent_ref(bases, delta, w)
+            lab = hfagp_ref.flip_label_(label.clone())
+            return ref_gen.synthesis(lat, lab, noise_mode='const', jitter_coarse=jit, u_fine=u)['image']
+
+    if drive == '3dmm':
+        loop = FrameLoop(model, batch=1, size=64, drive='3dmm', params_len=plen)
+        for seed in (1, 2):
+            params = torch.randn(1, plen, generator=g)
+            label = hfagp_ref.synthetic_labels(1, seed=seed)
+            got = loop(params.cuda(), label.cuda()).clone()
+            assert pu.rel_err(got, oracle_image(params, label)) < pu.REL_TOL
+        return
+    torch.manual_seed(1)
+    aud_net, aud_att = AudioNet(64, 16).cuda().eval(), AudioAttNet().cuda().eval()
+    sd_net = {k: v.cpu() for k, v in aud_net.state_dict().items()}
+    sd_att = {k: v.cpu() for k, v in aud_att.state_dict().items()}
+    frames = 11
+    auds = torch.randn(frames, 16, 29, generator=g)
+    padded = audio_windows(auds.cuda(), 8)
+    loop = FrameLoop(model, batch=1, size=64, drive='audio', aud_net=aud_net, aud_att=aud_att)
+    for i in (0, 5, frames - 1):
+        # the reference's window, literally (run_recon_video_audio.py:323-339)
+        left, right = i - 4, i + 4
+        pad_l, pad_r = max(-left, 0), max(right - frames, 0)
+        win = auds[max(left, 0):min(right, frames)]
+        win = torch.cat((torch.zeros_like(win)[:pad_l], win), 0) if pad_l else win
+        win = torch.cat((win, torch.zeros_like(win)[:pad_r]), 0) if pad_r else win
+        assert torch.equal(padded[i:i + 8].cpu(), win)
+        with torch.no_grad():
+            feats = hfagp_ref.audionet_ref(sd_net, win)
+            smo = hfagp_ref.audioattnet_ref(sd_att, feats)
+        label = hfagp_ref.synthetic_labels(1, seed=20 + i)
+        got = loop(padded[i:i + 8], label.cuda()).clone()
+        assert pu.rel_err(got, oracle_image(smo.unsqueeze(0), label)) < pu.REL_TOL

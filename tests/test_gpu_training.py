@@ -157,7 +157,7 @@ def _oracle_lpips(native):
 def test_lpips_value_and_gradient_match_oracle(b, size):
     """hfa_gp_b200.lpips.LPIPS (stem / tcgen05 convs / max-pools / heads and their backward) vs the torch oracle."""
     from hfa_gp_b200.lpips import LPIPS
-    native = LPIPS(net='alex', seed=3).cuda().eval()
+    native = LPIPS(net='alex', seed=3, synthetic=True).cuda().eval()
     with torch.no_grad():                                   # exercise the biases (torch inits them non-zero already)
         for c in native.net.convs():
             c.bias.mul_(3.0)

@@ -147,3 +147,48 @@ def test_bench_counts_every_conv_tc_entry_point():
     header = open(os.path.join(ROOT, 'include', 'hfagp.h')).read()
     for e in entries:
         assert e in header
+
+
+def test_audio_windows_equal_the_reference_slicing():
+    """frame_loop.audio_windows: out[i:i+smo] must be the window run_recon_video_audio.py:323-339 /
+    trainer_audio.py:68-84 builds for frame i (slice [i-half, i+half), zero-padded where it leaves the clip)."""
+    from hfa_gp_b200.frame_loop import audio_windows
+    g = torch.Generator().manual_seed(0)
+    for frames, smo in ((10, 8), (3, 8), (9, 4)):
+        auds = torch.randn(frames, 16, 29, generator=g)
+        padded = audio_windows(auds, smo)
+        half = int(smo / 2)
+        for i in range(frames):
+            left_i, right_i = i - half, i + half
+            pad_left = pad_right = 0
+            if left_i < 0:
+                pad_left, left_i = -left_i, 0
+            if right_i > frames:
+                pad_right, right_i = right_i - frames, frames
+            win = auds[left_i:right_i]
+            if pad_left > 0:
+                win = torch.cat((torch.zeros_like(win)[:pad_left], win), dim=0)
+            if pad_right > 0:
+                win = torch.cat((win, torch.zeros_like(win)[:pad_right]), dim=0)
+            if win.shape[0] == smo:       # (a clip shorter than the window cannot fill it upstream either)
+                assert torch.equal(padded[i:i + smo], win)
+
+
+def test_lpips_refuses_to_run_without_weights(monkeypatch, tmp_path):
+    """a drop-in training run must not silently optimise a random-feature loss.  LPIPS() raises unless pretrained
+    weights are given (argument or HFAGP_LPIPS_WEIGHTS) or the run is declared synthetic; a saved state_dict loads by name."""
+    from hfa_gp_b200.lpips import LPIPS
+    monkeypatch.delenv('HFAGP_LPIPS_WEIGHTS', raising=False)
+    monkeypatch.delenv('HFAGP_SYNTHETIC_LPIPS', raising=False)
+    with pytest.raises(FileNotFoundError):
+        LPIPS(net='alex')
+    a = LPIPS(net='alex', seed=7, synthetic=True)
+    assert a.synthetic
+    path = tmp_path / 'lpips_alex.pt'
+    torch.save(a.state_dict(), path)
+    b = LPIPS(net='alex', seed=1, weights=str(path))
+    assert not b.synthetic
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    monkeypatch.setenv('HFAGP_SYNTHETIC_LPIPS', '1')
+    assert LPIPS(net='alex').synthetic
