@@ -247,7 +247,7 @@ def _max_over_ranks(vals, dev, world):
     return t.tolist()
 
 
-def train_record(rank, world, dev, steps, warmup, trainer='rgb', per_rank_batch=2, tune_generator=False):
+def train_record(rank, world, dev, steps, warmup, trainer='rgb', per_rank_batch=2, tune_generator=False, step_graph=True):
     """One training workload through the reference's Trainer surface, timed on the device (max over ranks):
     trainer='rgb'  BASELINE.json configs[2]: trainer_rgb.gen_update (encoder 256, latent_dim_shape 50, MSE + LPIPS-alex,
                    Adam; generator frozen unless tune_generator), batch `per_rank_batch` per rank (train_rgb.py:164: 2)
@@ -267,6 +267,8 @@ def train_record(rank, world, dev, steps, warmup, trainer='rgb', per_rank_batch=
     tr = (trainer_3dmm if trainer == '3dmm' else trainer_rgb).Trainer(ns, dev, rank)
     if tune_generator:
         tr.tune_generator()
+    if step_graph:
+        tr.enable_step_graph(warmup=2)
     optim = tr.w_optim if trainer == '3dmm' else tr.g_optim
     g = torch.Generator().manual_seed(4321 + rank)
     total = warmup + steps
@@ -305,8 +307,10 @@ def train_record(rank, world, dev, steps, warmup, trainer='rgb', per_rank_batch=
         'value': frames / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps, 'warmup': warmup,
         'per_rank_batch': bs, 'global_batch': bs * world, 'n_gpus': world,
         'allreduce_floats_per_step': optim.live_elements() if world > 1 else 0,
-        'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8, 'gpu_launches_per_step': (ops.launch_count() - n0) / steps,
+        'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
+        'gpu_launches_per_step': getattr(tr, 'graph_launches', None) if getattr(tr, '_graph', None) is not None else (ops.launch_count() - n0) / steps,
         'dtype': DTYPE, 'final_loss': loss_host,
+        'launch': 'one CUDA graph replay per step (Trainer.enable_step_graph)' if step_graph and not tune_generator else 'eager',
     }
     del tr, optim
     torch.cuda.empty_cache()
@@ -384,7 +388,7 @@ def train_bench(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     rec = train_record(rank, world, dev, args.steps, args.warmup, trainer=args.trainer, per_rank_batch=bs,
-                       tune_generator=args.tune_generator)
+                       tune_generator=args.tune_generator, step_graph=not args.no_graph)
     clocks = sampler.stop()
     if rank == 0:
         print(json.dumps({
@@ -561,9 +565,9 @@ def main():
         del loop
         torch.cuda.empty_cache()
         if world == 1:
-            extras['train'] = train_record(rank, world, dev, steps=5, warmup=3, trainer='rgb', per_rank_batch=2)
+            extras['train'] = train_record(rank, world, dev, steps=10, warmup=5, trainer='rgb', per_rank_batch=2)
         else:
-            extras['train'] = train_record(rank, world, dev, steps=5, warmup=3, trainer='3dmm', per_rank_batch=max(8 // world, 1))
+            extras['train'] = train_record(rank, world, dev, steps=10, warmup=5, trainer='3dmm', per_rank_batch=max(8 // world, 1))
         extras['reenact'] = reenact_record(rank, world, dev, frames_total=1000)
     frames = args.steps * fps_ * world
     value = frames / (ms / 1e3)

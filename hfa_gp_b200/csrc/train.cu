@@ -120,7 +120,11 @@ __global__ void mse_bwd_kernel(long long count, const float* __restrict__ a, con
 __global__ void __launch_bounds__(256) adam_kernel(long long count, float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ m, float* __restrict__ v, float grad_scale,
                                                   float omb1, float beta2, float omb2, float eps, float wd,
-                                                  float step_size, float bc2_sqrt) {
+                                                  float step_size, float bc2_sqrt, const float* __restrict__ sched) {
+  if (sched) {                                        // step-dependent scalars from device memory (CUDA-graph replays)
+    step_size = __ldg(sched);
+    bc2_sqrt = __ldg(sched + 1);
+  }
   const long long c4 = count >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   auto upd = [&](float& pv, float gv, float& mv, float& vv) {
@@ -210,7 +214,29 @@ extern "C" int hfagp_adam_step(long long count, float* p, const float* g, float*
   if (blocks < 1) blocks = 1;
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(count, p, g, m, v, grad_scale, (float)(1.0 - beta1), (float)beta2,
                                                         (float)(1.0 - beta2), (float)eps, (float)weight_decay, step_size,
-                                                        bc2_sqrt);
+                                                        bc2_sqrt, nullptr);
+  HFAGP_CHECK_LAUNCH("adam_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_adam_sched(double lr, double beta1, double beta2, long long step, float* sched_host) {
+  HFAGP_CHECK_ARG(sched_host && step >= 1, "adam_sched: bad args");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  sched_host[0] = (float)(lr / bc1);
+  sched_host[1] = (float)sqrt(bc2);
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_adam_step_dev(long long count, float* p, const float* g, float* m, float* v, float grad_scale,
+                                   double beta1, double beta2, double eps, double weight_decay, const float* sched,
+                                   void* stream) {
+  HFAGP_CHECK_ARG(p && g && m && v && sched && count > 0, "adam_step_dev: bad args");
+  HFAGP_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step_dev: buffers must be 16-byte aligned");
+  int blocks = cdiv(count >> 2, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(count, p, g, m, v, grad_scale, (float)(1.0 - beta1), (float)beta2,
+                                                        (float)(1.0 - beta2), (float)eps, (float)weight_decay, 0.f, 1.f, sched);
   HFAGP_CHECK_LAUNCH("adam_kernel");
   return HFAGP_OK;
 }

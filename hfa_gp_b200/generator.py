@@ -211,12 +211,17 @@ class TriPlaneGenerator(nn.Module):
     def _fingerprint(self):
         dev = None
         ver = 0
+        live = False
         for p in self.parameters():
             ver += p._version
             dev = p.device
+            live = live or p.requires_grad
         for b in self.buffers():
             ver += b._version
-        return (str(dev), ver, ops.param_epoch[0])
+        # optimiser steps write parameters through the C ABI without touching torch's version counters (param_epoch); a
+        # FROZEN generator is not among the parameters they update, so its packed weights survive the step (re-packing
+        # 26 layers — and reading ~20 noise strengths back to the host — every step is what made training host-bound)
+        return (str(dev), ver, ops.param_epoch[0] if live else -1)
 
     def _layers_in_order(self):
         cfg = self.cfg

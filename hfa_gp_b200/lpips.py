@@ -117,7 +117,8 @@ class LPIPS(nn.Module):
 
     # ------------------------------------------------------------------ kernel-layout weights (cached)
     def _packed(self):
-        key = (tuple(p._version for p in self.parameters()), str(next(self.parameters()).device), ops.param_epoch[0])
+        # (LPIPS weights are never trained: optimiser steps — ops.param_epoch — do not invalidate them)
+        key = (tuple(p._version for p in self.parameters()), str(next(self.parameters()).device))
         if self._pk is not None and self._pk_key == key:
             return self._pk
         convs = self.net.convs()

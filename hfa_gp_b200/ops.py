@@ -617,3 +617,15 @@ def adam_step(p, g, m, v, *, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_
     """In-place torch.optim.Adam update of the flat buffer ``p`` (see ``hfagp_adam_step``)."""
     _ok(_cabi.lib().hfagp_adam_step(p.numel(), ptr(p), ptr(g), ptr(m), ptr(v), grad_scale, lr, beta1, beta2, eps,
                                       weight_decay, int(step), stream()), 'hfagp_adam_step')
+
+
+def adam_sched(lr, beta1, beta2, step, sched_host, offset=0):
+    """Host only: sched_host[offset:offset+2] = (lr / (1 - beta1^step), sqrt(1 - beta2^step)), as ``hfagp_adam_step``
+    evaluates them (``hfagp_adam_sched``)."""
+    check(_cabi.lib().hfagp_adam_sched(lr, beta1, beta2, int(step), sched_host.data_ptr() + 4 * offset), 'hfagp_adam_sched')
+
+
+def adam_step_dev(p, g, m, v, sched, *, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """``adam_step`` with the step-dependent scalars read from the device pair ``sched`` (``hfagp_adam_step_dev``)."""
+    _ok(_cabi.lib().hfagp_adam_step_dev(p.numel(), ptr(p), ptr(g), ptr(m), ptr(v), grad_scale, beta1, beta2, eps,
+                                          weight_decay, ptr(sched), stream()), 'hfagp_adam_step_dev')

@@ -76,6 +76,10 @@ class FlatAdam:
             p.data = v
             p.grad = self._view(self.flat_grad, i)
         self.steps = [0, 0]                            # Adam step count of the early / late group
+        # step-dependent scalars (lr / (1 - b1^t), sqrt(1 - b2^t)) of both groups: pinned host pair + device copy, read by
+        # hfagp_adam_step_dev so that a captured step can be replayed (step_prepare() refreshes them each step)
+        self._sched_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(4)
+        self._sched_dev = torch.zeros(4, device=dev, dtype=torch.float32)
         self.world = 1
         if dist.is_available() and dist.is_initialized():
             self.world = dist.get_world_size(process_group)
@@ -107,20 +111,41 @@ class FlatAdam:
             if n:
                 dist.all_reduce(self.flat_grad[:n], op=dist.ReduceOp.SUM, group=self.process_group)
 
+    def _spans(self):
+        spans = [(0, self._live_elems, 0)]
+        if self._late_live():
+            spans.append((self._live_elems, self._total, 1))
+        return [(lo, hi, g) for lo, hi, g in spans if hi > lo]
+
     def step(self):
         self.sync_gradients()
         b1, b2 = self.betas
         kw = dict(lr=self.lr, beta1=b1, beta2=b2, eps=self.eps, weight_decay=self.weight_decay,
                   grad_scale=1.0 / self.world)
-        spans = [(0, self._live_elems, 0)]
-        if self._late_live():
-            spans.append((self._live_elems, self._total, 1))
-        for lo, hi, g in spans:
-            if hi > lo:
-                self.steps[g] += 1
-                ops.adam_step(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi],
-                              self.exp_avg_sq[lo:hi], step=self.steps[g], **kw)
+        for lo, hi, g in self._spans():
+            self.steps[g] += 1
+            ops.adam_step(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi],
+                          self.exp_avg_sq[lo:hi], step=self.steps[g], **kw)
         ops.param_epoch[0] += 1                        # packed-weight caches must be rebuilt
+
+    # ---- the same step in two halves, for a training step replayed from a CUDA graph: the host half advances the step
+    # counts and refreshes the device copy of the step-dependent scalars (outside the graph, every step); the device half
+    # (captured once) is the all-reduce + the Adam kernels reading those scalars from device memory
+    def step_prepare(self):
+        b1, b2 = self.betas
+        for _, _, g in self._spans():
+            self.steps[g] += 1
+            ops.adam_sched(self.lr, b1, b2, self.steps[g], self._sched_host, 2 * g)
+        self._sched_dev.copy_(self._sched_host, non_blocking=True)
+        ops.param_epoch[0] += 1
+
+    def step_launch(self):
+        self.sync_gradients()
+        b1, b2 = self.betas
+        for lo, hi, g in self._spans():
+            ops.adam_step_dev(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                              self._sched_dev[2 * g:2 * g + 2], beta1=b1, beta2=b2, eps=self.eps,
+                              weight_decay=self.weight_decay, grad_scale=1.0 / self.world)
 
     # ------------------------------------------------------------------ checkpoints (torch.optim.Adam layout)
     def _group_of(self, i) -> int:

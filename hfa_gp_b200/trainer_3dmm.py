@@ -21,14 +21,16 @@ class Trainer(_TrainerBase):
 
     def gen_update(self, real_image, label, params, person_2=False):
         self.gen.train()
-        self.w_optim.zero_grad()
-        generated_image = self.gen(params, label, person_2)
-        l2_loss, loss_lpips, generated_image = self._losses(real_image, generated_image)
-        l2_loss_3dmm = torch.zeros(1, device=self.device)
-        g_loss = l2_loss_3dmm + l2_loss + loss_lpips
-        g_loss.backward()
-        self.w_optim.step()
-        return l2_loss_3dmm, l2_loss, loss_lpips, generated_image
+
+        def fwd_bwd(real_image, label, params):
+            generated_image = self.gen(params, label, person_2)
+            l2_loss, loss_lpips, generated_image = self._losses(real_image, generated_image)
+            l2_loss_3dmm = torch.zeros(1, device=self.device)
+            g_loss = l2_loss_3dmm + l2_loss + loss_lpips
+            g_loss.backward()
+            return l2_loss_3dmm, l2_loss, loss_lpips, generated_image
+
+        return self._run_step(fwd_bwd, [real_image, label, params], 1, variant=(bool(person_2),))
 
     def sample(self, real_image, label, params, person_2=False):
         with torch.no_grad():

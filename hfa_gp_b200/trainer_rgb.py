@@ -100,6 +100,69 @@ class _TrainerBase(nn.Module):
     def l2_loss(self, real_images, generated_images):
         return MseFn.apply(real_images, generated_images)
 
+    # ------------------------------------------------------------------ the step as ONE CUDA graph (opt-in)
+    def enable_step_graph(self, warmup: int = 3):
+        """Replay ``gen_update`` from a CUDA graph instead of driving its ~900 launches from Python (the eager step is
+        host-bound, above all with 8 ranks sharing one host).  After ``warmup`` eager steps with unchanged input shapes the
+        whole step — gradient memset, encoder / head -> QR -> latent -> generator -> face_pool -> MSE + LPIPS, backward,
+        the flat gradient all-reduce (NCCL, captured) and the Adam kernels — is captured once; later calls copy their
+        inputs into static buffers, refresh Adam's two step-dependent scalars on the device and replay.  Results are
+        those of the eager step (same kernels, same order); the returned losses / image are static buffers overwritten by
+        the next call.  While ``tune_generator()`` has the generator's own weights live the step stays eager (their
+        re-packing reads scalars back to the host)."""
+        self._graph_warmup = warmup
+        self._graph = None
+        self._graph_key = None
+        self._graph_eager_left = warmup
+
+    def _run_step(self, fwd_bwd, tensors, label_pos, variant=()):
+        """zero_grad -> fwd_bwd(*tensors) -> step of every optimiser, eagerly or from the captured graph.
+        ``tensors[label_pos]`` is the label the forward flips in place (headnerf.py:108)."""
+        optims = list(self._optims().values())
+        if getattr(self, '_graph_warmup', None) is not None:
+            key = tuple((tuple(t.shape), t.dtype) for t in tensors) + tuple(variant)
+            if any(o._late_live() for o in optims):
+                key = None                              # generator weights are training: eager
+            if key is not None and key == self._graph_key and self._graph is not None:
+                return self._replay(tensors, label_pos, optims)
+            if key is not None and key == self._graph_key and self._graph_eager_left <= 0:
+                self._capture(fwd_bwd, tensors, optims)
+                return self._replay(tensors, label_pos, optims)
+            if key != self._graph_key:
+                self._graph, self._graph_key, self._graph_eager_left = None, key, self._graph_warmup
+            self._graph_eager_left -= 1
+        for o in optims:
+            o.zero_grad()
+        out = fwd_bwd(*tensors)
+        for o in optims:
+            o.step()
+        return out
+
+    def _capture(self, fwd_bwd, tensors, optims):
+        self._static_in = [t.detach().clone() for t in tensors]
+        ops.param_epoch[0] += 1          # every parameter-derived cache misses inside the capture: packing is captured too
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g):
+            for o in optims:
+                o.zero_grad()
+            self._static_out = fwd_bwd(*self._static_in)
+            for o in optims:
+                o.step_launch()
+        self.graph_launches = ops.launch_count() - n0   # kernels of libhfagp_sm100.so inside one replay
+        self._graph = g
+
+    def _replay(self, tensors, label_pos, optims):
+        for st, t in zip(self._static_in, tensors):
+            st.copy_(t, non_blocking=True)
+        for o in optims:
+            o.step_prepare()
+        self._graph.replay()
+        if label_pos is not None and tensors[label_pos].is_cuda:
+            tensors[label_pos].copy_(self._static_in[label_pos], non_blocking=True)    # the in-place GL flip stays visible
+        return self._static_out
+
     def tune_generator(self):
         for p in self.gen.module.generator.parameters():
             p.requires_grad = True
@@ -157,17 +220,19 @@ class Trainer(_TrainerBase):
 
     def gen_update(self, real_image, label, person_2=False, mask=None):
         self.gen.train()
-        self.g_optim.zero_grad()
-        weights_i = self.gen.module.get_weights(real_image)
-        if isinstance(weights_i, tuple):
-            weights_i = weights_i[0]
-        latent_i = self.gen.module.get_latent(weights_i, person_2)
-        generated_image = self.gen.module.get_image(latent_i, label)
-        l2_loss, loss_lpips, generated_image = self._losses(real_image, generated_image)
-        g_loss = l2_loss + loss_lpips
-        g_loss.backward()
-        self.g_optim.step()
-        return l2_loss, loss_lpips, generated_image
+
+        def fwd_bwd(real_image, label):
+            weights_i = self.gen.module.get_weights(real_image)
+            if isinstance(weights_i, tuple):
+                weights_i = weights_i[0]
+            latent_i = self.gen.module.get_latent(weights_i, person_2)
+            generated_image = self.gen.module.get_image(latent_i, label)
+            l2_loss, loss_lpips, generated_image = self._losses(real_image, generated_image)
+            g_loss = l2_loss + loss_lpips
+            g_loss.backward()
+            return l2_loss, loss_lpips, generated_image
+
+        return self._run_step(fwd_bwd, [real_image, label], 1, variant=(bool(person_2),))
 
     def sample(self, real_image, label, person_2=False):
         with torch.no_grad():

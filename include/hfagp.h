@@ -374,6 +374,14 @@ int hfagp_mse_bwd(long long count, const float* a, const float* b, float scale, 
 int hfagp_adam_step(long long count, float* p, const float* g, float* m, float* v, float grad_scale, double lr,
                     double beta1, double beta2, double eps, double weight_decay, long long step, void* stream);
 
+/* The same update with its two step-dependent scalars read from DEVICE memory, so that a training step captured in a
+ * CUDA graph can be replayed: hfagp_adam_sched (host only, no GPU work) evaluates sched_host[0] = lr / (1 - beta1^step)
+ * and sched_host[1] = sqrt(1 - beta2^step) in double exactly as hfagp_adam_step does; the caller copies the pair to
+ * `sched` (device, 2 floats) on the launching stream before each replay. */
+int hfagp_adam_sched(double lr, double beta1, double beta2, long long step, float* sched_host);
+int hfagp_adam_step_dev(long long count, float* p, const float* g, float* m, float* v, float grad_scale, double beta1,
+                        double beta2, double eps, double weight_decay, const float* sched, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * LPIPS(net='alex') (code/trainer_rgb.py:10,62,86-87 -> pip package `lpips`): what sits between its five AlexNet
  * convolutions, which run on hfagp_conv2d_tc_fwd with the bias + HFAGP_ACT_RELU epilogue.
