@@ -27,7 +27,7 @@ SYMBOLS = [
     'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8',
     'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
     'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd', 'hfagp_conv2d_wgrad_mod', 'hfagp_render_bwd_dec',
-    'hfagp_render_fwd_simt', 'hfagp_adam_sched', 'hfagp_adam_step_dev',
+    'hfagp_render_fwd_simt', 'hfagp_adam_sched', 'hfagp_adam_step_dev', 'hfagp_render_bookkeeping',
 ]
 
 
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     l.hfagp_mse_fwd.argtypes = [C.c_longlong, vp, vp, f32, vp, vp]
     l.hfagp_mse_bwd.argtypes = [C.c_longlong, vp, vp, f32, vp, i32, vp, vp]
     l.hfagp_adam_step.argtypes = [C.c_longlong, vp, vp, vp, vp, f32] + [C.c_double] * 5 + [C.c_longlong, vp]
+    l.hfagp_render_bookkeeping.argtypes = [i32] * 4 + [vp] * 8
     l.hfagp_adam_sched.argtypes = [C.c_double] * 3 + [C.c_longlong, vp]
     l.hfagp_adam_step_dev.argtypes = [C.c_longlong, vp, vp, vp, vp, f32] + [C.c_double] * 4 + [vp, vp]
     l.hfagp_nchw_to_nhwc.argtypes = [i32, i32, i32, i32, vp, vp, vp]

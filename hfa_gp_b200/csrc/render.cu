@@ -380,11 +380,7 @@ __global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(con
       for (int k = lane; k < SF; k += 32) {
         const float u = __ldg(p.u_fine + (size_t)ray * SF + k);
         // searchsorted(cdf[0..NB], u, right=True) = #{cdf[i] <= u}; cdf is non-decreasing (running sum of positives)
-        int ind = 0;
-        for (int len = NB + 1; len > 0;) {
-          const int half = len >> 1;
-          if (cdf[ind + half] <= u) { ind += half + 1; len -= half + 1; } else { len = half; }
-        }
+        const int ind = searchsorted_right(cdf, NB + 1, u);
         const int lo = max(ind - 1, 0), hi = min(ind, NB);
         const float c0 = cdf[lo], c1 = cdf[hi];
         float den = c1 - c0;
@@ -406,30 +402,7 @@ __global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(con
         constexpr int NE = decltype(ne_tag)::value;       // elements per lane = ceil(T / 32)
         float de[NE];
         int rk[NE];
-#pragma unroll
-        for (int e = 0; e < NE; ++e) { de[e] = lane + 32 * e < T ? dep[lane + 32 * e] : 0.f; rk[e] = 0; }
-        for (int j = 0; j < T; ++j) {
-          const float dj = dep[j];
-#pragma unroll
-          for (int e = 0; e < NE; ++e) rk[e] += dj < de[e] ? 1 : 0;
-        }
-        int rsum = 0;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) rsum += lane + 32 * e < T ? rk[e] : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
-        if (rsum != T * (T - 1) / 2) {
-#pragma unroll
-          for (int e = 0; e < NE; ++e) {
-            const int i = lane + 32 * e;
-            int rank = 0;
-            for (int j = 0; j < T; ++j) {
-              const float dj = dep[j];
-              rank += (dj < de[e] || (dj == de[e] && j < i)) ? 1 : 0;
-            }
-            rk[e] = rank;
-          }
-        }
+        stable_ranks<NE>(dep, T, lane, de, rk);
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
           const int i = lane + 32 * e;
@@ -726,6 +699,52 @@ __global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(con
 }  // namespace hfagp
 
 using namespace hfagp;
+
+namespace hfagp {
+// The integer stage of the renderer in isolation, one warp per ray, on caller-supplied floats (the very device
+// functions the render kernels call): searchsorted(right=True) / below / above of u against cdf, and the stable sort
+// permutation of the merged depth list.
+__global__ void __launch_bounds__(128) render_bookkeeping_kernel(int rays, int ncdf, int s_fine, int T, const float* __restrict__ cdf,
+                                                                 const float* __restrict__ u, const float* __restrict__ depths,
+                                                                 int32_t* __restrict__ inds, int32_t* __restrict__ below,
+                                                                 int32_t* __restrict__ above, int32_t* __restrict__ sort_idx) {
+  extern __shared__ float bk_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ray = blockIdx.x * 4 + warp;
+  if (ray >= rays) return;
+  float* c = bk_smem + warp * (ncdf + T);
+  float* dep = c + ncdf;
+  for (int i = lane; i < ncdf; i += 32) c[i] = cdf[(size_t)ray * ncdf + i];
+  for (int i = lane; i < T; i += 32) dep[i] = depths[(size_t)ray * T + i];
+  __syncwarp();
+  if (inds)
+    for (int k = lane; k < s_fine; k += 32) {
+      const int ind = searchsorted_right(c, ncdf, u[(size_t)ray * s_fine + k]);
+      inds[(size_t)ray * s_fine + k] = ind;
+      below[(size_t)ray * s_fine + k] = max(ind - 1, 0);
+      above[(size_t)ray * s_fine + k] = min(ind, ncdf - 1);
+    }
+  if (sort_idx) {
+    float de[4];
+    int rk[4];
+    stable_ranks<4>(dep, T, lane, de, rk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (lane + 32 * e < T) sort_idx[(size_t)ray * T + rk[e]] = lane + 32 * e;
+  }
+}
+}  // namespace hfagp
+
+extern "C" int hfagp_render_bookkeeping(int rays, int ncdf, int s_fine, int t_total, const float* cdf, const float* u,
+                                        const float* depths, int32_t* inds, int32_t* below, int32_t* above,
+                                        int32_t* sort_idx, void* stream) {
+  HFAGP_CHECK_ARG(rays > 0 && ncdf >= 1 && ncdf <= 128 && t_total >= 1 && t_total <= 128 && s_fine >= 0, "render_bookkeeping: bad dims");
+  HFAGP_CHECK_ARG(cdf && depths && (!inds || (u && below && above)), "render_bookkeeping: null pointer");
+  render_bookkeeping_kernel<<<(rays + 3) / 4, 128, 4 * (ncdf + t_total) * sizeof(float), (cudaStream_t)stream>>>(
+      rays, ncdf, s_fine, t_total, cdf, u, depths, inds, below, above, sort_idx);
+  HFAGP_CHECK_LAUNCH("render_bookkeeping_kernel");
+  return HFAGP_OK;
+}
 
 static int render_fwd_impl(bool allow_tc, const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
                            const float* lin, const float* jitter, const float* u_fine, const float* depth_range,

@@ -137,6 +137,48 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---- integer bookkeeping of the importance resampling, shared by every renderer kernel and by
+// hfagp_render_bookkeeping (which runs exactly this code on caller-supplied floats)
+// torch.searchsorted(cdf[0..n), u, right=True) = #{ i : cdf[i] <= u } for a non-decreasing cdf
+__device__ __forceinline__ int searchsorted_right(const float* cdf, int n, float u) {
+  int ind = 0;
+  for (int len = n; len > 0;) {
+    const int half = len >> 1;
+    if (cdf[ind + half] <= u) { ind += half + 1; len -= half + 1; } else { len = half; }
+  }
+  return ind;
+}
+// Stable ranks of the T depths dep[0..T) (coarse samples first, as torch.cat + sort sees them): lane holds elements
+// lane + 32 e.  Fast path counts strictly smaller depths against one broadcast read of each depth; if any two depths are
+// equal the ranks no longer sum to T(T-1)/2 and the exact (value, index) order is recomputed.
+template <int NE>
+__device__ __forceinline__ void stable_ranks(const float* dep, int T, int lane, float (&de)[NE], int (&rk)[NE]) {
+#pragma unroll
+  for (int e = 0; e < NE; ++e) { de[e] = lane + 32 * e < T ? dep[lane + 32 * e] : 0.f; rk[e] = 0; }
+  for (int j = 0; j < T; ++j) {
+    const float dj = dep[j];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) rk[e] += dj < de[e] ? 1 : 0;
+  }
+  int rsum = 0;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) rsum += lane + 32 * e < T ? rk[e] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+  if (rsum != T * (T - 1) / 2) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int i = lane + 32 * e;
+      int rank = 0;
+      for (int j = 0; j < T; ++j) {
+        const float dj = dep[j];
+        rank += (dj < de[e] || (dj == de[e] && j < i)) ? 1 : 0;
+      }
+      rk[e] = rank;
+    }
+  }
+}
+
 // render_tc.cu: the tcgen05 forward renderer (used by hfagp_render_fwd whenever its shared-memory plan fits)
 bool render_tc_supported(const HfagpRenderDesc& d);
 int render_tc_launch(const RenderParams& p, int sms, cudaStream_t stream);

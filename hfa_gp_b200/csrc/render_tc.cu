@@ -536,11 +536,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
           for (int k = lane; k < SF; k += 32) {
             const float u = __ldg(p.u_fine + (size_t)ray * SF + k);
             // searchsorted(cdf[0..NB], u, right=True) = #{cdf[i] <= u}
-            int ind = 0;
-            for (int len = NB + 1; len > 0;) {
-              const int half = len >> 1;
-              if (cdf[ind + half] <= u) { ind += half + 1; len -= half + 1; } else { len = half; }
-            }
+            const int ind = searchsorted_right(cdf, NB + 1, u);
             const int lo = max(ind - 1, 0), hi = min(ind, NB);
             const float c0 = cdf[lo], c1 = cdf[hi];
             float den = c1 - c0;
@@ -567,30 +563,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
           constexpr int NE = decltype(ne_tag)::value;       // elements per lane = ceil(T / 32)
           float de[NE];
           int rk[NE];
-#pragma unroll
-          for (int e = 0; e < NE; ++e) { de[e] = lane + 32 * e < T ? dep[lane + 32 * e] : 0.f; rk[e] = 0; }
-          for (int j = 0; j < T; ++j) {
-            const float dj = dep[j];
-#pragma unroll
-            for (int e = 0; e < NE; ++e) rk[e] += dj < de[e] ? 1 : 0;
-          }
-          int rsum = 0;
-#pragma unroll
-          for (int e = 0; e < NE; ++e) rsum += lane + 32 * e < T ? rk[e] : 0;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
-          if (rsum != T * (T - 1) / 2) {                    // ties: exact (value, index) order
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-              const int i = lane + 32 * e;
-              int rank = 0;
-              for (int j = 0; j < T; ++j) {
-                const float dj = dep[j];
-                rank += (dj < de[e] || (dj == de[e] && j < i)) ? 1 : 0;
-              }
-              rk[e] = rank;
-            }
-          }
+          stable_ranks<NE>(dep, T, lane, de, rk);
 #pragma unroll
           for (int e = 0; e < NE; ++e) {
             const int i = lane + 32 * e;

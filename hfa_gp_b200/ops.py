@@ -218,6 +218,19 @@ def render(planes, c, mlp, lin, jitter, u_fine, depth_range, *, res, s_coarse, s
     return feat, depth, wsum, book
 
 
+def render_bookkeeping(cdf, u, depths):
+    """cdf [R,NC], u [R,SF], depths [R,T] (fp32, device) -> inds, below, above [R,SF], sort_idx [R,T] (int32): the
+    renderer's integer stage on the given floats (``hfagp_render_bookkeeping``)."""
+    r, nc = cdf.shape
+    sf, t = u.shape[1], depths.shape[1]
+    dev = cdf.device
+    inds, below, above = (torch.empty((r, sf), device=dev, dtype=torch.int32) for _ in range(3))
+    sort_idx = torch.empty((r, t), device=dev, dtype=torch.int32)
+    _ok(_cabi.lib().hfagp_render_bookkeeping(r, nc, sf, t, ptr(cdf), ptr(u), ptr(depths), ptr(inds), ptr(below), ptr(above),
+                                               ptr(sort_idx), stream()), 'hfagp_render_bookkeeping')
+    return inds, below, above, sort_idx
+
+
 def render_bwd(planes, c, mlp, lin, jitter, u_fine, dfeat, *, res, s_coarse, s_fine, delta, box_scale, decoder=False):
     """d(feat) [N,res,res,32] -> d(planes) [N,PH,PW,96], see ``hfagp_render_bwd``.  ``decoder=True`` also returns the
     per-sample (features [S,32], d(raw decoder output) [S,33]) pair for the decoder's weight gradient."""

@@ -230,6 +230,16 @@ int hfagp_render_fwd_simt(const HfagpRenderDesc* desc, const float* planes, cons
                           float* feat, float* depth, float* wsum, int32_t* inds, int32_t* below, int32_t* above,
                           int32_t* sort_idx, float* depths_sorted, void* stream);
 
+/* The renderer's integer bookkeeping in isolation (north_star: "bit-exact for ray-index bookkeeping"): the same device
+ * functions the render kernels call, run on caller-supplied floats, one warp per ray:
+ *   inds = searchsorted(cdf[ray][0..ncdf), u[ray][k], right=True), below = max(inds-1, 0), above = min(inds, ncdf-1)
+ *   sort_idx[ray] = stable argsort of depths[ray][0..t_total)                      (ncdf, t_total <= 128)
+ * Given the reference's own cdf / depth floats the outputs must equal torch.searchsorted / clamp / torch.sort exactly
+ * (tests/test_gpu_parity.py::test_bookkeeping_on_oracle_floats).  inds (with below/above) or sort_idx may be null. */
+int hfagp_render_bookkeeping(int rays, int ncdf, int s_fine, int t_total, const float* cdf, const float* u,
+                             const float* depths, int32_t* inds, int32_t* below, int32_t* above, int32_t* sort_idx,
+                             void* stream);
+
 /* Backward of hfagp_render_fwd w.r.t. the planes (decoder frozen, trainer_rgb.py:59-60): per ray the forward is
  * recomputed from the same inputs (jitter / u_fine make it deterministic), then d(feat) is pushed through the
  * composite, the mid-point march (d sigma), the decoder MLP (tensor-pipe, split bf16) and the bilinear gather;

@@ -88,6 +88,25 @@ def reference_cameras(seed=11):
     np.savez_compressed(os.path.join(OUT, 'reference_cameras.npz'), **z)
 
 
+def train_step_full(kind):
+    """ONE full-size training step of the oracle (configs[2] 'rgb' / configs[3] '3dmm', batch 1, lr 3e-4): losses, probe
+    pixels of the pooled image, gradients of delta / bases (every 16th column) / the first and last head weights and the
+    updated delta.  ~1 min of CPU; the GPU test re-creates the inputs from oracle.train_ref.full_step_case."""
+    from oracle import train_ref
+    torch.set_num_threads(8)
+    c = train_ref.full_step_case(kind)
+    oracle = train_ref.TrainStepRef(c['sd'], c['bases'], c['delta'], c['generator'], c['size'], 3e-4, lpips=c['lpips'],
+                                    head=c['head'])
+    l2, lp, img = oracle.step(c['real'], c['label'], c['jitter'], c['u'], params=c['params'])
+    first, last = ('net_app.convs.0.0.weight', 'fc.4.weight') if kind == 'rgb' else ('fc.0.weight', 'fc.6.weight')
+    z = dict(l2=l2.numpy(), lpips=lp.numpy(), image_probe=img[:, :, ::8, ::8].numpy(), image_mean=img.mean().numpy(),
+             image_abs_mean=img.abs().mean().numpy(), d_delta=oracle.delta.grad.numpy(),
+             d_bases_sub=oracle.bases.grad[:, ::16].contiguous().numpy(), d_first=oracle.sd[first].grad.numpy(),
+             d_last=oracle.sd[last].grad.numpy(), delta_new=oracle.delta.detach().numpy())
+    np.savez_compressed(os.path.join(OUT, f'train_step_full_{kind}.npz'), **z)
+    print(kind, 'l2', float(l2), 'lpips', float(lp))
+
+
 def oracle_generator_tiny(seed=0):
     cfg = E.tiny_config()
     gen = E.make_generator(cfg, seed=seed, noise_strength=0.1)
@@ -111,4 +130,6 @@ if __name__ == '__main__':
     reference_encoder()
     reference_cameras()
     oracle_generator_tiny()
+    train_step_full('rgb')
+    train_step_full('3dmm')
     print(sorted(os.listdir(OUT)), [os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))])

@@ -65,3 +65,39 @@ class TrainStepRef:
         (l2 + lp).backward()
         self.opt.step()
         return l2.detach(), lp.detach(), image.detach()
+
+
+def full_step_case(kind: str = 'rgb', seed: int = 0, batch: int = 1):
+    """Everything one FULL-SIZE training step needs (BASELINE.json configs[2] 'rgb': encoder 256 -> 512x512 render pooled
+    to 256; configs[3] '3dmm': Weights_3DMM on [B,76] coefficients, one frame per rank), built from CPU generators only so
+    that the GPU box re-creates the identical tensors without running the oracle: head weights, bases / delta, the EG3D
+    generator (seeded random init, noise strength 0.1), LPIPS-alex weights (seeded), inputs and the renderer's two draws."""
+    from . import eg3d_ref, lpips_ref
+    cfg = eg3d_ref.GeneratorConfig()
+    g = torch.Generator().manual_seed(1000 + seed)
+    k, size = 50, 256
+    if kind == 'rgb':
+        sd = hfagp_ref.make_encoder_state(size=size, dim_motion=k, seed=seed + 4)
+        for key in sd:
+            if key.endswith('.bias'):
+                sd[key] = torch.randn(sd[key].shape, generator=g) * 0.2
+        head = 'encoder'
+    else:
+        dims = [76] + [512] * 6 + [k]
+        sd = {}
+        for j in range(7):
+            sd[f'fc.{j}.weight'] = torch.randn(dims[j + 1], dims[j], generator=g)
+            sd[f'fc.{j}.bias'] = torch.randn(dims[j + 1], generator=g) * 0.2
+        head = 'weights_3dmm'
+    bases = torch.randn(k, 14 * 512, generator=g)
+    delta = bases.mean(dim=0)
+    gen = eg3d_ref.make_generator(cfg, seed=seed, noise_strength=0.1)
+    lp = lpips_ref.LPIPS(net='alex', seed=seed + 3).eval()
+    rays = cfg.nrr ** 2
+    real = torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+    label = hfagp_ref.synthetic_labels(batch, seed=seed + 7)
+    params = torch.randn(batch, 76, generator=g)
+    jitter = torch.rand(batch, rays, cfg.depth_res, 1, generator=g)
+    u = torch.rand(batch * rays, cfg.depth_res_importance, generator=g)
+    return dict(cfg=cfg, size=size, k=k, head=head, sd=sd, bases=bases, delta=delta, generator=gen, lpips=lp, real=real,
+                label=label, params=params, jitter=jitter, u=u)

@@ -610,3 +610,39 @@ def test_driven_frame_loops_match_oracle(drive):
         label = hfagp_ref.synthetic_labels(1, seed=20 + i)
         got = loop(padded[i:i + 8], label.cuda()).clone()
         assert pu.rel_err(got, oracle_image(smo.unsqueeze(0), label)) < pu.REL_TOL
+
+
+@pytest.mark.parametrize('res,s,sf', [(16, 48, 48), (8, 33, 20), (8, 64, 64)])
+def test_bookkeeping_on_oracle_floats(res, s, sf):
+    """north_star: "bit-exact for ray-index bookkeeping".  The integer stage of the render kernels (the shared device
+    functions searchsorted_right / stable_ranks, run by hfagp_render_bookkeeping) is fed the ORACLE's own floats — its cdf,
+    its u and its unsorted merged depths — and must return torch.searchsorted(right=True), the clamped below / above and
+    the torch.sort permutation EXACTLY: no tie mask, no tolerance.  (The only freedom torch leaves is the order of exactly
+    equal depths under its non-stable sort; there the permuted depths must still be identical.)"""
+    cfg, planes, dec, c, jitter, u = _render_case(res, s, sf, 1, seed=2)
+    tap = {}
+    ro, rd = eg3d_ref.ray_sampler_ref(c[:, :16].view(-1, 4, 4), c[:, 16:25].view(-1, 3, 3), res)
+    with torch.no_grad():
+        eg3d_ref.render_ref(planes, dec, ro, rd, cfg, jitter, u, tap)
+    rays = res * res
+    cdf = tap['cdf'].reshape(rays, -1).contiguous()
+    depths = torch.cat([tap['depths_coarse'], tap['depths_fine']], dim=-2).reshape(rays, s + sf).contiguous()
+    ops = _ops()
+    inds, below, above, order = ops.render_bookkeeping(cdf.cuda(), u[:, :sf].contiguous().cuda(), depths.cuda())
+    assert torch.equal(inds.cpu().long(), tap['inds'])
+    assert torch.equal(below.cpu().long(), tap['below'])
+    assert torch.equal(above.cpu().long(), tap['above'])
+    order = order.cpu().long()
+    want = tap['sort_idx'].reshape(rays, s + sf)
+    assert torch.equal(torch.gather(depths, 1, order), tap['depths_sorted'].reshape(rays, s + sf))
+    neq = order != want
+    if bool(neq.any()):          # only inside runs of exactly equal depths
+        ds = torch.gather(depths, 1, want)
+        tie = torch.zeros_like(neq)
+        tie[:, 1:] |= ds[:, 1:] == ds[:, :-1]
+        tie[:, :-1] |= ds[:, 1:] == ds[:, :-1]
+        assert bool((~neq | tie).all())
+    # and a stable sort reproduces torch.sort(stable=True) bit for bit, ties included
+    dq = (depths * 64).round() / 64                       # force many exact ties
+    _, _, _, oq = ops.render_bookkeeping(cdf.cuda(), u[:, :sf].contiguous().cuda(), dq.cuda())
+    assert torch.equal(oq.cpu().long(), torch.sort(dq, dim=1, stable=True).indices)

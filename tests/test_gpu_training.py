@@ -504,3 +504,54 @@ def test_step_graph_replays_the_eager_step(which):
         # atomics shows up at the 1e-3 level in near-zero-gradient biases (measured 3e-3 worst); the images and losses
         # above are held to the forward tolerance
         assert pu.rel_l2(pg[n], p) < 1e-2, n
+
+
+@pytest.mark.parametrize('kind', ['rgb', '3dmm'])
+def test_full_size_training_step_matches_golden(kind):
+    """VERDICT r1 3(a,b): ONE gen_update at BASELINE.json's full sizes — configs[2] (trainer_rgb: encoder 256, 512x512
+    render pooled to 256) and configs[3] (trainer_3dmm: 76 coefficients, one frame per rank) — against the oracle's step
+    frozen in tests/golden/train_step_full_*.npz (oracle/make_golden.py; the oracle itself is not run here: its inputs are
+    re-created from the same CPU generators by oracle.train_ref.full_step_case).  Shipped tensor-core precision."""
+    import numpy as np
+    import os
+    from hfa_gp_b200 import trainer_3dmm, trainer_rgb
+    c = train_ref.full_step_case(kind)
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', f'train_step_full_{kind}.npz'))
+    args = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, batch_size=1, size=c['size'],
+                              latent_dim_style=512, latent_dim_shape=c['k'], run_id='synthetic', emb_dir='./none/', lr=3e-4,
+                              synthetic_generator=True, generator_seed=0, params_len=76)
+    tr = (trainer_3dmm if kind == '3dmm' else trainer_rgb).Trainer(args, torch.device('cuda'), 0)
+    gen = tr.gen.module
+    gen.generator.load_state_dict(c['generator'].state_dict())
+    head = gen.weights_3dmm if kind == '3dmm' else gen.encoder
+    with torch.no_grad():
+        for n, p in head.named_parameters():
+            p.copy_(c['sd'][n])
+        gen.bases.copy_(c['bases'])
+        gen.delta.copy_(c['delta'])
+    tr.lpips_loss.load_state_dict(c['lpips'].state_dict())
+    gen.generator.fixed_draws = (c['jitter'].cuda(), c['u'].cuda())
+    lab = c['label'].clone().cuda()
+    if kind == '3dmm':
+        _, l2, lpv, img = tr.gen_update(c['real'].cuda(), lab, c['params'].cuda())
+    else:
+        l2, lpv, img = tr.gen_update(c['real'].cuda(), lab)
+    t = lambda k_: torch.from_numpy(gold[k_])
+    assert abs(float(l2.detach()) - float(gold['l2'])) < 1e-3 * float(gold['l2'])
+    assert abs(float(lpv.detach()) - float(gold['lpips'])) < 2e-3 * float(gold['lpips'])
+    # the golden keeps every 8th pixel of the pooled image; the 1e-3 scale is the full image's
+    probe, want = img.detach().cpu()[:, :, ::8, ::8], t('image_probe')
+    scale = torch.clamp(want.abs(), min=float(gold['image_abs_mean']))
+    assert float(((probe - want).abs() / scale).max()) < 2e-3
+    assert abs(float(img.detach().mean()) - float(gold['image_mean'])) < 1e-4
+    names = dict(head.named_parameters())
+    first, last = ('net_app.convs.0.0.weight', 'fc.4.weight') if kind == 'rgb' else ('fc.0.weight', 'fc.6.weight')
+    _check(gen.delta.grad, t('d_delta'), 'tc', f'full {kind} d delta')
+    _check(gen.bases.grad[:, ::16], t('d_bases_sub'), 'tc', f'full {kind} d bases')
+    _check(names[first].grad, t('d_first'), 'tc', f'full {kind} d {first}')
+    _check(names[last].grad, t('d_last'), 'tc', f'full {kind} d {last}')
+    # Adam's first step: |update| = lr for every element whose gradient is not ~0; compare where the oracle's is solid
+    gref = t('d_delta')
+    solid = gref.abs() > 1e-3 * gref.pow(2).mean().sqrt()
+    upd, upd_ref = gen.delta.detach().cpu() - c['delta'], t('delta_new') - c['delta']
+    assert float((upd[solid] - upd_ref[solid]).abs().max()) < 0.05 * 3e-4
