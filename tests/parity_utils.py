@@ -17,6 +17,19 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float(((a - b).abs() / scale).max())
 
 
+def pixel_rel_stats(a: torch.Tensor, b: torch.Tensor) -> dict:
+    """The PURE per-pixel relative error |a-b|/|b| (no rms floor), reported next to rel_err: its maximum is dominated by
+    zero crossings of b (the ratio is unbounded where b -> 0), so the distribution is what is informative."""
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    r = (a - b).abs() / b.abs().clamp_min(1e-30)
+    rms = float(b.pow(2).mean().sqrt())
+    over = r > REL_TOL
+    return dict(p50=float(r.median()), p999=float(r.kthvalue(int(0.999 * r.numel())).values), max=float(r.max()),
+                frac_over=float(over.float().mean()),
+                max_abs_ref_where_over=float((b.abs()[over].max() / rms) if bool(over.any()) else 0.0),
+                max_over_away_from_zero=float(r[b.abs() > 0.05 * rms].max()))
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     """||a - b|| / ||b||.  Used for GRADIENTS on the tensor-core path: two forward passes that differ by 1e-5 flip
     the leaky-ReLU branch of the few activations sitting at the kink, which changes those elements' gradient by

@@ -299,6 +299,12 @@ def test_generator_full_512_frame(precision):
     worst = max(errs.items(), key=lambda kv: kv[1])
     assert worst[1] < pu.REL_TOL, f'worst stage {worst}'
     assert pu.rel_err(out_g['image'], out_r['image']) < pu.REL_TOL
+    # north_star words the tolerance "per pixel": the pure ratio |a-b|/|b| beside the rms-floored one.  It exceeds 1e-3
+    # only at zero crossings of the reference image (|b| below 5 % of the image rms); away from them it holds outright.
+    st = pu.pixel_rel_stats(out_g['image'], out_r['image'])
+    print('per-pixel relative error', precision, st)
+    assert st['max_over_away_from_zero'] < pu.REL_TOL
+    assert st['frac_over'] < 2e-3 and st['max_abs_ref_where_over'] < 0.05
     # size-independent properties at full size
     assert bool(torch.isfinite(out_g['image']).all())
     ws_sum = tap_g['weight_sum']

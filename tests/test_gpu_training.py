@@ -261,9 +261,16 @@ def test_trainer_rgb_steps_match_oracle(precision):
         # Adam's first steps move every element by ~lr regardless of gradient size: compare the UPDATE
         upd_r = oracle.sd[n].detach() - sd[n]
         upd = names[n].detach().cpu() - sd[n]
-        # (on the full tensor-core path the flipped-branch noise of the gradients reaches the SIGN of near-zero
-        # gradient elements, which Adam's first steps amplify to +-lr: only a loose bound is meaningful there)
-        assert pu.rel_l2(upd, upd_r) < (0.3 if precision == 'tc' else 5e-2), (n, pu.rel_l2(upd, upd_r))
+        # Adam's first steps move every element by ~lr whatever the size of its gradient, so the flipped-branch noise of
+        # the tensor-core path decides the SIGN of the update where the gradient is ~0.  The updates are therefore
+        # compared where the oracle's gradient is solid (|g| > 1e-3 rms in both steps' accumulated first moment), and
+        # held to the fp32 path's bound there; the whole tensor keeps a loose sanity bound.
+        m_ref = oracle.opt.state[oracle.sd[n]]['exp_avg']
+        solid = m_ref.abs() > 1e-2 * m_ref.pow(2).mean().sqrt()
+        e_solid = pu.rel_l2(upd[solid], upd_r[solid])
+        print(f'adam update {n}: rel-L2 all {pu.rel_l2(upd, upd_r):.3e} solid ({float(solid.float().mean()):.2f}) {e_solid:.3e}')
+        assert e_solid < 5e-2, (n, e_solid)
+        assert pu.rel_l2(upd, upd_r) < 5e-2, (n, pu.rel_l2(upd, upd_r))      # measured <= 1.4e-3 (tc), 3e-4 (fp32)
     assert pu.rel_err(gen.bases, oracle.bases) < 1e-3
     assert tr.g_optim.steps == [2, 0]
 
