@@ -31,6 +31,9 @@ int fail(int code, const char* fmt, ...);
       return ::hfagp::fail(HFAGP_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));   \
   } while (0)
 
+// programmatic dependent launch of the kernels that support it (tc_common.cuh); opt-in with HFAGP_PDL=1
+bool pdl_enabled();
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }

@@ -274,6 +274,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (TWO) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote arrival
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only shared / tensor memory: under programmatic dependent launch it overlapped the
+  // previous kernel's tail; global memory is read and written only from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform loop, elected lane issues): patches and weight tiles in the exact order the
@@ -891,20 +895,34 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, ma_hi, ma_lo, mb_hi, mb_lo, mb_half, p);
     if (e != cudaSuccess) return fail(HFAGP_E_CUDA, "%s: cluster launch failed: %s", who, cudaGetErrorString(e));
     return HFAGP_OK;
   }
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv_tc_kernel<false><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mb_half, p);
-  HFAGP_CHECK_LAUNCH("conv_tc_kernel");
+  {
+    const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, ma_hi, ma_lo, mb_hi, mb_lo, mb_half, p);
+    if (e != cudaSuccess) return fail(HFAGP_E_CUDA, "%s: launch failed: %s", who, cudaGetErrorString(e));
+  }
   return HFAGP_OK;
 }
 

@@ -64,4 +64,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining; pdl_wait() blocks until every prerequisite grid has
+// COMPLETED and its memory is visible, so a kernel that touches global memory only after pdl_wait() keeps stream-order
+// semantics and merely overlaps its prologue (barrier init, TMEM allocation, descriptor prefetch, launch latency) with the
+// predecessor's tail.  pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as this grid's CTAs have
+// all issued it (or exited).  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace hfagp

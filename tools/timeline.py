@@ -10,6 +10,7 @@ from hfa_gp_b200 import cam_utils
 ap = argparse.ArgumentParser()
 ap.add_argument('--seq', action='store_true')
 ap.add_argument('--frames', type=int, default=3)
+ap.add_argument('--graph', action='store_true', help='profile CUDA-graph replays of the frame loop (the product path)')
 args = ap.parse_args()
 dev = torch.device('cuda')
 ns = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='', synthetic_generator=True, generator_seed=0)
@@ -21,6 +22,11 @@ lab = cam_utils.cam_sampler(1, 'cpu').to(dev)
 def frame():
     with torch.no_grad():
         return model.get_image(model.get_latent(model.get_weights(img)), lab.clone())
+if args.graph:
+    from hfa_gp_b200.frame_loop import FrameLoop
+    loop = FrameLoop(model, batch=1, size=256, device=dev)
+    def frame():
+        return loop(img, lab, mutate_label=False)
 for _ in range(4):
     frame()
 torch.cuda.synchronize()
@@ -35,6 +41,18 @@ def short(n):
     return (n[:n.index('(')] if '(' in n else n)[:52]
 per = len(evs) // args.frames
 last = evs[-per:]
+if args.graph:
+    # gaps on the critical path: time not covered by any kernel between the first and the last kernel of the frame
+    iv = sorted((e.time_range.start, e.time_range.end) for e in last)
+    covered, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
+    for s_, e_ in iv[1:]:
+        if s_ > cur_e:
+            covered += cur_e - cur_s
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    covered += cur_e - cur_s
+    print(f'graph frame: span {iv[-1][1] - iv[0][0]:.1f} us, covered by >= 1 kernel {covered:.1f} us, idle gaps {iv[-1][1] - iv[0][0] - covered:.1f} us')
 if args.seq:
     t0 = last[0].time_range.start
     for e in last:
