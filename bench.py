@@ -564,11 +564,11 @@ def main():
     if not args.no_extras:
         del loop
         torch.cuda.empty_cache()
-        # configs[3] at EVERY N: global batch 8 split over the ranks (train_3dmm.py:93) -> strong scaling 1 -> 8 is readable
-        # from the per-N lines; configs[2] (trainer_rgb, batch 2) beside it on one GPU
+        # configs[3] at EVERY N: global batch 8 split over the ranks (train_3dmm.py:93) -> STRONG scaling 1 -> 8 is readable
+        # from the per-N lines; configs[2] (trainer_rgb, train_rgb.py:164 batch 2 PER RANK) -> WEAK scaling, with its flat
+        # 23 M-float gradient all-reduce per step at N > 1
         extras['train'] = train_record(rank, world, dev, steps=10, warmup=5, trainer='3dmm', per_rank_batch=max(8 // world, 1))
-        if world == 1:
-            extras['train_rgb'] = train_record(rank, world, dev, steps=10, warmup=5, trainer='rgb', per_rank_batch=2)
+        extras['train_rgb'] = train_record(rank, world, dev, steps=10, warmup=5, trainer='rgb', per_rank_batch=2)
         extras['reenact'] = reenact_record(rank, world, dev, frames_total=1000)
     frames = args.steps * fps_ * world
     value = frames / (ms / 1e3)
