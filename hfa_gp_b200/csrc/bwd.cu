@@ -37,11 +37,11 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
   const int c4 = d.c >> 2;
   const int planes = 256 / c4;                 // pixels processed side by side
   const int cq = threadIdx.x % c4, plane = threadIdx.x / c4;
-  if (plane >= planes) return;
+  const bool idle = plane >= planes;             // (256 is not always a multiple of c/4; idle lanes only meet the barrier)
   const int n = blockIdx.y;
   const int hw = d.h * d.w;
   const int p_begin = blockIdx.x * p.pix_per_block;
-  const int p_end = min(hw, p_begin + p.pix_per_block);
+  const int p_end = idle ? 0 : min(hw, p_begin + p.pix_per_block);
   const int c0 = cq * 4;
   const size_t nc = (size_t)n * d.c + c0;
 
@@ -64,64 +64,107 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
   float r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f}, rr[4] = {0.f, 0.f, 0.f, 0.f};
   float rb[4] = {0.f, 0.f, 0.f, 0.f}, rd[4] = {0.f, 0.f, 0.f, 0.f};
 
-  for (int pix = p_begin + plane; pix < p_end; pix += planes) {
-    const size_t q = ((size_t)n * hw + pix) * c4 + cq;
-    const float4 y4 = ld4_any(p.y, p.y_hi, p.y_lo, q);
-    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-    float gsum[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.g0) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p.g0) + q);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+  // U pixels per iteration with every load issued before the first dependent use (the stores of one pixel may alias the
+  // loads of the next as far as the compiler knows, so the batching is explicit): the kernel is a pure stream, and one
+  // pixel at a time left a single 16 B load chain in flight per thread
+  constexpr int U = 2;
+  for (int pix0 = p_begin + plane; pix0 < p_end; pix0 += planes * U) {
+    float4 y4[U], a0[U], a1[U], r4[U];
+    float nzv[U];
+    float di[U][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { gsum[k] = av[k] * sc0[k]; r0[k] = fmaf(av[k], yv[k], r0[k]); }
-    }
-    if (p.g1) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p.g1) + q);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * planes;
+      const bool ok = pix < p_end;
+      const size_t q = ((size_t)n * hw + (ok ? pix : p_begin)) * c4 + cq;
+      y4[u] = ld4_any(p.y, p.y_hi, p.y_lo, q);
+      a0[u] = p.g0 ? __ldg(reinterpret_cast<const float4*>(p.g0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a1[u] = p.g1 ? __ldg(reinterpret_cast<const float4*>(p.g1) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r4[u] = p.residual ? __ldg(reinterpret_cast<const float4*>(p.residual) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      nzv[u] = p.noise ? __ldg(p.noise + (ok ? pix : p_begin)) * d.noise_gain : 0.f;
+      if (p.dimg) {
+        const float* dp = p.dimg + ((size_t)n * hw + (ok ? pix : p_begin)) * d.rgb_k;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { gsum[k] = fmaf(av[k], sc1[k], gsum[k]); r1[k] = fmaf(av[k], yv[k], r1[k]); }
-    }
-    if (p.dimg) {
-      const float* di = p.dimg + ((size_t)n * hw + pix) * d.rgb_k;
-      float gr[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int o = 0; o < d.rgb_k; ++o) {
-        const float dv = __ldg(di + o);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gr[k] = fmaf(dv, wr[o][k], gr[k]);
+        for (int o = 0; o < 4; ++o) di[u][o] = o < d.rgb_k ? __ldg(dp + o) : 0.f;
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { gsum[k] = fmaf(gr[k], scr[k], gsum[k]); rr[k] = fmaf(gr[k], yv[k], rr[k]); }
     }
-    // derivative of  y = merge(clamp(act(pre) * gain))  w.r.t. pre
-    float av[4];
-    if (p.residual) {
-      const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual) + q);
-      av[0] = yv[0] * inv_rs - r4.x; av[1] = yv[1] * inv_rs - r4.y; av[2] = yv[2] * inv_rs - r4.z; av[3] = yv[3] * inv_rs - r4.w;
-    } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) av[k] = yv[k];
-    }
-    const float nz = p.noise ? __ldg(p.noise + pix) * d.noise_gain : 0.f;
-    float dzv[4];
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * planes;
+      if (pix >= p_end) break;
+      const size_t q = ((size_t)n * hw + pix) * c4 + cq;
+      const float yv[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w};
+      float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.g0) {
+        const float av[4] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float slope = av[k] > 0.f ? slope_pos : slope_neg;
-      const bool pass = !(d.clamp > 0.f) || fabsf(av[k]) < d.clamp;
-      const float dpre = pass ? gsum[k] * d.post_scale * slope : 0.f;
-      rb[k] += dpre;
-      if (p.ddcoef) {
-        const float z = (av[k] / slope - nz - bs[k]) / dco[k];   // conv output before demodulation
-        rd[k] = fmaf(dpre, z, rd[k]);
+        for (int k = 0; k < 4; ++k) { gsum[k] = av[k] * sc0[k]; r0[k] = fmaf(av[k], yv[k], r0[k]); }
       }
-      dzv[k] = dpre * dco[k];
+      if (p.g1) {
+        const float av[4] = {a1[u].x, a1[u].y, a1[u].z, a1[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { gsum[k] = fmaf(av[k], sc1[k], gsum[k]); r1[k] = fmaf(av[k], yv[k], r1[k]); }
+      }
+      if (p.dimg) {
+        float gr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gr[k] = fmaf(di[u][o], wr[o][k], gr[k]);      // wr[o] = 0 beyond rgb_k
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { gsum[k] = fmaf(gr[k], scr[k], gsum[k]); rr[k] = fmaf(gr[k], yv[k], rr[k]); }
+      }
+      // derivative of  y = merge(clamp(act(pre) * gain))  w.r.t. pre
+      float av[4];
+      if (p.residual) {
+        av[0] = yv[0] * inv_rs - r4[u].x; av[1] = yv[1] * inv_rs - r4[u].y; av[2] = yv[2] * inv_rs - r4[u].z; av[3] = yv[3] * inv_rs - r4[u].w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) av[k] = yv[k];
+      }
+      const float nz = nzv[u];
+      float dzv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float slope = av[k] > 0.f ? slope_pos : slope_neg;
+        const bool pass = !(d.clamp > 0.f) || fabsf(av[k]) < d.clamp;
+        const float dpre = pass ? gsum[k] * d.post_scale * slope : 0.f;
+        rb[k] += dpre;
+        if (p.ddcoef) {
+          const float z = (av[k] / slope - nz - bs[k]) / dco[k];   // conv output before demodulation
+          rd[k] = fmaf(dpre, z, rd[k]);
+        }
+        dzv[k] = dpre * dco[k];
+      }
+      if (p.dz || p.dz_hi) st4_any(p.dz, p.dz_hi, p.dz_lo, q, dzv);
     }
-    if (p.dz || p.dz_hi) st4_any(p.dz, p.dz_hi, p.dz_lo, q, dzv);
   }
-  if (p.ds0 && p.g0) atomic_add4(p.ds0 + nc, r0);
-  if (p.ds1 && p.g1) atomic_add4(p.ds1 + nc, r1);
-  if (p.dsrgb && p.dimg) atomic_add4(p.dsrgb + nc, rr);
-  if (p.dbias) atomic_add4(p.dbias + c0, rb);
-  if (p.ddcoef) atomic_add4(p.ddcoef + nc, rd);
+  // per-channel reductions: first across the block's side-by-side pixel lanes in shared memory, then ONE atomic per
+  // channel and block (every lane adding on its own put ~5 000 same-address atomics per channel in a row: the L2 unit
+  // serialises them, which — not the streaming — was what the kernel's time went into)
+  __shared__ float red[5][256 * 4];
+  const float* vals[5] = {r0, r1, rr, rb, rd};
+  const bool use[5] = {p.ds0 && p.g0, p.ds1 && p.g1, p.dsrgb && p.dimg, p.dbias != nullptr, p.ddcoef != nullptr};
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+    if (use[j]) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) red[j][(plane * c4 + cq) * 4 + k] = vals[j][k];
+    }
+  __syncthreads();
+  if (plane == 0) {
+    float* dst[5] = {p.ds0 ? p.ds0 + nc : nullptr, p.ds1 ? p.ds1 + nc : nullptr, p.dsrgb ? p.dsrgb + nc : nullptr,
+                     p.dbias ? p.dbias + c0 : nullptr, p.ddcoef ? p.ddcoef + nc : nullptr};
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (use[j]) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int pl = 0; pl < planes; ++pl)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[k] += red[j][(pl * c4 + cq) * 4 + k];
+        atomic_add4(dst[j], acc);
+      }
+  }
 }
 
 // dx[n][iy][ix][c] = gain * sum_{ky,kx} g[ky] g[kx] dy[n][(iy + pad0 - ky)/s][(ix + pad0 - kx)/s][c]   (exact divisions only)
