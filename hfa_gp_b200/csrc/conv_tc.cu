@@ -682,8 +682,8 @@ struct MapKeyHash {
 
 // rank-4 bf16 map (rank-3 tensors pass d3 = b3 = 1).  Cached: PyTorch's allocator hands the same
 // pointers back every frame, so steady state does no driver calls.
-static int get_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t b0,
-                   uint32_t b1, uint32_t b2, uint32_t b3, uint32_t estride, int rank) {
+int get_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t b0,
+            uint32_t b1, uint32_t b2, uint32_t b3, uint32_t estride, int rank) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{ptr, d0, d1, d2, d3, b0, b1, b2, b3, estride * 8u + (uint32_t)rank};

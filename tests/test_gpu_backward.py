@@ -291,3 +291,31 @@ def test_generator_weight_gradients(precision):
         assert e_l2 < (GRAD_TOL_TC_L2 if precision == 'tc' else GRAD_TOL) * 2, (n, e_l2)
         checked += 1
     assert checked > 100
+
+
+@pytest.mark.parametrize('n,cin,cout,h,k,stride,pad', [
+    (2, 64, 64, 32, 3, 1, 1),        # ResBlock conv1 (patch groups of 3 taps, N = 64)
+    (1, 128, 256, 34, 3, 2, 0),      # down-sampling conv2 after the blur: stride 2, single-tap groups, partial tiles
+    (2, 256, 128, 16, 1, 1, 0),      # 1x1 (skip / ToRGB-like), N = 128, two cout... one co tile
+    (1, 128, 128, 24, 3, 1, 1),      # N = 128: three accumulators of 128 columns
+])
+def test_wgrad_tensor_core_matches_autograd(n, cin, cout, h, k, stride, pad):
+    """hfagp_conv2d_wgrad on split-bf16 operands takes the tcgen05 kernel (csrc/wgrad_tc.cu: MN-major operands straight from
+    the channels-last activations, three split terms, K split over CTAs) and must reproduce autograd's weight gradient of
+    F.conv2d to fp32-class accuracy; the same call on fp32 operands (SIMT kernel) is checked beside it."""
+    from hfa_gp_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(n, cin, h, h, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g, requires_grad=True)
+    y = F.conv2d(x, w, stride=stride, padding=pad)
+    dz = torch.randn(y.shape, generator=g)
+    (y * dz).sum().backward()
+    want = w.grad.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
+    oh = y.shape[2]
+    taps = tuple((ky - pad, kx - pad, ky * k + kx) for ky in range(k) for kx in range(k))
+    xn, dzn = x.permute(0, 2, 3, 1).contiguous().cuda(), dz.permute(0, 2, 3, 1).contiguous().cuda()
+    for split in (True, False):
+        dw = torch.zeros(k * k, cout, cin, device='cuda')
+        ops.conv2d_wgrad(ops.split(xn) if split else xn, ops.split(dzn) if split else dzn, taps, dw, oh=oh, ow=oh,
+                         in_stride=stride, scale=0.5)
+        assert pu.rel_err(dw, 0.5 * want) < 2e-4, ('split' if split else 'fp32')
