@@ -493,7 +493,8 @@ namespace hfagp {
 // wgrad_tc.cu: the tcgen05 weight gradient (MN-major operands straight from the channels-last activations)
 bool wgrad_tc_supported(const HfagpConvDesc& d);
 int wgrad_tc_launch(const HfagpConvDesc& d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dz_hi,
-                    const uint16_t* dz_lo, float scale, float* dw, int num_sms, cudaStream_t stream);
+                    const uint16_t* dz_lo, const float* xscale, const float* dzscale, float scale, float* dw, int num_sms,
+                    cudaStream_t stream);
 }  // namespace hfagp
 
 static int wgrad_impl(const HfagpConvDesc* desc, const float* x, const uint16_t* x_hi, const uint16_t* x_lo,
@@ -507,11 +508,11 @@ static int wgrad_impl(const HfagpConvDesc* desc, const float* x, const uint16_t*
                   "conv2d_wgrad: cin and cout must be multiples of 4");
   HFAGP_CHECK_ARG(d.ntaps > 0 && d.ntaps <= HFAGP_MAX_TAPS && (d.in_stride == 1 || d.in_stride == 2), "conv2d_wgrad: bad taps/stride");
   HFAGP_CHECK_ARG(d.out_stride == 1 && d.out_h == d.oh && d.out_w == d.ow, "conv2d_wgrad: dz must be dense [n][oh][ow][cout]");
-  if (x_hi && dz_hi && !xscale && !dzscale && wgrad_tc_supported(d)) {
+  if (x_hi && dz_hi && wgrad_tc_supported(d)) {
     int dev = 0, sms = 148;
     HFAGP_CUDA(cudaGetDevice(&dev));
     HFAGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    return wgrad_tc_launch(d, x_hi, x_lo, dz_hi, dz_lo, scale, dw, sms, (cudaStream_t)stream);
+    return wgrad_tc_launch(d, x_hi, x_lo, dz_hi, dz_lo, xscale, dzscale, scale, dw, sms, (cudaStream_t)stream);
   }
   WgradParams p;
   p.batch = d.batch; p.in_h = d.in_h; p.in_w = d.in_w; p.cin = d.cin; p.cout = d.cout; p.oh = d.oh; p.ow = d.ow;

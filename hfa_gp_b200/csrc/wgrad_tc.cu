@@ -45,6 +45,12 @@ struct WtParams {
   int patch_rows;                         // 8 + max span
   float scale;
   float* dw;
+  // modulated convolutions (hfagp_conv2d_wgrad_mod): per-sample style factors.  They commute with the pixel sum, so they
+  // are applied to the finished per-sample accumulator: dw[t][co][ci] += scale * rowscale[n][co] * colscale[n][ci] * D_n
+  // (a work item then never mixes samples: per_sample = 1 deals the K splits out inside one sample)
+  const float* rowscale;                  // [batch][cout] or null  (the style of the dz-side operand)
+  const float* colscale;                  // [batch][cin]  or null  (the style of the x-side operand)
+  int per_sample;
 };
 
 __device__ __forceinline__ void tma_load_4d_wt(const CUtensorMap* map, void* smem, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -92,11 +98,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
   // ---- work item: (tap group, co tile, ci tile, K split)
   int w = blockIdx.x;
   const int ks = w % p.splits; w /= p.splits;
+  int sample = 0;
+  if (p.per_sample) { sample = w % p.batch; w /= p.batch; }
   const int cit = w % p.ci_tiles; w /= p.ci_tiles;
   const int cot = w % p.co_tiles; w /= p.co_tiles;
   const int g = w;
   const int t0 = p.gstart[g], ntap = p.gstart[g + 1] - t0;
-  const int c_begin = (int)((long long)p.chunks * ks / p.splits), c_end = (int)((long long)p.chunks * (ks + 1) / p.splits);
+  const int span_chunks = p.per_sample ? p.tiles_x * p.tiles_y : p.chunks;      // chunks this item's splits divide
+  const int c_base = p.per_sample ? sample * span_chunks : 0;
+  const int c_begin = c_base + (int)((long long)span_chunks * ks / p.splits);
+  const int c_end = c_base + (int)((long long)span_chunks * (ks + 1) / p.splits);
   const int N = p.nblk * 64;
   const uint32_t tmem_cols = 512;
 
@@ -175,6 +186,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
     mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (c_end > c_begin) {
+      const float rs = p.scale * ((p.rowscale && co < p.cout) ? __ldg(p.rowscale + (size_t)sample * p.cout + co) : 1.f);
+      const float* cs = p.colscale ? p.colscale + (size_t)sample * p.cin + cit * N : nullptr;
       for (int t = 0; t < ntap; ++t) {
         float* out = p.dw + ((size_t)p.twt[t0 + t] * p.cout + co) * p.cin + cit * N;
         for (int cb = 0; cb < N; cb += 32) {
@@ -182,10 +195,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
           tmem_ld32_wt(tmem_base + ((uint32_t)(q * 32) << 16) + t * N + cb, v);
           if (co < p.cout) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (cit * N + cb + j < p.cin)
-                atomicAdd(reinterpret_cast<float4*>(out + cb + j),
-                          make_float4(v[j] * p.scale, v[j + 1] * p.scale, v[j + 2] * p.scale, v[j + 3] * p.scale));
+            for (int j = 0; j < 32; j += 4) {
+              float4 f = make_float4(rs, rs, rs, rs);
+              if (cs) {                                   // warp-uniform address: one broadcast 16 B load
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + cb + j));
+                f.x *= c4.x; f.y *= c4.y; f.z *= c4.z; f.w *= c4.w;
+              }
+              atomicAdd(reinterpret_cast<float4*>(out + cb + j),
+                        make_float4(v[j] * f.x, v[j + 1] * f.y, v[j + 2] * f.z, v[j + 3] * f.w));
+            }
           }
         }
       }
@@ -200,14 +218,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
 }
 
 bool wgrad_tc_supported(const HfagpConvDesc& d) {
-  if ((d.cin & 63) || (d.cout & 63) || d.ow < 8 || d.oh < 8) return false;
+  // cin in whole 64-channel blocks; cout only needs TMA's 16 B row rule (the last dz box is zero-filled past cout)
+  if ((d.cin & 63) || (d.cout & 7) || d.cout < 32 || d.ow < 8 || d.oh < 8) return false;
   if ((long long)d.batch * d.oh * d.ow < 1024) return false;            // too little K to fill the pipe: SIMT kernel
   if (d.in_stride != 1 && d.in_stride != 2) return false;
   return true;
 }
 
 int wgrad_tc_launch(const HfagpConvDesc& d, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dz_hi,
-                    const uint16_t* dz_lo, float scale, float* dw, int num_sms, cudaStream_t stream) {
+                    const uint16_t* dz_lo, const float* xscale, const float* dzscale, float scale, float* dw, int num_sms,
+                    cudaStream_t stream) {
   WtParams p = {};
   p.batch = d.batch; p.oh = d.oh; p.ow = d.ow; p.cin = d.cin; p.cout = d.cout; p.in_stride = d.in_stride;
   p.tiles_x = cdiv(d.ow, 8); p.tiles_y = cdiv(d.oh, 8);
@@ -216,6 +236,8 @@ int wgrad_tc_launch(const HfagpConvDesc& d, const uint16_t* x_hi, const uint16_t
   p.co_tiles = cdiv(d.cout, 128);
   p.ci_tiles = d.cin / (p.nblk * 64);
   p.scale = scale; p.dw = dw;
+  p.colscale = xscale; p.rowscale = dzscale;
+  p.per_sample = (xscale || dzscale) ? 1 : 0;
   // tap groups: at stride 1 the taps sharing dx read one patch (consecutive dy, at most 512 / N accumulators)
   int order[HFAGP_MAX_TAPS];
   for (int t = 0; t < d.ntaps; ++t) order[t] = t;
@@ -243,9 +265,10 @@ int wgrad_tc_launch(const HfagpConvDesc& d, const uint16_t* x_hi, const uint16_t
   }
   p.gstart[p.ngroups] = d.ntaps;
   p.patch_rows = 8 + max_span;
-  const int items = p.ngroups * p.co_tiles * p.ci_tiles;
+  const int items = p.ngroups * p.co_tiles * p.ci_tiles * (p.per_sample ? d.batch : 1);
+  const int span_chunks = p.per_sample ? p.tiles_x * p.tiles_y : p.chunks;
   int splits = cdiv(2 * num_sms, items);
-  if (splits > p.chunks / 4) splits = p.chunks / 4;
+  if (splits > span_chunks / 4) splits = span_chunks / 4;
   if (splits < 1) splits = 1;
   p.splits = splits;
   const size_t stage = 2 * 2 * WT_ABLK + (size_t)p.nblk * 2 * p.patch_rows * 8 * WT_ROW;

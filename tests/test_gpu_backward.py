@@ -319,3 +319,27 @@ def test_wgrad_tensor_core_matches_autograd(n, cin, cout, h, k, stride, pad):
         ops.conv2d_wgrad(ops.split(xn) if split else xn, ops.split(dzn) if split else dzn, taps, dw, oh=oh, ow=oh,
                          in_stride=stride, scale=0.5)
         assert pu.rel_err(dw, 0.5 * want) < 2e-4, ('split' if split else 'fp32')
+
+
+@pytest.mark.parametrize('n,cin,cout,h,k,stride,pad', [(2, 128, 128, 16, 3, 1, 1), (2, 64, 96, 32, 1, 1, 0), (3, 64, 128, 18, 3, 2, 0)])
+def test_wgrad_tensor_core_with_style_factors(n, cin, cout, h, k, stride, pad):
+    """hfagp_conv2d_wgrad_mod on the tcgen05 kernel: per-sample style factors on either operand (a modulated convolution's
+    weight gradient, code/train_rgb.py:132-134 regime) are applied to the per-sample accumulators in the epilogue."""
+    from hfa_gp_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, cin, h, h, generator=g)
+    xs, = (torch.rand(n, cin, generator=g) + 0.5,)
+    w = torch.randn(cout, cin, k, k, generator=g, requires_grad=True)
+    y = F.conv2d(x * xs[:, :, None, None], w, stride=stride, padding=pad)
+    dz = torch.randn(y.shape, generator=g)
+    dzs = torch.rand(n, cout, generator=g) + 0.5
+    (y * dz * dzs[:, :, None, None]).sum().backward()
+    want = w.grad.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
+    oh = y.shape[2]
+    taps = tuple((ky - pad, kx - pad, ky * k + kx) for ky in range(k) for kx in range(k))
+    xn, dzn = x.permute(0, 2, 3, 1).contiguous().cuda(), dz.permute(0, 2, 3, 1).contiguous().cuda()
+    for split in (True, False):
+        dw = torch.zeros(k * k, cout, cin, device='cuda')
+        ops.conv2d_wgrad(ops.split(xn) if split else xn, ops.split(dzn) if split else dzn, taps, dw, oh=oh, ow=oh,
+                         in_stride=stride, xscale=xs.cuda(), dzscale=dzs.cuda())
+        assert pu.rel_err(dw, want) < 2e-4, ('split' if split else 'fp32')

@@ -10,6 +10,8 @@ ns = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=F
                         emb_dir='./', lr=3e-4)
 torch.manual_seed(0)
 tr = trainer_rgb.Trainer(ns, dev, 0)
+if '--tune' in sys.argv:
+    tr.tune_generator()
 real = (torch.rand(2, 3, 256, 256, device=dev) * 2 - 1)
 def step():
     tr.gen_update(real, trainer_rgb.cam_sampler(2, dev))
