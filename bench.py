@@ -317,14 +317,14 @@ def train_record(rank, world, dev, steps, warmup, trainer='rgb', per_rank_batch=
     return rec
 
 
-def reenact_record(rank, world, dev, frames_total=1000):
+def reenact_record(rank, world, dev, frames_total=1000, depth=1):
     """BASELINE.json configs[4]: run_recon_video_audio.py — a `frames_total`-frame batch reenactment from synthetic aud.npy
     features N(0,1) [F,16,29]: AudioNet -> AudioAttNet (8-frame window) -> HeadNeRF_Audio(aud_smo, label), frame i on rank
     i mod N, no communication (every rank holds the tiny feature file).  `value` = frames/s of the whole job with
     the features resident in HBM; `e2e` copies each frame's window + label from pinned host memory and reads the 512x512
     image back inside the timed region."""
     import torch
-    from hfa_gp_b200.frame_loop import FrameLoop, audio_windows
+    from hfa_gp_b200.frame_loop import FramePipeline, audio_windows
     from hfa_gp_b200.networks.headnerf import AudioAttNet, AudioNet, HeadNeRF_Audio
     from hfa_gp_b200 import cam_utils
 
@@ -339,22 +339,25 @@ def reenact_record(rank, world, dev, frames_total=1000):
     host_pad = audio_windows(auds, 8).pin_memory()
     host_labels = labels.pin_memory()
     dev_pad, dev_labels = host_pad.to(dev), host_labels.to(dev)
-    host_out = torch.empty(1, 3, 512, 512).pin_memory()
-    loop = FrameLoop(model, batch=1, size=ENC_SIZE, device=dev, drive='audio', aud_net=aud_net, aud_att=aud_att)
+    host_outs = [torch.empty(1, 3, 512, 512).pin_memory() for _ in range(depth)]
+    loop = FramePipeline(model, depth=depth, batch=1, size=ENC_SIZE, device=dev, drive='audio', aud_net=aud_net, aud_att=aud_att)
     mine = list(range(rank, frames_total, world))
     for i in mine[:5]:
-        loop(dev_pad[i:i + 8], dev_labels[i:i + 1], mutate_label=False)
+        loop.submit(dev_pad[i:i + 8], dev_labels[i:i + 1])
+    loop.join()
     _barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in mine:
-        loop(dev_pad[i:i + 8], dev_labels[i:i + 1], mutate_label=False)
+        loop.submit(dev_pad[i:i + 8], dev_labels[i:i + 1])
+    loop.join()
     e1.record()
     _barrier(world)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in mine:
-        host_out.copy_(loop(host_pad[i:i + 8], host_labels[i:i + 1]), non_blocking=True)
+        loop.submit(host_pad[i:i + 8], host_labels[i:i + 1], host_out=host_outs[loop.count % depth])
+    loop.join()
     f1.record()
     _barrier(world)
     ms, ms_e2e = _max_over_ranks([e0.elapsed_time(e1), f0.elapsed_time(f1)], dev, world)
@@ -365,7 +368,7 @@ def reenact_record(rank, world, dev, frames_total=1000):
         'ms_per_frame_per_gpu': ms / len(mine), 'gpu_launches_per_frame': loop.launches_per_replay,
         'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': (8 * 16 * 29 + 25) * 4,
                 'd2h_bytes_per_step': 3 * 512 * 512 * 4},
-        'dtype': DTYPE, 'scaling': 'strong (fixed clip, frames sharded)',
+        'dtype': DTYPE, 'scaling': 'strong (fixed clip, frames sharded)', 'frames_in_flight': depth,
     }
     del loop, model
     torch.cuda.empty_cache()
@@ -415,6 +418,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--frames-per-step', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--in-flight', type=int, default=3,
+                    help='frames in flight (hfa_gp_b200.frame_loop.FramePipeline): 1 = strictly one frame after the other')
     ap.add_argument('--no-graph', action='store_true', help='drive the frame loop eagerly instead of replaying the CUDA graph')
     ap.add_argument('--tune-generator', action='store_true',
                     help="with --workload train: the post-tune_iter regime (generator unfrozen, train_rgb.py:132-134)")
@@ -513,10 +518,29 @@ def main():
         kernel_calls[name] = kernel_calls.get(name, 0) + 1
 
     # ---- (b) the product path: the frame-loop body captured once as a CUDA graph (hfa_gp_b200.frame_loop)
-    loop = FrameLoop(model, batch=fps_, size=ENC_SIZE, device=dev, use_graph=not args.no_graph)
-    launches_per_step = loop.launches_per_replay
+    depth = max(args.in_flight, 1)
+    if depth > 1:
+        from hfa_gp_b200.frame_loop import FramePipeline
+        pipe = FramePipeline(model, depth=depth, batch=fps_, size=ENC_SIZE, device=dev)
+        launches_per_step = pipe.launches_per_replay
+        host_outs = [torch.empty(fps_, 3, 512, 512).pin_memory() for _ in range(depth)]
+
+        def loop(img, lab, mutate_label=True, host=False):
+            return pipe.submit(img, lab, host_out=host_outs[pipe.count % depth] if host else None)[0]
+        finish = pipe.join
+    else:
+        loop1 = FrameLoop(model, batch=fps_, size=ENC_SIZE, device=dev, use_graph=not args.no_graph)
+        launches_per_step = loop1.launches_per_replay
+
+        def loop(img, lab, mutate_label=True, host=False):
+            out = loop1(img, lab, mutate_label=mutate_label)
+            if host:
+                host_out.copy_(out, non_blocking=True)
+            return out
+        finish = lambda: None
     for i in range(args.warmup):
         loop(dev_frames[i], dev_labels[i])
+    finish()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -525,6 +549,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         loop(dev_frames[args.warmup + i], dev_labels[args.warmup + i])
+    finish()
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -533,12 +558,14 @@ def main():
 
     # ---- (c) end-to-end through the same public call with HOST buffers (H2D + D2H inside the timed region)
     for i in range(3):
-        host_out.copy_(loop(host_frames[i], host_labels[i]), non_blocking=True)
+        loop(host_frames[i], host_labels[i], host=True)
+    finish()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        host_out.copy_(loop(host_frames[args.warmup + i], host_labels[args.warmup + i]), non_blocking=True)
+        loop(host_frames[args.warmup + i], host_labels[args.warmup + i], host=True)
+    finish()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -555,21 +582,43 @@ def main():
     c0.record()
     for i in range(n_confirm):
         loop(dev_frames[args.warmup + i % args.steps], dev_labels[args.warmup + i % args.steps], mutate_label=False)
+    finish()
     c1.record()
     barrier()
     ms_confirm, = _max_over_ranks([c0.elapsed_time(c1)], dev, world)
+
+    # ---- (d') strictly one frame after the other (frames_in_flight = 1), for the record beside the pipelined headline
+    sequential = None
+    if depth > 1:
+        seq = FrameLoop(model, batch=fps_, size=ENC_SIZE, device=dev)
+        for i in range(args.warmup):
+            seq(dev_frames[i], dev_labels[i], mutate_label=False)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            seq(dev_frames[args.warmup + i], dev_labels[args.warmup + i], mutate_label=False)
+        s1.record()
+        barrier()
+        ms_seq, = _max_over_ranks([s0.elapsed_time(s1)], dev, world)
+        sequential = {'frames_in_flight': 1, 'ms_per_step': ms_seq / args.steps, 'value': args.steps * fps_ * world / (ms_seq / 1e3)}
+        del seq
 
     # ---- (e) the other configs of BASELINE.json through the same launch: training step and audio reenactment
     extras = {}
     if not args.no_extras:
         del loop
+        if depth > 1:
+            del pipe, finish
+        else:
+            del loop1
         torch.cuda.empty_cache()
         # configs[3] at EVERY N: global batch 8 split over the ranks (train_3dmm.py:93) -> STRONG scaling 1 -> 8 is readable
         # from the per-N lines; configs[2] (trainer_rgb, train_rgb.py:164 batch 2 PER RANK) -> WEAK scaling, with its flat
         # 23 M-float gradient all-reduce per step at N > 1
         extras['train'] = train_record(rank, world, dev, steps=10, warmup=5, trainer='3dmm', per_rank_batch=max(8 // world, 1))
         extras['train_rgb'] = train_record(rank, world, dev, steps=10, warmup=5, trainer='rgb', per_rank_batch=2)
-        extras['reenact'] = reenact_record(rank, world, dev, frames_total=1000)
+        extras['reenact'] = reenact_record(rank, world, dev, frames_total=1000, depth=depth)
     frames = args.steps * fps_ * world
     value = frames / (ms / 1e3)
     e2e = frames / (ms_e2e / 1e3)
@@ -607,7 +656,11 @@ def main():
             'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'frames_per_step': fps_, 'sharding': 'frame i -> rank i mod N, no collective',
                        'l2': 'per-frame working set ~1.25 GB (weights 113 MB + activations) exceeds the 126 MB L2; no flush',
-                       'launch': 'eager' if args.no_graph else 'one CUDA graph replay per frame (hfa_gp_b200.frame_loop.FrameLoop)'},
+                       'launch': 'eager' if args.no_graph else 'one CUDA graph replay per frame (hfa_gp_b200.frame_loop.FrameLoop)',
+                       'frames_in_flight': depth,
+                       'pipelining': ('%d batch-1 frame graphs on %d streams, frames dealt round-robin (FramePipeline): frame '
+                                      "i+1's copies and launch-sized kernels overlap frame i; \"sequential\" holds the "
+                                      'one-after-the-other number' % (depth, depth)) if depth > 1 else 'none'},
             'clocks': clocks,
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': fps_ * (3 * ENC_SIZE * ENC_SIZE + 25) * 4,
                     'd2h_bytes_per_step': fps_ * 3 * 512 * 512 * 4},
@@ -621,6 +674,8 @@ def main():
             'confirm': {'frames_per_rank': n_confirm, 'ms_per_step': ms_confirm / n_confirm,
                         'value': n_confirm * fps_ * world / (ms_confirm / 1e3)},
         }
+        if sequential is not None:
+            line['sequential'] = sequential
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_sample()

@@ -122,3 +122,42 @@ def audio_windows(auds: torch.Tensor, smo_size: int = 8) -> torch.Tensor:
     half = int(smo_size / 2)
     z = torch.zeros((half,) + tuple(auds.shape[1:]), dtype=auds.dtype, device=auds.device)
     return torch.cat((z, auds, z), dim=0)
+
+
+class FramePipeline:
+    """``depth`` frames in flight: ``depth`` FrameLoops (each its own captured graph and static buffers) on ``depth`` CUDA
+    streams, frames dealt round-robin.  Every frame is still one batch-1 graph replay of the reference's loop body; what
+    overlaps is frame i+1's host->device copy and its launch-sized kernels (the encoder and the 4^2..32^2 generator blocks
+    leave most SMs idle at batch 1) with frame i's large convolutions and its device->host copy.
+
+    ``submit(image, label, host_out=None)`` enqueues one frame and returns ``(image_out, event)``: ``image_out`` is the
+    slot's static output buffer (valid until the slot is used again, ``depth`` submits later); when ``host_out`` (pinned)
+    is given the result is also copied there on the slot's stream.  ``event`` completes when the frame (and its copy) is done.
+    ``join()`` makes the current stream wait for everything submitted."""
+
+    def __init__(self, model, depth: int = 2, device=None, **loop_kwargs):
+        if depth < 1:
+            raise HfagpError('FramePipeline needs depth >= 1')
+        self.loops = [FrameLoop(model, device=device, **loop_kwargs) for _ in range(depth)]
+        self.device = self.loops[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+        self.depth, self.count = depth, 0
+        self.launches_per_replay = self.loops[0].launches_per_replay
+
+    def submit(self, image, label, host_out=None):
+        k = self.count % self.depth
+        s = self.streams[k]
+        s.wait_stream(torch.cuda.current_stream(self.device))        # inputs may have been produced on the caller's stream
+        with torch.cuda.stream(s):
+            out = self.loops[k](image, label, mutate_label=False)
+            if host_out is not None:
+                host_out.copy_(out, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s)
+        self.count += 1
+        return out, ev
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)

@@ -16,6 +16,11 @@ The reference trains with ``torch.optim.Adam(self.gen.parameters(), lr=args.lr)`
     ``exp_avg_sq`` keyed by position in ``gen.parameters()``), so checkpoints interchange with the reference's
     ``"g_optim"`` / ``"w_optim"`` entries (``trainer_rgb.py:130-151``).
 
+Known divergence from ``torch.optim.Adam``: torch skips a parameter whose ``.grad`` is None on a step (and counts steps
+per parameter); here every parameter of a live group is stepped with the group's count and a zero gradient, so a parameter
+that stops receiving gradients (``bases_2`` / ``delta_2`` while ``person_2`` alternates) keeps moving on its decaying
+momentum for a few steps instead of freezing.  The trainers' default paths (one person) never hit this.
+
 Reference quirk handled on purpose: ``trainer_rgb.gen_update`` calls ``self.gen.module.*`` and so
 bypasses DDP's reducer — replicas silently diverge.  We implement the intended synchronous mean for all three
 trainers.
@@ -180,8 +185,14 @@ class FlatAdam:
             steps[self._group_of(i)].add(int(float(st['step'])))
         for gi in (0, 1):
             if len(steps[gi]) > 1:
-                raise HfagpError('per-parameter Adam step counts differ inside one group; cannot load into the flat optimiser')
-            self.steps[gi] = steps[gi].pop() if steps[gi] else 0
+                # torch.optim.Adam counts steps per parameter and skips parameters whose .grad is None (e.g. bases_2 /
+                # delta_2 on the steps person_2 is off); the flat optimiser steps a whole group with ONE count and a zero
+                # gradient for such parameters (their momentum keeps decaying).  Loading a reference checkpoint with mixed
+                # counts keeps the largest one: bias correction of the stragglers is then slightly ahead of torch's.
+                import warnings
+                warnings.warn(f'FlatAdam: per-parameter step counts {sorted(steps[gi])} differ inside one group; '
+                              f'using {max(steps[gi])} for all of them')
+            self.steps[gi] = max(steps[gi]) if steps[gi] else 0
 
 
 class DataParallelShard(torch.nn.Module):

@@ -652,3 +652,32 @@ def test_bookkeeping_on_oracle_floats(res, s, sf):
     dq = (depths * 64).round() / 64                       # force many exact ties
     _, _, _, oq = ops.render_bookkeeping(cdf.cuda(), u[:, :sf].contiguous().cuda(), dq.cuda())
     assert torch.equal(oq.cpu().long(), torch.sort(dq, dim=1, stable=True).indices)
+
+
+def test_frame_pipeline_equals_single_loop():
+    """FramePipeline (several frames in flight on several streams, one captured graph each) returns, frame for frame, what the
+    single FrameLoop returns — to the host buffers too — with slots reused several times over."""
+    import argparse
+    from hfa_gp_b200.frame_loop import FrameLoop, FramePipeline
+    from hfa_gp_b200.networks.headnerf import HeadNeRF_final
+    cfg = eg3d_ref.small14_config()
+    args = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='',
+                              synthetic_generator=True, generator_seed=0, generator_config=pu.product_config(cfg))
+    torch.manual_seed(0)
+    model = HeadNeRF_final(args, 64, 'cuda', 512, 50, 'x', './').cuda().eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(5)
+    rays = cfg.nrr ** 2
+    model.generator.fixed_draws = (torch.rand(1, rays, cfg.depth_res, 1, generator=g).cuda(),
+                                   torch.rand(rays, cfg.depth_res_importance, generator=g).cuda())
+    single = FrameLoop(model, batch=1, size=64)
+    pipe = FramePipeline(model, depth=3, batch=1, size=64)
+    frames = [(torch.rand(1, 3, 64, 64, generator=g) * 2 - 1).pin_memory() for _ in range(8)]
+    labels = [hfagp_ref.synthetic_labels(1, seed=s).pin_memory() for s in range(8)]
+    want = [single(f, l.clone()).clone() for f, l in zip(frames, labels)]
+    hosts = [torch.empty(1, 3, 64, 64).pin_memory() for _ in range(8)]
+    evs = [pipe.submit(f, l, host_out=h)[1] for f, l, h in zip(frames, labels, hosts)]
+    pipe.join()
+    torch.cuda.synchronize()
+    for w, h, e in zip(want, hosts, evs):
+        assert e.query()
+        assert pu.rel_err(h, w) < 1e-4
