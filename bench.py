@@ -35,7 +35,12 @@ ENC_SIZE, DIM_SHAPE = 256, 50
 TC_ENTRY_POINTS = ('hfagp_conv2d_tc_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd')
 # ncu dram__bytes_read.sum + dram__bytes_write.sum over the 42 conv_tc_kernel launches of one frame (profiles/r2_launches_start.csv:
 # 803.6 MB read + 211.1 MB written back before kernel end; the frame's algorithmic weight + activation bytes are ~1 250 MB)
-CONV_TC_DRAM_BYTES_PER_FRAME = 1_014_700_000
+# by frames per step: batch 1 profiles/r2_launches_start.csv (803.6 MB read + 211.1 MB written back before kernel end); batch 4
+# profiles/r2_launches_final.csv (`ncu ... python tools/one_frame.py 2 --serial --batch 4`: 2 974.9 MB read + 1 717.9 MB
+# written = 1 173 MB per frame; four frames' activations no longer fit L2 between producer and consumer)
+CONV_TC_DRAM_BYTES_PER_STEP = {1: 1_014_700_000, 4: 4_692_799_232}
+# render_tc_kernel, ncu dram read + write per launch: batch 1 profiles/r2_ncu_render_tc_v3.txt, batch 4 profiles/r2_launches_final.csv
+RENDER_DRAM_BYTES_PER_LAUNCH = {1: 22_568_960, 4: 93_288_192}
 DTYPE = 'bf16x3-split operands (hi*hi + lo*hi + hi*lo), fp32 accumulate'
 
 
@@ -416,7 +421,8 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--frames-per-step', type=int, default=1)
+    ap.add_argument('--frames-per-step', type=int, default=4,
+                    help='frames per step = batch of one frame-graph replay (independent frames of the video; the reference loop feeds 1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--in-flight', type=int, default=3,
                     help='frames in flight (hfa_gp_b200.frame_loop.FramePipeline): 1 = strictly one frame after the other')
@@ -601,8 +607,26 @@ def main():
         s1.record()
         barrier()
         ms_seq, = _max_over_ranks([s0.elapsed_time(s1)], dev, world)
-        sequential = {'frames_in_flight': 1, 'ms_per_step': ms_seq / args.steps, 'value': args.steps * fps_ * world / (ms_seq / 1e3)}
+        sequential = {'frames_in_flight': 1, 'frames_per_step': fps_, 'ms_per_step': ms_seq / args.steps,
+                      'value': args.steps * fps_ * world / (ms_seq / 1e3)}
         del seq
+    # ---- (d'') the reference loop's own granularity: ONE frame per replay, one replay after the other (frame latency)
+    single = None
+    if fps_ > 1 or depth > 1:
+        one = FrameLoop(model, batch=1, size=ENC_SIZE, device=dev)
+        for i in range(args.warmup):
+            one(dev_frames[i, :1], dev_labels[i, :1], mutate_label=False)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            one(dev_frames[args.warmup + i, :1], dev_labels[args.warmup + i, :1], mutate_label=False)
+        s1.record()
+        barrier()
+        ms_one, = _max_over_ranks([s0.elapsed_time(s1)], dev, world)
+        single = {'frames_in_flight': 1, 'frames_per_step': 1, 'ms_per_frame': ms_one / args.steps,
+                  'value': args.steps * world / (ms_one / 1e3)}
+        del one
 
     # ---- (e) the other configs of BASELINE.json through the same launch: training step and audio reenactment
     extras = {}
@@ -628,13 +652,14 @@ def main():
         render_roof = None
         if render_ms:
             ach = RENDER_ALG_BYTES * fps_ / (render_ms * 1e-3) / 1e9
-            render_roof = {'kernel': 'render_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                           'frac': ach / hbm_peak, 'traffic': 22_568_960, 'ms_per_launch': render_ms,
-                           'peak_source': peak_src,
-                           'note': 'algorithmic bytes 27 394 048 B/frame (SURVEY 8d); traffic = ncu dram read+write per launch '
-                                   '(profiles/r1_ncu_render_final.txt: 22.6 MB read, the 2.2 MB of outputs are still in L2 at '
-                                   'kernel end): no wasted HBM re-reads; the kernel is bound by on-chip gathers '
-                                   '(2.4 GB L1/L2->RF per frame) and the decoder MLP, see DESIGN.md'}
+            render_roof = {'kernel': 'render_tc_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
+                           'frac': ach / hbm_peak, 'traffic': RENDER_DRAM_BYTES_PER_LAUNCH.get(fps_), 'ms_per_launch': render_ms,
+                           'frames_per_launch': fps_, 'peak_source': peak_src,
+                           'note': 'algorithmic bytes 27 394 048 B/frame (SURVEY 8d) x frames per launch; traffic = ncu dram '
+                                   'read+write of one launch (profiles/r2_launches_final.csv: the planes are read once, most of '
+                                   'the outputs are still in L2 at kernel end): no wasted HBM '
+                                   're-reads; the kernel is bound by instruction issue and on-chip gathers (2.4 GB L1/L2->RF '
+                                   'per frame), see DESIGN.md 6'}
         # dominant kernel: conv_tc_kernel (tcgen05) — all its launches of one frame together
         tc_ms = sum(kernel_ms.get(k, 0.0) for k in TC_ENTRY_POINTS)
         tc_launches = sum(kernel_calls.get(k, 0) for k in TC_ENTRY_POINTS) // args.steps
@@ -643,11 +668,11 @@ def main():
         if tc_ms:
             ach_tf = tc_flops / (tc_ms * 1e-3) / 1e12
             roof = {'kernel': 'conv_tc_kernel', 'bound': 'tensor', 'achieved': ach_tf, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                    'frac': ach_tf / tf_peak, 'traffic': CONV_TC_DRAM_BYTES_PER_FRAME,
-                    'ms_per_frame': tc_ms, 'launches_per_frame': tc_launches,
+                    'frac': ach_tf / tf_peak, 'traffic': CONV_TC_DRAM_BYTES_PER_STEP.get(fps_),
+                    'ms_per_step': tc_ms, 'ms_per_frame': tc_ms / fps_, 'launches_per_step': tc_launches,
                     'share_of_step': tc_ms / (ms / args.steps),
                     'tensor_pipe_frac': 3.0 * ach_tf / tf_peak, 'peak_source': peak_src + ', sustained bf16',
-                    'note': 'achieved = algorithmic fp32 FLOPs of the tensor-core convolutions (%.1f GFLOP/frame) / summed '
+                    'note': 'achieved = algorithmic fp32 FLOPs of the tensor-core convolutions (%.1f GFLOP/step) / summed '
                             'CUDA-event time of their launches; every algorithmic FMA is 3 bf16 MMAs (split-bf16, '
                             'fp32-class accuracy), so the tensor pipe delivers tensor_pipe_frac of its peak' % (tc_flops / 1e9)}
         line = {
@@ -656,11 +681,12 @@ def main():
             'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'frames_per_step': fps_, 'sharding': 'frame i -> rank i mod N, no collective',
                        'l2': 'per-frame working set ~1.25 GB (weights 113 MB + activations) exceeds the 126 MB L2; no flush',
-                       'launch': 'eager' if args.no_graph else 'one CUDA graph replay per frame (hfa_gp_b200.frame_loop.FrameLoop)',
-                       'frames_in_flight': depth,
-                       'pipelining': ('%d batch-1 frame graphs on %d streams, frames dealt round-robin (FramePipeline): frame '
-                                      "i+1's copies and launch-sized kernels overlap frame i; \"sequential\" holds the "
-                                      'one-after-the-other number' % (depth, depth)) if depth > 1 else 'none'},
+                       'launch': 'eager' if args.no_graph else 'one CUDA graph replay per step of %d frames (hfa_gp_b200.frame_loop.FrameLoop, batch=%d)' % (fps_, fps_),
+                       'frames_in_flight': depth * fps_,
+                       'pipelining': ('%d frame graphs (batch %d each) on %d streams, steps dealt round-robin (FramePipeline): step '
+                                      "i+1's copies and launch-sized kernels overlap step i; \"sequential\" holds the "
+                                      'one-replay-after-the-other number, \"single_frame\" the reference loop\'s one frame per '
+                                      'replay' % (depth, fps_, depth)) if depth > 1 else 'none'},
             'clocks': clocks,
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': fps_ * (3 * ENC_SIZE * ENC_SIZE + 25) * 4,
                     'd2h_bytes_per_step': fps_ * 3 * 512 * 512 * 4},
@@ -668,14 +694,16 @@ def main():
             'roofline': roof,
             'render_roofline': render_roof,
             'stage_ms': stage_avg,
-            'kernel_ms_per_frame': {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])[:10]},
-            'cabi_gpu_ms_per_frame': sum(kernel_ms.values()),
+            'kernel_ms_per_frame': {k: round(v / fps_, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])[:10]},
+            'cabi_gpu_ms_per_frame': sum(kernel_ms.values()) / fps_,
             'event_bracket_overhead_us': 1e3 * event_overhead_ms,
-            'confirm': {'frames_per_rank': n_confirm, 'ms_per_step': ms_confirm / n_confirm,
+            'confirm': {'frames_per_rank': n_confirm * fps_, 'ms_per_step': ms_confirm / n_confirm,
                         'value': n_confirm * fps_ * world / (ms_confirm / 1e3)},
         }
         if sequential is not None:
             line['sequential'] = sequential
+        if single is not None:
+            line['single_frame'] = single
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_sample()

@@ -27,7 +27,7 @@ SYMBOLS = [
     'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8',
     'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
     'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd', 'hfagp_conv2d_wgrad_mod', 'hfagp_render_bwd_dec',
-    'hfagp_render_fwd_simt', 'hfagp_adam_sched', 'hfagp_adam_step_dev', 'hfagp_render_bookkeeping',
+    'hfagp_render_fwd_simt', 'hfagp_decoder_wgrad', 'hfagp_set_device', 'hfagp_device_sm_count', 'hfagp_adam_sched', 'hfagp_adam_step_dev', 'hfagp_render_bookkeeping',
 ]
 
 
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
     l.hfagp_render_fwd_simt.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
     l.hfagp_render_bwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 9
     l.hfagp_render_bwd_dec.argtypes = [C.POINTER(RenderDesc)] + [vp] * 11
+    l.hfagp_decoder_wgrad.argtypes = [C.c_longlong] + [vp] * 5
     l.hfagp_blur_fwd.argtypes = [i32] * 7 + [f32] + [vp] * 7
     l.hfagp_blur_up.argtypes = [i32] * 7 + [f32, vp, vp, vp]
     l.hfagp_act_bwd.argtypes = [C.POINTER(ActBwdDesc)] + [vp] * 23
@@ -149,7 +150,7 @@ class _TimedLib:
 
     def __getattr__(self, name):
         fn = getattr(self._cdll, name)
-        if name in ('hfagp_last_error', 'hfagp_abi_version') or not name.startswith('hfagp_'):
+        if name in ('hfagp_last_error', 'hfagp_abi_version', 'hfagp_set_device', 'hfagp_device_sm_count') or not name.startswith('hfagp_'):
             return fn
         sink = self._sink
 
@@ -186,11 +187,15 @@ def check(rc: int, what: str):
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
-    """Device pointer of a contiguous fp32/int32 CUDA tensor (None passes NULL)."""
+    """Device pointer of a contiguous CUDA tensor on the CURRENT device (None passes NULL).  The element type is the
+    callee's contract (fp32 unless the C signature says uint16_t / int32_t / uint8_t) and is not checked here."""
     if t is None:
         return None
     if not t.is_cuda:
         raise HfagpError('hot-path tensors must live on a CUDA device (no CPU fallback)')
+    if t.device.index != torch.cuda.current_device():
+        raise HfagpError(f'tensor lives on cuda:{t.device.index} but the current device (whose stream the kernels are '
+                         f'enqueued on) is cuda:{torch.cuda.current_device()}')
     if not t.is_contiguous():
         raise HfagpError('hot-path tensors must be contiguous')
     return t.data_ptr()

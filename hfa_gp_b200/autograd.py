@@ -58,7 +58,7 @@ def _unpack_conv(dw, k):
 
 def _demod_term(pl, styles, dcoef, ddc):
     """d(dcoef)/dW folded back: -W[t][o][i] * sum_n ddcoef[n][o] dcoef[n][o]^3 styles[n][i]^2   (tiny tensors)"""
-    coef = torch.einsum('no,ni->oi', ddc * dcoef * dcoef * dcoef, styles * styles)
+    coef = ((ddc * dcoef * dcoef * dcoef)[:, :, None] * (styles * styles)[:, None, :]).sum(0)   # [O, I]; batch is tiny
     return -pl.w * coef[None]
 
 
@@ -274,28 +274,19 @@ class SuperresFn(torch.autograd.Function):
         return dfeat, dflat, None, None, None
 
 
-def _decoder_param_grads(gen, f, do, chunk=1 << 20):
+def _decoder_param_grads(gen, f, do, mlp):
     """Weight gradient of the OSG decoder (32 -> 64 softplus -> 1+32) from the per-sample operands the render
-    backward kernel wrote: features f [S,32] and d(raw output) do [S,33].  The hidden layer is recomputed in fp32;
-    the four reductions over S = batch * rays * samples are plain GEMMs (torch, fp32), chunked to bound memory."""
+    backward kernel wrote: features f [S,32] and d(raw output) do [S,33].  ``hfagp_decoder_wgrad`` recomputes the hidden
+    layer and does the four reductions over S = batch * rays * samples; the result is w.r.t. the effective
+    (gain-multiplied) weights, so each slice is scaled by its gain on the way into .grad."""
     d0, d2 = gen.decoder.net[0], gen.decoder.net[2]
-    w0 = (d0.weight.detach() * d0.weight_gain).float()
-    b0 = (d0.bias.detach() * d0.bias_gain).float()
-    w1 = (d2.weight.detach() * d2.weight_gain).float()
-    dw0 = torch.zeros_like(w0); db0 = torch.zeros_like(b0); dw1 = torch.zeros_like(w1); db1 = torch.zeros(w1.shape[0], device=w1.device)
-    for s0 in range(0, f.shape[0], chunk):
-        fc, dc = f[s0:s0 + chunk], do[s0:s0 + chunk]
-        pre = torch.addmm(b0, fc, w0.t())
-        h = torch.nn.functional.softplus(pre)
-        dw1 += dc.t() @ h
-        db1 += dc.sum(0)
-        dpre = (dc @ w1) * torch.sigmoid(pre)
-        dw0 += dpre.t() @ fc
-        db0 += dpre.sum(0)
-    _acc(d0.weight, dw0 * d0.weight_gain)
-    _acc(d0.bias, db0 * d0.bias_gain)
-    _acc(d2.weight, dw1 * d2.weight_gain)
-    _acc(d2.bias, db1 * d2.bias_gain)
+    g = ops.decoder_wgrad(f, do, mlp)
+    n0, n1 = d0.weight.numel(), d2.weight.numel()
+    h, o = d0.weight.shape[0], d2.weight.shape[0]
+    _acc(d0.weight, g[:n0] * d0.weight_gain)
+    _acc(d0.bias, g[n0:n0 + h] * d0.bias_gain)
+    _acc(d2.weight, g[n0 + h:n0 + h + n1] * d2.weight_gain)
+    _acc(d2.bias, g[n0 + h + n1:n0 + h + n1 + o] * d2.bias_gain)
 
 
 class RenderFn(torch.autograd.Function):
@@ -323,7 +314,7 @@ class RenderFn(torch.autograd.Function):
         if not dec:
             return out, None, None, None, None, None, None, None
         dplanes, f, do = out
-        _decoder_param_grads(gen, f, do)
+        _decoder_param_grads(gen, f, do, pk['mlp'])
         return dplanes, None, None, None, None, None, None, None
 
 

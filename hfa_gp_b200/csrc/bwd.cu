@@ -509,9 +509,7 @@ static int wgrad_impl(const HfagpConvDesc* desc, const float* x, const uint16_t*
   HFAGP_CHECK_ARG(d.ntaps > 0 && d.ntaps <= HFAGP_MAX_TAPS && (d.in_stride == 1 || d.in_stride == 2), "conv2d_wgrad: bad taps/stride");
   HFAGP_CHECK_ARG(d.out_stride == 1 && d.out_h == d.oh && d.out_w == d.ow, "conv2d_wgrad: dz must be dense [n][oh][ow][cout]");
   if (x_hi && dz_hi && wgrad_tc_supported(d)) {
-    int dev = 0, sms = 148;
-    HFAGP_CUDA(cudaGetDevice(&dev));
-    HFAGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = device_sm_count();
     return wgrad_tc_launch(d, x_hi, x_lo, dz_hi, dz_lo, xscale, dzscale, scale, dw, sms, (cudaStream_t)stream);
   }
   WgradParams p;

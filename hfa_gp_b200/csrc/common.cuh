@@ -1,6 +1,7 @@
 // Shared helpers for libhfagp_sm100.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>
@@ -33,6 +34,24 @@ int fail(int code, const char* fmt, ...);
 
 // programmatic dependent launch of the kernels that support it (tc_common.cuh); opt-in with HFAGP_PDL=1
 bool pdl_enabled();
+
+// Per-DEVICE one-time setup (cudaFuncSetAttribute applies to the device that is current when it is called, so a
+// process that drives several GPUs must repeat it on each): runs `f` the first time the calling thread's current
+// device is seen through `mask`; returns f's error (cudaSuccess afterwards).  f is idempotent, so a benign race between
+// two first callers only repeats it.
+template <typename F>
+inline cudaError_t per_device_once(std::atomic<uint64_t>& mask, F&& f) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = f();
+  if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+// SM count of the current device (cached per device ordinal)
+int device_sm_count();
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

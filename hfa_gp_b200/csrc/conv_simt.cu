@@ -189,55 +189,48 @@ __global__ void conv_epilogue_kernel(const ConvParams p, const float* __restrict
 // evaluated separably in registers: a thread owns 4 channels of TWO adjacent output columns and UPFIR_R (4) output rows;
 // it walks the R+3 input rows once (5 float4 loads per row), forms the two horizontal sums and scatters them into
 // the vertical accumulators.  3.4 loads per output instead of 16; the epilogue is branch-free.
-template <int UPFIR_R>
-__global__ void __launch_bounds__(256) upfir_act_kernel(int batch, int h2, int w2, int c, const float* __restrict__ t,
+// C4C > 0: channel quads per pixel known at compile time (column offsets become immediates of one row pointer).
+// Grid: x = (column pair, channel quad), y = row band, z = sample — no 64-bit index arithmetic per thread.
+// The activation gain is folded into the scale / shift (leaky ReLU is positively homogeneous).
+template <int UPFIR_R, int C4C>
+__global__ void __launch_bounds__(256) upfir_act_kernel(int h2, int w2, int c, const float* __restrict__ t,
                                                        const float* __restrict__ dcoef,
                                                        const float* __restrict__ noise, float noise_gain,
                                                        const float* __restrict__ bias, int act, float act_gain,
                                                        float clamp, float* __restrict__ y,
                                                        __nv_bfloat16* __restrict__ y_hi,
                                                        __nv_bfloat16* __restrict__ y_lo) {
-  const int c4 = c >> 2;
+  const int c4 = C4C > 0 ? C4C : (c >> 2);
   const int wp = (w2 + 1) >> 1;                       // column pairs
-  const int hb = (h2 + UPFIR_R - 1) / UPFIR_R;        // row bands
-  const size_t total = (size_t)batch * hb * wp * c4;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cq = idx % c4;
-  size_t r = idx / c4;
-  const int px = r % wp;
-  r /= wp;
-  const int band = r % hb, n = r / hb;
-  const int ox0 = px * 2, oy0 = band * UPFIR_R;
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= (uint32_t)(wp * c4)) return;
+  const int px = (int)(i / (uint32_t)c4), cq = (int)(i - (uint32_t)px * c4);
+  const int n = blockIdx.z;
+  const int ox0 = px * 2, oy0 = blockIdx.y * UPFIR_R;
   const int th = h2 + 1, tw = w2 + 1;
-  const float4* tn = reinterpret_cast<const float4*>(t) + (size_t)n * th * tw * c4 + cq;
   const float g[4] = {0.25f, 0.75f, 0.75f, 0.25f};
   float acc[UPFIR_R][2][4];
 #pragma unroll
-  for (int i = 0; i < UPFIR_R; ++i)
+  for (int r = 0; r < UPFIR_R; ++r)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[i][0][k] = acc[i][1][k] = 0.f;
+    for (int k = 0; k < 4; ++k) acc[r][0][k] = acc[r][1][k] = 0.f;
 
-  // the five input columns ox0-1 .. ox0+3 are all inside the row except for the first and the last column pair:
-  // interior threads walk a pointer, no per-load index arithmetic or bounds tests
+  // the five input columns ox0-1 .. ox0+3 are all inside the row except for the first and the last column pair
   const bool interior_x = ox0 >= 1 && ox0 + 3 < tw;
   const long long rstride = (long long)tw * c4;
-  const float4* rowp = tn + ((long long)(oy0 - 1) * tw + (ox0 - 1)) * c4;     // (row oy0-1, column ox0-1); may lie outside
+  // (row oy0-1, column ox0-1); may lie outside, only dereferenced where valid
+  const float4* rp = reinterpret_cast<const float4*>(t) + (((long long)n * th + oy0 - 1) * tw + (ox0 - 1)) * c4 + cq;
 #pragma unroll
-  for (int rr = 0; rr < UPFIR_R + 3; ++rr) {
-    const int iy = oy0 + rr - 1;
-    if (iy < 0 || iy >= th) continue;
-    const float4* rp = rowp + rr * rstride;
+  for (int rr = 0; rr < UPFIR_R + 3; ++rr, rp += rstride) {
+    if ((unsigned)(oy0 + rr - 1) >= (unsigned)th) continue;
     float4 v[5];
     if (interior_x) {
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) v[kx] = __ldg(rp + kx * c4);
     } else {
 #pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
-        const int ix = ox0 + kx - 1;
-        v[kx] = (ix >= 0 && ix < tw) ? __ldg(rp + kx * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int kx = 0; kx < 5; ++kx)
+        v[kx] = (unsigned)(ox0 + kx - 1) < (unsigned)tw ? __ldg(rp + kx * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float ha[4], hb2[4];
     ha[0] = g[0] * v[0].x + g[1] * v[1].x + g[2] * v[2].x + g[3] * v[3].x;
@@ -248,43 +241,46 @@ __global__ void __launch_bounds__(256) upfir_act_kernel(int batch, int h2, int w
     hb2[1] = g[0] * v[1].y + g[1] * v[2].y + g[2] * v[3].y + g[3] * v[4].y;
     hb2[2] = g[0] * v[1].z + g[1] * v[2].z + g[2] * v[3].z + g[3] * v[4].z;
     hb2[3] = g[0] * v[1].w + g[1] * v[2].w + g[2] * v[3].w + g[3] * v[4].w;
-    // input row rr (iy = oy0 + rr - 1) feeds output rows i = rr - ky, ky = 0..3
+    // input row rr (iy = oy0 + rr - 1) feeds output rows r = rr - ky, ky = 0..3
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
-      const int i = rr - ky;
-      if (i < 0 || i >= UPFIR_R) continue;
+      const int r = rr - ky;
+      if (r < 0 || r >= UPFIR_R) continue;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        acc[i][0][k] = fmaf(g[ky], ha[k], acc[i][0][k]);
-        acc[i][1][k] = fmaf(g[ky], hb2[k], acc[i][1][k]);
+        acc[r][0][k] = fmaf(g[ky], ha[k], acc[r][0][k]);
+        acc[r][1][k] = fmaf(g[ky], hb2[k], acc[r][1][k]);
       }
     }
   }
   float sc[4], sh[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    sc[k] = dcoef ? __ldg(dcoef + (size_t)n * c + cq * 4 + k) : 1.f;
-    sh[k] = bias ? __ldg(bias + cq * 4 + k) : 0.f;
+  {
+    const float4 s4 = dcoef ? __ldg(reinterpret_cast<const float4*>(dcoef + (size_t)n * (c4 * 4)) + cq) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sc[0] = s4.x * act_gain; sc[1] = s4.y * act_gain; sc[2] = s4.z * act_gain; sc[3] = s4.w * act_gain;
+    sh[0] = b4.x * act_gain; sh[1] = b4.y * act_gain; sh[2] = b4.z * act_gain; sh[3] = b4.w * act_gain;
   }
+  const float ng = noise_gain * act_gain;
   const float slope = act_slope(act);
   const float cl = clamp > 0.f ? clamp : __int_as_float(0x7f800000);
+  const bool two = ox0 + 1 < w2;
+  const float* np = noise ? noise + (size_t)oy0 * w2 + ox0 : nullptr;
+  size_t oq = (((size_t)n * h2 + oy0) * w2 + ox0) * c4 + cq;
 #pragma unroll
-  for (int i = 0; i < UPFIR_R; ++i) {
-    const int oy = oy0 + i;
-    if (oy >= h2) break;
+  for (int r = 0; r < UPFIR_R; ++r, oq += (size_t)w2 * c4) {
+    if (oy0 + r >= h2) break;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int ox = ox0 + j;
-      if (ox >= w2) continue;
-      const float nz = noise ? __ldg(noise + (size_t)oy * w2 + ox) * noise_gain : 0.f;
+      if (j == 1 && !two) continue;
+      const float nz = np ? __ldg(np + r * w2 + j) * ng : 0.f;
       float o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float a = fmaf(acc[i][j][k], sc[k], sh[k] + nz);
-        a = fmaxf(a, slope * a) * act_gain;
+        float a = fmaf(acc[r][j][k], sc[k], sh[k] + nz);
+        a = fmaxf(a, slope * a);
         o[k] = fminf(fmaxf(a, -cl), cl);
       }
-      st4_any(y, y_hi, y_lo, (((size_t)n * h2 + oy) * w2 + ox) * c4 + cq, o);
+      st4_any(y, y_hi, y_lo, oq + j * c4, o);
     }
   }
 }
@@ -370,43 +366,6 @@ __global__ void torgb_finalize_kernel(int batch, int h, int w_, int k, const flo
 }
 
 // ---------------------------------------------------------------- encoder blur
-__global__ void blur_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow, float gain,
-                            const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi,
-                            const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
-                            __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
-  const int c4 = c >> 2;
-  size_t total = (size_t)batch * oh * ow * c4;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int cq = idx % c4;
-  size_t pix = idx / c4;
-  int ox = pix % ow;
-  size_t r = pix / ow;
-  int oy = r % oh;
-  int n = r / oh;
-  const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-  const size_t nb = (size_t)n * h * w_ * c4;
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int ky = 0; ky < 4; ++ky) {
-    int iy = oy * stride + ky - pad0;
-    if (iy < 0 || iy >= h) continue;
-#pragma unroll
-    for (int kx = 0; kx < 4; ++kx) {
-      int ix = ox * stride + kx - pad0;
-      if (ix < 0 || ix >= w_) continue;
-      float wgt = g[ky] * g[kx] * gain;
-      float4 v = ld4_any(x, x_hi, x_lo, nb + ((size_t)iy * w_ + ix) * c4 + cq);
-      s[0] = fmaf(wgt, v.x, s[0]);
-      s[1] = fmaf(wgt, v.y, s[1]);
-      s[2] = fmaf(wgt, v.z, s[2]);
-      s[3] = fmaf(wgt, v.w, s[3]);
-    }
-  }
-  st4_any(y, y_hi, y_lo, idx, s);
-}
-
-
 // any channel count (3-channel images of the super-resolution skip path), fp32 only
 __global__ void blur_scalar_kernel(int batch, int h, int w_, int c, int pad0, int stride, int oh, int ow, float gain,
                                    const float* __restrict__ x, float* __restrict__ y) {
@@ -514,19 +473,22 @@ extern "C" int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float
   HFAGP_CHECK_ARG(t && ((y != nullptr) != (y_hi != nullptr && y_lo != nullptr)),
                   "upfir_act_fwd: give t and either y or (y_hi, y_lo)");
   HFAGP_CHECK_ARG(batch > 0 && h2 > 0 && w2 > 0 && c > 0 && (c & 3) == 0, "upfir_act_fwd: c must be a multiple of 4");
-  static const int r_env = getenv("HFAGP_UPFIR_R") ? atoi(getenv("HFAGP_UPFIR_R")) : 0;
-  const int R = r_env ? r_env : 4;     // measured on B200 (tools/prof_upfir.py): 2: 100 us, 4: 85 us, 8: 91 us, 16: 142 us (512^2 x 128)
-  size_t total = (size_t)batch * cdiv(h2, R) * cdiv(w2, 2) * (c >> 2);
+  HFAGP_CHECK_ARG(act_gain > 0.f, "upfir_act_fwd: act_gain must be positive (it is folded into the scale)");
+  HFAGP_CHECK_ARG(batch <= 65535 && cdiv(h2, 4) <= 65535 && (long long)cdiv(w2, 2) * (c >> 2) < (1ll << 31), "upfir_act_fwd: dims too large");
+  // 4 output rows per thread: measured on B200 (tools/prof_upfir.py, 512^2 x 128): 2 rows 100 us, 4: 85 us, 8: 91 us, 16: 142 us
+  // (58 us after the index arithmetic went 32-bit / immediate); 1 row per thread while that would leave SMs idle
+  const unsigned gx = (unsigned)cdiv((size_t)cdiv(w2, 2) * (c >> 2), 256);
+  const bool big = (long long)gx * cdiv(h2, 4) * batch >= 148 * 6;
   auto* hi_ = reinterpret_cast<__nv_bfloat16*>(y_hi);
   auto* lo_ = reinterpret_cast<__nv_bfloat16*>(y_lo);
-  if (R == 4)
-    upfir_act_kernel<4><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_);
-  else if (R == 2)
-    upfir_act_kernel<2><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_);
-  else if (R == 16)
-    upfir_act_kernel<16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_);
-  else
-    upfir_act_kernel<8><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(batch, h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_);
+#define HFAGP_UPFIR_LAUNCH(R, C4C) \
+  upfir_act_kernel<R, C4C><<<dim3(gx, cdiv(h2, R), batch), 256, 0, (cudaStream_t)stream>>>(h2, w2, c, t, dcoef, noise, noise_gain, bias, act, act_gain, clamp, y, hi_, lo_)
+  if (!big) HFAGP_UPFIR_LAUNCH(1, 0);
+  else if (c == 512) HFAGP_UPFIR_LAUNCH(4, 128);
+  else if (c == 256) HFAGP_UPFIR_LAUNCH(4, 64);
+  else if (c == 128) HFAGP_UPFIR_LAUNCH(4, 32);
+  else HFAGP_UPFIR_LAUNCH(4, 0);
+#undef HFAGP_UPFIR_LAUNCH
   HFAGP_CHECK_LAUNCH("upfir_act_kernel");
   return HFAGP_OK;
 }
@@ -548,48 +510,75 @@ extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout
   return HFAGP_OK;
 }
 
-// stride-1 blur, two adjacent output columns per thread: the 4x5 input window is loaded once (10 loads per output
-// instead of 16) and both horizontal sums are formed per row
-__global__ void blur2_kernel(int batch, int h, int w_, int c, int pad0, int oh, int ow, float gain,
-                             const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi,
-                             const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
-                             __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
-  const int c4 = c >> 2, wp = (ow + 1) >> 1;
-  const size_t total = (size_t)batch * oh * wp * c4;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cq = idx % c4;
-  size_t r = idx / c4;
-  const int px = r % wp;
-  r /= wp;
-  const int oy = r % oh, n = r / oh;
-  const int ox0 = px * 2;
+// [1,3,3,1]^2 / 64 blur, stride 1 or 2, evaluated separably in registers: a thread owns 4 channels of two adjacent
+// output columns and R output rows, walks the (R-1)*STRIDE + 4 input rows once (STRIDE + 4 loads each), forms the two
+// horizontal sums per row and scatters them into the vertical accumulators (stride 1: 4.4 loads per output instead of
+// 16, stride 2: 9).  Grid: x = (column pair, channel quad), y = row band, z = sample.
+template <int STRIDE, int R>
+__global__ void __launch_bounds__(256) blur_tile_kernel(int h, int w_, int c4, int pad0, int oh, int ow, float gain,
+                                                       const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi,
+                                                       const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
+                                                       __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+  constexpr int NC = STRIDE + 4, NR = (R - 1) * STRIDE + 4;
+  const int wp = (ow + 1) >> 1;
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= (uint32_t)(wp * c4)) return;
+  const int px = (int)(i / (uint32_t)c4), cq = (int)(i - (uint32_t)px * c4);
+  const int n = blockIdx.z, ox0 = px * 2, oy0 = blockIdx.y * R;
+  const int ix0 = ox0 * STRIDE - pad0, iy0 = oy0 * STRIDE - pad0;
   const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-  const size_t nb = (size_t)n * h * w_ * c4 + cq;
-  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[R][2][4];
 #pragma unroll
-  for (int ky = 0; ky < 4; ++ky) {
-    const int iy = oy + ky - pad0;
-    if (iy < 0 || iy >= h) continue;
-    float4 v[5];
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int kx = 0; kx < 5; ++kx) {
-      const int ix = ox0 + kx - pad0;
-      v[kx] = (ix >= 0 && ix < w_) ? ld4_any(x, x_hi, x_lo, nb + ((size_t)iy * w_ + ix) * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 4; ++k) acc[r][0][k] = acc[r][1][k] = 0.f;
+  const bool interior_x = ix0 >= 0 && ix0 + NC <= w_;
+  const long long rstride = (long long)w_ * c4;
+  long long q = (((long long)n * h + iy0) * w_ + ix0) * c4 + cq;       // (row iy0, column ix0); may lie outside
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr, q += rstride) {
+    if ((unsigned)(iy0 + rr) >= (unsigned)h) continue;
+    float4 v[NC];
+#pragma unroll
+    for (int kx = 0; kx < NC; ++kx)
+      v[kx] = (interior_x || (unsigned)(ix0 + kx) < (unsigned)w_) ? ld4_any(x, x_hi, x_lo, (size_t)(q + (long long)kx * c4))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    float ha[4], hb[4];
+    ha[0] = g[0] * v[0].x + g[1] * v[1].x + g[2] * v[2].x + g[3] * v[3].x;
+    ha[1] = g[0] * v[0].y + g[1] * v[1].y + g[2] * v[2].y + g[3] * v[3].y;
+    ha[2] = g[0] * v[0].z + g[1] * v[1].z + g[2] * v[2].z + g[3] * v[3].z;
+    ha[3] = g[0] * v[0].w + g[1] * v[1].w + g[2] * v[2].w + g[3] * v[3].w;
+    hb[0] = g[0] * v[STRIDE].x + g[1] * v[STRIDE + 1].x + g[2] * v[STRIDE + 2].x + g[3] * v[STRIDE + 3].x;
+    hb[1] = g[0] * v[STRIDE].y + g[1] * v[STRIDE + 1].y + g[2] * v[STRIDE + 2].y + g[3] * v[STRIDE + 3].y;
+    hb[2] = g[0] * v[STRIDE].z + g[1] * v[STRIDE + 1].z + g[2] * v[STRIDE + 2].z + g[3] * v[STRIDE + 3].z;
+    hb[3] = g[0] * v[STRIDE].w + g[1] * v[STRIDE + 1].w + g[2] * v[STRIDE + 2].w + g[3] * v[STRIDE + 3].w;
+    // input row rr feeds output row r with tap ky = rr - r * STRIDE
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int ky = rr - r * STRIDE;
+      if (ky < 0 || ky >= 4) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[r][0][k] = fmaf(g[ky], ha[k], acc[r][0][k]);
+        acc[r][1][k] = fmaf(g[ky], hb[k], acc[r][1][k]);
+      }
     }
-    const float wy = g[ky] * gain;
-    a[0] = fmaf(wy, g[0] * v[0].x + g[1] * v[1].x + g[2] * v[2].x + g[3] * v[3].x, a[0]);
-    a[1] = fmaf(wy, g[0] * v[0].y + g[1] * v[1].y + g[2] * v[2].y + g[3] * v[3].y, a[1]);
-    a[2] = fmaf(wy, g[0] * v[0].z + g[1] * v[1].z + g[2] * v[2].z + g[3] * v[3].z, a[2]);
-    a[3] = fmaf(wy, g[0] * v[0].w + g[1] * v[1].w + g[2] * v[2].w + g[3] * v[3].w, a[3]);
-    b[0] = fmaf(wy, g[0] * v[1].x + g[1] * v[2].x + g[2] * v[3].x + g[3] * v[4].x, b[0]);
-    b[1] = fmaf(wy, g[0] * v[1].y + g[1] * v[2].y + g[2] * v[3].y + g[3] * v[4].y, b[1]);
-    b[2] = fmaf(wy, g[0] * v[1].z + g[1] * v[2].z + g[2] * v[3].z + g[3] * v[4].z, b[2]);
-    b[3] = fmaf(wy, g[0] * v[1].w + g[1] * v[2].w + g[2] * v[3].w + g[3] * v[4].w, b[3]);
   }
-  const size_t o = (((size_t)n * oh + oy) * ow + ox0) * c4 + cq;
-  st4_any(y, y_hi, y_lo, o, a);
-  if (ox0 + 1 < ow) st4_any(y, y_hi, y_lo, o + c4, b);
+  const bool two = ox0 + 1 < ow;
+  size_t oq = (((size_t)n * oh + oy0) * ow + ox0) * c4 + cq;
+#pragma unroll
+  for (int r = 0; r < R; ++r, oq += (size_t)ow * c4) {
+    if (oy0 + r >= oh) break;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = acc[r][0][k] * gain;
+    st4_any(y, y_hi, y_lo, oq, o);
+    if (two) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = acc[r][1][k] * gain;
+      st4_any(y, y_hi, y_lo, oq + c4, o);
+    }
+  }
 }
 
 extern "C" int hfagp_torgb_finalize_fwd(int batch, int h, int w_, int k, const float* acc, const float* bias, float clamp,
@@ -611,18 +600,24 @@ extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad
   int oh = (h + pad0 + pad1 - 4) / stride + 1;
   int ow = (w_ + pad0 + pad1 - 4) / stride + 1;
   HFAGP_CHECK_ARG(oh > 0 && ow > 0, "blur_fwd: empty output");
-  if ((c & 3) == 0 && stride == 1) {
-    size_t total = (size_t)batch * oh * cdiv(ow, 2) * (c >> 2);
-    blur2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        batch, h, w_, c, pad0, oh, ow, gain, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
-        reinterpret_cast<const __nv_bfloat16*>(x_lo), y, reinterpret_cast<__nv_bfloat16*>(y_hi),
-        reinterpret_cast<__nv_bfloat16*>(y_lo));
-  } else if ((c & 3) == 0) {
-    size_t total = (size_t)batch * oh * ow * (c >> 2);
-    blur_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        batch, h, w_, c, pad0, stride, oh, ow, gain, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
-        reinterpret_cast<const __nv_bfloat16*>(x_lo), y, reinterpret_cast<__nv_bfloat16*>(y_hi),
-        reinterpret_cast<__nv_bfloat16*>(y_lo));
+  if ((c & 3) == 0) {
+    HFAGP_CHECK_ARG(batch <= 65535 && oh <= 65535 * 2 && (long long)cdiv(ow, 2) * (c >> 2) < (1ll << 31), "blur_fwd: dims too large");
+    auto* xh = reinterpret_cast<const __nv_bfloat16*>(x_hi);
+    auto* xl = reinterpret_cast<const __nv_bfloat16*>(x_lo);
+    auto* yh = reinterpret_cast<__nv_bfloat16*>(y_hi);
+    auto* yl = reinterpret_cast<__nv_bfloat16*>(y_lo);
+    const unsigned gx = (unsigned)cdiv((size_t)cdiv(ow, 2) * (c >> 2), 256);
+    // rows per thread: the register-blocked form only once it still fills the machine (~6 CTAs per SM); the encoder's
+    // batch-1 tensors are small enough that thread count matters more than loads per output
+    static const int big_env = getenv("HFAGP_BLUR_BIG") ? atoi(getenv("HFAGP_BLUR_BIG")) : -1;   // profiling override
+    const bool big = big_env >= 0 ? big_env != 0 : (long long)gx * cdiv(oh, stride == 1 ? 4 : 2) * batch >= 148 * 6;
+#define HFAGP_BLUR_LAUNCH(S, R) \
+  blur_tile_kernel<S, R><<<dim3(gx, cdiv(oh, R), batch), 256, 0, (cudaStream_t)stream>>>(h, w_, c >> 2, pad0, oh, ow, gain, x, xh, xl, y, yh, yl)
+    if (stride == 1 && big) HFAGP_BLUR_LAUNCH(1, 4);
+    else if (stride == 1) HFAGP_BLUR_LAUNCH(1, 1);
+    else if (big) HFAGP_BLUR_LAUNCH(2, 2);
+    else HFAGP_BLUR_LAUNCH(2, 1);
+#undef HFAGP_BLUR_LAUNCH
   } else {
     HFAGP_CHECK_ARG(x && y, "blur_fwd: split-bf16 I/O needs c%%4 == 0");
     size_t total = (size_t)batch * oh * ow * c;

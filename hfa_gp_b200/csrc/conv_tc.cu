@@ -875,19 +875,13 @@ static int launch_tc(const HfagpConvDesc* descs, int ndesc, const uint16_t* x_hi
   mb_half = mb_hi;
   if (two && (rc = get_map(&mb_half, w_hi, d.cin, d.cout, wz, 1, TC_BK, p.bn / 2, 1, 1, 1, 3))) return rc;
 
-  static std::once_flag attr_once;
-  static int num_sms = 148;
-  static cudaError_t attr_rc = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_rc = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_rc == cudaSuccess)
-      attr_rc = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      num_sms = n;
+  static std::atomic<uint64_t> attr_done{0};
+  const cudaError_t attr_rc = per_device_once(attr_done, [] {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e != cudaSuccess ? e : cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_rc != cudaSuccess) return fail(HFAGP_E_CUDA, "%s: cudaFuncSetAttribute(max dynamic smem) failed: %s", who, cudaGetErrorString(attr_rc));
+  const int num_sms = device_sm_count();
   if (two) {
     const int pairs = p.total_tiles < num_sms / 2 ? p.total_tiles : num_sms / 2;
     cudaLaunchConfig_t cfg = {};

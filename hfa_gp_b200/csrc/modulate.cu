@@ -207,3 +207,22 @@ int fail(int code, const char* fmt, ...) {
 
 extern "C" int hfagp_abi_version(void) { return HFAGP_ABI_VERSION; }
 extern "C" const char* hfagp_last_error(void) { return hfagp::err_buf(); }
+
+namespace hfagp {
+int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cache[dev & 63].store(n, std::memory_order_relaxed);
+  return n;
+}
+}  // namespace hfagp
+
+extern "C" int hfagp_device_sm_count(void) { return hfagp::device_sm_count(); }
+extern "C" int hfagp_set_device(int device) {
+  HFAGP_CUDA(cudaSetDevice(device));
+  return HFAGP_OK;
+}

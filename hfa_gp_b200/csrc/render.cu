@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(con
         constexpr int NE = decltype(ne_tag)::value;       // elements per lane = ceil(T / 32)
         float de[NE];
         int rk[NE];
-        stable_ranks<NE>(dep, T, lane, de, rk);
+        stable_ranks<NE>(dep, T, lane, de, rk, S);
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
           const int i = lane + 32 * e;
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(128) render_bookkeeping_kernel(int rays, int n
   if (sort_idx) {
     float de[4];
     int rk[4];
-    stable_ranks<4>(dep, T, lane, de, rk);
+    stable_ranks<4>(dep, T, lane, de, rk, T - s_fine);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       if (lane + 32 * e < T) sort_idx[(size_t)ray * T + rk[e]] = lane + 32 * e;
@@ -760,9 +760,7 @@ static int render_fwd_impl(bool allow_tc, const HfagpRenderDesc* desc, const flo
   HFAGP_CHECK_ARG((long long)d.plane_h * d.plane_w * 96 < (1ll << 31), "render_fwd: plane too large for 32-bit tap offsets");
   RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, depth_range, feat, depth, wsum, inds, below, above, sort_idx, depths_sorted,
                  nullptr, nullptr};
-  int dev = 0, sms = 148;
-  HFAGP_CUDA(cudaGetDevice(&dev));
-  HFAGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = device_sm_count();
   if (allow_tc && render_tc_supported(d)) return render_tc_launch(p, sms, (cudaStream_t)stream);
   int nwarps = R_WARPS;
   size_t smem = ((WEIGHT_BYTES + 15) & ~15) + nwarps * render_warp_bytes(d.s_coarse, d.s_fine);
@@ -770,8 +768,8 @@ static int render_fwd_impl(bool allow_tc, const HfagpRenderDesc* desc, const flo
     nwarps = R_WARPS / 2;
     smem = ((WEIGHT_BYTES + 15) & ~15) + nwarps * render_warp_bytes(d.s_coarse, d.s_fine);
   }
-  static std::once_flag attr_once;   // opt in to the full 227 KB once; not repeated on the (graph-captured) hot path
-  std::call_once(attr_once, [] { cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  static std::atomic<uint64_t> attr_done{0};   // opt in to the full 227 KB once per device; not repeated on the (graph-captured) hot path
+  HFAGP_CUDA(per_device_once(attr_done, [] { return cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   HFAGP_CHECK_ARG(smem <= 227 * 1024, "render_fwd: shared memory need exceeds 227 KB");
   const long long strips = (long long)d.batch * ((d.res + nwarps - 1) / nwarps) * d.res;
   const int blocks = (int)(strips < sms ? strips : sms);   // persistent: one CTA per SM
@@ -810,12 +808,10 @@ static int render_bwd_impl(const HfagpRenderDesc* desc, const float* planes, con
                  nullptr, dfeat, dplanes, dump_f, dump_do};
   const int nwarps = 8;
   const size_t smem = WEIGHT_BYTES_BWD + nwarps * render_warp_bytes(d.s_coarse, d.s_fine, true);
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] { cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  static std::atomic<uint64_t> attr_done{0};
+  HFAGP_CUDA(per_device_once(attr_done, [] { return cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   HFAGP_CHECK_ARG(smem <= 227 * 1024, "render_bwd: shared memory need exceeds 227 KB");
-  int dev = 0, sms = 148;
-  HFAGP_CUDA(cudaGetDevice(&dev));
-  HFAGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = device_sm_count();
   const long long strips = (long long)d.batch * ((d.res + nwarps - 1) / nwarps) * d.res;
   const int blocks = (int)(strips < sms ? strips : sms);
   render_kernel<true><<<blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(p);

@@ -151,11 +151,37 @@ __device__ __forceinline__ int searchsorted_right(const float* cdf, int n, float
 // Stable ranks of the T depths dep[0..T) (coarse samples first, as torch.cat + sort sees them): lane holds elements
 // lane + 32 e.  Fast path counts strictly smaller depths against one broadcast read of each depth; if any two depths are
 // equal the ranks no longer sum to T(T-1)/2 and the exact (value, index) order is recomputed.
+// The first S depths are the coarse samples: strictly increasing whenever the jitter stays inside its stratum (checked,
+// not assumed), so a coarse sample's rank among them is its index and a fine sample's is a lower bound — only the SF
+// fine depths are counted by comparison (half the work of the all-pairs count).  S = 0 selects the all-pairs count.
 template <int NE>
-__device__ __forceinline__ void stable_ranks(const float* dep, int T, int lane, float (&de)[NE], int (&rk)[NE]) {
+__device__ __forceinline__ void stable_ranks(const float* dep, int T, int lane, float (&de)[NE], int (&rk)[NE], int S = 0) {
 #pragma unroll
   for (int e = 0; e < NE; ++e) { de[e] = lane + 32 * e < T ? dep[lane + 32 * e] : 0.f; rk[e] = 0; }
-  for (int j = 0; j < T; ++j) {
+  bool inc = S > 1;
+  if (inc) {
+    bool ok = true;
+    for (int j = lane; j + 1 < S; j += 32) ok = ok && dep[j] < dep[j + 1];
+    inc = __all_sync(0xffffffffu, ok);
+  }
+  const int j0 = inc ? S : 0;
+  if (inc) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int i = lane + 32 * e;
+      if (i < S) {
+        rk[e] = i;
+      } else {                                       // #{coarse depths < de[e]}: lower bound in the sorted prefix
+        int lo = 0;
+        for (int len = S; len > 0;) {
+          const int half = len >> 1;
+          if (dep[lo + half] < de[e]) { lo += half + 1; len -= half + 1; } else { len = half; }
+        }
+        rk[e] = lo;
+      }
+    }
+  }
+  for (int j = j0; j < T; ++j) {
     const float dj = dep[j];
 #pragma unroll
     for (int e = 0; e < NE; ++e) rk[e] += dj < de[e] ? 1 : 0;

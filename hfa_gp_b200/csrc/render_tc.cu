@@ -26,6 +26,7 @@
 // Replaces (forward): ImportanceRenderer.forward + OSGDecoder + MipRayMarcher2 of NVlabs/eg3d, reached through
 // code/networks/headnerf.py:112.
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 #include "common.cuh"
@@ -135,7 +136,7 @@ __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::
 
 // PWC > 0: plane width known at compile time (the four taps of a plane are immediate offsets from one address)
 template <int PWC, int RT_NA1, int ESPLIT>
-__global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderParams p, const int tw_log2) {
   // SWIZZLE_128B operand tiles need 1024 B alignment (a profiler may put its own static shared memory in front of the
   // dynamic window).  The alignment is added as an integer OFFSET to the shared array — no pointer/integer round trip —
   // so every access below stays a shared-space (LDS/STS) access.
@@ -210,8 +211,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
   const uint32_t tmem_base = *tmem_slot;
 
   const int res = d.res;
-  const int ytiles = (res + RT_RAYS - 1) / RT_RAYS;
-  const long long strips = (long long)d.batch * ytiles * res;
+  // a strip = a (1 << tw_log2) x (16 >> tw_log2) block of pixels: neighbouring rays share texels in all three planes
+  const int tile_w = 1 << tw_log2, tile_h = RT_RAYS >> tw_log2;
+  const int xtiles = (res + tile_w - 1) / tile_w, ytiles = (res + tile_h - 1) / tile_h;
+  const long long strips = (long long)d.batch * ytiles * xtiles;
   const int nt_c = (S + RT_TILE - 1) / RT_TILE, nt_f = (SF + RT_TILE - 1) / RT_TILE;
 
   if (warp == RT_RAYS) {
@@ -287,12 +290,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
     uint32_t gt = 0;                                 // global tile counter (same sequence as the MMA warp's)
 
     for (long long strip = blockIdx.x; strip < strips; strip += gridDim.x) {
-      const int n = (int)(strip / ((long long)ytiles * res));
-      const int rem = (int)(strip - (long long)n * ytiles * res);
-      const int yt = rem / res, px = rem - yt * res;
-      const int py = yt * RT_RAYS + warp;
-      const bool rvalid = py < res;                  // warp-uniform; an invalid ray still serves its epilogue rows
-      const long long ray = ((long long)n * res + (rvalid ? py : res - 1)) * res + px;
+      const int n = (int)(strip / ((long long)ytiles * xtiles));
+      const int rem = (int)(strip - (long long)n * ytiles * xtiles);
+      const int yt = rem / xtiles, xt = rem - yt * xtiles;
+      const int px_ = xt * tile_w + (warp & (tile_w - 1)), py_ = yt * tile_h + (warp >> tw_log2);
+      const bool rvalid = px_ < res && py_ < res;    // warp-uniform; an invalid ray still serves its epilogue rows
+      const int px = min(px_, res - 1), py = min(py_, res - 1);
+      const long long ray = ((long long)n * res + py) * res + px;
       const float* cam = p.cam + (size_t)n * 25;
       // this lane's channel quad of texel (0,0): the gather adds 32-bit texel offsets to it
       const char* lb = reinterpret_cast<const char*>(p.planes + (size_t)n * PH * PW * (3 * RC)) + (lane & 7) * 16;
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
       float ax, bx, ay, by;
       {
         const float inv = 1.0f / res, half = 0.5f / res;
-        const float xc = px * inv + half, yc = (rvalid ? py : res - 1) * inv + half;
+        const float xc = px * inv + half, yc = py * inv + half;
         const float fx = __ldg(cam + 16), sk = __ldg(cam + 17), cx = __ldg(cam + 18);
         const float fy = __ldg(cam + 20), cy = __ldg(cam + 21);
         const float rfx = 1.0f / fx, rfy = 1.0f / fy;
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
           constexpr int NE = decltype(ne_tag)::value;       // elements per lane = ceil(T / 32)
           float de[NE];
           int rk[NE];
-          stable_ranks<NE>(dep, T, lane, de, rk);
+          stable_ranks<NE>(dep, T, lane, de, rk, S);
 #pragma unroll
           for (int e = 0; e < NE; ++e) {
             const int i = lane + 32 * e;
@@ -653,18 +657,21 @@ bool render_tc_supported(const HfagpRenderDesc& d) {
 template <int PWC, int NA1, int ES>
 static int rt_launch_variant(const RenderParams& p, int blocks, cudaStream_t stream) {
   const size_t smem = rt_smem_bytes(p.d.s_coarse, p.d.s_fine, NA1);
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] { cudaFuncSetAttribute(render_tc_kernel<PWC, NA1, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  static std::atomic<uint64_t> attr_done{0};
+  HFAGP_CUDA(per_device_once(attr_done, [] { return cudaFuncSetAttribute(render_tc_kernel<PWC, NA1, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   if (smem > 227 * 1024) return fail(HFAGP_E_INVALID, "render_tc: shared memory plan does not fit");
-  render_tc_kernel<PWC, NA1, ES><<<blocks, RT_THREADS, smem, stream>>>(p);
+  static const int tw_log2 = [] { const char* e = getenv("HFAGP_RT_TILE_W_LOG2"); const int v = e ? atoi(e) : 2; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
+  const int xt = (p.d.res + (1 << tw_log2) - 1) >> tw_log2, th = RT_RAYS >> tw_log2;
+  const long long strips = (long long)p.d.batch * xt * ((p.d.res + th - 1) / th);
+  if (strips < blocks) blocks = (int)strips;
+  render_tc_kernel<PWC, NA1, ES><<<blocks, RT_THREADS, smem, stream>>>(p, tw_log2);
   HFAGP_CHECK_LAUNCH("render_tc_kernel");
   return HFAGP_OK;
 }
 
 int render_tc_launch(const RenderParams& p, int sms, cudaStream_t stream) {
   const HfagpRenderDesc& d = p.d;
-  const long long strips = (long long)d.batch * ((d.res + RT_RAYS - 1) / RT_RAYS) * d.res;
-  const int blocks = (int)(strips < sms ? strips : sms);
+  const int blocks = sms;                            // clipped to the number of strips by the variant
   if (d.plane_w == 256) return rt_launch_variant<256, 2, 1>(p, blocks, stream);
   return rt_launch_variant<0, 2, 1>(p, blocks, stream);
 }

@@ -282,8 +282,8 @@ int wgrad_tc_launch(const HfagpConvDesc& d, const uint16_t* x_hi, const uint16_t
   if ((rc = get_map(&mz_lo, dz_lo, d.cout, d.ow, d.oh, d.batch, 64, 8, 8, 1, 1, 4))) return rc;
   if ((rc = get_map(&mx_hi, x_hi, d.cin, d.in_w, d.in_h, d.batch, 64, bw, bh, 1, es, 4))) return rc;
   if ((rc = get_map(&mx_lo, x_lo, d.cin, d.in_w, d.in_h, d.batch, 64, bw, bh, 1, es, 4))) return rc;
-  static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  static std::atomic<uint64_t> attr_done{0};
+  HFAGP_CUDA(per_device_once(attr_done, [] { return cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   wgrad_tc_kernel<<<items * splits, WT_THREADS, smem, stream>>>(mz_hi, mz_lo, mx_hi, mx_lo, p);
   HFAGP_CHECK_LAUNCH("wgrad_tc_kernel");
   return HFAGP_OK;

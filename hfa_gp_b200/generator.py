@@ -368,7 +368,7 @@ class TriPlaneGenerator(nn.Module):
                 tap[name + '.conv0'] = self._as_f32(x)
         s1, st = next(styles_iter), next(styles_iter)
         plt = pk['layers'][id(blk.torgb)]
-        if rec is None and plt.cout <= 4 and self._use_tc(blk.cout) and blk.cout % 32 == 0:
+        if rec is None and plt.cout <= 4 and self._use_tc(blk.cout) and blk.cout % 32 == 0 and not ops.deterministic():
             # super-resolution blocks: the 3-channel ToRGB rides on conv1's epilogue (its activations are still in
             # registers there) instead of re-reading the whole layer output
             wrgb, _ = ops.modulate(plt.w, st, False)                       # [n][1][k][cout]

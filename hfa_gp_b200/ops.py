@@ -5,6 +5,7 @@ Every function enqueues on ``torch.cuda.current_stream()`` and returns torch-own
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Optional, Sequence, Tuple
 
@@ -231,6 +232,14 @@ def render_bookkeeping(cdf, u, depths):
     return inds, below, above, sort_idx
 
 
+def decoder_wgrad(f, do, mlp):
+    """Per-sample decoder operands (f [S,32], do [S,33], see render_bwd(decoder=True)) -> gradient of the packed
+    effective decoder weights [4257] (W0 [64,32], b0 [64], W1 [33,64], b1 [33]); see ``hfagp_decoder_wgrad``."""
+    dmlp = torch.zeros_like(mlp)
+    _ok(_cabi.lib().hfagp_decoder_wgrad(f.shape[0], ptr(f), ptr(do), ptr(mlp), ptr(dmlp), stream()), 'hfagp_decoder_wgrad')
+    return dmlp
+
+
 def render_bwd(planes, c, mlp, lin, jitter, u_fine, dfeat, *, res, s_coarse, s_fine, delta, box_scale, decoder=False):
     """d(feat) [N,res,res,32] -> d(planes) [N,PH,PW,96], see ``hfagp_render_bwd``.  ``decoder=True`` also returns the
     per-sample (features [S,32], d(raw decoder output) [S,33]) pair for the decoder's weight gradient."""
@@ -346,17 +355,49 @@ def modulate_split(w: torch.Tensor, styles: torch.Tensor, demodulate: bool):
     return Split(hi, lo), dcoef
 
 
-NUM_SMS = 148
+NUM_SMS = 148          # B200; the value used when no device can be asked (host-logic tests)
+_sm_count = {}
+_deterministic = os.environ.get('HFAGP_DETERMINISTIC', '0') not in ('', '0')
 
 
-def _ksplit(tiles: int, cin: int, taps, in_stride: int) -> int:
+def set_deterministic(on: bool = True) -> bool:
+    """Bit-reproducible frames (or HFAGP_DETERMINISTIC=1): the forward path stops using the two features whose fp32
+    atomics make the summation order vary run to run — split-K for the layers with few output tiles (they run as plain
+    tcgen05 convolutions on the SMs their tiles cover) and the ToRGB fused into the super-resolution conv1 epilogue (the
+    separate ToRGB kernel reads the layer output instead).  Results stay within the parity tolerance of the default
+    path, ~10 % slower per frame at batch 1.  Decide BEFORE a frame graph is captured.  Returns the previous setting.
+    (Gradient kernels still accumulate with red.global.add; the reference's own CUDA backward is not deterministic
+    either.)"""
+    global _deterministic
+    prev, _deterministic = _deterministic, bool(on)
+    return prev
+
+
+def deterministic() -> bool:
+    return _deterministic
+
+
+def num_sms() -> int:
+    """SM count of the current device (``hfagp_device_sm_count``, cached per device ordinal)."""
+    if not torch.cuda.is_available():
+        return NUM_SMS
+    dev = torch.cuda.current_device()
+    if dev not in _sm_count:
+        _sm_count[dev] = int(_cabi.lib().hfagp_device_sm_count())
+    return _sm_count[dev]
+
+
+def _ksplit(tiles: int, cin: int, taps, in_stride: int, sms: int = None) -> int:
     """Split-K factor for a tensor-core convolution with ``tiles`` output tiles: 1 unless the tiles would leave
     three quarters of the SMs idle.  Units of K = 64-channel chunks x tap groups (taps sharing dx at stride 1)."""
+    if _deterministic:
+        return 1
+    sms = num_sms() if sms is None else sms
     groups = len({t[1] for t in taps}) if in_stride == 1 else len(taps)
     units = -(-cin // 64) * groups
-    if tiles * 4 > NUM_SMS or units < 4:
+    if tiles * 4 > sms or units < 4:
         return 1
-    return max(1, min(units, NUM_SMS // tiles))
+    return max(1, min(units, sms // tiles))
 
 
 def modulate_split_multi(entries, styles_flat, batch):

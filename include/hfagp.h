@@ -17,6 +17,10 @@
  *   - activations are fp32, channels-last:  x[n][y][x][c]  ("NHWC").
  *   - conv weights are fp32 packed  w[tap][cout][cin]  (tap = ky*kw + kx), see hfagp_pack notes.
  *   - re-entrant: forward and backward may be driven from different host threads.
+ *   - device: work goes to the device that is CURRENT on the calling thread (the one `stream` belongs to); the
+ *     caller selects it with cudaSetDevice / hfagp_set_device before the call.  One-time kernel attributes (dynamic
+ *     shared-memory opt-in) and the SM count used for grid sizing are kept per device ordinal, so one process may
+ *     drive several GPUs.
  */
 #ifndef HFAGP_H_
 #define HFAGP_H_
@@ -43,6 +47,10 @@ enum { HFAGP_ACT_LINEAR = 0, HFAGP_ACT_LRELU = 1 /* slope 0.2 */, HFAGP_ACT_RELU
 
 int hfagp_abi_version(void);
 const char* hfagp_last_error(void);
+/* cudaSetDevice(device) for the calling thread (the `device` argument of SURVEY 8b, hoisted out of every signature). */
+int hfagp_set_device(int device);
+/* SM count of the current device: the persistent grids (one CTA per SM) and the split-K heuristic are sized by it. */
+int hfagp_device_sm_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution, channels-last.
@@ -257,6 +265,15 @@ int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes, const flo
 int hfagp_render_bwd_dec(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
                          const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
                          float* dplanes, float* dump_f, float* dump_do, void* stream);
+
+/* Weight gradient of the OSG decoder MLP from the per-sample operands hfagp_render_bwd_dec wrote: dump_f [samples][32],
+ * dump_do [samples][33].  The hidden layer is recomputed in fp32 per 64-sample tile, the four reductions over samples
+ * (dW0, db0, dW1, db1) are accumulated in registers and ADDED to dmlp, which has the packing of `mlp`
+ * (W0 [64][32], b0 [64], W1 [33][64], b1 [33] = 4257 floats; caller zeroes it).  Gradients are w.r.t. the effective
+ * (gain-multiplied) weights in `mlp`.  Replaces: autograd of OSGDecoder's parameters (eg3d triplane.py), reached when
+ * tune_generator() has unfrozen the generator (code/train_rgb.py:132-134). */
+int hfagp_decoder_wgrad(long long samples, const float* dump_f, const float* dump_do, const float* mlp, float* dmlp,
+                        void* stream);
 
 /* [1,3,3,1]^2/64 FIR, zero-pad (pad0,pad1), optional output stride and gain:
  *   y[n][oy][ox][c] = gain * sum_{ky,kx} g[ky] g[kx] x[n][oy*stride + ky - pad0][ox*stride + kx - pad0][c]

@@ -235,6 +235,29 @@ def test_render_backward(res, s, sf, batch):
     assert e_l2 < 1e-3 and e_max < 5e-3, (e_max, e_l2)
 
 
+@pytest.mark.parametrize('samples', [64, 1000, 20011])
+def test_decoder_weight_gradient_kernel(samples):
+    """hfagp_decoder_wgrad (hidden layer recomputed, four reductions over the samples) against fp64 autograd of the same
+    32 -> 64 softplus -> 33 MLP on the same per-sample operands; ragged sample counts exercise the zero-filled tail."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(samples)
+    f = torch.randn(samples, 32, generator=g)
+    do = torch.randn(samples, 33, generator=g) * 0.1
+    w0 = (torch.randn(64, 32, generator=g) / math.sqrt(32)).requires_grad_()
+    b0 = (torch.randn(64, generator=g) * 0.1).requires_grad_()
+    w1 = (torch.randn(33, 64, generator=g) / 8).requires_grad_()
+    b1 = torch.zeros(33, requires_grad=True)
+    out = F.softplus(f.double() @ w0.double().t() + b0.double()) @ w1.double().t() + b1.double()
+    (out * do.double()).sum().backward()
+    want = torch.cat([w0.grad.reshape(-1), b0.grad, w1.grad.reshape(-1), b1.grad]).float()
+    mlp = torch.cat([w0.detach().reshape(-1), b0.detach(), w1.detach().reshape(-1), b1.detach()]).cuda()
+    got = ops.decoder_wgrad(f.cuda(), do.cuda(), mlp).cpu()
+    for name, lo, hi in (('dW0', 0, 2048), ('db0', 2048, 2112), ('dW1', 2112, 2112 + 2112), ('db1', 4224, 4257)):
+        e = pu.rel_l2(got[lo:hi], want[lo:hi])
+        print(f'decoder_wgrad S={samples} {name}: rel-L2 {e:.3e}')
+        assert e < 1e-4, (name, e)
+
+
 @pytest.mark.parametrize('precision', ['tc', 'fp32'])
 def test_generator_backward_to_ws(precision):
     """loss(image) -> d(ws) through super-resolution, renderer and backbone (generator frozen), vs the oracle."""

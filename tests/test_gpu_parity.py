@@ -554,6 +554,37 @@ def test_frame_loop_full_size_properties_and_egress():
     assert pu.rel_err(out['image'], a) < 5e-4                           # eager synthesis == graph replay (same caveat)
 
 
+def test_deterministic_mode_reproduces_frames_bit_for_bit():
+    """ops.set_deterministic(): no split-K atomics, no fused-ToRGB atomics — two replays of the full-size frame graph
+    (and a freshly captured second graph) give identical bits, within the parity tolerance of the default path."""
+    import argparse
+    from hfa_gp_b200 import ops
+    from hfa_gp_b200.frame_loop import FrameLoop
+    from hfa_gp_b200.networks.headnerf import HeadNeRF_final
+    args = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='',
+                              synthetic_generator=True, generator_seed=0)
+    torch.manual_seed(0)
+    model = HeadNeRF_final(args, 256, 'cuda', 512, 50, 'x', './').cuda().eval().requires_grad_(False)
+    cfg = model.generator.cfg
+    g = torch.Generator().manual_seed(11)
+    rays = cfg.nrr ** 2
+    model.generator.fixed_draws = (torch.rand(1, rays, cfg.depth_res, 1, generator=g).cuda(),
+                                   torch.rand(rays, cfg.depth_res_importance, generator=g).cuda())
+    img = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).cuda()
+    label = hfagp_ref.synthetic_labels(1, seed=5).cuda()
+    default = FrameLoop(model, batch=1, size=256)(img, label.clone()).clone()
+    prev = ops.set_deterministic(True)
+    try:
+        loop = FrameLoop(model, batch=1, size=256)
+        a = loop(img, label.clone()).clone()
+        b = loop(img, label.clone()).clone()
+        c = FrameLoop(model, batch=1, size=256)(img, label.clone()).clone()
+    finally:
+        ops.set_deterministic(prev)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert pu.rel_err(a, default) < 5e-4
+
+
 @pytest.mark.parametrize('drive', ['3dmm', 'audio'])
 def test_driven_frame_loops_match_oracle(drive):
     """configs[4] / run_recon_video_{3dmm,audio}.py: the graph-captured frame loop of the driven avatars
