@@ -392,7 +392,7 @@ def train_bench(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    bs = args.frames_per_step if args.frames_per_step > 1 else (2 if args.trainer == 'rgb' else max(8 // world, 1))
+    bs = args.frames_per_step if args.frames_per_step >= 1 else (2 if args.trainer == 'rgb' else max(8 // world, 1))
     sampler = ClockSampler(local_rank)
     sampler.start()
     rec = train_record(rank, world, dev, args.steps, args.warmup, trainer=args.trainer, per_rank_batch=bs,
@@ -421,8 +421,9 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--frames-per-step', type=int, default=4,
-                    help='frames per step = batch of one frame-graph replay (independent frames of the video; the reference loop feeds 1)')
+    ap.add_argument('--frames-per-step', type=int, default=0,
+                    help='frames per step = batch of one frame-graph replay (independent frames of the video; the reference loop feeds 1). '
+                         'Default: 4 for the frame loop; with --workload train the per-rank batch (default 2 rgb / 8 // world 3dmm)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--in-flight', type=int, default=3,
                     help='frames in flight (hfa_gp_b200.frame_loop.FramePipeline): 1 = strictly one frame after the other')
@@ -464,7 +465,7 @@ def main():
                             synthetic_generator=True, generator_seed=0)
     torch.manual_seed(0)
     model = HeadNeRF_final(ns, ENC_SIZE, dev, 512, DIM_SHAPE, 'bench', './').to(dev).eval().requires_grad_(False)
-    fps_ = args.frames_per_step
+    fps_ = args.frames_per_step if args.frames_per_step >= 1 else 4
     total = args.warmup + args.steps
     g = torch.Generator().manual_seed(1234 + rank)
     # synthetic frames: this rank's shard of the video (frame i -> rank i mod world): pinned host + device copies

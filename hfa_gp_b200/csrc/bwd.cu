@@ -32,7 +32,11 @@ __device__ __forceinline__ void atomic_add4(float* p, const float v[4]) {
   for (int k = 0; k < 4; ++k) atomicAdd(p + k, v[k]);
 }
 
-__global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
+// Specialised on which optional operands exist (second gradient stream, fused small-ToRGB gradient, residual merge): the
+// common call — one gradient stream into a modulated layer — then fits 3 CTAs per SM instead of 1-2 (the generic form
+// needs 128+ registers for operands it never touches, and this is a latency-bound stream kernel).
+template <bool HAS_G1, bool HAS_DIMG, bool HAS_RES>
+__global__ void __launch_bounds__(256, (HAS_G1 || HAS_DIMG) ? 2 : 3) act_bwd_kernel(const ActBwdParams p) {
   const HfagpActBwdDesc& d = p.d;
   const int c4 = d.c >> 2;
   const int planes = 256 / c4;                 // pixels processed side by side
@@ -51,14 +55,19 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (p.s0) sc0[k] = __ldg(p.s0 + nc + k);
-    if (p.g1 && p.s1) sc1[k] = __ldg(p.s1 + nc + k);
-    if (p.dimg) scr[k] = p.srgb ? __ldg(p.srgb + nc + k) : 1.f;
+    if (HAS_G1 && p.s1) sc1[k] = __ldg(p.s1 + nc + k);
+    if (HAS_DIMG) scr[k] = p.srgb ? __ldg(p.srgb + nc + k) : 1.f;
     if (p.dcoef) dco[k] = __ldg(p.dcoef + nc + k);
     if (p.bias) bs[k] = __ldg(p.bias + c0 + k);
 #pragma unroll
-    for (int o = 0; o < 4; ++o) wr[o][k] = (p.dimg && o < d.rgb_k) ? __ldg(p.wrgb + (size_t)o * d.c + c0 + k) : 0.f;
+    for (int o = 0; o < 4; ++o) wr[o][k] = (HAS_DIMG && o < d.rgb_k) ? __ldg(p.wrgb + (size_t)o * d.c + c0 + k) : 0.f;
   }
   const float slope_pos = d.act_gain, slope_neg = act_slope(d.act) * d.act_gain;
+  // reciprocals once per thread instead of two fp32 divisions per element (ReLU's zero slope: that side has dpre = 0)
+  const float inv_pos = 1.f / slope_pos, inv_neg = slope_neg != 0.f ? 1.f / slope_neg : 0.f;
+  float inv_dco[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) inv_dco[k] = 1.f / dco[k];
   const float inv_rs = d.residual_scale != 0.f ? 1.f / d.residual_scale : 1.f;
 
   float r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f}, rr[4] = {0.f, 0.f, 0.f, 0.f};
@@ -79,10 +88,10 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
       const size_t q = ((size_t)n * hw + (ok ? pix : p_begin)) * c4 + cq;
       y4[u] = ld4_any(p.y, p.y_hi, p.y_lo, q);
       a0[u] = p.g0 ? __ldg(reinterpret_cast<const float4*>(p.g0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      a1[u] = p.g1 ? __ldg(reinterpret_cast<const float4*>(p.g1) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      r4[u] = p.residual ? __ldg(reinterpret_cast<const float4*>(p.residual) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a1[u] = HAS_G1 ? __ldg(reinterpret_cast<const float4*>(p.g1) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r4[u] = HAS_RES ? __ldg(reinterpret_cast<const float4*>(p.residual) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       nzv[u] = p.noise ? __ldg(p.noise + (ok ? pix : p_begin)) * d.noise_gain : 0.f;
-      if (p.dimg) {
+      if (HAS_DIMG) {
         const float* dp = p.dimg + ((size_t)n * hw + (ok ? pix : p_begin)) * d.rgb_k;
 #pragma unroll
         for (int o = 0; o < 4; ++o) di[u][o] = o < d.rgb_k ? __ldg(dp + o) : 0.f;
@@ -100,12 +109,12 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) { gsum[k] = av[k] * sc0[k]; r0[k] = fmaf(av[k], yv[k], r0[k]); }
       }
-      if (p.g1) {
+      if (HAS_G1) {
         const float av[4] = {a1[u].x, a1[u].y, a1[u].z, a1[u].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) { gsum[k] = fmaf(av[k], sc1[k], gsum[k]); r1[k] = fmaf(av[k], yv[k], r1[k]); }
       }
-      if (p.dimg) {
+      if (HAS_DIMG) {
         float gr[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int o = 0; o < 4; ++o)
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
       }
       // derivative of  y = merge(clamp(act(pre) * gain))  w.r.t. pre
       float av[4];
-      if (p.residual) {
+      if (HAS_RES) {
         av[0] = yv[0] * inv_rs - r4[u].x; av[1] = yv[1] * inv_rs - r4[u].y; av[2] = yv[2] * inv_rs - r4[u].z; av[3] = yv[3] * inv_rs - r4[u].w;
       } else {
 #pragma unroll
@@ -126,12 +135,13 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
       float dzv[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float slope = av[k] > 0.f ? slope_pos : slope_neg;
+        const bool pos = av[k] > 0.f;
+        const float slope = pos ? slope_pos : slope_neg;
         const bool pass = !(d.clamp > 0.f) || fabsf(av[k]) < d.clamp;
         const float dpre = pass ? gsum[k] * d.post_scale * slope : 0.f;
         rb[k] += dpre;
         if (p.ddcoef) {
-          const float z = (av[k] / slope - nz - bs[k]) / dco[k];   // conv output before demodulation
+          const float z = (av[k] * (pos ? inv_pos : inv_neg) - nz - bs[k]) * inv_dco[k];   // conv output before demodulation
           rd[k] = fmaf(dpre, z, rd[k]);
         }
         dzv[k] = dpre * dco[k];
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
   // serialises them, which — not the streaming — was what the kernel's time went into)
   __shared__ float red[5][256 * 4];
   const float* vals[5] = {r0, r1, rr, rb, rd};
-  const bool use[5] = {p.ds0 && p.g0, p.ds1 && p.g1, p.dsrgb && p.dimg, p.dbias != nullptr, p.ddcoef != nullptr};
+  const bool use[5] = {p.ds0 && p.g0, p.ds1 && HAS_G1, p.dsrgb && HAS_DIMG, p.dbias != nullptr, p.ddcoef != nullptr};
 #pragma unroll
   for (int j = 0; j < 5; ++j)
     if (use[j]) {
@@ -421,7 +431,19 @@ extern "C" int hfagp_act_bwd(const HfagpActBwdDesc* desc, const float* y, const 
   if (ppb < planes * 8) ppb = planes * 8;
   p.pix_per_block = ppb;
   dim3 grid(cdiv(hw, ppb), d.batch);
-  act_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+#define HFAGP_ACT_BWD(G1, DI, RS) act_bwd_kernel<G1, DI, RS><<<grid, 256, 0, (cudaStream_t)stream>>>(p)
+  const int variant = (g1 ? 4 : 0) | (dimg ? 2 : 0) | (residual ? 1 : 0);
+  switch (variant) {
+    case 0: HFAGP_ACT_BWD(false, false, false); break;
+    case 1: HFAGP_ACT_BWD(false, false, true); break;
+    case 2: HFAGP_ACT_BWD(false, true, false); break;
+    case 3: HFAGP_ACT_BWD(false, true, true); break;
+    case 4: HFAGP_ACT_BWD(true, false, false); break;
+    case 5: HFAGP_ACT_BWD(true, false, true); break;
+    case 6: HFAGP_ACT_BWD(true, true, false); break;
+    default: HFAGP_ACT_BWD(true, true, true); break;
+  }
+#undef HFAGP_ACT_BWD
   HFAGP_CHECK_LAUNCH("act_bwd_kernel");
   return HFAGP_OK;
 }

@@ -92,6 +92,44 @@ def test_upconv_matches_oracle(n, cin, cout, h):
     assert pu.rel_err(pu.to_nchw(y), ref) < 1e-4
 
 
+@pytest.mark.parametrize('n,h2,c', [(1, 256, 128), (1, 128, 256), (2, 64, 512), (1, 256, 24), (3, 9, 16)])
+def test_upfir_register_tiled_forms(n, h2, c):
+    """hfagp_upfir_act_fwd at sizes that take the 4-rows-per-thread kernels (channel count as template parameter: 128 / 256 /
+    512, generic otherwise) and the 1-row form, fp32 and split-bf16 outputs: FIR [1,3,3,1]^2/16 with one pixel of zero padding
+    on the (2H+1)^2 intermediate, then demodulation, noise, bias, leaky ReLU * sqrt(2), clamp (eg3d upfirdn2d + bias_act)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n * 1000 + h2 + c)
+    t = torch.randn(n, c, h2 + 1, h2 + 1, generator=g)
+    dcoef = torch.rand(n, c, generator=g) + 0.5
+    noise = torch.randn(h2, h2, generator=g)
+    b = torch.randn(c, generator=g) * 0.1
+    f = eg3d_ref.setup_filter() * 4
+    y = F.conv2d(F.pad(t, [1, 1, 1, 1]), f[None, None].repeat(c, 1, 1, 1), groups=c)
+    y = y * dcoef[:, :, None, None] + noise[None, None] * 0.3
+    ref = eg3d_ref.bias_act_ref(y, b, act='lrelu', clamp=1.5)
+    tg = nhwc(t)
+    got = ops.upfir_act(tg, dcoef=dcoef.cuda(), noise=noise.cuda(), noise_gain=0.3, bias=b.cuda(), clamp=1.5)
+    assert pu.rel_err(pu.to_nchw(got), ref) < 1e-5
+    if c % 8 == 0:
+        gs = ops.upfir_act(tg, dcoef=dcoef.cuda(), noise=noise.cuda(), noise_gain=0.3, bias=b.cuda(), clamp=1.5, split_out=True)
+        assert pu.rel_err(pu.to_nchw(gs.float()), ref) < 1e-4
+
+
+@pytest.mark.parametrize('n,h,c,stride,pad', [(4, 128, 128, 1, 2), (8, 128, 128, 2, 1), (1, 256, 64, 1, 2), (1, 256, 64, 2, 1),
+                                              (2, 15, 8, 1, 2), (2, 14, 8, 2, 1)])
+def test_blur_register_tiled_forms(n, h, c, stride, pad):
+    """hfagp_blur_fwd in its 4-/2-rows-per-thread forms (batched encoder sizes) and the 1-row form, fp32 and split-bf16
+    I/O, against the reference's Blur (upfirdn2d_native, encoder3d.py:23-75) followed by the stride the next conv applies."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(h * 10 + c + stride)
+    x = torch.randn(n, c, h, h, generator=g)
+    ref = hfagp_ref.blur_ref(x, hfagp_ref.blur_kernel(), pad, pad)[:, :, ::stride, ::stride]
+    xg = nhwc(x)
+    assert pu.rel_err(pu.to_nchw(ops.blur(xg, pad, pad, stride=stride)), ref) < 1e-5
+    ys = ops.blur(ops.split(xg), pad, pad, stride=stride, split_out=True)
+    assert pu.rel_err(pu.to_nchw(ys.float()), ref) < 1e-4
+
+
 def test_modulate_and_styles():
     ops = _ops()
     g = torch.Generator().manual_seed(4)
