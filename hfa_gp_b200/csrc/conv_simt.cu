@@ -513,13 +513,17 @@ extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout
 // [1,3,3,1]^2 / 64 blur, stride 1 or 2, evaluated separably in registers: a thread owns 4 channels of two adjacent
 // output columns and R output rows, walks the (R-1)*STRIDE + 4 input rows once (STRIDE + 4 loads each), forms the two
 // horizontal sums per row and scatters them into the vertical accumulators (stride 1: 4.4 loads per output instead of
-// 16, stride 2: 9).  Grid: x = (column pair, channel quad), y = row band, z = sample.
-template <int STRIDE, int R>
-__global__ void __launch_bounds__(256) blur_tile_kernel(int h, int w_, int c4, int pad0, int oh, int ow, float gain,
+// 16, stride 2: 9).  Grid: x = (column pair, channel quad), y = row band, z = sample.  Specialised on the input format
+// (fp32 | split bf16) and, for the encoder's channel counts, on the channel quads per pixel (C4C > 0: column offsets are
+// immediates of one row pointer): the generic per-load "which format / inside the row?" selection cost 47 instructions
+// per 16-byte load (ncu, profiles/r2_ncu_blur_b4_start.txt).
+template <int STRIDE, int R, int C4C, bool SPLIT_IN>
+__global__ void __launch_bounds__(256) blur_tile_kernel(int h, int w_, int c4_rt, int pad0, int oh, int ow, float gain,
                                                        const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi,
                                                        const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
                                                        __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
   constexpr int NC = STRIDE + 4, NR = (R - 1) * STRIDE + 4;
+  const int c4 = C4C > 0 ? C4C : c4_rt;
   const int wp = (ow + 1) >> 1;
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= (uint32_t)(wp * c4)) return;
@@ -534,15 +538,29 @@ __global__ void __launch_bounds__(256) blur_tile_kernel(int h, int w_, int c4, i
     for (int k = 0; k < 4; ++k) acc[r][0][k] = acc[r][1][k] = 0.f;
   const bool interior_x = ix0 >= 0 && ix0 + NC <= w_;
   const long long rstride = (long long)w_ * c4;
-  long long q = (((long long)n * h + iy0) * w_ + ix0) * c4 + cq;       // (row iy0, column ix0); may lie outside
+  const long long q0 = (((long long)n * h + iy0) * w_ + ix0) * c4 + cq;       // (row iy0, column ix0); may lie outside
+  const float4* xp = reinterpret_cast<const float4*>(x) + q0;
+  const uint2* hp = reinterpret_cast<const uint2*>(x_hi) + q0;
+  const uint2* lp = reinterpret_cast<const uint2*>(x_lo) + q0;
+  auto ld = [&](int kx) -> float4 {
+    if (!SPLIT_IN) return __ldg(xp + kx * c4);
+    const uint2 a = __ldg(hp + kx * c4), b = __ldg(lp + kx * c4);
+    return make_float4(__uint_as_float(a.x << 16) + __uint_as_float(b.x << 16),
+                       __uint_as_float(a.x & 0xffff0000u) + __uint_as_float(b.x & 0xffff0000u),
+                       __uint_as_float(a.y << 16) + __uint_as_float(b.y << 16),
+                       __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u));
+  };
 #pragma unroll
-  for (int rr = 0; rr < NR; ++rr, q += rstride) {
+  for (int rr = 0; rr < NR; ++rr, xp += rstride, hp += rstride, lp += rstride) {
     if ((unsigned)(iy0 + rr) >= (unsigned)h) continue;
     float4 v[NC];
+    if (interior_x) {
 #pragma unroll
-    for (int kx = 0; kx < NC; ++kx)
-      v[kx] = (interior_x || (unsigned)(ix0 + kx) < (unsigned)w_) ? ld4_any(x, x_hi, x_lo, (size_t)(q + (long long)kx * c4))
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kx = 0; kx < NC; ++kx) v[kx] = ld(kx);
+    } else {
+#pragma unroll
+      for (int kx = 0; kx < NC; ++kx) v[kx] = (unsigned)(ix0 + kx) < (unsigned)w_ ? ld(kx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float ha[4], hb[4];
     ha[0] = g[0] * v[0].x + g[1] * v[1].x + g[2] * v[2].x + g[3] * v[3].x;
     ha[1] = g[0] * v[0].y + g[1] * v[1].y + g[2] * v[2].y + g[3] * v[3].y;
@@ -581,6 +599,24 @@ __global__ void __launch_bounds__(256) blur_tile_kernel(int h, int w_, int c4, i
   }
 }
 
+template <int STRIDE, int R>
+static void blur_tile_launch(dim3 grid, cudaStream_t stream, int h, int w_, int c4, int pad0, int oh, int ow, float gain, const float* x,
+                             const __nv_bfloat16* xh, const __nv_bfloat16* xl, float* y, __nv_bfloat16* yh, __nv_bfloat16* yl) {
+#define HFAGP_BLUR_GO(C4C) \
+  do { \
+    if (x) blur_tile_kernel<STRIDE, R, C4C, false><<<grid, 256, 0, stream>>>(h, w_, c4, pad0, oh, ow, gain, x, xh, xl, y, yh, yl); \
+    else blur_tile_kernel<STRIDE, R, C4C, true><<<grid, 256, 0, stream>>>(h, w_, c4, pad0, oh, ow, gain, x, xh, xl, y, yh, yl); \
+  } while (0)
+  switch (c4) {
+    case 16: HFAGP_BLUR_GO(16); break;
+    case 32: HFAGP_BLUR_GO(32); break;
+    case 64: HFAGP_BLUR_GO(64); break;
+    case 128: HFAGP_BLUR_GO(128); break;
+    default: HFAGP_BLUR_GO(0); break;
+  }
+#undef HFAGP_BLUR_GO
+}
+
 extern "C" int hfagp_torgb_finalize_fwd(int batch, int h, int w_, int k, const float* acc, const float* bias, float clamp,
                                         const float* up_img, float* y, void* stream) {
   HFAGP_CHECK_ARG(acc && y && batch > 0 && h > 0 && w_ > 0 && k >= 1 && k <= 4, "torgb_finalize_fwd: bad args");
@@ -612,7 +648,7 @@ extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad
     static const int big_env = getenv("HFAGP_BLUR_BIG") ? atoi(getenv("HFAGP_BLUR_BIG")) : -1;   // profiling override
     const bool big = big_env >= 0 ? big_env != 0 : (long long)gx * cdiv(oh, stride == 1 ? 4 : 2) * batch >= 148 * 6;
 #define HFAGP_BLUR_LAUNCH(S, R) \
-  blur_tile_kernel<S, R><<<dim3(gx, cdiv(oh, R), batch), 256, 0, (cudaStream_t)stream>>>(h, w_, c >> 2, pad0, oh, ow, gain, x, xh, xl, y, yh, yl)
+  blur_tile_launch<S, R>(dim3(gx, cdiv(oh, R), batch), (cudaStream_t)stream, h, w_, c >> 2, pad0, oh, ow, gain, x, xh, xl, y, yh, yl)
     if (stride == 1 && big) HFAGP_BLUR_LAUNCH(1, 4);
     else if (stride == 1) HFAGP_BLUR_LAUNCH(1, 1);
     else if (big) HFAGP_BLUR_LAUNCH(2, 2);

@@ -251,11 +251,11 @@ class ResBlock(nn.Module):
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 skip = self.skip.run(x, tc=tc)
-            out = self.conv1.run(x, tc=tc, split_out=tc)
+            out = self.conv1.run(x, tc=tc)           # fp32: its only reader is conv2's blur (one 16 B load per tap)
             cur.wait_stream(side)
             return self.conv2.run(out, residual=skip, tc=tc, split_out=tc)
         skip = self.skip.run(x, tc=tc, rec=rs)                        # fp32: it is the residual operand
-        out = self.conv1.run(x, tc=tc, split_out=tc, rec=r1)
+        out = self.conv1.run(x, tc=tc, split_out=tc and rec is not None, rec=r1)
         y = self.conv2.run(out, residual=skip, tc=tc, split_out=tc, rec=r2)   # (conv2(out) + skip) / sqrt(2) in the epilogue
         if rec is not None:
             rec.update(skip=rs, conv1=r1, conv2=r2)

@@ -11,20 +11,21 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--seq', action='store_true')
 ap.add_argument('--frames', type=int, default=3)
 ap.add_argument('--graph', action='store_true', help='profile CUDA-graph replays of the frame loop (the product path)')
+ap.add_argument('--batch', type=int, default=1, help='frames per replay (bench.py --frames-per-step)')
 args = ap.parse_args()
 dev = torch.device('cuda')
 ns = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='', synthetic_generator=True, generator_seed=0)
 torch.manual_seed(0)
 model = HeadNeRF_final(ns, 256, dev, 512, 50, 'bench', './').to(dev).eval().requires_grad_(False)
-img = torch.rand(1, 3, 256, 256, device=dev) * 2 - 1
-lab = cam_utils.cam_sampler(1, 'cpu').to(dev)
+img = torch.rand(args.batch, 3, 256, 256, device=dev) * 2 - 1
+lab = cam_utils.cam_sampler(args.batch, 'cpu').to(dev)
 
 def frame():
     with torch.no_grad():
         return model.get_image(model.get_latent(model.get_weights(img)), lab.clone())
 if args.graph:
     from hfa_gp_b200.frame_loop import FrameLoop
-    loop = FrameLoop(model, batch=1, size=256, device=dev)
+    loop = FrameLoop(model, batch=args.batch, size=256, device=dev)
     def frame():
         return loop(img, lab, mutate_label=False)
 for _ in range(4):
