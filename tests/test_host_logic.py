@@ -93,6 +93,22 @@ def test_ksplit_heuristic():
         assert k >= 1 and k * tiles <= ops.NUM_SMS
 
 
+def test_deterministic_mode_disables_split_k():
+    """ops.set_deterministic(): no layer may take the split-K path (fp32 atomics); the previous setting is returned, and
+    the SM count used by the heuristic can be given explicitly (a part with fewer SMs splits less)."""
+    assert ops.deterministic() is False
+    prev = ops.set_deterministic(True)
+    try:
+        assert prev is False and ops.deterministic() is True
+        for tiles in (1, 4, 32):
+            assert ops._ksplit(tiles, 512, ops.TAPS_3X3, 1) == 1
+    finally:
+        ops.set_deterministic(prev)
+    assert ops._ksplit(4, 512, ops.TAPS_3X3, 1) == 24
+    assert ops._ksplit(4, 512, ops.TAPS_3X3, 1, sms=64) == 16
+    assert ops.num_sms() == ops.NUM_SMS or torch.cuda.is_available()
+
+
 def test_bench_flop_accounting_matches_the_layer_table():
     spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
     bench = importlib.util.module_from_spec(spec)
