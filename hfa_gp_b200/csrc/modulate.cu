@@ -222,6 +222,19 @@ int device_sm_count() {
 }  // namespace hfagp
 
 extern "C" int hfagp_device_sm_count(void) { return hfagp::device_sm_count(); }
+extern "C" size_t hfagp_conv2d_tc_acc_workspace_bytes(const HfagpConvDesc* d) {
+  if (!d || d->batch <= 0 || d->out_h <= 0 || d->out_w <= 0 || d->cout <= 0) return 0;
+  return sizeof(float) * (size_t)d->batch * d->out_h * d->out_w * d->cout;
+}
+extern "C" size_t hfagp_render_bwd_dec_workspace_bytes(const HfagpRenderDesc* d, size_t* dump_f_bytes, size_t* dump_do_bytes) {
+  size_t samples = 0;
+  if (d && d->batch > 0 && d->res > 0 && d->s_coarse + d->s_fine > 0)
+    samples = (size_t)d->batch * d->res * d->res * (size_t)(d->s_coarse + d->s_fine);
+  const size_t fb = samples * 32 * sizeof(float), db = samples * 33 * sizeof(float);
+  if (dump_f_bytes) *dump_f_bytes = fb;
+  if (dump_do_bytes) *dump_do_bytes = db;
+  return fb + db;
+}
 extern "C" int hfagp_set_device(int device) {
   HFAGP_CUDA(cudaSetDevice(device));
   return HFAGP_OK;

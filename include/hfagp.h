@@ -131,6 +131,12 @@ int hfagp_conv2d_tc_multi_fwd(const HfagpConvDesc* descs, int ndesc, const uint1
                               const float* noise, const float* bias, const float* residual, const float* up_img,
                               float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
 
+/* Caller-provided scratch, as pure functions of the shapes ("workspace is caller-provided"): the library never
+ * allocates.  hfagp_conv2d_tc_acc_workspace_bytes = the zeroed fp32 accumulator acc[n][out_h][out_w][cout] of the split-K
+ * form below (descs[0] carries the full output geometry); 0 for a null / degenerate descriptor.  (The renderer's
+ * counterpart, hfagp_render_bwd_dec_workspace_bytes, is declared with its descriptor further down.) */
+size_t hfagp_conv2d_tc_acc_workspace_bytes(const HfagpConvDesc* desc);
+
 /* Split-K form for layers with few output tiles (the 4^2..32^2 blocks: a handful of 128-pixel tiles would leave
  * most SMs idle while each CTA streams megabytes of weights): every tile's K range (K chunks x tap groups) is dealt
  * out to up to `ksplit` CTAs, which ADD their raw fp32 partial sums into acc[n][out_h][out_w][cout] with 16-byte
@@ -265,6 +271,9 @@ int hfagp_render_bwd(const HfagpRenderDesc* desc, const float* planes, const flo
 int hfagp_render_bwd_dec(const HfagpRenderDesc* desc, const float* planes, const float* c, const float* mlp,
                          const float* lin, const float* jitter, const float* u_fine, const float* dfeat,
                          float* dplanes, float* dump_f, float* dump_do, void* stream);
+/* Bytes of the two per-sample operand dumps above (dump_f [samples][32], dump_do [samples][33]; samples = batch * res^2 *
+ * (s_coarse + s_fine)): a pure function of the shapes, returns their sum. */
+size_t hfagp_render_bwd_dec_workspace_bytes(const HfagpRenderDesc* desc, size_t* dump_f_bytes, size_t* dump_do_bytes);
 
 /* Weight gradient of the OSG decoder MLP from the per-sample operands hfagp_render_bwd_dec wrote: dump_f [samples][32],
  * dump_do [samples][33].  The hidden layer is recomputed in fp32 per 64-sample tile, the four reductions over samples

@@ -40,6 +40,22 @@ def test_invalid_arguments_fail_without_touching_the_gpu():
         _cabi.check(rc, 'hfagp_conv2d_fwd')
 
 
+def test_workspace_queries_are_pure_functions_of_the_shapes():
+    """hfagp_*_workspace_bytes (caller-provided scratch): no device is touched."""
+    from hfa_gp_b200 import _cabi
+    lib = _cabi.lib()
+    d = _cabi.ConvDesc()
+    assert lib.hfagp_conv2d_tc_acc_workspace_bytes(ctypes.byref(d)) == 0
+    d.batch, d.out_h, d.out_w, d.cout = 2, 16, 16, 512
+    assert lib.hfagp_conv2d_tc_acc_workspace_bytes(ctypes.byref(d)) == 2 * 16 * 16 * 512 * 4
+    r = _cabi.RenderDesc(2, 128, 256, 256, 48, 48, 0.02, 2.0)
+    fb, db = ctypes.c_size_t(), ctypes.c_size_t()
+    tot = lib.hfagp_render_bwd_dec_workspace_bytes(ctypes.byref(r), ctypes.byref(fb), ctypes.byref(db))
+    samples = 2 * 128 * 128 * 96
+    assert fb.value == samples * 32 * 4 and db.value == samples * 33 * 4 and tot == fb.value + db.value
+    assert lib.hfagp_device_sm_count() > 0          # 148 when no device can be asked
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, 'hfa_gp_b200')
     for dp, _, files in os.walk(pkg):
