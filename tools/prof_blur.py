@@ -27,6 +27,6 @@ for res, c in ((256, 64), (128, 128), (64, 256), (32, 512), (16, 512), (8, 512))
         oh = (res + 2 * pad - 4) // stride + 1
         mb = (res * res + oh * oh) * c * 4 * B / 1e6
         tot += us
-        print(f'blur {B}x{res}^2 x{c} stride {stride}: {us:7.1f} us  {mb / us / 1e3:6.2f} TB/s')
+        print(f'blur {B}x{res}^2 x{c} stride {stride}: {us:7.1f} us  {mb / us:6.2f} TB/s')
         del g, outs
 print(f'total {tot:.1f} us per {B}-frame step')
