@@ -427,7 +427,7 @@ extern "C" int hfagp_act_bwd(const HfagpActBwdDesc* desc, const float* y, const 
   const int hw = d.h * d.w;
   const int planes = 256 / (d.c >> 2);
   // ~4 waves of CTAs, at least 8 pixels per side-by-side lane so the atomics stay a small share
-  int ppb = cdiv((long long)hw * d.batch, 148 * 4);
+  int ppb = cdiv((long long)hw * d.batch, device_sm_count() * 4);
   if (ppb < planes * 8) ppb = planes * 8;
   p.pix_per_block = ppb;
   dim3 grid(cdiv(hw, ppb), d.batch);
@@ -498,7 +498,7 @@ extern "C" int hfagp_linear_bwd(int batch, int cin, int cout, const float* dy, c
   HFAGP_CHECK_ARG(!dw || x, "linear_bwd: dw needs x");
   if (dx) {
     // few long rows (the encoder's 8192-wide final map): slice the output channels over more CTAs
-    const int slices = ((long long)batch * cin < 148 * 256 * 2 && cout >= 64) ? 8 : 1;
+    const int slices = ((long long)batch * cin < (long long)device_sm_count() * 256 * 2 && cout >= 64) ? 8 : 1;
     if (slices > 1) HFAGP_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)batch * cin, (cudaStream_t)stream));
     linear_bwd_dx_kernel<<<dim3(cdiv((long long)batch * cin, 256), slices), 256, 0, (cudaStream_t)stream>>>(batch, cin, cout, dy, w, w_gain, dx);
     HFAGP_CHECK_LAUNCH("linear_bwd_dx_kernel");
@@ -544,7 +544,7 @@ static int wgrad_impl(const HfagpConvDesc* desc, const float* x, const uint16_t*
   p.xscale = xscale; p.dzscale = dzscale;
   const long long K = (long long)d.batch * d.oh * d.ow;
   const int tiles = cdiv(d.cout, WG_T) * cdiv(d.cin, WG_T);
-  int splits = cdiv(148 * 6, (long long)tiles * d.ntaps);
+  int splits = cdiv(device_sm_count() * 6, (long long)tiles * d.ntaps);
   const int max_splits = cdiv(K, 4 * WG_K);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -438,7 +438,7 @@ extern "C" int hfagp_conv2d_fwd(const HfagpConvDesc* desc, const float* x, const
   cudaStream_t st = (cudaStream_t)stream;
   // large tiles when they still fill the machine, small tiles otherwise
   long long big_ctas = (long long)cdiv(M, 128) * cdiv(d.cout, 128) * d.batch;
-  if (big_ctas >= 148 && d.cout >= 96) {
+  if (big_ctas >= device_sm_count() && d.cout >= 96) {
     dim3 grid(cdiv(M, 128), cdiv(d.cout, 128), d.batch);
     conv_igemm_kernel<8, 8><<<grid, 256, 0, st>>>(p);
   } else {
@@ -474,11 +474,11 @@ extern "C" int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float
                   "upfir_act_fwd: give t and either y or (y_hi, y_lo)");
   HFAGP_CHECK_ARG(batch > 0 && h2 > 0 && w2 > 0 && c > 0 && (c & 3) == 0, "upfir_act_fwd: c must be a multiple of 4");
   HFAGP_CHECK_ARG(act_gain > 0.f, "upfir_act_fwd: act_gain must be positive (it is folded into the scale)");
-  HFAGP_CHECK_ARG(batch <= 65535 && cdiv(h2, 4) <= 65535 && (long long)cdiv(w2, 2) * (c >> 2) < (1ll << 31), "upfir_act_fwd: dims too large");
+  HFAGP_CHECK_ARG(batch <= 65535 && h2 <= 65535 && (long long)cdiv(w2, 2) * (c >> 2) < (1ll << 31), "upfir_act_fwd: dims too large");
   // 4 output rows per thread: measured on B200 (tools/prof_upfir.py, 512^2 x 128): 2 rows 100 us, 4: 85 us, 8: 91 us, 16: 142 us
   // (58 us after the index arithmetic went 32-bit / immediate); 1 row per thread while that would leave SMs idle
   const unsigned gx = (unsigned)cdiv((size_t)cdiv(w2, 2) * (c >> 2), 256);
-  const bool big = (long long)gx * cdiv(h2, 4) * batch >= 148 * 6;
+  const bool big = (long long)gx * cdiv(h2, 4) * batch >= device_sm_count() * 6;
   auto* hi_ = reinterpret_cast<__nv_bfloat16*>(y_hi);
   auto* lo_ = reinterpret_cast<__nv_bfloat16*>(y_lo);
 #define HFAGP_UPFIR_LAUNCH(R, C4C) \
@@ -637,7 +637,7 @@ extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad
   int ow = (w_ + pad0 + pad1 - 4) / stride + 1;
   HFAGP_CHECK_ARG(oh > 0 && ow > 0, "blur_fwd: empty output");
   if ((c & 3) == 0) {
-    HFAGP_CHECK_ARG(batch <= 65535 && oh <= 65535 * 2 && (long long)cdiv(ow, 2) * (c >> 2) < (1ll << 31), "blur_fwd: dims too large");
+    HFAGP_CHECK_ARG(batch <= 65535 && oh <= 65535 && (long long)cdiv(ow, 2) * (c >> 2) < (1ll << 31), "blur_fwd: dims too large");
     auto* xh = reinterpret_cast<const __nv_bfloat16*>(x_hi);
     auto* xl = reinterpret_cast<const __nv_bfloat16*>(x_lo);
     auto* yh = reinterpret_cast<__nv_bfloat16*>(y_hi);
@@ -646,7 +646,7 @@ extern "C" int hfagp_blur_fwd(int batch, int h, int w_, int c, int pad0, int pad
     // rows per thread: the register-blocked form only once it still fills the machine (~6 CTAs per SM); the encoder's
     // batch-1 tensors are small enough that thread count matters more than loads per output
     static const int big_env = getenv("HFAGP_BLUR_BIG") ? atoi(getenv("HFAGP_BLUR_BIG")) : -1;   // profiling override
-    const bool big = big_env >= 0 ? big_env != 0 : (long long)gx * cdiv(oh, stride == 1 ? 4 : 2) * batch >= 148 * 6;
+    const bool big = big_env >= 0 ? big_env != 0 : (long long)gx * cdiv(oh, stride == 1 ? 4 : 2) * batch >= device_sm_count() * 6;
 #define HFAGP_BLUR_LAUNCH(S, R) \
   blur_tile_launch<S, R>(dim3(gx, cdiv(oh, R), batch), (cudaStream_t)stream, h, w_, c >> 2, pad0, oh, ow, gain, x, xh, xl, y, yh, yl)
     if (stride == 1 && big) HFAGP_BLUR_LAUNCH(1, 4);

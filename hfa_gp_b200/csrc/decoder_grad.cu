@@ -186,6 +186,7 @@ using namespace hfagp;
 extern "C" int hfagp_decoder_wgrad(long long samples, const float* f, const float* dout, const float* mlp, float* dmlp,
                                    void* stream) {
   HFAGP_CHECK_ARG(f && dout && mlp && dmlp && samples > 0, "decoder_wgrad: null pointer or no samples");
+  HFAGP_CHECK_ARG((reinterpret_cast<uintptr_t>(f) & 15) == 0, "decoder_wgrad: dump_f must be 16-byte aligned");
   const int sms = device_sm_count();
   static std::atomic<uint64_t> attr_done{0};
   HFAGP_CUDA(per_device_once(attr_done, [] { return cudaFuncSetAttribute(decoder_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DgSmem)); }));

@@ -186,7 +186,7 @@ extern "C" int hfagp_facepool_bwd(int batch, int h, int w_, int c, int f, const 
 extern "C" int hfagp_mse_fwd(long long count, const float* a, const float* b, float scale, float* loss, void* stream) {
   HFAGP_CHECK_ARG(a && b && loss && count > 0, "mse_fwd: bad args");
   int blocks = cdiv(count >> 2, 256 * 4);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
   if (blocks < 1) blocks = 1;
   mse_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(count, a, b, scale, loss);
   HFAGP_CHECK_LAUNCH("mse_fwd_kernel");
@@ -210,7 +210,7 @@ extern "C" int hfagp_adam_step(long long count, float* p, const float* g, float*
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
   int blocks = cdiv(count >> 2, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
   if (blocks < 1) blocks = 1;
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(count, p, g, m, v, grad_scale, (float)(1.0 - beta1), (float)beta2,
                                                         (float)(1.0 - beta2), (float)eps, (float)weight_decay, step_size,
@@ -233,7 +233,7 @@ extern "C" int hfagp_adam_step_dev(long long count, float* p, const float* g, fl
   HFAGP_CHECK_ARG(p && g && m && v && sched && count > 0, "adam_step_dev: bad args");
   HFAGP_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step_dev: buffers must be 16-byte aligned");
   int blocks = cdiv(count >> 2, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
   if (blocks < 1) blocks = 1;
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(count, p, g, m, v, grad_scale, (float)(1.0 - beta1), (float)beta2,
                                                         (float)(1.0 - beta2), (float)eps, (float)weight_decay, 0.f, 1.f, sched);

@@ -222,6 +222,8 @@ class Trainer(_TrainerBase):
         self.gen.train()
 
         def fwd_bwd(real_image, label):
+            m = self.gen.module
+            m.prefetch_basis(m.bases if not person_2 or m.args.same_bases else m.bases_2)   # QR next to the encoder forward
             weights_i = self.gen.module.get_weights(real_image)
             if isinstance(weights_i, tuple):
                 weights_i = weights_i[0]

@@ -1,4 +1,4 @@
-"""Which torch (ATen) ops still launch glue kernels inside one trainer_rgb.gen_update step, grouped by Python call site."""
+"""Which torch (ATen) ops still launch glue kernels inside one trainer_rgb.gen_update step, by op and input shapes."""
 import argparse, collections, sys
 sys.path.insert(0, '.')
 import torch
@@ -18,14 +18,12 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], with_stack=True) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
     step()
     torch.cuda.synchronize()
-ka = prof.key_averages(group_by_stack_n=6)
-rows = [(e.device_time_total, e.count, e.key, e.stack) for e in ka if e.device_time_total > 0 and e.key.startswith('aten::')]
+ka = prof.key_averages(group_by_input_shape=True)
+rows = [(e.self_device_time_total, e.count, e.key, str(e.input_shapes)) for e in ka if e.self_device_time_total > 0 and e.key.startswith('aten::')]
 rows.sort(key=lambda r: -r[0])
-tot = sum(r[0] for r in rows)
-print('aten device time total us', tot)
-for t, c, k, st in rows[:40]:
-    site = [s for s in st if 'hfa_gp_b200' in s or 'oracle' in s]
-    print(f'{t:8.1f} us n={c:3d} {k:28s} {(site[0] if site else (st[0] if st else "?"))[-110:]}')
+print('aten self device time total us', sum(r[0] for r in rows))
+for t, c, k, sh in rows[:45]:
+    print(f'{t:8.1f} us n={c:3d} {k:24s} {sh[:120]}')
