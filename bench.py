@@ -36,11 +36,11 @@ TC_ENTRY_POINTS = ('hfagp_conv2d_tc_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_conv
 # ncu dram__bytes_read.sum + dram__bytes_write.sum over the 42 conv_tc_kernel launches of one frame (profiles/r2_launches_start.csv:
 # 803.6 MB read + 211.1 MB written back before kernel end; the frame's algorithmic weight + activation bytes are ~1 250 MB)
 # by frames per step: batch 1 profiles/r2_launches_start.csv (803.6 MB read + 211.1 MB written back before kernel end); batch 4
-# profiles/r2_launches_final.csv (`ncu ... python tools/one_frame.py 2 --serial --batch 4`: 2 974.9 MB read + 1 717.9 MB
-# written = 1 173 MB per frame; four frames' activations no longer fit L2 between producer and consumer)
-CONV_TC_DRAM_BYTES_PER_STEP = {1: 1_014_700_000, 4: 4_692_799_232}
+# profiles/r2_launches_final.csv (`ncu ... python tools/one_frame.py 2 --serial --batch 4`: 2 982.9 MB read + 1 722.3 MB
+# written = 1 176 MB per frame; four frames' activations no longer fit L2 between producer and consumer)
+CONV_TC_DRAM_BYTES_PER_STEP = {1: 1_014_700_000, 4: 4_705_195_776}
 # render_tc_kernel, ncu dram read + write per launch: batch 1 profiles/r2_ncu_render_tc_v3.txt, batch 4 profiles/r2_launches_final.csv
-RENDER_DRAM_BYTES_PER_LAUNCH = {1: 22_568_960, 4: 93_288_192}
+RENDER_DRAM_BYTES_PER_LAUNCH = {1: 22_568_960, 4: 93_645_568}
 DTYPE = 'bf16x3-split operands (hi*hi + lo*hi + hi*lo), fp32 accumulate'
 
 
