@@ -623,6 +623,43 @@ def test_deterministic_mode_reproduces_frames_bit_for_bit():
     assert pu.rel_err(a, default) < 5e-4
 
 
+def test_batched_replay_equals_frame_by_frame():
+    """bench.py's default feeds FOUR independent frames per graph replay (FrameLoop(batch=4)) and keeps three replays in
+    flight (FramePipeline): every frame must come out as it does from the reference loop's one-frame-per-call form —
+    different frames, labels, per-frame ray jitter — up to the split-K summation order (layer shapes, hence K splits and
+    the CTA-pair choice, depend on the batch)."""
+    import argparse
+    from hfa_gp_b200.frame_loop import FrameLoop, FramePipeline
+    from hfa_gp_b200.networks.headnerf import HeadNeRF_final
+    args = argparse.Namespace(out_pose=False, person_2=False, init=False, same_bases=False, run_id_2='',
+                              synthetic_generator=True, generator_seed=0)
+    torch.manual_seed(0)
+    model = HeadNeRF_final(args, 256, 'cuda', 512, 50, 'x', './').cuda().eval().requires_grad_(False)
+    cfg = model.generator.cfg
+    g = torch.Generator().manual_seed(21)
+    rays = cfg.nrr ** 2
+    B = 4
+    jit = torch.rand(B, rays, cfg.depth_res, 1, generator=g).cuda()
+    u = torch.rand(B * rays, cfg.depth_res_importance, generator=g).cuda()
+    imgs = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).cuda()
+    labels = hfagp_ref.synthetic_labels(B, seed=9).cuda()
+    model.generator.fixed_draws = (jit, u)
+    batched = FrameLoop(model, batch=B, size=256)(imgs, labels.clone()).clone()
+    pipe = FramePipeline(model, depth=3, batch=B, size=256)
+    outs = [pipe.submit(imgs, labels.clone())[0] for _ in range(3)]
+    pipe.join()
+    torch.cuda.synchronize()
+    for o in outs:
+        assert pu.rel_err(o, batched) < 5e-4
+    worst = 0.0
+    for i in range(B):
+        model.generator.fixed_draws = (jit[i:i + 1], u[i * rays:(i + 1) * rays])
+        one = FrameLoop(model, batch=1, size=256)(imgs[i:i + 1], labels[i:i + 1].clone()).clone()
+        worst = max(worst, pu.rel_err(batched[i:i + 1], one))
+    print(f'batched vs frame-by-frame: worst rel err {worst:.3e}')
+    assert worst < 5e-4
+
+
 @pytest.mark.parametrize('drive', ['3dmm', 'audio'])
 def test_driven_frame_loops_match_oracle(drive):
     """configs[4] / run_recon_video_{3dmm,audio}.py: the graph-captured frame loop of the driven avatars
