@@ -27,7 +27,7 @@ SYMBOLS = [
     'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8',
     'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
     'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd', 'hfagp_conv2d_wgrad_mod', 'hfagp_render_bwd_dec',
-    'hfagp_render_fwd_simt', 'hfagp_decoder_wgrad', 'hfagp_set_device', 'hfagp_device_sm_count', 'hfagp_conv2d_tc_acc_workspace_bytes', 'hfagp_render_bwd_dec_workspace_bytes', 'hfagp_adam_sched', 'hfagp_adam_step_dev', 'hfagp_render_bookkeeping',
+    'hfagp_render_fwd_simt', 'hfagp_decoder_wgrad', 'hfagp_modconv_wgrad_finish', 'hfagp_set_device', 'hfagp_device_sm_count', 'hfagp_conv2d_tc_acc_workspace_bytes', 'hfagp_render_bwd_dec_workspace_bytes', 'hfagp_adam_sched', 'hfagp_adam_step_dev', 'hfagp_render_bookkeeping',
 ]
 
 
@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
     l.hfagp_render_bwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 9
     l.hfagp_render_bwd_dec.argtypes = [C.POINTER(RenderDesc)] + [vp] * 11
     l.hfagp_decoder_wgrad.argtypes = [C.c_longlong] + [vp] * 5
+    l.hfagp_modconv_wgrad_finish.argtypes = [i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     l.hfagp_conv2d_tc_acc_workspace_bytes.argtypes = [C.POINTER(ConvDesc)]
     l.hfagp_conv2d_tc_acc_workspace_bytes.restype = C.c_size_t
     l.hfagp_render_bwd_dec_workspace_bytes.argtypes = [C.POINTER(RenderDesc), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]

@@ -67,18 +67,24 @@ def _layer_param_grads(m, rec, dz, ddc, db, h, w, up):
     weight (style-scaled wgrad + demodulation term), bias, noise_strength."""
     pl, styles, dcoef = rec['pl'], rec['styles'], rec['dcoef']
     x = rec['x']
-    dwp = torch.zeros_like(pl.w)
     if up:
         # transposed conv: dW[(ky,kx)][o][i] = sum dt[2m+k][o] * x[m][i] * s[i]  — wgrad with the roles swapped
         # (dense operand = layer input, strided operand = gradient), result [t][i][o]
         hin, win = x.shape[1], x.shape[2]
-        dwt = torch.zeros((9, pl.cin, pl.cout), device=dwp.device)
-        ops.conv2d_wgrad(dz, x, TAPS_UP_T, dwt, oh=hin, ow=win, in_stride=2, dzscale=styles)
-        dwp += dwt.transpose(1, 2)
+        dwp = torch.zeros((9, pl.cin, pl.cout), device=pl.w.device)
+        ops.conv2d_wgrad(dz, x, TAPS_UP_T, dwp, oh=hin, ow=win, in_stride=2, dzscale=styles)
     else:
+        dwp = torch.zeros_like(pl.w)
         ops.conv2d_wgrad(x, dz, ops.TAPS_3X3, dwp, oh=h, ow=w, xscale=styles)
-    dwp += _demod_term(pl, styles, dcoef, ddc)
-    _acc(m.weight, _unpack_conv(dwp, 3))
+    # + demodulation term, unpacked into [O][I][k][k] and added to .grad in one pass (hfagp_modconv_wgrad_finish)
+    if m.weight.grad is None:
+        m.weight.grad = torch.zeros_like(m.weight)
+    if m.weight.grad.is_contiguous() and m.weight.grad.dtype == torch.float32:
+        ops.modconv_wgrad_finish(dwp, pl.w, m.weight.grad, transposed=up, ddcoef=ddc.contiguous(), dcoef=dcoef.contiguous(),
+                                 styles=styles.contiguous())
+    else:
+        full = dwp.transpose(1, 2) if up else dwp
+        _acc(m.weight, _unpack_conv(full + _demod_term(pl, styles, dcoef, ddc), 3))
     _acc(m.bias, db)
     if rec.get('noise_buf') is not None:
         dzf = dz.float() if isinstance(dz, ops.Split) else dz

@@ -403,6 +403,65 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
   }
 }
 
+// Last step of a modulated convolution's weight gradient (generator unfrozen): the style-scaled wgrad dw (packed
+// [tap][o][i], or [tap][i][o] when the layer is an up-sampling one and the wgrad ran with the roles swapped) plus the
+// demodulation term  -W[t][o][i] * sum_n ddcoef[n][o] dcoef[n][o]^3 styles[n][i]^2,  unpacked into the parameter layout and
+// ADDED to grad[o][i][tap].  A 32 x 32 (o, i) tile per block goes through shared memory so that both the reads (along the
+// fast index of dw) and the writes (taps * 32 consecutive floats per o) are coalesced.  One launch replaces ~10 elementwise
+// passes over the 9.4 MB weight tensor.
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256) modconv_wgrad_finish_kernel(int taps, int cout, int cin, int batch, const float* __restrict__ dw,
+                                                                  const float* __restrict__ w, const float* __restrict__ ddcoef,
+                                                                  const float* __restrict__ dcoef, const float* __restrict__ styles,
+                                                                  float* __restrict__ grad) {
+  __shared__ float tile[32][33];
+  __shared__ float a_s[8][32], s2_s[8][32];                   // per sample: ddcoef * dcoef^3 for the tile's o, styles^2 for its i
+  const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 8 rows of 32
+  const bool demod = ddcoef != nullptr;
+  float coef[4] = {0.f, 0.f, 0.f, 0.f};                       // this thread's (o = o0 + ty + 8 r, i = i0 + tx)
+  if (demod) {
+    for (int n0 = 0; n0 < batch; n0 += 8) {
+      __syncthreads();
+      const int nn = n0 + ty;
+      if (nn < batch) {
+        const int o = o0 + tx, i = i0 + tx;
+        float a = 0.f, s2 = 0.f;
+        if (o < cout) { const float dc = __ldg(dcoef + (size_t)nn * cout + o); a = __ldg(ddcoef + (size_t)nn * cout + o) * dc * dc * dc; }
+        if (i < cin) { const float sv = __ldg(styles + (size_t)nn * cin + i); s2 = sv * sv; }
+        a_s[ty][tx] = a;
+        s2_s[ty][tx] = s2;
+      }
+      __syncthreads();
+      const int cnt = min(8, batch - n0);
+      for (int n = 0; n < cnt; ++n)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) coef[r] = fmaf(a_s[n][ty + 8 * r], s2_s[n][tx], coef[r]);
+    }
+  }
+  for (int t = 0; t < taps; ++t) {
+    if (TRANSPOSED) {
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {                           // dw[t][i][o]: coalesced along o, transposed through the tile
+        const int i = i0 + ty + 8 * r, o = o0 + tx;
+        tile[ty + 8 * r][tx] = (i < cin && o < cout) ? __ldg(dw + ((size_t)t * cin + i) * cout + o) : 0.f;
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int o = o0 + ty + 8 * r, i = i0 + tx;
+      if (o < cout && i < cin) {
+        const size_t q = ((size_t)t * cout + o) * cin + i;
+        float v = TRANSPOSED ? tile[tx][ty + 8 * r] : __ldg(dw + q);
+        if (demod) v = fmaf(-__ldg(w + q), coef[r], v);
+        grad[((size_t)o * cin + i) * taps + t] += v;          // (gathering the taps in registers first measured slower)
+      }
+    }
+  }
+}
+
 }  // namespace hfagp
 
 using namespace hfagp;
@@ -566,4 +625,18 @@ extern "C" int hfagp_conv2d_wgrad_mod(const HfagpConvDesc* desc, const float* x,
                                       const uint16_t* x_lo, const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo,
                                       const float* xscale, const float* dzscale, float scale, float* dw, void* stream) {
   return wgrad_impl(desc, x, x_hi, x_lo, dz, dz_hi, dz_lo, xscale, dzscale, scale, dw, stream);
+}
+
+extern "C" int hfagp_modconv_wgrad_finish(int taps, int cout, int cin, int batch, const float* dw, int dw_transposed, const float* w,
+                                          const float* ddcoef, const float* dcoef, const float* styles, float* grad, void* stream) {
+  HFAGP_CHECK_ARG(dw && grad && taps > 0 && cout > 0 && cin > 0, "modconv_wgrad_finish: bad args");
+  HFAGP_CHECK_ARG(!ddcoef || (w && dcoef && styles && batch > 0), "modconv_wgrad_finish: the demodulation term needs w, dcoef, styles");
+  HFAGP_CHECK_ARG(cdiv(cout, 32) <= 65535, "modconv_wgrad_finish: cout too large");
+  const dim3 grid(cdiv(cin, 32), cdiv(cout, 32));
+  if (dw_transposed)
+    modconv_wgrad_finish_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(taps, cout, cin, batch, dw, w, ddcoef, dcoef, styles, grad);
+  else
+    modconv_wgrad_finish_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(taps, cout, cin, batch, dw, w, ddcoef, dcoef, styles, grad);
+  HFAGP_CHECK_LAUNCH("modconv_wgrad_finish_kernel");
+  return HFAGP_OK;
 }

@@ -248,8 +248,11 @@ def render_bwd(planes, c, mlp, lin, jitter, u_fine, dfeat, *, res, s_coarse, s_f
     d = RenderDesc(n, res, ph, pw, s_coarse, s_fine, delta, box_scale)
     if decoder:
         total = n * res * res * (s_coarse + s_fine)
-        f = torch.zeros((total, 32), device=planes.device, dtype=torch.float32)
-        do = torch.zeros((total, 33), device=planes.device, dtype=torch.float32)
+        # every sample of every VALID ray is written by the kernel; rays only go missing when res is not a multiple of the
+        # 8 rays of a backward strip (then those rows must read as zero): skip 0.8 GB of memset per step otherwise
+        alloc = torch.empty if res % 8 == 0 else torch.zeros
+        f = alloc((total, 32), device=planes.device, dtype=torch.float32)
+        do = alloc((total, 33), device=planes.device, dtype=torch.float32)
         _ok(_cabi.lib().hfagp_render_bwd_dec(C.byref(d), ptr(planes), ptr(c), ptr(mlp), ptr(lin), ptr(jitter), ptr(u_fine),
                                              ptr(dfeat), ptr(dplanes), ptr(f), ptr(do), stream()), 'hfagp_render_bwd_dec')
         return dplanes, f, do
@@ -522,6 +525,15 @@ def demod_bwd(w2, styles, dcoef, ddcoef, dstyles):
     cout, cin = w2.shape
     _ok(_cabi.lib().hfagp_demod_bwd(styles.shape[0], cout, cin, ptr(w2), ptr(styles), ptr(dcoef), ptr(ddcoef),
                                       ptr(dstyles), stream()), 'hfagp_demod_bwd')
+
+
+def modconv_wgrad_finish(dw, w, grad, *, transposed=False, ddcoef=None, dcoef=None, styles=None):
+    """grad[O][I][k][k] += unpack(dw) - w * sum_n ddcoef dcoef^3 styles^2 (see ``hfagp_modconv_wgrad_finish``).
+    ``dw``: packed [taps][O][I] ([taps][I][O] when ``transposed``); ``w``: the packed unmodulated weight [taps][O][I]."""
+    taps, cout, cin = w.shape          # (only the shape of ``w`` is used when there is no demodulation term)
+    batch = styles.shape[0] if styles is not None else 0
+    _ok(_cabi.lib().hfagp_modconv_wgrad_finish(taps, cout, cin, batch, ptr(dw), 1 if transposed else 0, ptr(w), ptr(ddcoef),
+                                                 ptr(dcoef), ptr(styles), ptr(grad), stream()), 'hfagp_modconv_wgrad_finish')
 
 
 def linear_bwd(dy, x, w, w_gain, b_gain, need_dx=True, dw=None, db=None):

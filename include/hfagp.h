@@ -379,6 +379,15 @@ int hfagp_conv2d_wgrad_mod(const HfagpConvDesc* desc, const float* x, const uint
                            const float* dz, const uint16_t* dz_hi, const uint16_t* dz_lo, const float* xscale,
                            const float* dzscale, float scale, float* dw, void* stream);
 
+/* Last step of a modulated convolution's weight gradient (generator unfrozen, code/train_rgb.py:132-134): the style-scaled
+ * wgrad dw (packed [tap][cout][cin]; [tap][cin][cout] when dw_transposed — up-sampling layers, whose wgrad runs with the
+ * roles of the operands swapped) plus, when ddcoef is given, the demodulation term
+ *   - w[tap][o][i] * sum_n ddcoef[n][o] dcoef[n][o]^3 styles[n][i]^2        (w: the packed, unmodulated weight)
+ * is unpacked into the parameter layout and ADDED to grad[cout][cin][taps] (= the parameter's .grad, [O][I][k][k]).
+ * Replaces: autograd of modulated_conv2d w.r.t. its weight (eg3d networks_stylegan2.py). */
+int hfagp_modconv_wgrad_finish(int taps, int cout, int cin, int batch, const float* dw, int dw_transposed, const float* w,
+                               const float* ddcoef, const float* dcoef, const float* styles, float* grad, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Around the render path inside one training step (Trainer.gen_update, code/trainer_rgb.py:73-98).
  * ------------------------------------------------------------------------------------------- */

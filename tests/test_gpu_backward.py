@@ -235,6 +235,31 @@ def test_render_backward(res, s, sf, batch):
     assert e_l2 < 1e-3 and e_max < 5e-3, (e_max, e_l2)
 
 
+@pytest.mark.parametrize('taps,cout,cin,batch,transposed', [(9, 64, 96, 2, False), (9, 40, 24, 3, True), (1, 512, 512, 9, False),
+                                                            (9, 128, 256, 2, True)])
+def test_modconv_wgrad_finish(taps, cout, cin, batch, transposed):
+    """hfagp_modconv_wgrad_finish: unpack(dw) - w * sum_n ddcoef dcoef^3 styles^2, added to grad[O][I][k][k]; packed and
+    role-swapped ([tap][I][O]) inputs, ragged 32 x 32 tiles, more samples than one staging round."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(taps * 1000 + cout + cin)
+    k = int(math.isqrt(taps))
+    dw = torch.randn(taps, cout, cin, generator=g)
+    w = torch.randn(taps, cout, cin, generator=g)
+    ddc, dco = torch.randn(batch, cout, generator=g), torch.rand(batch, cout, generator=g) + 0.5
+    st = torch.randn(batch, cin, generator=g)
+    grad0 = torch.randn(cout, cin, k, k, generator=g)
+    coef = torch.einsum('no,ni->oi', (ddc * dco ** 3).double(), (st * st).double())
+    want = grad0.double() + (dw.double() - w.double() * coef[None]).view(k, k, cout, cin).permute(2, 3, 0, 1)
+    grad = grad0.clone().cuda()
+    dw_in = dw.transpose(1, 2).contiguous() if transposed else dw
+    ops.modconv_wgrad_finish(dw_in.cuda(), w.cuda(), grad, transposed=transposed, ddcoef=ddc.cuda(), dcoef=dco.cuda(), styles=st.cuda())
+    assert pu.rel_err(grad, want.float()) < 1e-5
+    # without the demodulation term (ToRGB-style layers): plain unpack + accumulate
+    grad = grad0.clone().cuda()
+    ops.modconv_wgrad_finish(dw_in.cuda(), w.cuda(), grad, transposed=transposed)
+    assert pu.rel_err(grad, (grad0.double() + dw.double().view(k, k, cout, cin).permute(2, 3, 0, 1)).float()) < 1e-6
+
+
 @pytest.mark.parametrize('samples', [64, 1000, 20011])
 def test_decoder_weight_gradient_kernel(samples):
     """hfagp_decoder_wgrad (hidden layer recomputed, four reductions over the samples) against fp64 autograd of the same
