@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import math
+
 import torch
 
 from . import _cabi
@@ -56,6 +58,79 @@ def from_uint8(frames: torch.Tensor) -> torch.Tensor:
     ops._ok(_cabi.lib().hfagp_frame_from_uint8(n, h, w, c, ptr(frames.contiguous()), ptr(out), stream()),
             'hfagp_frame_from_uint8')
     return out
+
+
+_TABLES = {}
+
+
+def pil_bilinear_table(in_size: int, out_size: int):
+    """Pillow's coefficient table for resampling one axis from ``in_size`` to ``out_size`` with the bilinear filter:
+    ``precompute_coeffs`` (double arithmetic, filter support scaled by the down-sampling factor, weights normalised to
+    sum 1) followed by ``normalize_coeffs_8bpc`` (22-bit fixed point, round half away from zero) — src/libImaging/
+    Resample.c.  Returns ``(ksize, bounds [out,2] int32 = (first, count), coeffs [out,ksize] int32)`` as CPU tensors."""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = filterscale                                # bilinear: filter support 1.0
+    ksize = int(math.ceil(support)) * 2 + 1
+    inv = 1.0 / filterscale
+    bounds = torch.zeros((out_size, 2), dtype=torch.int32)
+    coeffs = torch.zeros((out_size, ksize), dtype=torch.int32)
+    one = 1 << 22
+    for o in range(out_size):
+        center = (o + 0.5) * scale
+        first = max(int(center - support + 0.5), 0)
+        count = min(int(center + support + 0.5), in_size) - first
+        w = [max(1.0 - abs((k + first - center + 0.5) * inv), 0.0) for k in range(count)]
+        tot = 0.0
+        for v in w:
+            tot += v
+        for k in range(count):
+            v = w[k] / tot if tot != 0.0 else w[k]
+            coeffs[o, k] = int(0.5 + v * one) if v >= 0 else int(-0.5 + v * one)
+        bounds[o, 0], bounds[o, 1] = first, count
+    return ksize, bounds, coeffs
+
+
+def _table(in_size, out_size, device):
+    key = (in_size, out_size, str(device))
+    if key not in _TABLES:
+        ksize, b, c = pil_bilinear_table(in_size, out_size)
+        _TABLES[key] = (ksize, b.to(device), c.to(device))
+    return _TABLES[key]
+
+
+def resize_output_size(h: int, w: int, size: int):
+    """``transforms.Resize(int)``: the shorter side becomes ``size``, the other keeps the aspect ratio."""
+    return (int(size * h / w), size) if w <= h else (size, int(size * w / h))
+
+
+def resize_uint8(frames: torch.Tensor, out_h: int, out_w: int, normalized: bool = False) -> torch.Tensor:
+    """uint8 [N,H,W,C] decoded frames on the device -> what ``PIL.Image.resize((out_w, out_h), BILINEAR)`` gives for each
+    of them, bit for bit: uint8 [N,out_h,out_w,C], or with ``normalized`` the ToTensor + Normalize(0.5, 0.5) of that as
+    fp32 [N,C,out_h,out_w] (the encoder's input) straight from the vertical pass (``hfagp_frame_resize_u8``)."""
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or not frames.is_cuda:
+        raise HfagpError('resize_uint8 expects a CUDA uint8 tensor [N,H,W,C]')
+    frames = frames.contiguous()
+    n, h, w, c = frames.shape
+    dev = frames.device
+    kh, bh, ch_ = _table(w, out_w, dev) if out_w != w else (0, None, None)
+    kv, bv, cv = _table(h, out_h, dev)
+    tmp = torch.empty((n, h, out_w, c), device=dev, dtype=torch.uint8) if out_w != w else None
+    if normalized:
+        y8, yf = None, torch.empty((n, c, out_h, out_w), device=dev, dtype=torch.float32)
+    else:
+        y8, yf = torch.empty((n, out_h, out_w, c), device=dev, dtype=torch.uint8), None
+    ops._ok(_cabi.lib().hfagp_frame_resize_u8(n, h, w, c, out_h, out_w, kh, ptr(bh), ptr(ch_), kv, ptr(bv), ptr(cv), ptr(frames),
+                                              ptr(tmp), ptr(y8), ptr(yf), stream()), 'hfagp_frame_resize_u8')
+    return yf if normalized else y8
+
+
+def ingest(frames: torch.Tensor, size: int) -> torch.Tensor:
+    """The reference's frame transform ``Resize(size) -> ToTensor -> Normalize([0.5]*3, [0.5]*3)`` (train_rgb.py:78-81,
+    run_recon_video_3dmm.py:258-261) on decoded uint8 frames [N,H,W,3] already on the device -> fp32 [N,3,h',w']."""
+    n, h, w, c = frames.shape
+    oh, ow = resize_output_size(h, w, size)
+    return resize_uint8(frames, oh, ow, normalized=True)
 
 
 class FrameSink:
@@ -110,15 +185,18 @@ class FrameSink:
 
 class FrameFeeder:
     """Asynchronous ingress: decoded uint8 frames ``[N,H,W,3]`` (numpy or CPU tensor) are staged in pinned memory,
-    copied host->device on a side stream and normalised on the device; ``next()`` returns fp32 ``[N,3,H,W]``.
+    copied host->device on a side stream and (resized and) normalised on the device; ``next()`` returns fp32 ``[N,3,H,W]``.
     A slot is reused only when its previous occupants are done with it: the host write waits for the previous
     host->device copy out of the pinned buffer, and the copy into the device buffer waits (on the device) for the
     ``from_uint8`` kernel that last read it — a GPU that lags the host cannot see frames overwritten."""
 
-    def __init__(self, height: int, width: int, channels: int = 3, batch: int = 1, depth: int = 4, device=None):
+    def __init__(self, height: int, width: int, channels: int = 3, batch: int = 1, depth: int = 4, device=None,
+                 size: Optional[int] = None):
+        """``size``: also apply the reference's ``transforms.Resize(size)`` (Pillow bilinear, bit-exact) on the device, so
+        the decoded frames cross PCIe as they come out of the decoder and ``next()`` returns the encoder's input."""
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         shape = (batch, height, width, channels)
-        self.depth = depth
+        self.depth, self.size = depth, size
         self.host = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(depth)]
         self.dev = [torch.empty(shape, device=self.device, dtype=torch.uint8) for _ in range(depth)]
         self.ready = [None] * depth                    # host->device copy of the slot's current frame
@@ -147,7 +225,7 @@ class FrameFeeder:
         s = self.tail % self.depth
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self.ready[s])
-        out = from_uint8(self.dev[s])
+        out = from_uint8(self.dev[s]) if self.size is None else ingest(self.dev[s], self.size)
         self.consumed[s] = torch.cuda.Event()
         self.consumed[s].record(cur)
         self.tail += 1

@@ -471,6 +471,17 @@ int hfagp_frame_to_uint8(long long count, const float* x, int mode, unsigned cha
  * loader (code/train_rgb.py:78-81; code/dataset.py:205-214), bit-exact: v = u8/255 ; y = (v - 0.5) / 0.5. */
 int hfagp_frame_from_uint8(int batch, int h, int w_, int c, const unsigned char* x, float* y, void* stream);
 
+/* transforms.Resize on the decoded frame, as Pillow does it (the reference's ingress: Resize(args.size) -> ToTensor ->
+ * Normalize on a PIL image, run_recon_video_3dmm.py:258-261, run_recon_video_audio.py:258-261, train_rgb.py:78-81):
+ * two-pass fixed-point bilinear resampling of uint8 x[n][h][w][c] — horizontal pass into tmp[n][h][out_w][c] (skipped
+ * when out_w == w), vertical pass into y_u8[n][out_h][out_w][c] and / or y_f32[n][c][out_h][out_w] = ((u8/255)-0.5)/0.5.
+ * Each pass: u8 = clip8(((1 << 21) + sum_{k < count} pixel[first + k] * coeffs[o][k]) >> 22), with bounds[o] = (first,
+ * count) and the int32 coefficient tables of Pillow's precompute_coeffs / normalize_coeffs_8bpc (22-bit fixed point),
+ * computed by the caller (hfa_gp_b200/frameio.py: pil_bilinear_table).  Bit-exact against PIL.Image.resize(BILINEAR). */
+int hfagp_frame_resize_u8(int batch, int h, int w_, int c, int out_h, int out_w, int ksize_h, const int* bounds_h,
+                          const int* coeffs_h, int ksize_v, const int* bounds_v, const int* coeffs_v, const unsigned char* x,
+                          unsigned char* tmp, unsigned char* y_u8, float* y_f32, void* stream);
+
 /* Layout helpers (elementwise, bandwidth-bound): NCHW <-> NHWC for the frame entering the encoder
  * and the image leaving the super-resolution head. */
 int hfagp_nchw_to_nhwc(int batch, int c, int h, int w_, const float* x, float* y, void* stream);

@@ -106,3 +106,33 @@ def test_rings_survive_a_gpu_that_lags_the_host():
     assert (popped[0] == first).all()                 # later pushes wrapped onto its slot: the popped frame owns its bytes
     for im, p_ in zip(imgs, popped):
         assert (torch.from_numpy(p_) == frameio_ref.save_image_uint8(im.cpu())).all()
+
+
+@pytest.mark.parametrize('n,h,w,size', [(2, 512, 512, 256), (1, 500, 500, 256), (1, 300, 420, 256), (1, 200, 200, 256),
+                                        (1, 256, 256, 256), (3, 37, 53, 16)])
+def test_resize_bit_exact(n, h, w, size):
+    """hfagp_frame_resize_u8 (Pillow's two-pass fixed-point bilinear resampler on the device) against the oracle, which
+    tests/test_oracle_frameio.py pins to PIL.Image.resize itself: uint8 output and the fused ToTensor + Normalize output."""
+    from hfa_gp_b200 import frameio
+    g = torch.Generator().manual_seed(n * 1000 + h + w)
+    u8 = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+    u8.view(-1)[:4] = torch.tensor([0, 255, 1, 254], dtype=torch.uint8)
+    oh, ow = frameio.resize_output_size(h, w, size)
+    want = frameio_ref.resize_uint8(u8, oh, ow)
+    got = frameio.resize_uint8(u8.cuda(), oh, ow)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (n, oh, ow, 3)
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(frameio.ingest(u8.cuda(), size).cpu(), frameio_ref.to_tensor_normalize(want))
+
+
+def test_feeder_with_resize_returns_the_reference_transform():
+    """FrameFeeder(size=...) = decoded 512^2 uint8 frame -> Resize(256) -> ToTensor -> Normalize, on the device."""
+    from hfa_gp_b200 import frameio
+    g = torch.Generator().manual_seed(12)
+    feeder = frameio.FrameFeeder(96, 96, batch=2, depth=2, size=48)
+    frames = [torch.randint(0, 256, (2, 96, 96, 3), generator=g, dtype=torch.uint8) for _ in range(3)]
+    for f in frames:
+        feeder.push(f.numpy())
+        got = feeder.next()
+        want = frameio_ref.to_tensor_normalize(frameio_ref.resize_uint8(f, 48, 48))
+        assert torch.equal(got.cpu(), want)
