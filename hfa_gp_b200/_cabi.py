@@ -24,7 +24,7 @@ SYMBOLS = [
     'hfagp_nhwc_to_nchw', 'hfagp_conv2d_tc_fwd', 'hfagp_split_bf16', 'hfagp_modulate_split_fwd',
     'hfagp_blur_up', 'hfagp_act_bwd', 'hfagp_styles_bwd', 'hfagp_demod_bwd', 'hfagp_linear_bwd',
     'hfagp_conv2d_wgrad', 'hfagp_render_bwd', 'hfagp_latent_bwd', 'hfagp_facepool_fwd', 'hfagp_facepool_bwd',
-    'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8', 'hfagp_frame_resize_u8',
+    'hfagp_mse_fwd', 'hfagp_mse_bwd', 'hfagp_adam_step', 'hfagp_conv2d_tc_multi_fwd', 'hfagp_conv2d_tc_acc_fwd', 'hfagp_conv_epilogue_fwd', 'hfagp_frame_to_uint8', 'hfagp_frame_from_uint8', 'hfagp_frame_resize_u8', 'hfagp_stem_conv1x1_fwd',
     'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
     'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd', 'hfagp_conv2d_wgrad_mod', 'hfagp_render_bwd_dec',
     'hfagp_render_fwd_simt', 'hfagp_decoder_wgrad', 'hfagp_modconv_wgrad_finish', 'hfagp_set_device', 'hfagp_device_sm_count', 'hfagp_conv2d_tc_acc_workspace_bytes', 'hfagp_render_bwd_dec_workspace_bytes', 'hfagp_adam_sched', 'hfagp_adam_step_dev', 'hfagp_render_bookkeeping',
@@ -124,6 +124,7 @@ def lib() -> C.CDLL:
     l.hfagp_conv_epilogue_fwd.argtypes = [C.POINTER(ConvDesc)] + [vp] * 10
     l.hfagp_frame_to_uint8.argtypes = [C.c_longlong, vp, i32, vp, vp]
     l.hfagp_frame_from_uint8.argtypes = [i32, i32, i32, i32, vp, vp, vp]
+    l.hfagp_stem_conv1x1_fwd.argtypes = [i32] * 5 + [vp, vp, vp, i32, f32, vp, vp, vp]
     l.hfagp_frame_resize_u8.argtypes = [i32] * 7 + [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     l.hfagp_lpips_stem_fwd.argtypes = [i32, i32, i32] + [vp] * 6
     l.hfagp_lpips_stem_bwd.argtypes = [i32, i32, i32] + [vp] * 4

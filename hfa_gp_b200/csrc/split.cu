@@ -22,6 +22,36 @@ __global__ void split4_kernel(size_t count4, const float* __restrict__ x, __nv_b
   st4_split(hi, lo, i, v);
 }
 
+// The encoder's first layer at inference: ConvLayer(3, C, 1) = 1x1 convolution of the NCHW frame + FusedLeakyReLU
+// (encoder3d.py:142-179 with kernel_size 1), written straight as the split-bf16 channels-last operand of the next
+// tensor-core convolution: replaces nchw_to_nhwc + the SIMT implicit GEMM + the fp32 -> split pass (three round trips of the
+// 67 MB activation at batch 4) by one kernel that reads the 3 MB frame and writes the operand once.
+// thread = (pixel, 4 output channels); w [cout][cin] fp32 (equalised-lr scale folded in), cin <= 4.
+__global__ void __launch_bounds__(256) stem_conv1x1_kernel(int hw, int cin, int cout4, const float* __restrict__ x,
+                                                          const float* __restrict__ w, const float* __restrict__ bias, float slope,
+                                                          float gain, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= (uint32_t)hw * cout4) return;
+  const int pix = i / cout4, cq = i - pix * cout4;
+  const int n = blockIdx.y;
+  const float* xp = x + (size_t)n * cin * hw + pix;
+  float xin[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xin[c] = c < cin ? __ldg(xp + (size_t)c * hw) : 0.f;
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int co = cq * 4 + k;
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < cin) a = fmaf(xin[c], __ldg(w + co * cin + c), a);
+    a += bias ? __ldg(bias + co) : 0.f;
+    o[k] = fmaxf(a, slope * a) * gain;
+  }
+  st4_split(y_hi, y_lo, ((size_t)n * hw + pix) * cout4 + cq, o);
+}
+
 // block per (o, n): wmod = w * s written as split bf16, dcoef from the fp32 products.  A thread owns 4 consecutive
 // input channels (its style values stay in registers) and walks the taps: 16-byte loads, 8-byte stores.
 __global__ void modulate_split_kernel(int ntaps, int cout, int cin, const float* __restrict__ w,
@@ -154,5 +184,18 @@ extern "C" int hfagp_modulate_split_fwd(int batch, int ntaps, int cout, int cin,
       ntaps, cout, cin, w, styles, reinterpret_cast<__nv_bfloat16*>(wmod_hi), reinterpret_cast<__nv_bfloat16*>(wmod_lo),
       dcoef);
   HFAGP_CHECK_LAUNCH("modulate_split_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_stem_conv1x1_fwd(int batch, int h, int w_, int cin, int cout, const float* x_nchw, const float* w,
+                                      const float* bias, int act, float act_gain, uint16_t* y_hi, uint16_t* y_lo, void* stream) {
+  HFAGP_CHECK_ARG(x_nchw && w && y_hi && y_lo && batch > 0 && batch <= 65535 && h > 0 && w_ > 0, "stem_conv1x1_fwd: bad args");
+  HFAGP_CHECK_ARG(cin >= 1 && cin <= 4 && cout >= 4 && (cout & 3) == 0, "stem_conv1x1_fwd: cin <= 4 and cout % 4 == 0 required");
+  HFAGP_CHECK_ARG((long long)h * w_ * (cout >> 2) < (1ll << 31), "stem_conv1x1_fwd: frame too large");
+  const int hw = h * w_;
+  stem_conv1x1_kernel<<<dim3(cdiv((long long)hw * (cout >> 2), 256), batch), 256, 0, (cudaStream_t)stream>>>(
+      hw, cin, cout >> 2, x_nchw, w, bias, act_slope(act), act_gain, reinterpret_cast<__nv_bfloat16*>(y_hi),
+      reinterpret_cast<__nv_bfloat16*>(y_lo));
+  HFAGP_CHECK_LAUNCH("stem_conv1x1_kernel");
   return HFAGP_OK;
 }

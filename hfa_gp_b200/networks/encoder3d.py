@@ -298,8 +298,17 @@ class EncoderApp(nn.Module):
     def _forward_impl(self, x, tape):
         tc = self.precision == 'tc'
         recs = [({} if tape is not None else None) for _ in self.convs[:-1]]
-        h = ops.nchw_to_nhwc(x.detach().float().contiguous())
-        h = self.convs[0].run(h, split_out=tc, rec=recs[0])           # cin = 3: exact-fp32 SIMT kernel
+        first = self.convs[0]
+        c0 = next(m for m in first.children() if isinstance(m, EqualConv2d))
+        a0 = list(first.children())[-1]
+        if (tc and tape is None and first.kernel_size == 1 and not first.downsample and c0.weight.shape[1] <= 4
+                and c0.weight.shape[0] % 4 == 0 and isinstance(a0, FusedLeakyReLU)):
+            # inference: frame -> first layer's output in the next convolution's operand format, one kernel
+            h = ops.stem_conv1x1(x.detach().float().contiguous(), c0.packed()[0], a0.bias.detach().reshape(-1).contiguous(),
+                                 act=ACT_LRELU, act_gain=SQRT2)
+        else:
+            h = ops.nchw_to_nhwc(x.detach().float().contiguous())
+            h = first.run(h, split_out=tc, rec=recs[0])                   # cin = 3: exact-fp32 SIMT kernel
         side = None
         if tape is None and self.overlap_streams:
             side = self.__dict__.get('_side')

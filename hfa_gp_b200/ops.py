@@ -304,6 +304,18 @@ def latent(weights, q, delta, dim_total):
     return out
 
 
+def stem_conv1x1(x_nchw, w, bias, act=ACT_LRELU, act_gain=math.sqrt(2.0)) -> 'Split':
+    """NCHW frame [N,cin<=4,H,W] -> split-bf16 channels-last [N,H,W,cout] through a 1x1 convolution + bias + activation
+    (``hfagp_stem_conv1x1_fwd``); ``w`` [cout][cin] fp32."""
+    n, cin, h, wd = x_nchw.shape
+    cout = w.shape[0]
+    hi = torch.empty((n, h, wd, cout), device=x_nchw.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    _ok(_cabi.lib().hfagp_stem_conv1x1_fwd(n, h, wd, cin, cout, ptr(x_nchw), ptr(w), ptr(bias), act, act_gain, ptr(hi), ptr(lo),
+                                           stream()), 'hfagp_stem_conv1x1_fwd')
+    return Split(hi, lo)
+
+
 def nchw_to_nhwc(x):
     n, c, h, w = x.shape
     out = torch.empty((n, h, w, c), device=x.device, dtype=torch.float32)

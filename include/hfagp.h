@@ -131,6 +131,13 @@ int hfagp_conv2d_tc_multi_fwd(const HfagpConvDesc* descs, int ndesc, const uint1
                               const float* noise, const float* bias, const float* residual, const float* up_img,
                               float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
 
+/* The encoder's first layer at inference, ConvLayer(3, C, 1) (code/networks/encoder3d.py:142-179, kernel_size 1): 1x1
+ * convolution of the NCHW frame x[n][cin][h][w] (cin <= 4) with w[cout][cin] (equalised-lr scale folded in) + bias +
+ * activation * act_gain, written directly as the split-bf16 channels-last operand y[n][h][w][cout] of the following
+ * tensor-core convolution (one pass instead of layout change + SIMT convolution + split). */
+int hfagp_stem_conv1x1_fwd(int batch, int h, int w_, int cin, int cout, const float* x_nchw, const float* w,
+                           const float* bias, int act, float act_gain, uint16_t* y_hi, uint16_t* y_lo, void* stream);
+
 /* Caller-provided scratch, as pure functions of the shapes ("workspace is caller-provided"): the library never
  * allocates.  hfagp_conv2d_tc_acc_workspace_bytes = the zeroed fp32 accumulator acc[n][out_h][out_w][cout] of the split-K
  * form below (descs[0] carries the full output geometry); 0 for a null / degenerate descriptor.  (The renderer's
