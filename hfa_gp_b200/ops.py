@@ -35,6 +35,8 @@ def _conv_desc(key, build):
     d = _desc_cache.get(key)
     if d is None:
         d = build()
+        if len(_desc_cache) >= 4096:      # keys are shapes and constant epilogue settings: a long-running process that
+            _desc_cache.clear()           # keeps seeing new shapes must not grow without bound
         _desc_cache[key] = d
     return d
 
