@@ -235,6 +235,24 @@ def test_render_backward(res, s, sf, batch):
     assert e_l2 < 1e-3 and e_max < 5e-3, (e_max, e_l2)
 
 
+@pytest.mark.parametrize('n,h,cin,split', [(2, 64, 128, True), (1, 37, 256, True), (3, 16, 24, False), (2, 48, 512, True)])
+def test_wgrad_narrow_1x1_output(n, h, cin, split):
+    """The 3-channel ToRGB's weight gradient (cout padded to 4, 1x1, per-sample style factors) takes the streaming
+    wgrad_cout4_kernel: against fp64 einsum, fp32 and split-bf16 layer inputs, channel counts beyond one 32-quad sweep."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n * 100 + h + cin)
+    x = torch.randn(n, h, h, cin, generator=g)
+    dz = torch.randn(n, h, h, 4, generator=g)
+    st = torch.randn(n, cin, generator=g)
+    want = torch.einsum('nhwo,nhwi,ni->oi', dz.double(), x.double(), st.double()).float() * 0.5
+    dw = torch.zeros(1, 4, cin, device='cuda')
+    xin = ops.split(x.cuda()) if split else x.cuda()
+    ops.conv2d_wgrad(xin, dz.cuda(), ops.TAPS_1X1, dw, oh=h, ow=h, scale=0.5, xscale=st.cuda())
+    e = pu.rel_l2(dw[0], want)
+    print(f'wgrad 1x1 cout 4 [{n},{h},{h},{cin}] split={split}: rel-L2 {e:.3e}')
+    assert e < (2e-5 if split else 1e-5)
+
+
 @pytest.mark.parametrize('taps,cout,cin,batch,transposed', [(9, 64, 96, 2, False), (9, 40, 24, 3, True), (1, 512, 512, 9, False),
                                                             (9, 128, 256, 2, True)])
 def test_modconv_wgrad_finish(taps, cout, cin, batch, transposed):
