@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libhfagp_sm100.so')
+# HFAGP_LIB: A/B-measure another build of the same ABI (profiling aid; the default is the in-tree library)
+LIB_PATH = os.environ.get('HFAGP_LIB') or os.path.join(_HERE, 'libhfagp_sm100.so')
 MAX_TAPS = 32
 ACT_LINEAR, ACT_LRELU, ACT_RELU = 0, 1, 2
 

@@ -107,6 +107,23 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
   lo = pack_bf16x2(a - ah, b - bh);
 }
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: two fp32 operations per issue slot; a pair is a 64-bit register,
+// element 0 in the low half)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// split_pair on a packed pair
+__device__ __forceinline__ void split_pair2(f32x2 ab, uint32_t& hi, uint32_t& lo) {
+  float a, b;
+  upk2(ab, a, b);
+  hi = pack_bf16x2(a, b);
+  float ra, rb;
+  upk2(sub2(ab, pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u))), ra, rb);
+  lo = pack_bf16x2(ra, rb);
+}
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

@@ -42,9 +42,11 @@ constexpr int RT_N2 = 48;                           // layer-2 N: 32 colours, si
 constexpr int RT_B1 = 64 * 128;                     // bytes of one layer-1 weight tile (64 rows x 128 B)
 constexpr int RT_B2 = RT_N2 * 128;
 constexpr int RT_A = 128 * 128;                     // bytes of one A tile (128 rows x 128 B)
-constexpr int RT_REC = 80;                          // tap record of one sample: 3 plane offsets (+pad), 3 x 4 bilinear weights;
-                                                    // 80 B apart = conflict-free 16 B reads by 4 samples at once
+constexpr int RT_REC = 112;                         // tap record of one sample: 3 plane offsets (+pad), 3 x 4 bilinear weights, each
+                                                    // stored TWICE (the (w, w) operand of a packed FFMA2);
+                                                    // 112 B apart = conflict-free 16 B reads by 4 samples at once
 constexpr int RT_TAPS = RT_TILE * RT_REC;           // tap records of one tile of one ray
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr uint32_t RT_TMEM_COLS = 512;              // D1[2] at 0 / 64, D2[2] at 128 / 192, A2[2] (hi 32 | lo 32 columns) at 256 / 320
 
 // per-ray scratch: colq [T][16] u32 ; dep, sig, sdep, ssig [Tp] fp32 ; tap records (alias sdep.. when they fit) ;
@@ -134,6 +136,25 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(RT_RAYS * 32) : "memory"); }
 
+// The decoder's activations on packed pairs, in log2 units (the layer weights carry the log2(e) / ln 2 factors, see the
+// weight set-up): h' = softplus(x) / ln 2 = max(x', 0) + log2(1 + 2^-|x'|) with x' = x log2(e)
+__device__ __forceinline__ f32x2 softplus2_log2(f32x2 x) {
+  float x0, x1, t0, t1;
+  upk2(x, x0, x1);
+  upk2(add2(pk2(ex2f(-fabsf(x0)), ex2f(-fabsf(x1))), pk2(1.f, 1.f)), t0, t1);
+  return add2(pk2(lg2f(t0), lg2f(t1)), pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+// two colours: e = -x log2(e) (already in that form) -> round(65535 / (1 + 2^e)) packed as two u16: the 1 / 65535 is
+// folded into the denominator, the rounding done by adding 2^23 (round-to-nearest-even, as __float2uint_rn)
+__device__ __forceinline__ uint32_t sigmoid2_q16(f32x2 e) {
+  float e0, e1, d0, d1, y0, y1;
+  upk2(e, e0, e1);
+  constexpr float RQ = 1.f / QSCALE;
+  upk2(fma2(pk2(ex2f(e0), ex2f(e1)), pk2(RQ, RQ), pk2(RQ, RQ)), d0, d1);
+  upk2(add2(pk2(rcpf(d0), rcpf(d1)), pk2(8388608.f, 8388608.f)), y0, y1);
+  return __byte_perm(__float_as_uint(y0), __float_as_uint(y1), 0x5410);
+}
+
 // PWC > 0: plane width known at compile time (the four taps of a plane are immediate offsets from one address)
 template <int PWC, int RT_NA1, int ESPLIT>
 __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderParams p, const int tw_log2) {
@@ -170,7 +191,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
     const float* B1 = W1 + RO * RH;
     for (int i = threadIdx.x; i < RH * RC; i += blockDim.x) {      // (n, k): layer 1, K = channel
       const int n = i >> 5, k = i & 31;
-      const float v = __ldg(W0 + i);
+      const float v = __ldg(W0 + i) * LOG2E;         // hidden pre-activations in log2 units: x' = x log2(e)
       const __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
       *reinterpret_cast<__nv_bfloat16*>(b1a + sw128(n, k)) = h;
       *reinterpret_cast<__nv_bfloat16*>(b1a + sw128(n, k + 32)) = h;
@@ -180,13 +201,15 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
     for (int i = threadIdx.x; i < RT_N2 * RH; i += blockDim.x) {   // (n, k): layer 2, K = hidden unit
       const int n = i >> 6, k = i & 63;
       const int o = n < 32 ? n + 1 : (n == 32 ? 0 : -1);           // output permutation: colours first, then sigma
-      const float v = o >= 0 ? __ldg(W1 + o * RH + k) : 0.f;
+      // the hidden layer is kept as h' = softplus(x) / ln 2, so sigma's row carries the ln 2; a colour's row computes
+      // -log2(e) x (the exponent its sigmoid needs): -log2(e) ln 2 = -1, i.e. the row is just negated
+      const float v = o > 0 ? -__ldg(W1 + o * RH + k) : (o == 0 ? __ldg(W1 + k) * LN2 : 0.f);
       const __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
       *reinterpret_cast<__nv_bfloat16*>(b2h + sw128(n, k)) = h;
       *reinterpret_cast<__nv_bfloat16*>(b2l + sw128(n, k)) = l;
     }
-    for (int i = threadIdx.x; i < RH; i += blockDim.x) b0s[i] = __ldg(B0 + i);
-    for (int i = threadIdx.x; i < RT_N2; i += blockDim.x) b1s[i] = i < 32 ? __ldg(B1 + i + 1) : (i == 32 ? __ldg(B1) : 0.f);
+    for (int i = threadIdx.x; i < RH; i += blockDim.x) b0s[i] = __ldg(B0 + i) * LOG2E;
+    for (int i = threadIdx.x; i < RT_N2; i += blockDim.x) b1s[i] = i < 32 ? -LOG2E * __ldg(B1 + i + 1) : (i == 32 ? __ldg(B1) : 0.f);
     if (threadIdx.x == 0) {
       for (int s = 0; s < RT_NA1; ++s) mbar_init(&a1_full[s], RT_RAYS);
       for (int s = 0; s < 2; ++s) {
@@ -362,7 +385,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
           const float wy1 = y0 == yb ? wb : (y0 == yb + 1 ? wt : 0.f);
           uint8_t* rec = taps + sl * RT_REC;
           *reinterpret_cast<uint32_t*>(rec + pidx * 4) = (uint32_t)(yb * row_b + xb * TEXEL_B + pidx * (RC * 4));
-          *reinterpret_cast<float4*>(rec + 16 + pidx * 16) = make_float4(wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1);
+          const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+          *reinterpret_cast<float4*>(rec + 16 + pidx * 32) = make_float4(w00, w00, w10, w10);
+          *reinterpret_cast<float4*>(rec + 32 + pidx * 32) = make_float4(w01, w01, w11, w11);
         }
         __syncwarp();
         const int sq = lane >> 3, cg = lane & 7;
@@ -371,34 +396,31 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
           const int sl = q + sq;
           const uint8_t* rec = taps + sl * RT_REC;
           const uint4 off = *reinterpret_cast<const uint4*>(rec);
-          float4 w[3];
-#pragma unroll
-          for (int pi = 0; pi < 3; ++pi) w[pi] = *reinterpret_cast<const float4*>(rec + 16 + pi * 16);
           const uint32_t offs[3] = {off.x, off.y, off.z};
-          float4 v[12];
+          ulonglong2 v[12];                          // 12 taps x 4 channels as fp32 pairs
 #pragma unroll
           for (int pi = 0; pi < 3; ++pi) {
             const char* b0 = lb + offs[pi];
-            v[4 * pi + 0] = __ldg(reinterpret_cast<const float4*>(b0));
-            v[4 * pi + 1] = __ldg(reinterpret_cast<const float4*>(b0 + TEXEL_B));
-            v[4 * pi + 2] = __ldg(reinterpret_cast<const float4*>(b0 + row_b));
-            v[4 * pi + 3] = __ldg(reinterpret_cast<const float4*>(b0 + row_b + TEXEL_B));
+            v[4 * pi + 0] = __ldg(reinterpret_cast<const ulonglong2*>(b0));
+            v[4 * pi + 1] = __ldg(reinterpret_cast<const ulonglong2*>(b0 + TEXEL_B));
+            v[4 * pi + 2] = __ldg(reinterpret_cast<const ulonglong2*>(b0 + row_b));
+            v[4 * pi + 3] = __ldg(reinterpret_cast<const ulonglong2*>(b0 + row_b + TEXEL_B));
           }
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          f32x2 a01 = 0ull, a23 = 0ull;              // (+0, +0)
 #pragma unroll
           for (int pi = 0; pi < 3; ++pi) {
-            const float ww[4] = {w[pi].x, w[pi].y, w[pi].z, w[pi].w};
+            const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(rec + 16 + pi * 32);      // (w00, w00), (w10, w10)
+            const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(rec + 32 + pi * 32);      // (w01, w01), (w11, w11)
+            const f32x2 ww[4] = {wa.x, wa.y, wb.x, wb.y};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              a.x = fmaf(ww[k], v[4 * pi + k].x, a.x);
-              a.y = fmaf(ww[k], v[4 * pi + k].y, a.y);
-              a.z = fmaf(ww[k], v[4 * pi + k].z, a.z);
-              a.w = fmaf(ww[k], v[4 * pi + k].w, a.w);
+              a01 = fma2(ww[k], v[4 * pi + k].x, a01);
+              a23 = fma2(ww[k], v[4 * pi + k].y, a23);
             }
           }
           uint2 hi, lo;
-          split_pair(a.x, a.y, hi.x, lo.x);
-          split_pair(a.z, a.w, hi.y, lo.y);
+          split_pair2(a01, hi.x, lo.x);
+          split_pair2(a23, hi.y, lo.y);
           const int row = warp * RT_TILE + sl;
           uint8_t* rp = abuf + row * 128 + (cg & 1) * 8;
           *reinterpret_cast<uint2*>(rp + ((((cg >> 1)) ^ (row & 7)) << 4)) = hi;       // channels 4cg.. of the hi half
@@ -423,9 +445,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {              // biases: broadcast 16 B reads
-            const float4 b = *reinterpret_cast<const float4*>(b0s + 16 * ch + 4 * j);
-            split_pair(softplus_fast(v[4 * j] + b.x), softplus_fast(v[4 * j + 1] + b.y), hi[2 * j], lo[2 * j]);
-            split_pair(softplus_fast(v[4 * j + 2] + b.z), softplus_fast(v[4 * j + 3] + b.w), hi[2 * j + 1], lo[2 * j + 1]);
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(b0s + 16 * ch + 4 * j);
+            split_pair2(softplus2_log2(add2(pk2(v[4 * j], v[4 * j + 1]), b.x)), hi[2 * j], lo[2 * j]);
+            split_pair2(softplus2_log2(add2(pk2(v[4 * j + 2], v[4 * j + 3]), b.y)), hi[2 * j + 1], lo[2 * j + 1]);
           }
           // layer-2 A operand straight into TMEM (row = lane, two bf16 per 32-bit column): no shared-memory round trip
           const uint32_t a2 = trow + 256 + (g & 1) * 64 + ch * 8;
@@ -453,11 +475,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) render_tc_kernel(const RenderPa
             uint32_t qv[4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const float4 b = *reinterpret_cast<const float4*>(b1s + 8 * ch + 4 * j);
-              const uint32_t q0 = __float2uint_rn(sigmoid01(c[4 * j] + b.x) * QSCALE), q1 = __float2uint_rn(sigmoid01(c[4 * j + 1] + b.y) * QSCALE);
-              const uint32_t q2 = __float2uint_rn(sigmoid01(c[4 * j + 2] + b.z) * QSCALE), q3 = __float2uint_rn(sigmoid01(c[4 * j + 3] + b.w) * QSCALE);
-              qv[2 * j] = q0 | (q1 << 16);
-              qv[2 * j + 1] = q2 | (q3 << 16);
+              const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(b1s + 8 * ch + 4 * j);
+              qv[2 * j] = sigmoid2_q16(add2(pk2(c[4 * j], c[4 * j + 1]), b.x));
+              qv[2 * j + 1] = sigmoid2_q16(add2(pk2(c[4 * j + 2], c[4 * j + 3]), b.y));
             }
             *reinterpret_cast<uint4*>(ecolq + s * 16 + colqx(s, 4 * ch)) = make_uint4(qv[0], qv[1], qv[2], qv[3]);
             if (ch == 3) esig[s] = c[8] + b1s[32];
