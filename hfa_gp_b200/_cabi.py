@@ -29,6 +29,7 @@ SYMBOLS = [
     'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
     'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd', 'hfagp_conv2d_wgrad_mod', 'hfagp_render_bwd_dec',
     'hfagp_render_fwd_simt', 'hfagp_decoder_wgrad', 'hfagp_modconv_wgrad_finish', 'hfagp_set_device', 'hfagp_device_sm_count', 'hfagp_conv2d_tc_acc_workspace_bytes', 'hfagp_render_bwd_dec_workspace_bytes', 'hfagp_adam_sched', 'hfagp_adam_step_dev', 'hfagp_render_bookkeeping',
+    'hfagp_basis_qr_workspace_bytes', 'hfagp_basis_qr_fwd', 'hfagp_basis_qr_bwd', 'hfagp_basis_qr_info',
 ]
 
 
@@ -100,6 +101,11 @@ def lib() -> C.CDLL:
     l.hfagp_render_bwd_dec_workspace_bytes.argtypes = [C.POINTER(RenderDesc), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     l.hfagp_render_bwd_dec_workspace_bytes.restype = C.c_size_t
     l.hfagp_blur_fwd.argtypes = [i32] * 7 + [f32] + [vp] * 7
+    l.hfagp_basis_qr_workspace_bytes.argtypes = [i32, i32]
+    l.hfagp_basis_qr_workspace_bytes.restype = C.c_size_t
+    l.hfagp_basis_qr_fwd.argtypes = [i32, i32, vp, f32, vp, vp, vp, vp]
+    l.hfagp_basis_qr_bwd.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+    l.hfagp_basis_qr_info.argtypes = [vp, i32, i32, C.POINTER(C.c_int), vp]
     l.hfagp_blur_up.argtypes = [i32] * 7 + [f32, vp, vp, vp]
     l.hfagp_act_bwd.argtypes = [C.POINTER(ActBwdDesc)] + [vp] * 23
     l.hfagp_styles_bwd.argtypes = [i32, i32, i32, i32] + [vp] * 8

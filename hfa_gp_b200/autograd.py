@@ -71,10 +71,10 @@ def _layer_param_grads(m, rec, dz, ddc, db, h, w, up):
         # transposed conv: dW[(ky,kx)][o][i] = sum dt[2m+k][o] * x[m][i] * s[i]  — wgrad with the roles swapped
         # (dense operand = layer input, strided operand = gradient), result [t][i][o]
         hin, win = x.shape[1], x.shape[2]
-        dwp = torch.zeros((9, pl.cin, pl.cout), device=pl.w.device)
+        dwp = ops.zeros((9, pl.cin, pl.cout), pl.w.device)
         ops.conv2d_wgrad(dz, x, TAPS_UP_T, dwp, oh=hin, ow=win, in_stride=2, dzscale=styles)
     else:
-        dwp = torch.zeros_like(pl.w)
+        dwp = ops.zeros(pl.w.shape, pl.w.device)
         ops.conv2d_wgrad(x, dz, ops.TAPS_3X3, dwp, oh=h, ow=w, xscale=styles)
     # + demodulation term, unpacked into [O][I][k][k] and added to .grad in one pass (hfagp_modconv_wgrad_finish)
     if m.weight.grad is None:
@@ -102,7 +102,7 @@ def _torgb_param_grads(m, rt, dimg_t, h, w):
     dz = dimg_t.contiguous()
     if kp != k:
         dz = torch.nn.functional.pad(dz, (0, kp - k))
-    dwp = torch.zeros((1, kp, pl.cin), device=dz.device)
+    dwp = ops.zeros((1, kp, pl.cin), dz.device)
     ops.conv2d_wgrad(x, dz, ops.TAPS_1X1, dwp, oh=h, ow=w, xscale=rt['styles'])
     _acc(m.weight, dwp[0, :k])
     _acc(m.bias, dimg_t.sum((0, 1, 2)))
@@ -135,8 +135,8 @@ def blocks_backward(gen, recs, dimg, dviews, wgrads=False):
         if gx is not None:
             kw.update(g0=gx[0], s0=gx[1], ds0=gx[2])
         # ---- conv1: activation / demodulation backward, then its data gradient
-        ddc = torch.zeros((b, pl1.cout), device=dev)
-        db1 = torch.zeros(pl1.cout, device=dev) if wgrads else None
+        ddc = ops.zeros((b, pl1.cout), dev)
+        db1 = ops.zeros((pl1.cout,), dev) if wgrads else None
         use_tc1 = tc and pl1.bwd()['wT_split'] is not None
         dz1 = ops.act_bwd(y1, dcoef=r1['dcoef'], noise=r1['noise'], noise_gain=pl1.noise_gain, bias=pl1.bias,
                           act=ACT_LRELU, act_gain=SQRT2, clamp=pl1.clamp, out='split' if use_tc1 else 'f32',
@@ -156,8 +156,8 @@ def blocks_backward(gen, recs, dimg, dviews, wgrads=False):
             continue
         # ---- conv0 (x2 up): act/demod backward at 2H, FIR transpose, then the stride-2 data gradient
         pl0 = r0['pl']
-        ddc0 = torch.zeros((b, pl0.cout), device=dev)
-        db0 = torch.zeros(pl0.cout, device=dev) if wgrads else None
+        ddc0 = ops.zeros((b, pl0.cout), dev)
+        db0 = ops.zeros((pl0.cout,), dev) if wgrads else None
         dz0 = ops.act_bwd(r0['y'], g0=dxu1, s0=r1['styles'], ds0=dviews[pl1.index], dcoef=r0['dcoef'],
                           noise=r0['noise'], noise_gain=pl0.noise_gain, bias=pl0.bias, act=ACT_LRELU, act_gain=SQRT2,
                           clamp=pl0.clamp, out='f32', ddcoef=ddc0, dbias=db0)
@@ -240,7 +240,7 @@ class BackboneFn(torch.autograd.Function):
     def backward(ctx, dplanes):
         gen = ctx.gen
         pk = gen._ensure_packed()
-        dflat = torch.zeros(ctx.total, device=dplanes.device)
+        dflat = ops.zeros((ctx.total,), dplanes.device)
         blocks_backward(gen, ctx.recs, dplanes.contiguous(), _dviews(pk, dflat, ctx.batch),
                         wgrads=any(p.requires_grad for p in gen.parameters()))
         ctx.recs = None
@@ -270,7 +270,7 @@ class SuperresFn(torch.autograd.Function):
     def backward(ctx, dimg):
         gen = ctx.gen
         pk = gen._ensure_packed()
-        dflat = torch.zeros(ctx.total, device=dimg.device)
+        dflat = ops.zeros((ctx.total,), dimg.device)
         gx, drgb_lo = blocks_backward(gen, ctx.recs, dimg.contiguous(), _dviews(pk, dflat, ctx.batch),
                                       wgrads=any(p.requires_grad for p in gen.parameters()))
         # first SR layer reads the feature image itself: dfeat = dxu * styles, d(styles) += sum dxu * feat
@@ -341,8 +341,8 @@ class LinearFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         dy = dy.contiguous()
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dw = torch.zeros_like(w) if need_dw else None
-        db = torch.zeros(w.shape[0], device=w.device) if (need_dw and ctx.has_bias) else None
+        dw = ops.zeros(w.shape, w.device) if need_dw else None
+        db = ops.zeros((w.shape[0],), w.device) if (need_dw and ctx.has_bias) else None
         dx = ops.linear_bwd(dy, x, w, ctx.scale, ctx.lr_mul, need_dx=need_dx, dw=dw, db=db)
         return dx, dw, db, None, None
 
@@ -366,9 +366,24 @@ class EncoderAppFn(torch.autograd.Function):
         return (None, None) + out
 
 
+class BasisQRFn(torch.autograd.Function):
+    """Q of ``torch.qr(bases.T + 1e-8)`` (headnerf.py:92) and its backward on the C ABI (csrc/qr.cu): no LAPACK call,
+    ~0.1 ms instead of cuSOLVER's 0.8 ms latency chain in front of every step's generator forward."""
+
+    @staticmethod
+    def forward(ctx, bases):
+        q, rinv = ops.basis_qr(bases)
+        ctx.save_for_backward(q, rinv)
+        return q
+
+    @staticmethod
+    def backward(ctx, gq):
+        q, rinv = ctx.saved_tensors
+        return ops.basis_qr_bwd(gq, q, rinv)
+
+
 class LatentFn(torch.autograd.Function):
-    """ws = weights . Q^T + delta (headnerf.py:96-100); Q comes from torch.linalg.qr, whose own autograd carries
-    d(Q) on to ``bases``."""
+    """ws = weights . Q^T + delta (headnerf.py:96-100); Q comes from BasisQRFn, which carries d(Q) on to ``bases``."""
 
     @staticmethod
     def forward(ctx, weights, q, delta):

@@ -239,9 +239,15 @@ __global__ void styles_bwd_kernel(const StyleBwdTable tb, int num_ws, int w_dim,
   const int cin = tb.cin[l];
   const float* ds = dstyles + tb.off[l] + (size_t)n * cin;
   const float* a = tb.aw[l];
+  // gridDim.z slices of the input channels: at batch 1 the 26 layers alone would leave most SMs idle behind 512-long
+  // dependent chains
+  const int per = (cin + gridDim.z - 1) / gridDim.z;
+  const int i0 = blockIdx.z * per, i1 = min(cin, i0 + per);
+  if (i0 >= i1) return;
   for (int k = threadIdx.x; k < w_dim; k += blockDim.x) {
     float acc = 0.f;
-    for (int i = 0; i < cin; ++i) acc = fmaf(__ldg(ds + i), __ldg(a + (size_t)i * w_dim + k), acc);
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) acc = fmaf(__ldg(ds + i), __ldg(a + (size_t)i * w_dim + k), acc);
     atomicAdd(dws + ((size_t)n * num_ws + tb.widx[l]) * w_dim + k, acc * tb.gain[l] * inv_sqrt);
   }
 }
@@ -591,7 +597,8 @@ extern "C" int hfagp_styles_bwd(int nlayers, int batch, int num_ws, int w_dim, c
     tb.widx[l] = widx_host[l];
     tb.gain[l] = post_gain_host[l];
   }
-  styles_bwd_kernel<<<dim3(nlayers, batch), 256, 0, (cudaStream_t)stream>>>(tb, num_ws, w_dim, 1.0f / sqrtf((float)w_dim),
+  const int slices = batch >= 8 ? 2 : 8;
+  styles_bwd_kernel<<<dim3(nlayers, batch, slices), 256, 0, (cudaStream_t)stream>>>(tb, num_ws, w_dim, 1.0f / sqrtf((float)w_dim),
                                                                           dstyles, dws);
   HFAGP_CHECK_LAUNCH("styles_bwd_kernel");
   return HFAGP_OK;

@@ -19,6 +19,7 @@
 // n-tiles are, after softplus, exactly the layer-2 A fragment of one k-step, so the hidden layer never leaves
 // registers.
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 #include "common.cuh"
@@ -29,7 +30,7 @@ namespace hfagp {
 // BWD = false: the forward renderer.  BWD = true: recompute the forward per ray (same code), then back-propagate
 // d(feat) through the composite / march / decoder MLP / bilinear gather into d(planes) (8 rays per CTA).
 template <bool BWD>
-__global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(BWD ? 384 : R_WARPS * 32, 1) render_kernel(const RenderParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const HfagpRenderDesc& d = p.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -628,6 +629,9 @@ __global__ void __launch_bounds__(BWD ? 256 : R_WARPS * 32, 1) render_kernel(con
 #pragma unroll
                 for (int k = 0; k < 12; ++k) {
                   const Tap rec = tp[k];
+#ifdef HFAGP_DBG_SCATTER_MASK
+                  if (!((HFAGP_DBG_SCATTER_MASK >> (k >> 2)) & 1)) continue;
+#endif
                   if (rec.w != 0.f)
                     red_add_v4(reinterpret_cast<float*>(lbw + rec.off), rec.w * d4.x, rec.w * d4.y, rec.w * d4.z, rec.w * d4.w);
                 }
@@ -806,7 +810,10 @@ static int render_bwd_impl(const HfagpRenderDesc* desc, const float* planes, con
   HFAGP_CHECK_ARG((long long)d.plane_h * d.plane_w * 96 < (1ll << 31), "render_bwd: plane too large for 32-bit tap offsets");
   RenderParams p{d, planes, c, mlp, lin, jitter, u_fine, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                  nullptr, dfeat, dplanes, dump_f, dump_do};
-  const int nwarps = 8;
+  // rays (warps) per CTA: as many as the shared-memory plan allows, at most 12 (167 registers per thread at 384 threads)
+  static const int nw_env = [] { const char* e = getenv("HFAGP_RBWD_WARPS"); return e ? atoi(e) : 0; }();      // profiling override
+  int nwarps = nw_env >= 1 && nw_env <= 12 ? nw_env : 12;
+  while (nwarps > 1 && WEIGHT_BYTES_BWD + nwarps * render_warp_bytes(d.s_coarse, d.s_fine, true) > 227 * 1024) --nwarps;
   const size_t smem = WEIGHT_BYTES_BWD + nwarps * render_warp_bytes(d.s_coarse, d.s_fine, true);
   static std::atomic<uint64_t> attr_done{0};
   HFAGP_CUDA(per_device_once(attr_done, [] { return cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));

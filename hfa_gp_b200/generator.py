@@ -372,7 +372,7 @@ class TriPlaneGenerator(nn.Module):
             # super-resolution blocks: the 3-channel ToRGB rides on conv1's epilogue (its activations are still in
             # registers there) instead of re-reading the whole layer output
             wrgb, _ = ops.modulate(plt.w, st, False)                       # [n][1][k][cout]
-            acc = torch.zeros((x.shape[0], blk.res, blk.res, plt.cout), device=wrgb.device, dtype=torch.float32)
+            acc = ops.zeros((x.shape[0], blk.res, blk.res, plt.cout), wrgb.device)
             x = self._conv_layer(x, blk.conv1, s1, noise_mode, pk, split_out=tc_next, rgb=(wrgb[:, 0], acc))
             if tap is not None:
                 tap[name + '.conv1'] = self._as_f32(x)

@@ -201,7 +201,7 @@ class LpipsFn(torch.autograd.Function):
             cur = ops.conv2d_tc(cur, pk['w'][k], pk['taps'][k], LPIPS.CHNS[k], oh=oh, ow=ow, bias=pk['b'][k],
                                 act=ACT_RELU, split_out=True)
             feats.append(cur)
-        out = torch.zeros(b, device=x.device, dtype=torch.float32)
+        out = ops.zeros((b,), x.device)
         for k, f in enumerate(feats):
             _, h, w, c = f.shape
             ops._ok(_cabi.lib().hfagp_lpips_head_fwd(b, h * w, c, None, ptr(f.hi), ptr(f.lo), ptr(pk['lin'][k]), ptr(out),

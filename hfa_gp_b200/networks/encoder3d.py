@@ -198,7 +198,7 @@ class ConvLayer(nn.Sequential):
         residual = rec['residual']
         kw = dict(g0=g0, g1=g1, out='split' if (tc and need_dx) else 'f32')
         if act is not None:
-            db = torch.zeros(cout, device=g0.device)
+            db = ops.zeros((cout,), g0.device)
             dz = ops.act_bwd(rec['y'], residual=residual, residual_scale=INV_SQRT2, act=ACT_LRELU, act_gain=SQRT2,
                              post_scale=INV_SQRT2 if residual is not None else 1.0, dbias=db, **kw)
             grads[act.bias] = db.view(1, -1, 1, 1)
@@ -209,7 +209,7 @@ class ConvLayer(nn.Sequential):
         cin_p = (cin + 3) // 4 * 4
         if cin_p != cin:
             x_in = torch.nn.functional.pad(x_in, (0, cin_p - cin))
-        dwp = torch.zeros((k * k, cout, cin_p), device=g0.device)
+        dwp = ops.zeros((k * k, cout, cin_p), g0.device)
         ops.conv2d_wgrad(x_in, dz, rec['taps'], dwp, oh=rec['oh'], ow=rec['ow'], in_stride=rec['stride'],
                          scale=conv.scale)
         grads[conv.weight] = dwp[:, :, :cin].reshape(k, k, cout, cin).permute(2, 3, 0, 1)
@@ -335,7 +335,7 @@ class EncoderApp(nn.Module):
         grads = {}
         last = self.convs[-1]
         o, i, k, _ = last.weight.shape
-        dwl = torch.zeros((o, k * k * i), device=dout.device)
+        dwl = ops.zeros((o, k * k * i), dout.device)
         dflat = ops.linear_bwd(dout, tape['flat'], last.packed_linear(), 1.0, 1.0, dw=dwl)
         grads[last.weight] = dwl.view(o, k, k, i).permute(0, 3, 1, 2) * last.scale
         dy = dflat.view(tape['shape'])

@@ -81,15 +81,14 @@ class _LatentSubspace:
         cache = self.__dict__.get('_q_cache')
         if cache is not None and cache[0] == key and not torch.is_grad_enabled():
             return cache[1]
-        q, _ = torch.linalg.qr((bases.detach() + 1e-8).T, mode='reduced')     # [14*dim, K], LAPACK/cuSOLVER geqrf
-        q = q.contiguous()
+        q, _ = ops.basis_qr(bases.detach(), eps=1e-8, check_info=not torch.cuda.is_current_stream_capturing())        # [14*dim, K], LAPACK's Q without LAPACK
         self.__dict__['_q_cache'] = (key, q)
         return q
 
     def prefetch_basis(self, bases):
-        """Training: start the QR factorisation of ``bases`` (0.6 ms of cuSOLVER, independent of the frame) on a side
-        stream so that it runs next to the encoder forward; ``_latent_from`` picks the result up.  Autograd runs the
-        factorisation's backward on the same side stream and joins it at the end of ``backward()``."""
+        """Training: start the QR factorisation of ``bases`` (independent of the frame) on a side stream so that it
+        runs next to the encoder forward; ``_latent_from`` picks the result up.  Autograd runs the factorisation's
+        backward on the same side stream and joins it at the end of ``backward()``."""
         if not (torch.is_grad_enabled() and bases.requires_grad and bases.is_cuda):
             return
         cur = torch.cuda.current_stream(bases.device)
@@ -97,8 +96,9 @@ class _LatentSubspace:
         if side is None or side.device != bases.device:
             side = self.__dict__['_qr_stream'] = torch.cuda.Stream(device=bases.device)
         side.wait_stream(cur)
+        from ..autograd import BasisQRFn
         with torch.cuda.stream(side):
-            q, _ = torch.linalg.qr((bases + 1e-8).T, mode='reduced')
+            q = BasisQRFn.apply(bases)
         self.__dict__['_q_prefetched'] = (bases, q, side)
 
     def _latent_from(self, weights, bases, delta):
@@ -107,8 +107,8 @@ class _LatentSubspace:
         b = weights.shape[0]
         if torch.is_grad_enabled() and (weights.requires_grad or bases.requires_grad or delta.requires_grad):
             # training (trainer_rgb.py:79-80): the QR factorisation is recomputed under autograd, as the
-            # reference does every call (headnerf.py:92), so d(Q) reaches ``bases`` through torch's QR backward
-            from ..autograd import LatentFn
+            # reference does every call (headnerf.py:92), so d(Q) reaches ``bases`` through the factorisation's backward
+            from ..autograd import BasisQRFn, LatentFn
             pre = self.__dict__.pop('_q_prefetched', None)
             if pre is not None and pre[0] is bases:
                 q, side = pre[1], pre[2]
@@ -116,7 +116,7 @@ class _LatentSubspace:
                 cur.wait_stream(side)
                 q.record_stream(cur)
             else:
-                q, _ = torch.linalg.qr((bases + 1e-8).T, mode='reduced')
+                q = BasisQRFn.apply(bases)
             return LatentFn.apply(weights, q, delta).view(b, -1, self.dim)
         q = self._q_factor(bases)
         out = ops.latent(weights.detach().float().contiguous(), q, delta.detach().contiguous(), q.shape[0])

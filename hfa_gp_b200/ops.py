@@ -21,6 +21,52 @@ _launches = [0]
 param_epoch = [0]
 
 
+# ---- zero-initialised scratch of a captured training step.  A step asks for ~60 small zeroed tensors (split-K and atomic
+# accumulators, per-channel gradient sums, loss scalars); as separate fills each is a ~3 us node on the step graph's
+# critical path.  While an arena is active (Trainer._capture only — eager steps never see it) they are carved out of ONE
+# buffer that the graph zeroes with a single memset at its top.  Tensors from it live until the next replay, exactly like
+# every other tensor allocated inside a captured step.
+_zero_arena = None
+ZERO_ARENA_MAX_ITEM = 1 << 20          # larger requests keep their own fill (bandwidth, not latency)
+
+
+class ZeroArena:
+    def __init__(self, device):
+        self.device, self.buf, self.off, self.need = torch.empty(0, device=device).device, None, 0, 0
+
+    def materialise(self):
+        """Before the capture: allocate what the measured eager steps asked for."""
+        if self.buf is None and self.need:
+            self.buf = torch.empty(self.need, device=self.device, dtype=torch.uint8)
+
+    def begin(self):
+        """Top of a step: measuring (no buffer yet: requests are only counted) or, inside the capture, the one memset."""
+        global _zero_arena
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off = 0
+        _zero_arena = self
+
+    def end(self):
+        global _zero_arena
+        self.need = max(self.need, self.off)
+        _zero_arena = None
+
+
+def zeros(shape, device, dtype=torch.float32):
+    """``torch.zeros`` for scratch consumed inside the current step (see ZeroArena)."""
+    a = _zero_arena
+    if a is not None and (device == a.device or torch.empty(0, device=device).device == a.device):
+        shape = tuple(shape) if not isinstance(shape, int) else (shape,)
+        n = math.prod(shape) * torch.empty((), dtype=dtype).element_size()
+        if 0 < n <= ZERO_ARENA_MAX_ITEM:
+            off = a.off
+            a.off = off + (n + 255) // 256 * 256
+            if a.buf is not None and a.off <= a.buf.numel():
+                return a.buf[off:off + n].view(dtype).view(shape)
+    return torch.zeros(shape, device=device, dtype=dtype)
+
+
 def launch_count() -> int:
     """Kernels launched through the C ABI so far (every entry point enqueues exactly one kernel)."""
     return _launches[0]
@@ -237,7 +283,7 @@ def render_bookkeeping(cdf, u, depths):
 def decoder_wgrad(f, do, mlp):
     """Per-sample decoder operands (f [S,32], do [S,33], see render_bwd(decoder=True)) -> gradient of the packed
     effective decoder weights [4257] (W0 [64,32], b0 [64], W1 [33,64], b1 [33]); see ``hfagp_decoder_wgrad``."""
-    dmlp = torch.zeros_like(mlp)
+    dmlp = zeros(mlp.shape, mlp.device)
     _ok(_cabi.lib().hfagp_decoder_wgrad(f.shape[0], ptr(f), ptr(do), ptr(mlp), ptr(dmlp), stream()), 'hfagp_decoder_wgrad')
     return dmlp
 
@@ -296,6 +342,40 @@ def linear(x, w, b, w_gain, b_gain):
     _ok(_cabi.lib().hfagp_linear_fwd(n, cin, cout, ptr(x), ptr(w), ptr(b), w_gain, b_gain, ptr(out), stream()),
           'hfagp_linear_fwd')
     return out
+
+
+def _qr_workspace(k, m, dev):
+    return torch.empty((_cabi.lib().hfagp_basis_qr_workspace_bytes(k, m),), device=dev, dtype=torch.uint8)
+
+
+def basis_qr(bases, eps=1e-8, check_info=False):
+    """``torch.qr(bases.T + eps)`` of get_latent without LAPACK (``hfagp_basis_qr_fwd``): bases [K, M] ->
+    (q [M, K] with LAPACK's column signs, rinv [K, K] = R^-1 for the backward).  ``check_info`` reads the device flag a
+    non-positive Cholesky pivot raises (synchronises; off inside a training step)."""
+    k, m = bases.shape
+    b = bases.detach().float().contiguous()
+    q = torch.empty((m, k), device=b.device, dtype=torch.float32)
+    rinv = torch.empty((k, k), device=b.device, dtype=torch.float32)
+    ws = _qr_workspace(k, m, b.device)
+    _ok(_cabi.lib().hfagp_basis_qr_fwd(k, m, ptr(b), float(eps), ptr(q), ptr(rinv), ptr(ws), stream()), 'hfagp_basis_qr_fwd')
+    _launches[0] += 4                     # Gram, k x k, apply + Gram, k x k + signs, apply
+    if check_info:
+        info = C.c_int(0)
+        check(_cabi.lib().hfagp_basis_qr_info(ptr(ws), k, m, C.byref(info), stream()), 'hfagp_basis_qr_info')
+        if info.value:
+            raise _cabi.HfagpError('basis_qr: the basis is rank deficient or too ill conditioned for CholeskyQR2')
+    return q, rinv
+
+
+def basis_qr_bwd(gq, q, rinv):
+    """Gradient of ``basis_qr``'s q w.r.t. bases: gq [M, K] -> gbases [K, M] (``hfagp_basis_qr_bwd``)."""
+    m, k = q.shape
+    gq = gq.float().contiguous()
+    gb = torch.empty((k, m), device=q.device, dtype=torch.float32)
+    ws = _qr_workspace(k, m, q.device)
+    _ok(_cabi.lib().hfagp_basis_qr_bwd(k, m, ptr(gq), ptr(q), ptr(rinv), ptr(gb), ptr(ws), stream()), 'hfagp_basis_qr_bwd')
+    _launches[0] += 2
+    return gb
 
 
 def latent(weights, q, delta, dim_total):
@@ -489,7 +569,7 @@ def conv2d_tc(x: Split, w: Split, taps, cout: int, *, oh: int, ow: int, in_strid
     ksplit = _ksplit(n * -(-oh * ow // 128) * -(-cout // 128), cin, taps, in_stride)
     if ksplit > 1 and out_stride == 1 and (oh, ow) == (out_h, out_w) and cout % 4 == 0:
         # few output tiles, long K (the 4^2..32^2 layers): split K over the idle SMs, then one elementwise epilogue
-        acc = torch.zeros((n, out_h, out_w, cout), device=x.device, dtype=torch.float32)
+        acc = zeros((n, out_h, out_w, cout), x.device)
         _ok(_cabi.lib().hfagp_conv2d_tc_acc_fwd(C.byref(d), 1, ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), w_taps_total,
                                                 ksplit, ptr(acc), stream()), 'hfagp_conv2d_tc_acc_fwd')
         y = None if is_split else out
@@ -595,7 +675,7 @@ class StyleTableBwd:
 
     def run(self, dstyles_flat, offs, batch, num_ws, w_dim):
         t = self.t
-        dws = torch.zeros((batch, num_ws, w_dim), device=dstyles_flat.device, dtype=torch.float32)
+        dws = zeros((batch, num_ws, w_dim), dstyles_flat.device)
         off_arr = (C.c_int64 * t.n)(*offs)
         _ok(_cabi.lib().hfagp_styles_bwd(t.n, batch, num_ws, w_dim, t.aw, t.cin, t.widx, t.gain, off_arr,
                                            ptr(dstyles_flat), ptr(dws), stream()), 'hfagp_styles_bwd')
@@ -678,7 +758,7 @@ def facepool_bwd(dy_nchw, h, wd):
 
 
 def mse(a, b):
-    loss = torch.zeros((), device=a.device, dtype=torch.float32)
+    loss = zeros((1,), a.device).view(())
     _ok(_cabi.lib().hfagp_mse_fwd(a.numel(), ptr(a), ptr(b), 1.0 / a.numel(), ptr(loss), stream()), 'hfagp_mse_fwd')
     return loss
 

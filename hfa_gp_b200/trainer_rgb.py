@@ -130,7 +130,18 @@ class _TrainerBase(nn.Module):
                 return self._replay(tensors, label_pos, optims)
             if key != self._graph_key:
                 self._graph, self._graph_key, self._graph_eager_left = None, key, self._graph_warmup
+                self.__dict__['_zero_arena'] = ops.ZeroArena(self.device)      # (a captured graph keeps its own)
             self._graph_eager_left -= 1
+            arena = self.__dict__.setdefault('_zero_arena', ops.ZeroArena(self.device))
+            arena.begin()                               # no buffer yet: counts the step's small zeroed scratch
+            try:
+                return self._eager_step(fwd_bwd, tensors, optims)
+            finally:
+                arena.end()
+        return self._eager_step(fwd_bwd, tensors, optims)
+
+    @staticmethod
+    def _eager_step(fwd_bwd, tensors, optims):
         for o in optims:
             o.zero_grad()
         out = fwd_bwd(*tensors)
@@ -141,15 +152,21 @@ class _TrainerBase(nn.Module):
     def _capture(self, fwd_bwd, tensors, optims):
         self._static_in = [t.detach().clone() for t in tensors]
         ops.param_epoch[0] += 1          # every parameter-derived cache misses inside the capture: packing is captured too
+        arena = self.__dict__.setdefault('_zero_arena', ops.ZeroArena(self.device))
+        arena.materialise()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
         with torch.cuda.graph(g):
-            for o in optims:
-                o.zero_grad()
-            self._static_out = fwd_bwd(*self._static_in)
-            for o in optims:
-                o.step_launch()
+            arena.begin()                               # ONE memset for the step's ~60 small zeroed tensors
+            try:
+                for o in optims:
+                    o.zero_grad()
+                self._static_out = fwd_bwd(*self._static_in)
+                for o in optims:
+                    o.step_launch()
+            finally:
+                arena.end()
         self.graph_launches = ops.launch_count() - n0   # kernels of libhfagp_sm100.so inside one replay
         self._graph = g
 

@@ -400,10 +400,24 @@ int hfagp_modconv_wgrad_finish(int taps, int cout, int cin, int batch, const flo
  * ------------------------------------------------------------------------------------------- */
 
 /* Backward of hfagp_latent_fwd: dweights[n][k] = sum_j dws[n][j] q[j][k] ; dq[j][k] = sum_n dws[n][j] weights[n][k] ;
- * ddelta[j] = sum_n dws[n][j].  Outputs are WRITTEN; each may be NULL.  d(bases) continues through the QR
- * factorisation in the host framework (torch.linalg.qr autograd), as in the reference (headnerf.py:92-100). */
+ * ddelta[j] = sum_n dws[n][j].  Outputs are WRITTEN; each may be NULL.  d(bases) continues through
+ * hfagp_basis_qr_bwd (headnerf.py:92-100). */
 int hfagp_latent_bwd(int batch, int k, int dim, const float* dws, const float* weights, const float* q,
                      float* dweights, float* dq, float* ddelta, void* stream);
+
+/* Orthonormal basis of the latent subspace: Q, _ = torch.qr(bases.T + eps) of get_latent (code/networks/headnerf.py:92,
+ * :187, :247; eps = 1e-8 there) for bases[k][m] row-major, 1 <= k <= 64, m >= k (m = 14*512).  q[m][k] row-major is
+ * LAPACK's reduced Q factor (same column signs: CholeskyQR2 + Householder sign reconstruction, Gram matrices in fp64
+ * — see csrc/qr.cu); rinv[k][k] = R^-1 (upper triangular) is kept for the backward.  The factorisation needs
+ * cond(bases) < ~1e3: a Cholesky pivot below that floor sets a device flag readable with hfagp_basis_qr_info (which synchronises the stream; validation use).
+ * `workspace`: hfagp_basis_qr_workspace_bytes(k, m) bytes of device memory, 256-byte aligned; contents are scratch.
+ * hfagp_basis_qr_bwd: the autograd backward of that factorisation for a gradient arriving at Q only (R is unused
+ * downstream): gbases[k][m] (WRITTEN) = ((gQ + Q Y) R^-T)^T with Y = X + X^T - diag(X), X = triu(-Q^T gQ). */
+size_t hfagp_basis_qr_workspace_bytes(int k, int m);
+int hfagp_basis_qr_fwd(int k, int m, const float* bases, float eps, float* q, float* rinv, void* workspace, void* stream);
+int hfagp_basis_qr_bwd(int k, int m, const float* gq, const float* q, const float* rinv, float* gbases, void* workspace,
+                       void* stream);
+int hfagp_basis_qr_info(const void* workspace, int k, int m, int* info_host, void* stream);
 
 /* face_pool = AdaptiveAvgPool2d((size,size)) of the generated image (code/trainer_rgb.py:63,84) for an integer
  * factor f = h/size, fused with the layout change: x[n][h][w][c] channels-last -> y[n][c][h/f][w/f]; c <= 4.

@@ -90,6 +90,35 @@ def test_latent_backward_matches_autograd():
         _check(a.grad, bb.grad, 'fp32', f'latent d{name}')
 
 
+@pytest.mark.parametrize('k,m', [(50, 14 * 512), (20, 14 * 512), (64, 1000), (1, 77), (7, 7)])
+def test_basis_qr_matches_lapack(k, m):
+    """hfagp_basis_qr_fwd / _bwd (CholeskyQR2 + Householder sign reconstruction) against the factorisation the
+    reference calls, torch.qr on the CPU (LAPACK geqrf), and its autograd backward in fp64."""
+    from hfa_gp_b200 import ops
+    g = torch.Generator().manual_seed(k * 1000 + m)
+    bases = torch.randn(k, m, generator=g)
+    a = (bases + 1e-8).T
+    q_ref, r_ref = torch.linalg.qr(a, mode='reduced')
+    q, rinv = ops.basis_qr(bases.cuda(), eps=1e-8, check_info=True)
+    q, rinv = q.cpu(), rinv.cpu()
+    assert float((q - q_ref).abs().max()) < 2e-6, 'Q differs from LAPACK (column signs?)'
+    assert float((q.T @ q - torch.eye(k)).abs().max()) < 2e-6
+    assert float((rinv.double() @ r_ref.double() - torch.eye(k, dtype=torch.float64)).abs().max()) < 1e-4
+    assert float(torch.tril(rinv, -1).abs().max()) == 0.0
+    # closer to the fp64 factor than LAPACK's fp32 result
+    qd, _ = torch.linalg.qr(a.double(), mode='reduced')
+    assert float((q.double() - qd).abs().max()) <= float((q_ref.double() - qd).abs().max()) + 1e-7
+    # backward: gradient arriving at Q only
+    gq = torch.randn(m, k, generator=g)
+    bd = bases.double().requires_grad_(True)
+    qq, _ = torch.linalg.qr((bd + 1e-8).T, mode='reduced')
+    (qq * gq.double()).sum().backward()
+    gb = ops.basis_qr_bwd(gq.cuda(), q.cuda(), rinv.cuda()).cpu()
+    assert pu.rel_err(gb, bd.grad.float()) < 2e-5
+    with pytest.raises(Exception):
+        ops.basis_qr(torch.ones(3, 40).cuda(), check_info=True)          # rank deficient: flagged, not silently wrong
+
+
 def test_facepool_and_mse_kernels():
     from hfa_gp_b200 import autograd as ag
     g = torch.Generator().manual_seed(1)

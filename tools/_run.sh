@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "render or full_512 or generator_tiny" 2>&1 | tail -4
-echo NEW; timeout 100 python tools/prof_render.py 8 2>&1 | tail -1
-echo BASE; HFAGP_LIB=$PWD/hfa_gp_b200/libhfagp_base.so timeout 100 python tools/prof_render.py 8 2>&1 | tail -1
-echo NEW; timeout 100 python tools/prof_render.py 8 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_training.py -m gpu -x -q -k "basis_qr or latent or full_size" 2>&1 | tail -5
+timeout 300 python tools/timeline_train_graph.py --trainer 3dmm --batch 1 --seq > gpurun_out/tl_3dmm_b1.txt 2>&1; grep -v "^ *[0-9.]* " gpurun_out/tl_3dmm_b1.txt | head -4; grep "qr_" gpurun_out/tl_3dmm_b1.txt | head -8
