@@ -326,6 +326,13 @@ class RenderFn(torch.autograd.Function):
 
 # ------------------------------------------------------------------ encoder / latent / loss (trainer_rgb.py:79-91)
 
+def _grad_slot(p):
+    """True when leaf ``p`` has a dense fp32 ``.grad`` a kernel can accumulate into in place."""
+    g = getattr(p, 'grad', None)
+    return (g is not None and p.is_leaf and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape
+            and g.device == p.device)
+
+
 class LinearFn(torch.autograd.Function):
     """EqualLinear with activation=None (encoder3d.py:128-136): y = x W^T * scale + b * lr_mul."""
 
@@ -334,6 +341,7 @@ class LinearFn(torch.autograd.Function):
         w = weight.detach().contiguous()
         ctx.save_for_backward(x, w)
         ctx.scale, ctx.lr_mul, ctx.has_bias = scale, lr_mul, bias is not None
+        ctx.leaves = (weight, bias)
         return ops.linear(x, w, None if bias is None else bias.detach(), scale, lr_mul)
 
     @staticmethod
@@ -341,8 +349,16 @@ class LinearFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         dy = dy.contiguous()
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_db = need_dw and ctx.has_bias
+        weight, bias = ctx.leaves
+        ctx.leaves = None
+        # the kernel ACCUMULATES: when the leaves already own gradient storage (FlatAdam binds every .grad to its flat
+        # buffer, zeroed once per step) it adds straight into it — no zero-fill, no AccumulateGrad add per tensor
+        if (need_dw and _grad_slot(weight) and (not need_db or _grad_slot(bias))):
+            dx = ops.linear_bwd(dy, x, w, ctx.scale, ctx.lr_mul, need_dx=need_dx, dw=weight.grad, db=bias.grad if need_db else None)
+            return dx, None, None, None, None
         dw = ops.zeros(w.shape, w.device) if need_dw else None
-        db = ops.zeros((w.shape[0],), w.device) if (need_dw and ctx.has_bias) else None
+        db = ops.zeros((w.shape[0],), w.device) if need_db else None
         dx = ops.linear_bwd(dy, x, w, ctx.scale, ctx.lr_mul, need_dx=need_dx, dw=dw, db=db)
         return dx, dw, db, None, None
 

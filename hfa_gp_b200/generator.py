@@ -530,11 +530,22 @@ class TriPlaneGenerator(nn.Module):
         if not ws.requires_grad:
             # only generator parameters are being trained: the stage Functions carry the graph through ws
             ws = ws.detach().requires_grad_(True)
+        # the renderer's random draws and depth range depend on nothing: a side stream runs their ~10 small kernels next
+        # to the backbone (as the inference path does)
+        cur = torch.cuda.current_stream(ws.device)
+        if self._side is None or self._side.device != ws.device:
+            self._side = torch.cuda.Stream(device=ws.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            jitter, u, depth_range, kw = self._render_inputs(b, res, ws.device, jitter_coarse, u_fine, pk)
         styles_flat = ag.StylesFn.apply(ws.float().contiguous(), self)
         planes = ag.BackboneFn.apply(styles_flat, self, noise_mode, b, tap)
         if tap is not None:
             tap['planes'] = planes
-        jitter, u, depth_range, kw = self._render_inputs(b, res, ws.device, jitter_coarse, u_fine, pk)
+        cur.wait_stream(self._side)
+        for t_ in (jitter, u, depth_range):
+            if t_ is not None:
+                t_.record_stream(cur)
         feat, depth, wsum = ag.RenderFn.apply(planes, self, c, jitter, u, depth_range, kw, False)
         img = ag.SuperresFn.apply(feat, styles_flat, self, b, tap)
         return {'image': img.permute(0, 3, 1, 2), 'image_raw': feat[..., :3].permute(0, 3, 1, 2),
