@@ -29,7 +29,7 @@ SYMBOLS = [
     'hfagp_lpips_stem_fwd', 'hfagp_lpips_stem_bwd', 'hfagp_maxpool3s2_fwd', 'hfagp_maxpool3s2_bwd', 'hfagp_lpips_head_fwd',
     'hfagp_lpips_head_bwd', 'hfagp_modulate_split_multi_fwd', 'hfagp_conv2d_tc_rgb_fwd', 'hfagp_torgb_finalize_fwd', 'hfagp_conv2d_wgrad_mod', 'hfagp_render_bwd_dec',
     'hfagp_render_fwd_simt', 'hfagp_decoder_wgrad', 'hfagp_modconv_wgrad_finish', 'hfagp_set_device', 'hfagp_device_sm_count', 'hfagp_conv2d_tc_acc_workspace_bytes', 'hfagp_render_bwd_dec_workspace_bytes', 'hfagp_adam_sched', 'hfagp_adam_step_dev', 'hfagp_render_bookkeeping',
-    'hfagp_basis_qr_workspace_bytes', 'hfagp_basis_qr_fwd', 'hfagp_basis_qr_bwd', 'hfagp_basis_qr_info',
+    'hfagp_torgb_small_mask_fwd', 'hfagp_pack_conv_weight', 'hfagp_unpack_conv_wgrad', 'hfagp_basis_qr_workspace_bytes', 'hfagp_basis_qr_fwd', 'hfagp_basis_qr_bwd', 'hfagp_basis_qr_info',
 ]
 
 
@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     l.hfagp_conv2d_fwd.argtypes = [C.POINTER(ConvDesc)] + [vp] * 9
     l.hfagp_upfir_act_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, f32, vp, i32, f32, f32, vp, vp, vp, vp]
     l.hfagp_torgb_small_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp]
+    l.hfagp_torgb_small_mask_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]
     l.hfagp_styles_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     l.hfagp_modulate_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
     l.hfagp_render_fwd.argtypes = [C.POINTER(RenderDesc)] + [vp] * 16
@@ -101,6 +102,8 @@ def lib() -> C.CDLL:
     l.hfagp_render_bwd_dec_workspace_bytes.argtypes = [C.POINTER(RenderDesc), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     l.hfagp_render_bwd_dec_workspace_bytes.restype = C.c_size_t
     l.hfagp_blur_fwd.argtypes = [i32] * 7 + [f32] + [vp] * 7
+    l.hfagp_pack_conv_weight.argtypes = [i32, i32, i32, vp, f32, vp, vp, vp, vp, vp, vp]
+    l.hfagp_unpack_conv_wgrad.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     l.hfagp_basis_qr_workspace_bytes.argtypes = [i32, i32]
     l.hfagp_basis_qr_workspace_bytes.restype = C.c_size_t
     l.hfagp_basis_qr_fwd.argtypes = [i32, i32, vp, f32, vp, vp, vp, vp]

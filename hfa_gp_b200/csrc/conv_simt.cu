@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) torgb_small_kernel(int batch, int h, int 
                                                          const __nv_bfloat16* __restrict__ x_lo,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          float clamp, const float* __restrict__ up_img,
-                                                         float* __restrict__ y) {
+                                                         float* __restrict__ y, unsigned char* __restrict__ mask) {
   extern __shared__ __align__(16) float wsm[];          // [cout][cin] of sample n
   const int n = blockIdx.y;
   const int c4 = cin >> 2;
@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(256) torgb_small_kernel(int batch, int h, int 
     if (valid && l8 < cout) {
       float v = l8 == 0 ? acc[0] : l8 == 1 ? acc[1] : l8 == 2 ? acc[2] : acc[3];
       if (bias) v += __ldg(bias + l8);
+      if (mask) mask[gp * cout + l8] = fabsf(v) < clamp;          // d clamp(v) / dv, for the backward pass
       if (clamp > 0.f) v = fminf(fmaxf(v, -clamp), clamp);
       if (up_img) {
         const int oy = pix / w_, ox = pix - oy * w_;
@@ -493,9 +494,9 @@ extern "C" int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float
   return HFAGP_OK;
 }
 
-extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const uint16_t* x_hi,
-                                     const uint16_t* x_lo, const float* w, const float* bias, float clamp,
-                                     const float* up_img, float* y, void* stream) {
+static int torgb_small_impl(int batch, int h, int w_, int cin, int cout, const float* x, const uint16_t* x_hi,
+                            const uint16_t* x_lo, const float* w, const float* bias, float clamp,
+                            const float* up_img, float* y, unsigned char* mask, void* stream) {
   HFAGP_CHECK_ARG(w && y && ((x != nullptr) != (x_hi != nullptr && x_lo != nullptr)),
                   "torgb_small_fwd: give w, y and either x or (x_hi, x_lo)");
   HFAGP_CHECK_ARG(cout >= 1 && cout <= 4 && (cin & 3) == 0, "torgb_small_fwd: cout<=4 and cin%%4==0 required");
@@ -505,9 +506,22 @@ extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout
   dim3 grid(cdiv((long long)h * w_, pix_per_block), batch);
   torgb_small_kernel<<<grid, 256, (size_t)cout * cin * 4, (cudaStream_t)stream>>>(
       batch, h, w_, cin, cout, x, reinterpret_cast<const __nv_bfloat16*>(x_hi),
-      reinterpret_cast<const __nv_bfloat16*>(x_lo), w, bias, clamp, up_img, y);
+      reinterpret_cast<const __nv_bfloat16*>(x_lo), w, bias, clamp, up_img, y, mask);
   HFAGP_CHECK_LAUNCH("torgb_small_kernel");
   return HFAGP_OK;
+}
+
+extern "C" int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const uint16_t* x_hi,
+                                     const uint16_t* x_lo, const float* w, const float* bias, float clamp,
+                                     const float* up_img, float* y, void* stream) {
+  return torgb_small_impl(batch, h, w_, cin, cout, x, x_hi, x_lo, w, bias, clamp, up_img, y, nullptr, stream);
+}
+
+extern "C" int hfagp_torgb_small_mask_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const uint16_t* x_hi,
+                                          const uint16_t* x_lo, const float* w, const float* bias, float clamp,
+                                          const float* up_img, float* y, unsigned char* mask, void* stream) {
+  HFAGP_CHECK_ARG(mask && clamp > 0.f, "torgb_small_mask_fwd: needs a mask buffer and a clamp");
+  return torgb_small_impl(batch, h, w_, cin, cout, x, x_hi, x_lo, w, bias, clamp, up_img, y, mask, stream);
 }
 
 // [1,3,3,1]^2 / 64 blur, stride 1 or 2, evaluated separably in registers: a thread owns 4 channels of two adjacent

@@ -160,6 +160,187 @@ extern "C" int hfagp_modulate_split_multi_fwd(int nlayers, int batch, const floa
   return HFAGP_OK;
 }
 
+// A convolution weight in torch layout w[O][I][T] (T = kh*kw taps) times the equalised-lr scale -> every operand form
+// the encoder's forward and backward read, in ONE pass: pk[t][O][I] fp32, its split-bf16 pair, and the transposed
+// split-bf16 pair pkT[t][I][O] of the data-gradient convolution (each may be NULL).  Replaces, per layer and training
+// step, mul + permute-copy + split + transpose-copy + split (five passes over the weight, five launches).
+// block = a 32 (o) x 32 (i) tile with all its taps staged in shared memory ([T][32][33]); TC > 0: tap count known at
+// compile time (the index arithmetic of the contiguous runs is then shifts and constant divisions); a thread writes
+// two neighbouring elements (4-byte bf16x2 / 8-byte fp32 stores).
+// tap stride of the staged tile: 4 banks of skew per tap, so that the run-order walk (consecutive threads = consecutive
+// taps of one (o, i)) does not put the 9 taps of an element on one bank
+constexpr int PW_TS = 32 * 33 + 4;
+template <int TC>
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(int O, int I, int T_rt, const float* __restrict__ w, float scale,
+                                                              float* __restrict__ pk, __nv_bfloat16* __restrict__ hi,
+                                                              __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ hiT,
+                                                              __nv_bfloat16* __restrict__ loT) {
+  extern __shared__ float pw_tile[];
+  const int T = TC > 0 ? TC : T_rt;
+  const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int ni = min(32, I - i0), no = min(32, O - o0);
+  const int run = ni * T;                              // contiguous floats of one output channel inside the tile
+  if (TC > 0 && ni == 32) {
+#pragma unroll 6                                       // (a block is latency bound: keep several loads in flight per thread)
+    for (int idx = threadIdx.x; idx < no * (32 * TC); idx += 256) {
+      const int ol = idx / (32 * TC), rem = idx - ol * (32 * TC);
+      const int il = rem / TC, t = rem - il * TC;
+      pw_tile[t * PW_TS + ol * 33 + il] = __ldg(w + ((size_t)(o0 + ol) * I + i0) * TC + rem) * scale;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < no * run; idx += 256) {
+      const int ol = idx / run, rem = idx - ol * run;
+      const int il = rem / T, t = rem - il * T;
+      pw_tile[t * PW_TS + ol * 33 + il] = __ldg(w + ((size_t)(o0 + ol) * I + i0) * T + rem) * scale;
+    }
+  }
+  __syncthreads();
+  const bool pairs = ((I | O) & 1) == 0;               // even extents: 2 elements per thread, aligned vector stores
+  if (pairs) {
+#pragma unroll 2
+    for (int idx = threadIdx.x; idx < T * 512; idx += 256) {
+      const int t = idx >> 9, a = (idx >> 4) & 31, b = (idx & 15) * 2;
+      if (a < no && b < ni) {                          // (o, i..i+1)
+        const float v0 = pw_tile[t * PW_TS + a * 33 + b], v1 = pw_tile[t * PW_TS + a * 33 + b + 1];
+        const size_t at = ((size_t)t * O + o0 + a) * I + i0 + b;
+        if (pk) *reinterpret_cast<float2*>(pk + at) = make_float2(v0, v1);
+        if (hi) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split2(v0, h0, l0);
+          split2(v1, h1, l1);
+          *reinterpret_cast<__nv_bfloat162*>(hi + at) = __nv_bfloat162(h0, h1);
+          *reinterpret_cast<__nv_bfloat162*>(lo + at) = __nv_bfloat162(l0, l1);
+        }
+      }
+      if (hiT && a < ni && b < no) {                   // (i, o..o+1)
+        const float v0 = pw_tile[t * PW_TS + b * 33 + a], v1 = pw_tile[t * PW_TS + (b + 1) * 33 + a];
+        const size_t at = ((size_t)t * I + i0 + a) * O + o0 + b;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split2(v0, h0, l0);
+        split2(v1, h1, l1);
+        *reinterpret_cast<__nv_bfloat162*>(hiT + at) = __nv_bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162*>(loT + at) = __nv_bfloat162(l0, l1);
+      }
+    }
+    return;
+  }
+  for (int idx = threadIdx.x; idx < T * 1024; idx += 256) {
+    const int t = idx >> 10, a = (idx >> 5) & 31, b = idx & 31;
+    if (a < no && b < ni) {                            // (o, i) = (a, b): consecutive threads along i
+      const float v = pw_tile[t * PW_TS + a * 33 + b];
+      const size_t at = ((size_t)t * O + o0 + a) * I + i0 + b;
+      if (pk) pk[at] = v;
+      if (hi) split2(v, hi[at], lo[at]);
+    }
+    if (hiT && a < ni && b < no) {                     // (i, o) = (a, b): consecutive threads along o
+      const float v = pw_tile[t * PW_TS + b * 33 + a];
+      const size_t at = ((size_t)t * I + i0 + a) * O + o0 + b;
+      split2(v, hiT[at], loT[at]);
+    }
+  }
+}
+
+// The inverse walk for the weight gradient: dw[t][O][Ip] (the layout the wgrad kernels accumulate in; Ip >= I padded input
+// channels) -> grad[O][I][T] += dw, torch's layout, in place.  Replaces a strided AccumulateGrad add per layer.
+template <int TC>
+__global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(int O, int I, int Ip, int T_rt, const float* __restrict__ dw,
+                                                               float* __restrict__ grad) {
+  extern __shared__ float pw_tile[];
+  const int T = TC > 0 ? TC : T_rt;
+  const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int ni = min(32, I - i0), no = min(32, O - o0);
+  if ((Ip & 3) == 0 && ni == 32) {
+#pragma unroll 3
+    for (int idx = threadIdx.x; idx < T * 256; idx += 256) {         // 16-byte loads along i
+      const int t = idx >> 8, a = (idx >> 3) & 31, b = (idx & 7) * 4;
+      if (a < no) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dw + ((size_t)t * O + o0 + a) * Ip + i0 + b));
+        float* d = pw_tile + t * PW_TS + a * 33 + b;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < T * 1024; idx += 256) {
+      const int t = idx >> 10, a = (idx >> 5) & 31, b = idx & 31;
+      if (a < no && b < ni) pw_tile[t * PW_TS + a * 33 + b] = __ldg(dw + ((size_t)t * O + o0 + a) * Ip + i0 + b);
+    }
+  }
+  __syncthreads();
+  if (TC > 0 && ni == 32) {
+    const int n = no * (32 * TC);
+    for (int base = threadIdx.x; base < n; base += 256 * 6) {       // six independent read-modify-writes per thread and trip
+      float g[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int idx = base + u * 256;
+        if (idx < n) {
+          const int ol = idx / (32 * TC), rem = idx - ol * (32 * TC);
+          g[u] = grad[((size_t)(o0 + ol) * I + i0) * TC + rem];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int idx = base + u * 256;
+        if (idx < n) {
+          const int ol = idx / (32 * TC), rem = idx - ol * (32 * TC);
+          const int il = rem / TC, t = rem - il * TC;
+          grad[((size_t)(o0 + ol) * I + i0) * TC + rem] = g[u] + pw_tile[t * PW_TS + ol * 33 + il];
+        }
+      }
+    }
+    return;
+  }
+  const int run = ni * T;
+  for (int idx = threadIdx.x; idx < no * run; idx += 256) {
+    const int ol = idx / run, rem = idx - ol * run;
+    const int il = rem / T, t = rem - il * T;
+    grad[((size_t)(o0 + ol) * I + i0) * T + rem] += pw_tile[t * PW_TS + ol * 33 + il];
+  }
+}
+
+template <int TC>
+static int pack_launch(int cout, int cin, int taps, const float* w, float scale, float* pk, uint16_t* pk_hi, uint16_t* pk_lo,
+                       uint16_t* pkt_hi, uint16_t* pkt_lo, cudaStream_t st) {
+  const size_t smem = (size_t)taps * PW_TS * sizeof(float);
+  static std::atomic<uint64_t> attr_done{0};
+  HFAGP_CUDA(per_device_once(attr_done, [] { return cudaFuncSetAttribute(pack_conv_weight_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * PW_TS * 4); }));
+  pack_conv_weight_kernel<TC><<<dim3(cdiv(cin, 32), cdiv(cout, 32)), 256, smem, st>>>(
+      cout, cin, taps, w, scale, pk, reinterpret_cast<__nv_bfloat16*>(pk_hi), reinterpret_cast<__nv_bfloat16*>(pk_lo),
+      reinterpret_cast<__nv_bfloat16*>(pkt_hi), reinterpret_cast<__nv_bfloat16*>(pkt_lo));
+  HFAGP_CHECK_LAUNCH("pack_conv_weight_kernel");
+  return HFAGP_OK;
+}
+template <int TC>
+static int unpack_launch(int cout, int cin, int cin_padded, int taps, const float* dw, float* grad, cudaStream_t st) {
+  const size_t smem = (size_t)taps * PW_TS * sizeof(float);
+  static std::atomic<uint64_t> attr_done{0};
+  HFAGP_CUDA(per_device_once(attr_done, [] { return cudaFuncSetAttribute(unpack_conv_wgrad_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * PW_TS * 4); }));
+  unpack_conv_wgrad_kernel<TC><<<dim3(cdiv(cin, 32), cdiv(cout, 32)), 256, smem, st>>>(cout, cin, cin_padded, taps, dw, grad);
+  HFAGP_CHECK_LAUNCH("unpack_conv_wgrad_kernel");
+  return HFAGP_OK;
+}
+
+extern "C" int hfagp_unpack_conv_wgrad(int cout, int cin, int cin_padded, int taps, const float* dw, float* grad, void* stream) {
+  HFAGP_CHECK_ARG(dw && grad && cout > 0 && cin > 0 && cin_padded >= cin && taps > 0 && taps <= 49, "unpack_conv_wgrad: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (taps == 9) return unpack_launch<9>(cout, cin, cin_padded, taps, dw, grad, st);
+  if (taps == 1) return unpack_launch<1>(cout, cin, cin_padded, taps, dw, grad, st);
+  if (taps == 16) return unpack_launch<16>(cout, cin, cin_padded, taps, dw, grad, st);
+  return unpack_launch<0>(cout, cin, cin_padded, taps, dw, grad, st);
+}
+
+extern "C" int hfagp_pack_conv_weight(int cout, int cin, int taps, const float* w, float scale, float* pk, uint16_t* pk_hi,
+                                      uint16_t* pk_lo, uint16_t* pkt_hi, uint16_t* pkt_lo, void* stream) {
+  HFAGP_CHECK_ARG(w && cout > 0 && cin > 0 && taps > 0 && taps <= 49, "pack_conv_weight: bad args");
+  HFAGP_CHECK_ARG((pk_hi != nullptr) == (pk_lo != nullptr) && (pkt_hi != nullptr) == (pkt_lo != nullptr),
+                  "pack_conv_weight: give both halves of a split pair");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (taps == 9) return pack_launch<9>(cout, cin, taps, w, scale, pk, pk_hi, pk_lo, pkt_hi, pkt_lo, st);
+  if (taps == 1) return pack_launch<1>(cout, cin, taps, w, scale, pk, pk_hi, pk_lo, pkt_hi, pkt_lo, st);
+  if (taps == 16) return pack_launch<16>(cout, cin, taps, w, scale, pk, pk_hi, pk_lo, pkt_hi, pkt_lo, st);
+  return pack_launch<0>(cout, cin, taps, w, scale, pk, pk_hi, pk_lo, pkt_hi, pkt_lo, st);
+}
+
 extern "C" int hfagp_split_bf16(long long count, const float* x, uint16_t* hi, uint16_t* lo, void* stream) {
   HFAGP_CHECK_ARG(x && hi && lo && count > 0, "split_bf16: bad args");
   if ((count & 3) == 0 && (((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0) {

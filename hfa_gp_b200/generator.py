@@ -330,8 +330,9 @@ class TriPlaneGenerator(nn.Module):
         if pl.cout <= 4:
             wmod, _ = ops.modulate(pl.w, styles, False)
             if rec is not None and pl.clamp > 0:
-                # training: the clamp mask of the ToRGB branch needs its output before the skip-image add
-                rec['mask'] = ops.torgb_small(x, wmod, pl.bias, 0.0, None, pl.cout).abs() < pl.clamp
+                # training: the clamp's derivative mask (taken before the skip-image add) comes out of the same pass
+                out, rec['mask'] = ops.torgb_small(x, wmod, pl.bias, pl.clamp, img, pl.cout, want_mask=True)
+                return out
             return ops.torgb_small(x, wmod, pl.bias, pl.clamp, img, pl.cout)
         if rec is not None and pl.clamp > 0:
             raise HfagpError('backward of a clamped wide ToRGB is not implemented (EG3D clamps only the 3-channel SR ToRGB)')
@@ -539,6 +540,9 @@ class TriPlaneGenerator(nn.Module):
         with torch.cuda.stream(self._side):
             jitter, u, depth_range, kw = self._render_inputs(b, res, ws.device, jitter_coarse, u_fine, pk)
         styles_flat = ag.StylesFn.apply(ws.float().contiguous(), self)
+        # every tensor-core layer's weights modulated in ONE launch (as at inference) instead of one launch per layer
+        offs, _ = pk['styles'].offsets(b)
+        self._premod = self._modulate_all(pk, styles_flat.detach(), offs, b)
         planes = ag.BackboneFn.apply(styles_flat, self, noise_mode, b, tap)
         if tap is not None:
             tap['planes'] = planes
@@ -548,6 +552,7 @@ class TriPlaneGenerator(nn.Module):
                 t_.record_stream(cur)
         feat, depth, wsum = ag.RenderFn.apply(planes, self, c, jitter, u, depth_range, kw, False)
         img = ag.SuperresFn.apply(feat, styles_flat, self, b, tap)
+        self._premod = None
         return {'image': img.permute(0, 3, 1, 2), 'image_raw': feat[..., :3].permute(0, 3, 1, 2),
                 'image_depth': depth.view(b, 1, res, res)}
 

@@ -70,8 +70,12 @@ class EqualConv2d(nn.Module):
         until the parameter is written again."""
         key = (self.weight._version, self.weight.device, self.weight.data_ptr(), ops.param_epoch[0])
         if self._pk is None or self._pk_key != key:
-            o, i, kh, kw = self.weight.shape
-            self._pk = (self.weight.detach() * self.scale).permute(2, 3, 0, 1).reshape(kh * kw, o, i).contiguous().float()
+            # one pass writes the fp32 operand, its split-bf16 pair and (while training) the transposed pair of the
+            # data-gradient convolution; the fp32 transposed form is built on demand (exact-fp32 path only)
+            grad = torch.is_grad_enabled() and self.weight.requires_grad
+            self._pk, self._pks, pkts = ops.pack_conv_weight(self.weight, self.scale, want_split=True, want_t=grad)
+            self._pks_src = self._pk
+            self._pkt, self._pkt_src, self._pkts = None, (self._pk if pkts is not None else None), pkts
             self._pk_key = key
         return self._pk
 
@@ -86,11 +90,13 @@ class EqualConv2d(nn.Module):
         """[k*k][I][O] (scale folded in): the operand of the data-gradient convolution; fp32 or split bf16."""
         pk = self.packed()
         if getattr(self, '_pkt_src', None) is not pk:
-            self._pkt, self._pkt_src, self._pkts = pk.transpose(1, 2).contiguous(), pk, None
+            self._pkt, self._pkt_src, self._pkts = None, pk, None
         if not split:
+            if self._pkt is None:
+                self._pkt = pk.transpose(1, 2).contiguous()
             return self._pkt
         if self._pkts is None:
-            self._pkts = ops.split(self._pkt)
+            self._pkts = ops.split(pk.transpose(1, 2).contiguous())
         return self._pkts
 
     def packed_linear(self):
@@ -197,11 +203,15 @@ class ConvLayer(nn.Sequential):
         tc = (rec['tc'] if BACKWARD_TC_OVERRIDE is None else BACKWARD_TC_OVERRIDE) and cout % 8 == 0 and cin % 8 == 0
         residual = rec['residual']
         kw = dict(g0=g0, g1=g1, out='split' if (tc and need_dx) else 'f32')
+        from ..autograd import _grad_slot
         if act is not None:
-            db = ops.zeros((cout,), g0.device)
+            # the kernels accumulate: straight into the leaves' gradient storage when they have it (FlatAdam's flat buffer)
+            inplace_b = _grad_slot(act.bias)
+            db = act.bias.grad.view(-1) if inplace_b else ops.zeros((cout,), g0.device)
             dz = ops.act_bwd(rec['y'], residual=residual, residual_scale=INV_SQRT2, act=ACT_LRELU, act_gain=SQRT2,
                              post_scale=INV_SQRT2 if residual is not None else 1.0, dbias=db, **kw)
-            grads[act.bias] = db.view(1, -1, 1, 1)
+            if not inplace_b:
+                grads[act.bias] = db.view(1, -1, 1, 1)
         else:
             dz = ops.act_bwd(rec['y'], act=ACT_LINEAR, act_gain=1.0, post_scale=post_scale, **kw)
         # ---- weight gradient (fp32 SIMT split-K); the equalised-lr scale is d(packed)/d(weight)
@@ -212,7 +222,10 @@ class ConvLayer(nn.Sequential):
         dwp = ops.zeros((k * k, cout, cin_p), g0.device)
         ops.conv2d_wgrad(x_in, dz, rec['taps'], dwp, oh=rec['oh'], ow=rec['ow'], in_stride=rec['stride'],
                          scale=conv.scale)
-        grads[conv.weight] = dwp[:, :, :cin].reshape(k, k, cout, cin).permute(2, 3, 0, 1)
+        if _grad_slot(conv.weight):
+            ops.unpack_conv_wgrad(dwp, conv.weight.grad)
+        else:
+            grads[conv.weight] = dwp[:, :, :cin].reshape(k, k, cout, cin).permute(2, 3, 0, 1)
         if not need_dx:
             return None
         # ---- data gradient: the forward kernels on transposed weights, then the blur transpose

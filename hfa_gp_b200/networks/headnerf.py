@@ -224,6 +224,21 @@ class HeadNeRF_Audio(_DrivenAvatar):
     pass
 
 
+class _ExactConv1d(nn.Conv1d):
+    """nn.Conv1d (same parameters / state_dict keys) evaluated as unfold + fp32 matmul: cuDNN runs these tiny
+    convolutions in TF32 by default and picks its backward algorithm per call, which put run-to-run noise of up to 6e-2
+    (relative L2) on the gradient of AudioAttNet's first layer; the reference's fp32 arithmetic is what the path promises."""
+
+    def forward(self, x):
+        k, s, p = self.kernel_size[0], self.stride[0], self.padding[0]
+        cols = torch.nn.functional.pad(x, (p, p)).unfold(2, k, s)           # [N, C, L_out, k]
+        n, c, lo, _ = cols.shape
+        y = cols.permute(0, 2, 1, 3).reshape(n * lo, c * k) @ self.weight.reshape(self.out_channels, c * k).t()
+        if self.bias is not None:
+            y = y + self.bias
+        return y.view(n, lo, self.out_channels).permute(0, 2, 1)
+
+
 class AudioAttNet(nn.Module):
     """8-frame attention smoothing of audio features (tiny; stays in PyTorch per SURVEY §2 #4)."""
 
@@ -233,7 +248,7 @@ class AudioAttNet(nn.Module):
         chans = [dim_aud, 16, 8, 4, 2, 1]
         layers = []
         for a, b in zip(chans[:-1], chans[1:]):
-            layers += [nn.Conv1d(a, b, kernel_size=3, stride=1, padding=1, bias=True), nn.LeakyReLU(0.02, True)]
+            layers += [_ExactConv1d(a, b, kernel_size=3, stride=1, padding=1, bias=True), nn.LeakyReLU(0.02, True)]
         self.attentionConvNet = nn.Sequential(*layers)
         self.attentionNet = nn.Sequential(nn.Linear(seq_len, seq_len, bias=True), nn.Softmax(dim=1))
 
@@ -253,7 +268,7 @@ class AudioNet(nn.Module):
         chans = [29, 32, 32, 64, 64]
         layers = []
         for a, b in zip(chans[:-1], chans[1:]):
-            layers += [nn.Conv1d(a, b, kernel_size=3, stride=2, padding=1, bias=True), nn.LeakyReLU(0.02, True)]
+            layers += [_ExactConv1d(a, b, kernel_size=3, stride=2, padding=1, bias=True), nn.LeakyReLU(0.02, True)]
         self.encoder_conv = nn.Sequential(*layers)
         self.encoder_fc1 = nn.Sequential(nn.Linear(64, 64), nn.LeakyReLU(0.02, True), nn.Linear(64, dim_aud))
 

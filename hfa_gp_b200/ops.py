@@ -168,13 +168,19 @@ def upfir_act(t: torch.Tensor, *, dcoef=None, noise=None, noise_gain=0.0, bias=N
     return out
 
 
-def torgb_small(x, wmod, bias, clamp, up_img, cout):
+def torgb_small(x, wmod, bias, clamp, up_img, cout, want_mask=False):
+    """``want_mask``: also return the clamp's derivative mask (bool [n,h,w,cout]) for the backward pass."""
     n, h, wd, cin = x.shape
     out = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.float32)
     if isinstance(x, Split):
         xs = (None, ptr(x.hi), ptr(x.lo))
     else:
         xs = (ptr(x), None, None)
+    if want_mask:
+        mask = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.bool)
+        _ok(_cabi.lib().hfagp_torgb_small_mask_fwd(n, h, wd, cin, cout, *xs, ptr(wmod), ptr(bias), clamp, ptr(up_img),
+                                                   ptr(out), ptr(mask), stream()), 'hfagp_torgb_small_mask_fwd')
+        return out, mask
     _ok(_cabi.lib().hfagp_torgb_small_fwd(n, h, wd, cin, cout, *xs, ptr(wmod), ptr(bias), clamp, ptr(up_img),
                                           ptr(out), stream()), 'hfagp_torgb_small_fwd')
     return out
@@ -438,6 +444,30 @@ def split(x: torch.Tensor) -> Split:
     lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     _ok(_cabi.lib().hfagp_split_bf16(x.numel(), ptr(x), ptr(hi), ptr(lo), stream()), 'hfagp_split_bf16')
     return Split(hi, lo)
+
+
+def pack_conv_weight(weight: torch.Tensor, scale: float, want_split=True, want_t=True):
+    """torch conv weight [O,I,kh,kw] * scale -> (pk [kh*kw,O,I] fp32, Split(pk) | None, Split(pk transposed to
+    [kh*kw,I,O]) | None) in one pass (``hfagp_pack_conv_weight``)."""
+    o, i, kh, kw = weight.shape
+    t = kh * kw
+    w = weight.detach().float().contiguous()
+    dev = w.device
+    pk = torch.empty((t, o, i), device=dev, dtype=torch.float32)
+    sp = Split(torch.empty((t, o, i), device=dev, dtype=torch.bfloat16), torch.empty((t, o, i), device=dev, dtype=torch.bfloat16)) if want_split else None
+    spt = Split(torch.empty((t, i, o), device=dev, dtype=torch.bfloat16), torch.empty((t, i, o), device=dev, dtype=torch.bfloat16)) if want_t else None
+    _ok(_cabi.lib().hfagp_pack_conv_weight(o, i, t, ptr(w), float(scale), ptr(pk), ptr(sp.hi) if sp else None,
+                                           ptr(sp.lo) if sp else None, ptr(spt.hi) if spt else None,
+                                           ptr(spt.lo) if spt else None, stream()), 'hfagp_pack_conv_weight')
+    return pk, sp, spt
+
+
+def unpack_conv_wgrad(dwp: torch.Tensor, grad: torch.Tensor):
+    """grad [O,I,kh,kw] += dwp [kh*kw,O,I_padded] in place (``hfagp_unpack_conv_wgrad``)."""
+    o, i, kh, kw = grad.shape
+    t, o2, ip = dwp.shape
+    assert t == kh * kw and o2 == o and ip >= i
+    _ok(_cabi.lib().hfagp_unpack_conv_wgrad(o, i, ip, t, ptr(dwp), ptr(grad), stream()), 'hfagp_unpack_conv_wgrad')
 
 
 def modulate_split(w: torch.Tensor, styles: torch.Tensor, demodulate: bool):

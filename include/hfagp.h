@@ -192,6 +192,11 @@ int hfagp_upfir_act_fwd(int batch, int h2, int w2, int c, const float* t, const 
 int hfagp_torgb_small_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const uint16_t* x_hi,
                           const uint16_t* x_lo, const float* w, const float* bias, float clamp,
                           const float* up_img, float* y, void* stream);
+/* Training form of hfagp_torgb_small_fwd: also writes mask[n][h][w][cout] (one byte each) = |acc + bias| < clamp, the
+ * derivative of the clamp the backward pass multiplies d(image) with (instead of a second, unclamped evaluation). */
+int hfagp_torgb_small_mask_fwd(int batch, int h, int w_, int cin, int cout, const float* x, const uint16_t* x_hi,
+                               const uint16_t* x_lo, const float* w, const float* bias, float clamp, const float* up_img,
+                               float* y, unsigned char* mask, void* stream);
 
 /* Per-layer styles for a whole network in one launch:
  *   styles[l][n][i] = (ws[n][widx[l]][:] . A_l[i][:] * inv_sqrt_wdim + b_l[i]) * post_gain[l]
@@ -502,6 +507,17 @@ int hfagp_frame_from_uint8(int batch, int h, int w_, int c, const unsigned char*
 int hfagp_frame_resize_u8(int batch, int h, int w_, int c, int out_h, int out_w, int ksize_h, const int* bounds_h,
                           const int* coeffs_h, int ksize_v, const int* bounds_v, const int* coeffs_v, const unsigned char* x,
                           unsigned char* tmp, unsigned char* y_u8, float* y_f32, void* stream);
+
+/* A convolution weight in torch layout w[cout][cin][taps] (taps = kh*kw) times `scale` (EqualConv2d's equalised-lr
+ * factor, code/networks/encoder3d.py:86-103) -> the operand forms of the encoder's forward and backward convolutions in one
+ * pass: pk[t][cout][cin] fp32, its split-bf16 pair (pk_hi, pk_lo), the transposed split-bf16 pair pkt[t][cin][cout] of the
+ * data-gradient convolution.  Every output (pair) may be NULL. */
+int hfagp_pack_conv_weight(int cout, int cin, int taps, const float* w, float scale, float* pk, uint16_t* pk_hi,
+                           uint16_t* pk_lo, uint16_t* pkt_hi, uint16_t* pkt_lo, void* stream);
+
+/* The way back for the weight gradient: dw[t][cout][cin_padded] (the layout hfagp_conv2d_wgrad accumulates in) is ADDED to
+ * grad[cout][cin][taps], the torch layout of EqualConv2d.weight.grad (the equalised-lr scale is already in dw). */
+int hfagp_unpack_conv_wgrad(int cout, int cin, int cin_padded, int taps, const float* dw, float* grad, void* stream);
 
 /* Layout helpers (elementwise, bandwidth-bound): NCHW <-> NHWC for the frame entering the encoder
  * and the image leaving the super-resolution head. */

@@ -119,6 +119,27 @@ def test_basis_qr_matches_lapack(k, m):
         ops.basis_qr(torch.ones(3, 40).cuda(), check_info=True)          # rank deficient: flagged, not silently wrong
 
 
+@pytest.mark.parametrize('o,i,k', [(40, 3, 1), (64, 48, 3), (70, 33, 4), (128, 128, 3)])
+def test_conv_weight_pack_and_wgrad_unpack(o, i, k):
+    """hfagp_pack_conv_weight / hfagp_unpack_conv_wgrad against the torch expressions they replace
+    (EqualConv2d: weight * scale, permuted to [taps][O][I]; the gradient's way back)."""
+    from hfa_gp_b200 import ops
+    g = torch.Generator().manual_seed(o + i + k)
+    w = torch.randn(o, i, k, k, generator=g).cuda()
+    scale = 1.0 / (i * k * k) ** 0.5
+    want = (w * scale).permute(2, 3, 0, 1).reshape(k * k, o, i).contiguous()
+    pk, sp, spt = ops.pack_conv_weight(w, scale)
+    assert torch.equal(pk, want)
+    assert float((sp.hi.float() + sp.lo.float() - want).abs().max()) <= 2.0 ** -16 * float(want.abs().max())
+    assert torch.equal(spt.hi, sp.hi.transpose(1, 2).contiguous()) and torch.equal(spt.lo, sp.lo.transpose(1, 2).contiguous())
+    ip = (i + 3) // 4 * 4
+    dwp = torch.randn(k * k, o, ip, generator=g).cuda()
+    grad0 = torch.randn(o, i, k, k, generator=g).cuda()
+    grad = grad0.clone()
+    ops.unpack_conv_wgrad(dwp, grad)
+    assert torch.equal(grad, grad0 + dwp[:, :, :i].reshape(k, k, o, i).permute(2, 3, 0, 1))
+
+
 def test_facepool_and_mse_kernels():
     from hfa_gp_b200 import autograd as ag
     g = torch.Generator().manual_seed(1)
