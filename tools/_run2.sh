@@ -1,4 +1,2 @@
-mkdir -p gpurun_out
-timeout 500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_training.py -m gpu -q -x -k "basis_qr or conv_weight_pack or latent_backward" > gpurun_out/san_mem.txt 2>&1; echo memcheck rc=$?; grep "ERROR SUMMARY\|passed\|failed" gpurun_out/san_mem.txt | tail -3
-timeout 500 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_training.py -m gpu -q -x -k "basis_qr and 50-7168 or conv_weight_pack and 64-48" > gpurun_out/san_race.txt 2>&1; echo racecheck rc=$?; grep "RACECHECK SUMMARY\|passed\|failed" gpurun_out/san_race.txt | tail -3
-for k in 1 2 3 4 5 6; do timeout 300 python -m pytest tests/test_gpu_training.py -m gpu -q -k "audio or 3dmm_step or person_2" 2>&1 | grep -v "^E   *where\|^E   *+" | tail -8 | grep -v "^$"; done
+for k in 1 2 3 4 5 6 7 8; do timeout 300 python -m pytest tests/test_gpu_training.py -m gpu -q -k "audio" 2>&1 | grep -v "^E   *where\|^E   *+" | tail -4 | grep -v "^$"; done
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "driven or frame_loop" 2>&1 | tail -3
