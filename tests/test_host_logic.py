@@ -208,3 +208,64 @@ def test_lpips_refuses_to_run_without_weights(monkeypatch, tmp_path):
         assert ka == kb and torch.equal(va, vb)
     monkeypatch.setenv('HFAGP_SYNTHETIC_LPIPS', '1')
     assert LPIPS(net='alex').synthetic
+
+
+def test_zero_arena_counts_then_serves_zeroed_views():
+    """ops.ZeroArena (the one memset of a captured training step): a measuring pass only counts, the next pass serves
+    aligned, zeroed, non-overlapping views; large requests and other devices keep their own fill; nothing is served
+    once the arena is ended (eager steps never see it)."""
+    arena = ops.ZeroArena('cpu')
+    arena.begin()
+    a = ops.zeros((3, 5), 'cpu')
+    b = ops.zeros((7,), torch.device('cpu'))
+    big = ops.zeros((ops.ZERO_ARENA_MAX_ITEM // 4 + 1,), 'cpu')
+    arena.end()
+    assert arena.buf is None and arena.need == 256 + 256 and big.numel() * 4 > ops.ZERO_ARENA_MAX_ITEM
+    assert a.untyped_storage().data_ptr() != b.untyped_storage().data_ptr()        # measuring: plain torch.zeros
+    arena.materialise()
+    arena.buf.fill_(255)                                     # stale contents of the previous step
+    arena.begin()
+    a = ops.zeros((3, 5), 'cpu')
+    b = ops.zeros((7,), 'cpu')
+    c = ops.zeros((1000,), 'cpu')                            # more than was measured: falls back, still zero
+    arena.end()
+    assert a.shape == (3, 5) and b.shape == (7,) and a.dtype == torch.float32
+    assert float(a.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0 and float(c.abs().sum()) == 0.0
+    base = arena.buf.data_ptr()
+    assert a.data_ptr() == base and b.data_ptr() == base + 256       # 256-byte slots (the CUDA allocator aligns the base)
+    assert not (base <= c.data_ptr() < base + arena.buf.numel())
+    a.fill_(1.0)
+    assert float(b.abs().sum()) == 0.0                       # no overlap
+    outside = ops.zeros((3, 5), 'cpu')
+    assert not (base <= outside.data_ptr() < base + arena.buf.numel())
+
+
+def test_exact_conv1d_equals_conv1d_and_keeps_the_state_dict():
+    """The audio nets' Conv1d layers as unfold + matmul (networks/headnerf.py:_ExactConv1d) against F.conv1d, forward
+    and both gradients, for the two geometries the reference uses (headnerf.py:284-349)."""
+    from hfa_gp_b200.networks.headnerf import AudioAttNet, AudioNet, _ExactConv1d
+    torch.manual_seed(0)
+    for cin, cout, stride, length in [(29, 32, 2, 16), (32, 16, 1, 8), (2, 1, 1, 8)]:
+        m = _ExactConv1d(cin, cout, kernel_size=3, stride=stride, padding=1)
+        x = torch.randn(5, cin, length, requires_grad=True)
+        y, yr = m(x), F.conv1d(x, m.weight, m.bias, stride=stride, padding=1)
+        assert y.shape == yr.shape and float((y - yr).abs().max()) < 2e-6
+        g = torch.randn_like(y)
+        gx, gw, gb = torch.autograd.grad((y * g).sum(), [x, m.weight, m.bias])
+        gxr, gwr, gbr = torch.autograd.grad((yr * g).sum(), [x, m.weight, m.bias])
+        assert float((gx - gxr).abs().max()) < 1e-5 and float((gw - gwr).abs().max()) < 1e-5 and float((gb - gbr).abs().max()) < 1e-5
+    keys = set(AudioNet(64, 16).state_dict()) | set(AudioAttNet(64, 8).state_dict())
+    assert 'encoder_conv.0.weight' in keys and 'attentionConvNet.8.bias' in keys and 'attentionNet.0.weight' in keys
+
+
+def test_grad_slot_only_accepts_dense_fp32_leaf_gradients():
+    from hfa_gp_b200.autograd import _grad_slot
+    p = torch.nn.Parameter(torch.randn(4, 3))
+    assert not _grad_slot(p)                                 # no gradient storage yet: the Function returns a tensor
+    flat = torch.zeros(12)
+    p.grad = flat.view(4, 3)                                 # FlatAdam's binding
+    assert _grad_slot(p)
+    p.grad = torch.zeros(3, 4).t()
+    assert not _grad_slot(p)                                 # not contiguous
+    assert not _grad_slot(p * 2.0)                           # not a leaf
+    assert not _grad_slot(None)
