@@ -369,14 +369,18 @@ class TriPlaneGenerator(nn.Module):
                 tap[name + '.conv0'] = self._as_f32(x)
         s1, st = next(styles_iter), next(styles_iter)
         plt = pk['layers'][id(blk.torgb)]
-        if rec is None and plt.cout <= 4 and self._use_tc(blk.cout) and blk.cout % 32 == 0 and not ops.deterministic():
+        if plt.cout <= 4 and self._use_tc(blk.cout) and blk.cout % 32 == 0 and not ops.deterministic():
             # super-resolution blocks: the 3-channel ToRGB rides on conv1's epilogue (its activations are still in
-            # registers there) instead of re-reading the whole layer output
+            # registers there) instead of re-reading the whole layer output — at inference and in the training forward
             wrgb, _ = ops.modulate(plt.w, st, False)                       # [n][1][k][cout]
             acc = ops.zeros((x.shape[0], blk.res, blk.res, plt.cout), wrgb.device)
-            x = self._conv_layer(x, blk.conv1, s1, noise_mode, pk, split_out=tc_next, rgb=(wrgb[:, 0], acc))
+            x = self._conv_layer(x, blk.conv1, s1, noise_mode, pk, split_out=tc_next, rgb=(wrgb[:, 0], acc), rec=r1)
             if tap is not None:
                 tap[name + '.conv1'] = self._as_f32(x)
+            if rt is not None:
+                # what the backward of the ToRGB branch reads: conv1's output, the styles, the clamp's derivative mask
+                rt.update(pl=plt, x=x, styles=st, small=True,
+                          mask=((acc + plt.bias).abs() < plt.clamp) if plt.clamp > 0 else None)
             img = ops.torgb_finalize(acc, plt.bias, plt.clamp, img)
             if tap is not None:
                 tap[name + '.img'] = img

@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 > gpurun_out/bench_r2c_n8.json 2> gpurun_out/bench_r2c_n8.err; tail -3 gpurun_out/bench_r2c_n8.err
-python -c "
-import json; d=json.loads(open('gpurun_out/bench_r2c_n8.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['n_gpus'])
-for k in ('train','train_rgb','reenact'): print(k, d[k]['value'], d[k].get('ms_per_step'), d[k].get('allreduce_floats_per_step'), d[k].get('final_loss'))"
+timeout 1200 python -m pytest tests/test_gpu_training.py tests/test_gpu_backward.py -m gpu -x -q 2>&1 | tail -4
+timeout 300 python bench.py --workload train 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('train rgb', d['value'], d['ms_per_step'])"
+timeout 300 python bench.py --workload train --trainer 3dmm --frames-per-step 1 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('train 3dmm b1', d['value'], d['ms_per_step'])"
