@@ -34,13 +34,16 @@ struct TallMat {
 
 // rows [m0, m0 + rows) -> s[r][0..64): columns >= K and rows >= `rows` are zero
 __device__ __forceinline__ void load_rows(const TallMat& a, int m0, int rows, int K, float (*s)[QR_P], int maxrows) {
+  // (a block is latency bound: keep several independent loads in flight per thread)
   if (a.sm == 1) {          // consecutive threads along m
-    for (int idx = threadIdx.x; idx < maxrows * QR_MAXK; idx += blockDim.x) {
+#pragma unroll 8
+    for (int idx = threadIdx.x; idx < maxrows * QR_MAXK; idx += 256) {
       const int r = idx % maxrows, k = idx / maxrows;
       s[r][k] = (r < rows && k < K) ? __ldg(a.p + (long long)(m0 + r) + k * a.sk) + a.eps : 0.f;
     }
   } else {                  // consecutive threads along k
-    for (int idx = threadIdx.x; idx < maxrows * QR_MAXK; idx += blockDim.x) {
+#pragma unroll 8
+    for (int idx = threadIdx.x; idx < maxrows * QR_MAXK; idx += 256) {
       const int k = idx % QR_MAXK, r = idx / QR_MAXK;
       s[r][k] = (r < rows && k < K) ? __ldg(a.p + (long long)(m0 + r) * a.sm + k * a.sk) + a.eps : 0.f;
     }
@@ -119,7 +122,8 @@ __global__ void __launch_bounds__(256) qr_apply_kernel(int M, int K, TallMat x, 
       load_rows(term ? y : x, m0, rows, K, sx, QR_AROWS);
       if (term || c == 0 || M2) {                   // the single-term form keeps its matrix across chunks
         const float* Mt = term ? M2 : M1;
-        for (int idx = threadIdx.x; idx < QR_MAXK * QR_MAXK; idx += blockDim.x) {
+#pragma unroll 8
+        for (int idx = threadIdx.x; idx < QR_MAXK * QR_MAXK; idx += 256) {
           const int k = idx >> 6, j = idx & 63;
           sm[k][j] = (k < K && j < K) ? __ldg(Mt + k * K + j) : 0.f;
         }

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_training.py tests/test_gpu_backward.py -m gpu -x -q 2>&1 | tail -4
-timeout 300 python bench.py --workload train 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('train rgb', d['value'], d['ms_per_step'])"
-timeout 300 python bench.py --workload train --trainer 3dmm --frames-per-step 1 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('train 3dmm b1', d['value'], d['ms_per_step'])"
+timeout 600 python -m pytest tests/test_gpu_training.py -m gpu -x -q -k "basis_qr or latent or full_size or 3dmm_step" 2>&1 | tail -3
+timeout 300 python tools/timeline_train_graph.py --trainer 3dmm --batch 1 --seq > gpurun_out/tl_3dmm_b1.txt 2>&1; grep "busy\|batch 1:" gpurun_out/tl_3dmm_b1.txt; grep " qr_" gpurun_out/tl_3dmm_b1.txt | head -8
