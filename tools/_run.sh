@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_training.py -m gpu -x -q -k "basis_qr or latent or full_size or 3dmm_step" 2>&1 | tail -3
-timeout 300 python tools/timeline_train_graph.py --trainer 3dmm --batch 1 --seq > gpurun_out/tl_3dmm_b1.txt 2>&1; grep "busy\|batch 1:" gpurun_out/tl_3dmm_b1.txt; grep " qr_" gpurun_out/tl_3dmm_b1.txt | head -8
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:render_tc -s 2 -c 1 -o gpurun_out/render_tc_v4 -f python tools/prof_render.py 4 > gpurun_out/ncu_render.log 2>&1; tail -2 gpurun_out/ncu_render.log
+ls -la gpurun_out/*.ncu-rep
