@@ -5,7 +5,7 @@
 One training step (``/root/reference/code/trainer_rgb.py:73-98``)::
 
     weights = gen.get_weights(real)           encoder convolutions + EqualLinear head   (tcgen05 / SIMT kernels)
-    latent  = gen.get_latent(weights)         thin QR (torch) + hfagp_latent_fwd
+    latent  = gen.get_latent(weights)         thin QR (hfagp_basis_qr_fwd) + hfagp_latent_fwd
     image   = gen.get_image(latent, label)    backbone -> renderer -> super-resolution   (frozen generator)
     image   = face_pool(image)                hfagp_facepool_fwd  (AdaptiveAvgPool2d(size), :63,84)
     loss    = MSE(real, image) + LPIPS        hfagp_mse_fwd + hfa_gp_b200.lpips
