@@ -101,3 +101,29 @@ def test_golden_generator_vectors():
         assert bool(((tap[k] == torch.from_numpy(z[k]).long()) | near).all()), k
     ds_ref = torch.from_numpy(z['depths_sorted'])
     assert (tap['depths_sorted'].squeeze(-1) - ds_ref).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize('k,m', [(50, 14 * 512), (20, 300), (7, 7), (1, 33)])
+def test_qr_restatement_equals_torch_qr(k, m):
+    """oracle/qr_ref.py (CholeskyQR2 + Householder sign reconstruction — the algorithm of csrc/qr.cu) against the
+    call the reference makes, torch.qr / torch.linalg.qr on (bases + 1e-8).T (headnerf.py:92): same Q including the
+    column signs, same R, same gradient through Q."""
+    from oracle import qr_ref
+    g = torch.Generator().manual_seed(100 * k + m)
+    bases = torch.randn(k, m, generator=g, dtype=torch.float64)
+    a = (bases + 1e-8).T
+    q_ref, r_ref = torch.linalg.qr(a, mode='reduced')
+    q, r = qr_ref.cholqr2_signed(a)
+    assert float((q - q_ref).abs().max()) < 1e-12 and float((r - r_ref).abs().max()) < 1e-10 * float(r_ref.abs().max())
+    assert torch.equal(torch.sign(torch.diagonal(r)), torch.sign(torch.diagonal(r_ref)))
+    # fp32 input, as the product sees it: LAPACK's fp32 factor to its own rounding level
+    q32, _ = qr_ref.cholqr2_signed(a.float())
+    q32_ref, _ = torch.linalg.qr(a.float(), mode='reduced')
+    assert float((q32 - q32_ref).abs().max()) < 5e-6
+    # gradient arriving at Q only
+    gq = torch.randn(m, k, generator=g, dtype=torch.float64)
+    leaf = a.clone().requires_grad_(True)
+    qq, _ = torch.linalg.qr(leaf, mode='reduced')
+    (qq * gq).sum().backward()
+    ga = qr_ref.qr_backward_q_only(gq, q, r)
+    assert float((ga - leaf.grad).abs().max()) < 1e-9 * max(1.0, float(leaf.grad.abs().max()))
