@@ -107,14 +107,6 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
   lo = pack_bf16x2(a - ah, b - bh);
 }
-// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: two fp32 operations per issue slot; a pair is a 64-bit register,
-// element 0 in the low half)
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 // split_pair on a packed pair
 __device__ __forceinline__ void split_pair2(f32x2 ab, uint32_t& hi, uint32_t& lo) {
   float a, b;
