@@ -106,8 +106,8 @@ def lib() -> C.CDLL:
     l.hfagp_unpack_conv_wgrad.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     l.hfagp_basis_qr_workspace_bytes.argtypes = [i32, i32]
     l.hfagp_basis_qr_workspace_bytes.restype = C.c_size_t
-    l.hfagp_basis_qr_fwd.argtypes = [i32, i32, vp, f32, vp, vp, vp, vp]
-    l.hfagp_basis_qr_bwd.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+    l.hfagp_basis_qr_fwd.argtypes = [i32, i32, vp, f32, vp, vp, vp, i32, vp]
+    l.hfagp_basis_qr_bwd.argtypes = [i32, i32, vp, vp, vp, vp, vp, i32, vp]
     l.hfagp_basis_qr_info.argtypes = [vp, i32, i32, C.POINTER(C.c_int), vp]
     l.hfagp_blur_up.argtypes = [i32] * 7 + [f32, vp, vp, vp]
     l.hfagp_act_bwd.argtypes = [C.POINTER(ActBwdDesc)] + [vp] * 23

@@ -88,12 +88,12 @@ __device__ __forceinline__ double rcp_nr(double x) {
 }
 
 // G[K][K] (fp64, zeroed before the launch) += X^T Y over this CTA's rows
-__global__ void __launch_bounds__(256) qr_gram_kernel(int M, int K, TallMat x, TallMat y, int same, double* __restrict__ G) {
+__global__ void __launch_bounds__(256) qr_gram_kernel(int M, int K, int cpc, TallMat x, TallMat y, int same, double* __restrict__ G) {
   __shared__ __align__(16) float sx[QR_GROWS][QR_P], sy[QR_GROWS][QR_P];
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
   float acc[4][4] = {};
-  for (int c = 0; c < QR_CPC; ++c) {
-    const int m0 = (blockIdx.x * QR_CPC + c) * QR_GROWS;
+  for (int c = 0; c < cpc; ++c) {
+    const int m0 = (blockIdx.x * cpc + c) * QR_GROWS;
     if (m0 >= M) break;
     const int rows = min(QR_GROWS, M - m0);
     if (c) __syncthreads();
@@ -106,14 +106,14 @@ __global__ void __launch_bounds__(256) qr_gram_kernel(int M, int K, TallMat x, T
 }
 
 // out = X M1 (+ Y M2) for this CTA's rows; optionally G (fp64) += out^T out
-__global__ void __launch_bounds__(256) qr_apply_kernel(int M, int K, TallMat x, const float* __restrict__ M1, TallMat y,
+__global__ void __launch_bounds__(256) qr_apply_kernel(int M, int K, int cpc, TallMat x, const float* __restrict__ M1, TallMat y,
                                                        const float* __restrict__ M2, float* __restrict__ out, long long os_m,
                                                        long long os_k, double* __restrict__ G) {
   __shared__ __align__(16) float sx[QR_AROWS][QR_P], sm[QR_MAXK][QR_P], so[QR_AROWS][QR_P];
   const int tr = threadIdx.x >> 4, tj = threadIdx.x & 15;      // output rows 2 tr, 2 tr + 1; columns 4 tj .. 4 tj + 3
   float gacc[4][4] = {};
-  for (int c = 0; c < QR_CPC; ++c) {
-    const int m0 = (blockIdx.x * QR_CPC + c) * QR_AROWS;
+  for (int c = 0; c < cpc; ++c) {
+    const int m0 = (blockIdx.x * cpc + c) * QR_AROWS;
     if (m0 >= M) break;
     const int rows = min(QR_AROWS, M - m0);
     float acc[2][4] = {};
@@ -334,7 +334,7 @@ static int qr_small_attr() {
 }
 
 extern "C" int hfagp_basis_qr_fwd(int k, int m, const float* bases, float eps, float* q, float* rinv, void* workspace,
-                                  void* stream) {
+                                  int deterministic, void* stream) {
   HFAGP_CHECK_ARG(k >= 1 && k <= QR_MAXK && m >= k, "basis_qr: need 1 <= k <= 64 and m >= k (got k=%d m=%d)", k, m);
   HFAGP_CHECK_ARG(bases && q && rinv && workspace, "basis_qr: null pointer");
   if (int e = qr_small_attr()) return e;
@@ -342,12 +342,15 @@ extern "C" int hfagp_basis_qr_fwd(int k, int m, const float* bases, float eps, f
   const QrWs w = qr_ws(workspace, k);
   HFAGP_CUDA(cudaMemsetAsync(workspace, 0, (char*)w.q1 - (char*)workspace, st));
   const TallMat a{bases, 1, m, eps}, q1{w.q1, k, 1, 0.f};
-  const int ng = cdiv(m, QR_GROWS * QR_CPC), na = cdiv(m, QR_AROWS * QR_CPC);
-  qr_gram_kernel<<<ng, 256, 0, st>>>(m, k, a, a, 1, w.g1);
+  // deterministic: ONE CTA walks all rows wherever a Gram matrix is accumulated, so the fp64 sums have a fixed order
+  // (~1 ms instead of ~40 us; the factor is cached at inference)
+  const int cg = deterministic ? cdiv(m, QR_GROWS) : QR_CPC, ca = deterministic ? cdiv(m, QR_AROWS) : QR_CPC;
+  const int ng = cdiv(m, QR_GROWS * cg), na = cdiv(m, QR_AROWS * ca);
+  qr_gram_kernel<<<ng, 256, 0, st>>>(m, k, cg, a, a, 1, w.g1);
   qr_small_fwd_kernel<<<1, 512, 2 * k * k * 8, st>>>(k, 0, m == k, w.g1, w.ra, w.rinv1, nullptr, nullptr, w.info);
-  qr_apply_kernel<<<na, 256, 0, st>>>(m, k, a, w.ra, a, nullptr, w.q1, k, 1, w.g2);
+  qr_apply_kernel<<<na, 256, 0, st>>>(m, k, ca, a, w.ra, a, nullptr, w.q1, k, 1, w.g2);
   qr_small_fwd_kernel<<<1, 512, 3 * k * k * 8, st>>>(k, 1, m == k, w.g2, w.rb, w.rinv1, w.q1, rinv, w.info);
-  qr_apply_kernel<<<cdiv(m, QR_AROWS * QR_CPC), 256, 0, st>>>(m, k, q1, w.rb, q1, nullptr, q, k, 1, nullptr);
+  qr_apply_kernel<<<cdiv(m, QR_AROWS * QR_CPC), 256, 0, st>>>(m, k, QR_CPC, q1, w.rb, q1, nullptr, q, k, 1, nullptr);
   HFAGP_CHECK_LAUNCH("basis_qr_fwd");
   return HFAGP_OK;
 }
@@ -362,7 +365,7 @@ extern "C" int hfagp_basis_qr_info(const void* workspace, int k, int m, int* inf
 }
 
 extern "C" int hfagp_basis_qr_bwd(int k, int m, const float* gq, const float* q, const float* rinv, float* gbases,
-                                  void* workspace, void* stream) {
+                                  void* workspace, int deterministic, void* stream) {
   HFAGP_CHECK_ARG(k >= 1 && k <= QR_MAXK && m >= k, "basis_qr_bwd: bad dims k=%d m=%d", k, m);
   HFAGP_CHECK_ARG(gq && q && rinv && gbases && workspace, "basis_qr_bwd: null pointer");
   if (int e = qr_small_attr()) return e;
@@ -370,9 +373,10 @@ extern "C" int hfagp_basis_qr_bwd(int k, int m, const float* gq, const float* q,
   const QrWs w = qr_ws(workspace, k);
   const TallMat Q{q, k, 1, 0.f}, GQ{gq, k, 1, 0.f};
   HFAGP_CUDA(cudaMemsetAsync(w.g1, 0, (size_t)k * k * 8, st));
-  qr_gram_kernel<<<cdiv(m, QR_GROWS * QR_CPC), 256, 0, st>>>(m, k, Q, GQ, 0, w.g1);
+  const int cg = deterministic ? cdiv(m, QR_GROWS) : QR_CPC;
+  qr_gram_kernel<<<cdiv(m, QR_GROWS * cg), 256, 0, st>>>(m, k, cg, Q, GQ, 0, w.g1);
   qr_small_bwd_kernel<<<1, 512, 2 * k * k * 8, st>>>(k, w.g1, rinv, w.ra, w.rb);
-  qr_apply_kernel<<<cdiv(m, QR_AROWS * QR_CPC), 256, 0, st>>>(m, k, GQ, w.ra, Q, w.rb, gbases, 1, m, nullptr);
+  qr_apply_kernel<<<cdiv(m, QR_AROWS * QR_CPC), 256, 0, st>>>(m, k, QR_CPC, GQ, w.ra, Q, w.rb, gbases, 1, m, nullptr);
   HFAGP_CHECK_LAUNCH("basis_qr_bwd");
   return HFAGP_OK;
 }

@@ -363,7 +363,8 @@ def basis_qr(bases, eps=1e-8, check_info=False):
     q = torch.empty((m, k), device=b.device, dtype=torch.float32)
     rinv = torch.empty((k, k), device=b.device, dtype=torch.float32)
     ws = _qr_workspace(k, m, b.device)
-    _ok(_cabi.lib().hfagp_basis_qr_fwd(k, m, ptr(b), float(eps), ptr(q), ptr(rinv), ptr(ws), stream()), 'hfagp_basis_qr_fwd')
+    _ok(_cabi.lib().hfagp_basis_qr_fwd(k, m, ptr(b), float(eps), ptr(q), ptr(rinv), ptr(ws), int(_deterministic), stream()),
+        'hfagp_basis_qr_fwd')
     _launches[0] += 4                     # Gram, k x k, apply + Gram, k x k + signs, apply
     if check_info:
         info = C.c_int(0)
@@ -379,7 +380,8 @@ def basis_qr_bwd(gq, q, rinv):
     gq = gq.float().contiguous()
     gb = torch.empty((k, m), device=q.device, dtype=torch.float32)
     ws = _qr_workspace(k, m, q.device)
-    _ok(_cabi.lib().hfagp_basis_qr_bwd(k, m, ptr(gq), ptr(q), ptr(rinv), ptr(gb), ptr(ws), stream()), 'hfagp_basis_qr_bwd')
+    _ok(_cabi.lib().hfagp_basis_qr_bwd(k, m, ptr(gq), ptr(q), ptr(rinv), ptr(gb), ptr(ws), int(_deterministic), stream()),
+        'hfagp_basis_qr_bwd')
     _launches[0] += 2
     return gb
 

@@ -417,11 +417,14 @@ int hfagp_latent_bwd(int batch, int k, int dim, const float* dws, const float* w
  * cond(bases) < ~1e3: a Cholesky pivot below that floor sets a device flag readable with hfagp_basis_qr_info (which synchronises the stream; validation use).
  * `workspace`: hfagp_basis_qr_workspace_bytes(k, m) bytes of device memory, 256-byte aligned; contents are scratch.
  * hfagp_basis_qr_bwd: the autograd backward of that factorisation for a gradient arriving at Q only (R is unused
- * downstream): gbases[k][m] (WRITTEN) = ((gQ + Q Y) R^-T)^T with Y = X + X^T - diag(X), X = triu(-Q^T gQ). */
+ * downstream): gbases[k][m] (WRITTEN) = ((gQ + Q Y) R^-T)^T with Y = X + X^T - diag(X), X = triu(-Q^T gQ).
+ * `deterministic` != 0: the Gram matrices are accumulated by one CTA in row order instead of by fp64 atomics from many (the
+ * atomic order can move the last bit of the fp32 result from run to run); ~1 ms instead of ~40 us. */
 size_t hfagp_basis_qr_workspace_bytes(int k, int m);
-int hfagp_basis_qr_fwd(int k, int m, const float* bases, float eps, float* q, float* rinv, void* workspace, void* stream);
+int hfagp_basis_qr_fwd(int k, int m, const float* bases, float eps, float* q, float* rinv, void* workspace,
+                       int deterministic, void* stream);
 int hfagp_basis_qr_bwd(int k, int m, const float* gq, const float* q, const float* rinv, float* gbases, void* workspace,
-                       void* stream);
+                       int deterministic, void* stream);
 int hfagp_basis_qr_info(const void* workspace, int k, int m, int* info_host, void* stream);
 
 /* face_pool = AdaptiveAvgPool2d((size,size)) of the generated image (code/trainer_rgb.py:63,84) for an integer

@@ -117,6 +117,17 @@ def test_basis_qr_matches_lapack(k, m):
     assert pu.rel_err(gb, bd.grad.float()) < 2e-5
     with pytest.raises(Exception):
         ops.basis_qr(torch.ones(3, 40).cuda(), check_info=True)          # rank deficient: flagged, not silently wrong
+    # deterministic mode: the Gram matrices summed by one CTA in row order -> bit-identical from call to call
+    prev = ops.set_deterministic(True)
+    try:
+        qa, ra = ops.basis_qr(bases.cuda())
+        qb, rb = ops.basis_qr(bases.cuda())
+        ga = ops.basis_qr_bwd(gq.cuda(), qa, ra)
+        gb2 = ops.basis_qr_bwd(gq.cuda(), qa, ra)
+    finally:
+        ops.set_deterministic(prev)
+    assert torch.equal(qa, qb) and torch.equal(ra, rb) and torch.equal(ga, gb2)
+    assert float((qa.cpu() - q).abs().max()) < 1e-6 and pu.rel_err(ga.cpu(), gb) < 1e-5
 
 
 @pytest.mark.parametrize('o,i,k', [(40, 3, 1), (64, 48, 3), (70, 33, 4), (128, 128, 3)])
