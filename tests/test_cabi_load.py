@@ -70,3 +70,14 @@ def test_hot_path_refuses_cpu_tensors():
     from hfa_gp_b200 import _cabi
     with pytest.raises(_cabi.HfagpError):
         _cabi.ptr(torch.zeros(4))
+
+
+def test_workspace_queries_are_host_only_and_aligned():
+    """The *_workspace_bytes queries run without a GPU (no compute call): sizes are 256-byte multiples, grow with the
+    problem and reject nonsense."""
+    from hfa_gp_b200 import _cabi
+    lib = _cabi.lib()
+    a = lib.hfagp_basis_qr_workspace_bytes(50, 14 * 512)
+    b = lib.hfagp_basis_qr_workspace_bytes(64, 14 * 512)
+    assert (a - 256) % 256 == 0 and b > a >= 50 * 14 * 512 * 4
+    assert lib.hfagp_basis_qr_workspace_bytes(0, 100) == 0 and lib.hfagp_basis_qr_workspace_bytes(8, 0) == 0
